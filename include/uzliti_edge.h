@@ -1,0 +1,171 @@
+/* uzliti_edge.h — C-ABI of the B200 feature-edge estimation path.
+ *
+ * This is the drop-in boundary for ONE path of jan-frost/uzliti_slam: what
+ *   transformation_estimation/include/transformation_estimation/feature_transformation_estimator.h:33-58
+ * exposes (estimateEdgeImpl / estimateEdgeDirect / estimateSVD / consensus3D / setConfig) and what
+ *   transformation_estimation/include/transformation_estimation/transformation_estimator.h:45-67
+ * queues (estimateEdge), restated as plain C entry points: borrowed read-only host pointers in,
+ * caller-allocated result arrays out, no C++/torch/ROS types.  The C++ adapter in adapter/ maps
+ * SlamNode / FeatureData / SlamEdge onto these calls; INTEGRATION.md shows the reference-side binding.
+ *
+ * All functions return UZ_OK (0) or a negative uz_status.  A per-pair failure (no comparable camera
+ * pair, < 3 depth-valid matches) is NOT an error: it is reported in-band as result.ok == 0 with
+ * consensus == 0, mirroring transformation_estimator.cpp:53-55 (matching_score_ = 0, callback still fires).
+ * There is no CPU fallback: every compute entry point fails with UZ_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef UZLITI_EDGE_H
+#define UZLITI_EDGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UZ_DESC_BYTES 32          /* ORB/BRIEF-256: feature_extraction/external/aorb/aorb.h:54 (kBytes = 32) */
+#define UZ_MAX_FEATURES 4096      /* per camera (solve kernel keeps a pair on-chip); reference front-end caps at 400 (cfg/FeatureExtraction.cfg:11) */
+#define UZ_MAX_ITERATIONS 4096    /* cfg/FeatureLinkEstimation.cfg:11 allows 1..1000 */
+
+typedef enum {
+    UZ_OK = 0,
+    UZ_ERR_INVALID = -1,      /* bad argument (null pointer, size out of range, unknown keyframe handle) */
+    UZ_ERR_CUDA = -2,         /* CUDA runtime error or no usable device; see uz_last_error() */
+    UZ_ERR_NOMEM = -3,
+    UZ_ERR_UNSUPPORTED = -4   /* e.g. descriptor width != 32 bytes, non-binary feature type */
+} uz_status;
+
+/* graph_slam_msgs/msg/Features.msg:1-6 */
+enum { UZ_FEATURE_BRIEF = 1, UZ_FEATURE_ORB = 2, UZ_FEATURE_BRISK = 3, UZ_FEATURE_FREAK = 4,
+       UZ_FEATURE_SURF = 5, UZ_FEATURE_SIFT = 6 };
+
+typedef struct uz_context uz_context;
+
+/* Parameters of the path.  Mirrors transformation_estimation/cfg/FeatureLinkEstimation.cfg:9-13 plus the
+ * constants hard-coded in feature_transformation_estimator.cpp (:47 min 7 keypoints, :67 ratio 0.99,
+ * :118 min 3 matches).  uz_default_params() fills the reference's production values
+ * (iti_slam_launch/yaml/slam.yaml:35-36: threshold 0.1, 100 iterations; cfg default break 0.6). */
+typedef struct {
+    double  ransac_threshold;      /* config_.ransac_threshold  (consensus3D maxError, metres)   */
+    double  break_percentage;      /* config_.ransac_break_percentage                            */
+    int32_t ransac_iterations;     /* config_.ransac_iteration                                   */
+    int32_t do_prosac;             /* estimateSVD(..., do_prosac): 1 = growing-prefix shuffle     */
+    int32_t ratio_num, ratio_den;  /* keep best iff ratio_den*d0 < ratio_num*d1   (99/100 == :67) */
+    int32_t min_keypoints;         /* :47 (7)                                                    */
+    int32_t cross_check;           /* opt-in mutual-nearest filter; the reference has none (0)    */
+} uz_params;
+
+/* One FeatureData (graph_slam_common/include/graph_slam_common/sensor_data.h:49-70) as borrowed POD. */
+typedef struct {
+    const uint8_t* descriptors;    /* features_: n rows x 32 bytes, row stride desc_stride (cv::Mat CV_8U) */
+    const double*  positions;      /* feature_positions_: 3 x n column-major doubles (Eigen::MatrixXd)      */
+    const uint8_t* valid_3d;       /* valid_3d_: n bytes, non-zero = has depth                               */
+    int32_t n;
+    int32_t desc_stride;           /* bytes between descriptor rows (>= 32)                                  */
+    int32_t feature_type;          /* feature_type_                                                          */
+    int32_t sensor_frame;          /* sensor_frame_ interned by the caller (equal strings <=> equal tags)    */
+} uz_features;
+
+/* The SlamEdge fields estimateEdgeDirect fills (feature_transformation_estimator.cpp:147-156). */
+typedef struct {
+    int32_t ok;                    /* estimateEdgeImpl's bool                                            */
+    int32_t cam_from, cam_to;      /* index of the winning FeatureData in from/to sensor lists; -1 none  */
+    int32_t n_ratio_matches;       /* score of the winning camera pair (:78)                             */
+    int32_t n_matches;             /* M: matches left after the valid_3d filter (:115)                   */
+    int32_t consensus;             /* matching_score_ (:155); 0 when !ok                                 */
+    int32_t best_iteration;        /* index of the winning hypothesis, -1 if none                        */
+    int32_t iterations_run;        /* hypotheses evaluated before the early break (:239)                 */
+    double  mse;                   /* mean inlier residual norm (:285-290)                               */
+    double  info_scale;            /* information_ = I6 * info_scale, rotation block x100 more (:133-137)*/
+    double  T[16];                 /* transform_: row-major 4x4, maps to-frame points into the from-frame */
+} uz_edge_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+uz_status uz_create(int32_t device, uz_context** out);
+void      uz_destroy(uz_context* ctx);
+const char* uz_last_error(const uz_context* ctx);          /* never NULL */
+void      uz_default_params(uz_params* p);
+/* setConfig (feature_transformation_estimator.cpp:350-353).  Snapshotted per batch. */
+uz_status uz_set_params(uz_context* ctx, const uz_params* p);
+uz_status uz_get_params(const uz_context* ctx, uz_params* p);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL = own stream. */
+uz_status uz_set_stream(uz_context* ctx, void* cuda_stream);
+
+/* ---- device-resident keyframe store --------------------------------------------------------- */
+/* Adds one SlamNode's FEATURE sensor data (slam_node.h:93 sensor_data_) and returns a dense handle.
+ * Host buffers are copied before return.  Replaces what estimateEdge's by-value SlamNode copy carried
+ * (transformation_estimator.cpp:39). */
+uz_status uz_store_add(uz_context* ctx, const uz_features* cams, int32_t n_cams, int32_t* handle_out);
+uz_status uz_store_add_bulk(uz_context* ctx, const uz_features* cams, const int32_t* cams_per_keyframe,
+                            int32_t n_keyframes, int32_t* handles_out);
+uz_status uz_store_remove(uz_context* ctx, int32_t handle);
+uz_status uz_store_clear(uz_context* ctx);
+int32_t   uz_store_size(const uz_context* ctx);            /* live keyframes */
+int64_t   uz_store_bytes(const uz_context* ctx);           /* device bytes held by the store */
+
+/* ---- stage entry points (parity + direct callers) -------------------------------------------- */
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) (feature_transformation_estimator.cpp:38,58).
+ * idx/dist: nq x 2 int32, ordered by (distance, trainIdx); missing neighbours (nt < 2) are -1. */
+uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32_t q_stride,
+                        const uint8_t* train, int32_t nt, int32_t t_stride,
+                        int32_t* idx_out, int32_t* dist_out);
+
+/* estimateSVD (feature_transformation_estimator.cpp:178-184; second caller transformation_filter.cpp:272).
+ * P, Q: 3 x M column-major.  samples: optional iterations x 3 int32 sample list (NULL = the built-in
+ * replay of std::random_shuffle over rand() seed 1).  inlier_mask (optional): M bytes. */
+uz_status uz_estimate_svd(uz_context* ctx, const double* P, const double* Q, int32_t M,
+                          double max_error, int32_t iterations, double break_percentage, int32_t do_prosac,
+                          const int32_t* samples, double* T16_out, int32_t* consensus_out, double* mse_out,
+                          uint8_t* inlier_mask_out, int32_t* best_iteration_out, int32_t* iterations_run_out);
+
+/* consensus3D (feature_transformation_estimator.cpp:337-347). */
+uz_status uz_consensus3d(uz_context* ctx, const double* P, const double* Q, int32_t M, const double* T16,
+                         double thresh, uint8_t* set_out, int32_t* count_out);
+
+/* The sample list the built-in generator produces for (M, iterations, do_prosac): iterations x 3. */
+uz_status uz_sample_list(uz_context* ctx, int32_t M, int32_t iterations, int32_t do_prosac, int32_t* out);
+
+/* ---- the batched path ------------------------------------------------------------------------ */
+/* estimateEdge x n_pairs on keyframes already in the store (handles from uz_store_add).
+ * results: n_pairs records in HOST memory.  Blocks until done. */
+uz_status uz_estimate_edges(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
+                            int32_t n_pairs, uz_edge_result* results);
+
+/* Same, results written to DEVICE memory (n_pairs records), asynchronous on the context's stream; the
+ * caller synchronises.  This is the form the multi-GPU harness gathers over NCCL. */
+uz_status uz_estimate_edges_device(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
+                                   int32_t n_pairs, void* results_device);
+
+/* estimateEdgeDirect x n_pairs straight from host FeatureData (feature_transformation_estimator.cpp:32):
+ * from_cams/to_cams are concatenated per pair, n_from[i]/n_to[i] cameras each.  Uploads, runs, downloads. */
+uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, const int32_t* n_from,
+                                 const uz_features* to_cams, const int32_t* n_to, int32_t n_pairs,
+                                 uz_edge_result* results);
+
+/* Parity taps for the LAST uz_estimate_edges / uz_estimate_edges_host call (valid until the next call on this context):
+ * the sorted final_matches (:114) as (queryIdx, trainIdx, distance) triples and the final inlier mask.
+ * Enable with uz_set_debug(ctx, 1) BEFORE the call; capacity is in matches. Returns M through n_out. */
+uz_status uz_set_debug(uz_context* ctx, int32_t enable);
+uz_status uz_debug_pair(uz_context* ctx, int32_t pair_index, int32_t* matches_out, uint8_t* inlier_mask_out,
+                        int32_t capacity, int32_t* n_out);
+
+/* ---- introspection for the bench harness ----------------------------------------------------- */
+/* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
+int64_t   uz_launch_count(const uz_context* ctx);
+/* Device time (ms, CUDA events on the context stream) of the matching / solve kernels accumulated since
+ * the last uz_reset_timers(); timing is off unless enabled (events add launch overhead). */
+uz_status uz_enable_timers(uz_context* ctx, int32_t enable);
+uz_status uz_reset_timers(uz_context* ctx);
+uz_status uz_get_timers(uz_context* ctx, double* match_ms, double* solve_ms, int64_t* match_launches,
+                        int64_t* solve_launches, int64_t* descriptor_compares);
+/* Integer-pipe microbenchmark used for the roofline denominator: op 0 = POPC.b32, 1 = LOP3.b32,
+ * 2 = IMAD.u32, 3 = VIMNMX.u32, 4 = the match kernel's own compare mix.  Returns giga-ops/s. */
+uz_status uz_microbench(uz_context* ctx, int32_t op, double* gops_out);
+
+const char* uz_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UZLITI_EDGE_H */

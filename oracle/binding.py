@@ -1,0 +1,155 @@
+"""ctypes binding of the CPU oracle (oracle/uz_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under uzliti_slam_b200/ may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libuz_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "uz_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "CXX=g++"] + (["-B"] if force else []))
+    return _SO
+
+
+class Features(C.Structure):
+    _fields_ = [("descriptors", C.c_void_p), ("positions", C.c_void_p), ("valid_3d", C.c_void_p),
+                ("n", C.c_int32), ("desc_bytes", C.c_int32), ("desc_stride", C.c_int32),
+                ("feature_type", C.c_int32), ("sensor_frame", C.c_int32)]
+
+
+class Edge(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("cam_from", C.c_int32), ("cam_to", C.c_int32),
+                ("n_ratio_matches", C.c_int32), ("n_matches", C.c_int32), ("consensus", C.c_int32),
+                ("best_iteration", C.c_int32), ("iterations_run", C.c_int32),
+                ("mse", C.c_double), ("info_scale", C.c_double), ("T", C.c_double * 16)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.uzo_estimate_edge.restype = None
+        _lib.uzo_estimate_svd.restype = None
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def knn2(q, t):
+    """(idx[nq,2], dist[nq,2]) int32; missing neighbours are -1."""
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    nq = q.shape[0]
+    nb = q.shape[1] if q.ndim == 2 else t.shape[1]
+    idx = np.empty((nq, 2), np.int32)
+    dist = np.empty((nq, 2), np.int32)
+    lib().uzo_knn2(_p(q), nq, nb, _p(t), t.shape[0], nb, nb, _p(idx), _p(dist))
+    return idx, dist
+
+
+def ratio_pass(d0, d1):
+    return bool(lib().uzo_ratio_pass(int(d0), int(d1)))
+
+
+def sample_list(M, iterations, do_prosac=True):
+    out = np.zeros((iterations, 3), np.int32)
+    if M >= 3:
+        lib().uzo_sample_list(int(M), int(iterations), int(bool(do_prosac)), _p(out))
+    return out
+
+
+def glibc_rand(n, seed=1):
+    out = np.empty(n, np.int32)
+    lib().uzo_glibc_rand(C.c_uint(seed), n, _p(out))
+    return out
+
+
+def pose_svd(P, Q):
+    """P, Q: (k,3) float64 rows = points (memory == Eigen 3xk column-major).  4x4 T with T*p ~= q."""
+    P = np.ascontiguousarray(P, np.float64)
+    Q = np.ascontiguousarray(Q, np.float64)
+    T = np.empty(16, np.float64)
+    lib().uzo_pose_svd(_p(P), _p(Q), P.shape[0], _p(T))
+    return T.reshape(4, 4)
+
+
+def consensus3d(P, Q, T, thr):
+    P = np.ascontiguousarray(P, np.float64)
+    Q = np.ascontiguousarray(Q, np.float64)
+    T = np.ascontiguousarray(T, np.float64)
+    mask = np.zeros(P.shape[0], np.uint8)
+    c = lib().uzo_consensus3d(_p(P), _p(Q), P.shape[0], _p(T), C.c_double(thr), _p(mask))
+    return c, mask.astype(bool)
+
+
+def estimate_svd(P, Q, thr, iterations, bp, do_prosac=True, samples=None):
+    P = np.ascontiguousarray(P, np.float64)
+    Q = np.ascontiguousarray(Q, np.float64)
+    M = P.shape[0]
+    T = np.empty(16, np.float64)
+    cons = C.c_int32()
+    mse = C.c_double()
+    bi = C.c_int32()
+    ir = C.c_int32()
+    mask = np.zeros(max(M, 1), np.uint8)
+    sp = None
+    if samples is not None:
+        samples = np.ascontiguousarray(samples, np.int32)
+        sp = _p(samples)
+    lib().uzo_estimate_svd(_p(P), _p(Q), M, C.c_double(thr), int(iterations), C.c_double(bp),
+                           int(bool(do_prosac)), sp, _p(T), C.byref(cons), C.byref(mse), _p(mask),
+                           C.byref(bi), C.byref(ir))
+    return dict(T=T.reshape(4, 4), consensus=cons.value, mse=mse.value, mask=mask[:M].astype(bool),
+                best_iteration=bi.value, iterations_run=ir.value)
+
+
+def make_features(cams):
+    """cams: list of dicts(desc uint8[n,B], pos float64[n,3], valid uint8[n], feature_type, sensor_frame).
+    Returns (ctypes array, keepalive)."""
+    arr = (Features * max(len(cams), 1))()
+    keep = []
+    for i, c in enumerate(cams):
+        d = np.ascontiguousarray(c["desc"], np.uint8)
+        p = np.ascontiguousarray(c["pos"], np.float64)
+        v = np.ascontiguousarray(c["valid"], np.uint8)
+        keep += [d, p, v]
+        n = d.shape[0]
+        nb = d.shape[1] if d.ndim == 2 and n > 0 else 32
+        arr[i] = Features(d.ctypes.data, p.ctypes.data, v.ctypes.data, n, nb, nb,
+                          int(c.get("feature_type", 2)), int(c.get("sensor_frame", 0)))
+    return arr, keep
+
+
+def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac=True, min_keypoints=7,
+                  want_debug=True):
+    """estimateEdgeDirect over two keyframes (lists of camera dicts)."""
+    fa, k1 = make_features(cams_from)
+    ta, k2 = make_features(cams_to)
+    e = Edge()
+    maxm = max([c["desc"].shape[0] for c in cams_to] + [1])
+    matches = np.zeros((maxm, 3), np.int32)
+    mask = np.zeros(maxm, np.uint8)
+    lib().uzo_estimate_edge(fa, len(cams_from), ta, len(cams_to), C.c_double(thr), int(iterations),
+                            C.c_double(bp), int(bool(do_prosac)), int(min_keypoints), C.byref(e),
+                            _p(matches) if want_debug else None, _p(mask) if want_debug else None, maxm)
+    M = e.n_matches
+    return dict(ok=bool(e.ok), cam_from=e.cam_from, cam_to=e.cam_to, n_ratio_matches=e.n_ratio_matches,
+                n_matches=M, consensus=e.consensus, best_iteration=e.best_iteration,
+                iterations_run=e.iterations_run, mse=e.mse, info_scale=e.info_scale,
+                T=np.array(e.T[:], np.float64).reshape(4, 4), matches=matches[:M].copy(),
+                inlier_mask=mask[:M].astype(bool))

@@ -1,0 +1,517 @@
+// uz_oracle.cpp — CPU ORACLE for the feature-edge estimation hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+// (uzliti_slam_b200/csrc) never includes, links or calls anything in oracle/.
+//
+// It is a plain restatement of the reference algorithm, with the arithmetic of the
+// un-vendored third-party libraries written out:
+//   /root/reference/transformation_estimation/src/feature_transformation_estimator.cpp
+//     :32-159  estimateEdgeDirect  (camera-pair loop, kNN-2, ratio, valid filter, sort, gather, edge)
+//     :178-184 estimateSVD         (binds pose + consensus into prosac)
+//     :186-297 prosac              (growing-prefix shuffle, strict '>' update, early break, refit, mse)
+//     :299-314 estimatePoseSVD     (pcl::TransformationFromCorrespondences, float32, weight==1 bug)
+//     :337-347 consensus3D         (double, strict '<')
+//   /root/reference/transformation_estimation/src/transformation_estimator.cpp:53-55 (score 0 on failure)
+//
+// Third-party arithmetic restated here (sources are NOT under /root/reference):
+//   * OpenCV cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)  [ROS Indigo => OpenCV 2.4.8; checked live
+//     against python cv2 4.13 in tests/test_oracle_matching.py]: per query row the two train rows with
+//     the smallest Hamming distance, ordered by (distance, trainIdx) ascending.
+//   * PCL 1.7 pcl::TransformationFromCorrespondences::{add,getTransformation}
+//     (common/impl/transformation_from_correspondences.hpp): float32 incremental mean/covariance,
+//     then Eigen::JacobiSVD<Matrix3f>(FullU|FullV), R = U*diag(1,1,±1)*V^T, t = mean2 - R*mean1.
+//   * Eigen 3.2.0 JacobiSVD (src/SVD/JacobiSVD.h: compute, real_2x2_jacobi_svd) and
+//     JacobiRotation (src/Jacobi/Jacobi.h: makeJacobi, operator*, applyOnTheLeft/Right), restated
+//     from the published algorithm; square 3x3 => no QR preconditioner.
+//   * libstdc++ std::random_shuffle (bits/stl_algo.h) over glibc rand(): the REAL functions are
+//     called here (they exist in this container), seed restarted to 1 per prosac() call.
+//
+// PARITY STATUS: matching stage pinned against cv2 (live).  RANSAC stage: "parity unpinned" — the
+// reference has no tests/golden vectors and PCL/Eigen are not installable here, so the float32
+// solve is pinned only by (a) recovering planted ground-truth motions and (b) agreement with an
+// independent float64 Kabsch solve (numpy) within float32 round-off (tests/test_oracle_ransac.py).
+//
+// Build: see oracle/Makefile (g++ -O3 -march=native -ffp-contract=off -std=c++14).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1: brute-force Hamming kNN-2  (feature_transformation_estimator.cpp:38,58)
+// ---------------------------------------------------------------------------------------------
+inline int hamming(const uint8_t* a, const uint8_t* b, int nbytes) {
+    int d = 0, i = 0;
+    for (; i + 8 <= nbytes; i += 8) {
+        uint64_t x, y;
+        std::memcpy(&x, a + i, 8);
+        std::memcpy(&y, b + i, 8);
+        d += __builtin_popcountll(x ^ y);
+    }
+    for (; i < nbytes; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+    return d;
+}
+
+// idx/dist are nq x 2; missing neighbours (nt < 2) are (-1, -1).
+void knn2(const uint8_t* q, int nq, int qstride, const uint8_t* t, int nt, int tstride, int nbytes,
+          int32_t* idx, int32_t* dist) {
+    for (int i = 0; i < nq; ++i) {
+        int d0 = INT32_MAX, d1 = INT32_MAX, i0 = -1, i1 = -1;
+        const uint8_t* qi = q + (size_t)i * qstride;
+        for (int j = 0; j < nt; ++j) {
+            int d = hamming(qi, t + (size_t)j * tstride, nbytes);
+            // strict '<' while scanning j ascending == order by (distance, trainIdx)
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+            else if (d < d1) { d1 = d; i1 = j; }
+        }
+        idx[2 * i] = i0; idx[2 * i + 1] = i1;
+        dist[2 * i] = i0 < 0 ? -1 : d0; dist[2 * i + 1] = i1 < 0 ? -1 : d1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2: ratio test (:65-71) — literal float/double form of the reference.
+// ---------------------------------------------------------------------------------------------
+inline bool ratio_pass(int d0, int d1) {
+    float f0 = (float)d0, f1 = (float)d1;      // cv::DMatch::distance is float
+    return f0 < 0.99 * f1;                      // float < double*float, as written at :67
+}
+
+struct Match { int q, t, d; };
+
+// ---------------------------------------------------------------------------------------------
+// Stage 3: pose from correspondences (:299-314) — PCL add()/getTransformation() in float32.
+// ---------------------------------------------------------------------------------------------
+struct Rot { float c, s; };   // Eigen::JacobiRotation<float>
+
+// JacobiRotation::makeJacobi(x, y, z)  (Jacobi.h)
+inline Rot make_jacobi(float x, float y, float z) {
+    Rot r;
+    if (y == 0.f) { r.c = 1.f; r.s = 0.f; return r; }
+    float tau = (x - z) / (2.f * std::fabs(y));
+    float w = std::sqrt(tau * tau + 1.f);
+    float t = (tau > 0.f) ? 1.f / (tau + w) : 1.f / (tau - w);
+    float sign_t = t > 0.f ? 1.f : -1.f;
+    float n = 1.f / std::sqrt(t * t + 1.f);
+    r.s = -sign_t * (y / std::fabs(y)) * std::fabs(t) * n;
+    r.c = n;
+    return r;
+}
+
+// rows p,q of a 3x3 (row-major m[r][c]): x' = c*x + s*y ; y' = -s*x + c*y   (applyOnTheLeft)
+inline void rot_rows(float m[3][3], int p, int q, Rot j) {
+    for (int k = 0; k < 3; ++k) {
+        float x = m[p][k], y = m[q][k];
+        m[p][k] = j.c * x + j.s * y;
+        m[q][k] = -j.s * x + j.c * y;
+    }
+}
+// columns p,q with rotation j applied "in the plane" (x' = c*x + s*y ; y' = -s*x + c*y)
+inline void rot_cols(float m[3][3], int p, int q, Rot j) {
+    for (int k = 0; k < 3; ++k) {
+        float x = m[k][p], y = m[k][q];
+        m[k][p] = j.c * x + j.s * y;
+        m[k][q] = -j.s * x + j.c * y;
+    }
+}
+
+// Eigen::JacobiSVD<Matrix3f>(A, ComputeFullU|ComputeFullV): A = U * diag(sv) * V^T
+void jacobi_svd3(const float A[3][3], float U[3][3], float V[3][3], float sv[3]) {
+    const float precision = 2.f * std::numeric_limits<float>::epsilon();
+    const float considerAsZero = 2.f * std::numeric_limits<float>::denorm_min();
+    float W[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { W[r][c] = A[r][c]; U[r][c] = V[r][c] = (r == c) ? 1.f : 0.f; }
+
+    bool finished = false;
+    while (!finished) {
+        finished = true;
+        for (int p = 1; p < 3; ++p) {
+            for (int q = 0; q < p; ++q) {
+                float threshold = std::max(considerAsZero,
+                                           precision * std::max(std::fabs(W[p][p]), std::fabs(W[q][q])));
+                if (std::max(std::fabs(W[p][q]), std::fabs(W[q][p])) > threshold) {
+                    finished = false;
+                    // real_2x2_jacobi_svd(W, p, q, &j_left, &j_right)
+                    float m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+                    Rot rot1;
+                    float t = m00 + m11;
+                    float d = m10 - m01;
+                    if (t == 0.f) {
+                        rot1.c = 0.f;
+                        rot1.s = d > 0.f ? 1.f : -1.f;
+                    } else {
+                        float u = d / t;
+                        rot1.c = 1.f / std::sqrt(1.f + u * u);
+                        rot1.s = rot1.c * u;
+                    }
+                    // m.applyOnTheLeft(0,1,rot1)
+                    float n00 = rot1.c * m00 + rot1.s * m10;
+                    float n01 = rot1.c * m01 + rot1.s * m11;
+                    float n11 = -rot1.s * m01 + rot1.c * m11;
+                    Rot jr = make_jacobi(n00, n01, n11);
+                    // j_left = rot1 * j_right.transpose()
+                    Rot jrt = {jr.c, -jr.s};
+                    Rot jl = {rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
+                    rot_rows(W, p, q, jl);                 // m_workMatrix.applyOnTheLeft(p,q,j_left)
+                    rot_cols(U, p, q, jl);                 // m_matrixU.applyOnTheRight(p,q,j_left.transpose())
+                    rot_cols(W, p, q, jrt);                // m_workMatrix.applyOnTheRight(p,q,j_right)
+                    rot_cols(V, p, q, jrt);                // m_matrixV.applyOnTheRight(p,q,j_right)
+                }
+            }
+        }
+    }
+    // step 3: make the diagonal positive
+    for (int i = 0; i < 3; ++i) {
+        float a = std::fabs(W[i][i]);
+        sv[i] = a;
+        if (a != 0.f) {
+            float sgn = W[i][i] / a;
+            for (int r = 0; r < 3; ++r) U[r][i] *= sgn;
+        }
+    }
+    // step 4: sort descending
+    for (int i = 0; i < 3; ++i) {
+        int pos = 0;
+        float best = sv[i];
+        for (int k = i + 1; k < 3; ++k)
+            if (sv[k] > best) { best = sv[k]; pos = k - i; }
+        if (best == 0.f) break;
+        if (pos) {
+            pos += i;
+            std::swap(sv[i], sv[pos]);
+            for (int r = 0; r < 3; ++r) { std::swap(U[r][i], U[r][pos]); std::swap(V[r][i], V[r][pos]); }
+        }
+    }
+}
+
+inline float det3(const float m[3][3]) {      // Eigen bruteforce_det3_helper order
+    return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1])
+         - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])
+         + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+
+// P,Q: 3 x k column-major double (P.col(i) = P[3*i..3*i+2]).  T: 4x4 row-major double, T*p ~= q.
+void pose_svd(const double* P, const double* Q, int k, double T[16]) {
+    int n = 0;
+    float acc = 0.f;
+    float mean1[3] = {0, 0, 0}, mean2[3] = {0, 0, 0};
+    float cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < k; ++i) {
+        float p[3] = {(float)P[3 * i], (float)P[3 * i + 1], (float)P[3 * i + 2]};
+        float q[3] = {(float)Q[3 * i], (float)Q[3 * i + 1], (float)Q[3 * i + 2]};
+        // :305-309 — inverse_weight is computed, but weight = 1./weight with weight == 1: always 1.
+        float inverse_weight = p[2] * p[2] + q[2] * q[2];
+        float weight = 1;
+        if (inverse_weight > 0) weight = 1. / weight;
+        // pcl::TransformationFromCorrespondences::add
+        if (weight == 0.0f) continue;
+        ++n;
+        acc += weight;
+        float alpha = weight / acc;
+        float d1[3] = {p[0] - mean1[0], p[1] - mean1[1], p[2] - mean1[2]};
+        float d2[3] = {q[0] - mean2[0], q[1] - mean2[1], q[2] - mean2[2]};
+        float oma = 1.0f - alpha;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                cov[r][c] = oma * (cov[r][c] + alpha * (d2[r] * d1[c]));
+        for (int r = 0; r < 3; ++r) { mean1[r] += alpha * d1[r]; mean2[r] += alpha * d2[r]; }
+    }
+    (void)n;
+    float U[3][3], V[3][3], sv[3];
+    jacobi_svd3(cov, U, V, sv);
+    float sgn = (det3(U) * det3(V) < 0.0f) ? -1.0f : 1.0f;
+    float R[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + (U[r][2] * sgn) * V[c][2];
+    float t[3];
+    for (int r = 0; r < 3; ++r)
+        t[r] = mean2[r] - (R[r][0] * mean1[0] + R[r][1] * mean1[1] + R[r][2] * mean1[2]);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T[4 * r + c] = (double)R[r][c];
+        T[4 * r + 3] = (double)t[r];
+    }
+    T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 4: consensus3D (:337-347) — double, ((r0*x + r1*y) + r2*z) + t, strict '<'.
+// ---------------------------------------------------------------------------------------------
+inline double residual(const double T[16], const double* p, const double* q) {
+    double x = ((T[0] * p[0] + T[1] * p[1]) + T[2] * p[2]) + T[3];
+    double y = ((T[4] * p[0] + T[5] * p[1]) + T[6] * p[2]) + T[7];
+    double z = ((T[8] * p[0] + T[9] * p[1]) + T[10] * p[2]) + T[11];
+    double dx = x - q[0], dy = y - q[1], dz = z - q[2];
+    return std::sqrt((dx * dx + dy * dy) + dz * dz);
+}
+
+int consensus3d(const double* P, const double* Q, int M, const double T[16], double thr, uint8_t* set) {
+    int count = 0;
+    for (int i = 0; i < M; ++i) {
+        bool in = residual(T, P + 3 * i, Q + 3 * i) < thr;
+        set[i] = in;
+        count += in;
+    }
+    return count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 5: the sample-index list (:198-225).  Data independent: depends on (M, I, do_prosac) and
+// the rand() stream only.  Uses the REAL std::random_shuffle + glibc rand(), seed restarted to 1.
+// ---------------------------------------------------------------------------------------------
+void sample_list(int M, int iterations, int do_prosac, int32_t* out /* iterations x 3 */) {
+    std::vector<int> idx;
+    for (int i = 0; i < M; i++) idx.push_back(i);
+    std::srand(1);
+    for (int i = 0; i < iterations; i++) {
+        if (do_prosac) {
+            std::random_shuffle(idx.begin(),
+                                idx.begin() + std::min((int)std::ceil(((i + 3.) / iterations) * M), (int)M));
+        } else {
+            std::random_shuffle(idx.begin(), idx.end());
+        }
+        for (int j = 0; j < 3; ++j) out[3 * i + j] = idx[j];
+    }
+}
+
+struct ProsacOut {
+    double T[16];
+    int consensus;
+    double mse;
+    int best_iteration;   // index of the winning hypothesis, -1 if none
+    int iterations_run;   // hypotheses evaluated before break / exhaustion
+};
+
+// prosac (:186-297) with minCorrespondenceCount = 3, on an explicit sample list.
+void prosac(const double* P, const double* Q, int M, const int32_t* samples, int iterations,
+            double thr, double breakPercentage, ProsacOut* out, uint8_t* inlier_mask /* M */) {
+    const int minCount = 3;
+    int maxConsensus = 0;
+    std::vector<uint8_t> set(M), maxSet(M, 0);
+    double T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double Ttemp[16];
+    out->best_iteration = -1;
+    int i = 0;
+    for (; i < iterations; i++) {
+        double Pt[9], Qt[9];
+        for (int j = 0; j < minCount; ++j) {
+            int s = samples[3 * i + j];
+            for (int r = 0; r < 3; ++r) { Pt[3 * j + r] = P[3 * s + r]; Qt[3 * j + r] = Q[3 * s + r]; }
+        }
+        pose_svd(Pt, Qt, minCount, Ttemp);
+        int consensus = consensus3d(P, Q, M, Ttemp, thr, set.data());
+        if (consensus > maxConsensus) {
+            maxConsensus = consensus;
+            maxSet = set;
+            std::memcpy(T, Ttemp, sizeof(T));
+            out->best_iteration = i;
+            if (maxConsensus >= minCount && maxConsensus > breakPercentage * M) { ++i; break; }
+        }
+    }
+    out->iterations_run = i;
+    double mse = 0.;
+    if (maxConsensus >= minCount) {
+        std::vector<double> Pf(3 * (size_t)maxConsensus), Qf(3 * (size_t)maxConsensus);
+        int k = 0;
+        for (int c = 0; c < M; ++c)
+            if (maxSet[c]) {
+                for (int r = 0; r < 3; ++r) { Pf[3 * k + r] = P[3 * c + r]; Qf[3 * k + r] = Q[3 * c + r]; }
+                k++;
+            }
+        pose_svd(Pf.data(), Qf.data(), maxConsensus, T);
+        maxConsensus = consensus3d(P, Q, M, T, thr, maxSet.data());
+        for (int c = 0; c < M; ++c)
+            if (maxSet[c]) mse += residual(T, P + 3 * c, Q + 3 * c);
+        mse /= maxConsensus;                       // NaN if the refit recount dropped to 0 (as :290)
+    } else {
+        maxConsensus = 0;
+        static const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        std::memcpy(T, I4, sizeof(T));
+        std::fill(maxSet.begin(), maxSet.end(), 0);
+    }
+    std::memcpy(out->T, T, sizeof(T));
+    out->consensus = maxConsensus;
+    out->mse = mse;
+    if (inlier_mask) std::memcpy(inlier_mask, maxSet.data(), M);
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C" surface (ctypes)
+// =================================================================================================
+extern "C" {
+
+// One camera's FeatureData (graph_slam_common/include/graph_slam_common/sensor_data.h:49-70) as POD.
+struct uzo_features {
+    const uint8_t* descriptors;   // n x desc_bytes, row stride desc_stride   (cv::Mat features_)
+    const double* positions;      // 3 x n column-major                       (feature_positions_)
+    const uint8_t* valid_3d;      // n bytes                                   (valid_3d_)
+    int32_t n;
+    int32_t desc_bytes;
+    int32_t desc_stride;
+    int32_t feature_type;         // graph_slam_msgs/Features: BRIEF=1 ORB=2 BRISK=3 FREAK=4 SURF=5 SIFT=6
+    int32_t sensor_frame;         // interned sensor_frame_ string
+};
+
+struct uzo_edge {
+    int32_t ok;                   // estimateEdgeDirect return value
+    int32_t cam_from, cam_to;     // index of the winning FeatureData in each list (-1: none)
+    int32_t n_ratio_matches;      // score at :78
+    int32_t n_matches;            // M after the valid_3d filter (:115)
+    int32_t consensus;            // matching_score_ (:155); 0 when !ok (transformation_estimator.cpp:54)
+    int32_t best_iteration;
+    int32_t iterations_run;
+    double mse;
+    double info_scale;            // information_ = I6*info_scale, rotation block additionally x100 (:133-137)
+    double T[16];                 // transform_ row-major 4x4
+};
+
+int uzo_knn2(const uint8_t* q, int nq, int qstride, const uint8_t* t, int nt, int tstride, int nbytes,
+             int32_t* idx, int32_t* dist) {
+    knn2(q, nq, qstride, t, nt, tstride, nbytes, idx, dist);
+    return 0;
+}
+
+int uzo_ratio_pass(int d0, int d1) { return ratio_pass(d0, d1) ? 1 : 0; }
+
+void uzo_sample_list(int M, int iterations, int do_prosac, int32_t* out) {
+    sample_list(M, iterations, do_prosac, out);
+}
+
+// first n outputs of glibc rand() after srand(seed) — used to pin the product's own generator.
+void uzo_glibc_rand(unsigned seed, int n, int32_t* out) {
+    std::srand(seed);
+    for (int i = 0; i < n; ++i) out[i] = std::rand();
+}
+
+void uzo_pose_svd(const double* P, const double* Q, int k, double* T16) { pose_svd(P, Q, k, T16); }
+
+int uzo_consensus3d(const double* P, const double* Q, int M, const double* T16, double thr, uint8_t* set) {
+    return consensus3d(P, Q, M, T16, thr, set);
+}
+
+// estimateSVD (:178-184).  samples may be NULL (generated from rand() seed 1 as the reference would).
+void uzo_estimate_svd(const double* P, const double* Q, int M, double thr, int iterations, double bp,
+                      int do_prosac, const int32_t* samples, double* T16, int32_t* consensus, double* mse,
+                      uint8_t* inlier_mask, int32_t* best_iteration, int32_t* iterations_run) {
+    std::vector<int32_t> own;
+    if (!samples) {
+        own.resize(3 * (size_t)iterations);
+        if (M >= 3) sample_list(M, iterations, do_prosac, own.data());
+        samples = own.data();
+    }
+    ProsacOut po;
+    if (M < 3) {   // the reference would index idx[0..2] out of range; callers guard with :118
+        static const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        std::memcpy(T16, I4, sizeof(I4));
+        *consensus = 0; *mse = 0;
+        if (inlier_mask) std::memset(inlier_mask, 0, M);
+        if (best_iteration) *best_iteration = -1;
+        if (iterations_run) *iterations_run = 0;
+        return;
+    }
+    prosac(P, Q, M, samples, iterations, thr, bp, &po, inlier_mask);
+    std::memcpy(T16, po.T, sizeof(po.T));
+    *consensus = po.consensus;
+    *mse = po.mse;
+    if (best_iteration) *best_iteration = po.best_iteration;
+    if (iterations_run) *iterations_run = po.iterations_run;
+}
+
+// estimateEdgeDirect (:32-159) + the failure convention of transformation_estimator.cpp:53-55.
+// Optional parity outputs (may be NULL): matches_out (capacity max_matches x 3 int32: queryIdx,
+// trainIdx, distance — the sorted final_matches of :114) and inlier_mask (capacity max_matches).
+void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features* to, int n_to,
+                       double thr, int iterations, double bp, int do_prosac, int min_keypoints,
+                       uzo_edge* edge, int32_t* matches_out, uint8_t* inlier_mask, int max_matches) {
+    static const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::memset(edge, 0, sizeof(*edge));
+    std::memcpy(edge->T, I4, sizeof(I4));
+    edge->info_scale = 1.0;
+    edge->cam_from = edge->cam_to = -1;
+    edge->best_iteration = -1;
+
+    double best_matching_score = -1;
+    int best_f = -1, best_t = -1;
+    std::vector<Match> potential;
+    for (int a = 0; a < n_from; ++a) {
+        for (int b = 0; b < n_to; ++b) {
+            const uzo_features& F = from[a];
+            const uzo_features& Tt = to[b];
+            if (F.n >= min_keypoints && Tt.n >= min_keypoints && F.feature_type == Tt.feature_type &&
+                F.sensor_frame == Tt.sensor_frame) {
+                std::vector<Match> matches;
+                bool binary = F.feature_type >= 1 && F.feature_type <= 4;   // :54-57
+                if (binary) {
+                    std::vector<int32_t> idx(2 * (size_t)Tt.n), dist(2 * (size_t)Tt.n);
+                    knn2(Tt.descriptors, Tt.n, Tt.desc_stride, F.descriptors, F.n, F.desc_stride,
+                         F.desc_bytes, idx.data(), dist.data());
+                    for (int q = 0; q < Tt.n; ++q) {
+                        if (idx[2 * q] >= 0 && idx[2 * q + 1] >= 0) {                 // size() == 2
+                            if (ratio_pass(dist[2 * q], dist[2 * q + 1]))
+                                matches.push_back(Match{q, idx[2 * q], dist[2 * q]});
+                        }
+                    }
+                }
+                double score = (double)matches.size();
+                if (score > best_matching_score) {
+                    best_matching_score = score;
+                    best_f = a; best_t = b;
+                    potential = matches;
+                }
+            }
+        }
+    }
+    if (best_matching_score == -1) return;     // :93-95
+    edge->cam_from = best_f; edge->cam_to = best_t;
+    edge->n_ratio_matches = (int)potential.size();
+
+    const uzo_features& F = from[best_f];
+    const uzo_features& Tt = to[best_t];
+    std::vector<Match> fin;
+    for (const Match& m : potential)
+        if (F.valid_3d[m.t] && Tt.valid_3d[m.q]) fin.push_back(m);
+    // :114 std::sort by distance is UNSTABLE in the reference (order among equal distances is
+    // unspecified); the build fixes the total order (distance, queryIdx) on both sides.
+    std::stable_sort(fin.begin(), fin.end(), [](const Match& a, const Match& b) {
+        return a.d != b.d ? a.d < b.d : a.q < b.q;
+    });
+    edge->n_matches = (int)fin.size();
+    if (matches_out)
+        for (int i = 0; i < (int)fin.size() && i < max_matches; ++i) {
+            matches_out[3 * i] = fin[i].q; matches_out[3 * i + 1] = fin[i].t; matches_out[3 * i + 2] = fin[i].d;
+        }
+    if (fin.size() >= 3) {
+        int M = (int)fin.size();
+        std::vector<double> Xd(3 * (size_t)M), Pd(3 * (size_t)M);
+        for (int i = 0; i < M; ++i)
+            for (int r = 0; r < 3; ++r) {
+                Xd[3 * i + r] = F.positions[3 * (size_t)fin[i].t + r];
+                Pd[3 * i + r] = Tt.positions[3 * (size_t)fin[i].q + r];
+            }
+        std::vector<int32_t> samples(3 * (size_t)iterations);
+        sample_list(M, iterations, do_prosac, samples.data());
+        ProsacOut po;
+        std::vector<uint8_t> mask(M);
+        prosac(Pd.data(), Xd.data(), M, samples.data(), iterations, thr, bp, &po, mask.data());   // :130
+        if (inlier_mask) std::memcpy(inlier_mask, mask.data(), std::min(M, max_matches));
+        if (po.consensus > 0 && po.mse > 0) edge->info_scale = 0.1 * po.consensus / po.mse;      // :134-135
+        std::memcpy(edge->T, po.T, sizeof(po.T));
+        edge->consensus = po.consensus;
+        edge->mse = po.mse;
+        edge->best_iteration = po.best_iteration;
+        edge->iterations_run = po.iterations_run;
+        edge->ok = 1;
+    }
+}
+
+}  // extern "C"

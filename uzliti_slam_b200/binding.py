@@ -1,0 +1,318 @@
+"""ctypes binding of libuzliti_edge.so (include/uzliti_edge.h).  No compute happens in Python."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_SO = os.path.join(_HERE, "libuzliti_edge.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+EXPORTED_SYMBOLS = [
+    "uz_create", "uz_destroy", "uz_last_error", "uz_default_params", "uz_set_params", "uz_get_params",
+    "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_remove", "uz_store_clear",
+    "uz_store_size", "uz_store_bytes", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
+    "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
+    "uz_set_debug", "uz_debug_pair", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
+    "uz_get_timers", "uz_microbench", "uz_version",
+]
+
+
+class UzError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("ransac_threshold", C.c_double), ("break_percentage", C.c_double),
+                ("ransac_iterations", C.c_int32), ("do_prosac", C.c_int32),
+                ("ratio_num", C.c_int32), ("ratio_den", C.c_int32),
+                ("min_keypoints", C.c_int32), ("cross_check", C.c_int32)]
+
+
+class Features(C.Structure):
+    _fields_ = [("descriptors", C.c_void_p), ("positions", C.c_void_p), ("valid_3d", C.c_void_p),
+                ("n", C.c_int32), ("desc_stride", C.c_int32), ("feature_type", C.c_int32),
+                ("sensor_frame", C.c_int32)]
+
+
+class EdgeResult(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("cam_from", C.c_int32), ("cam_to", C.c_int32),
+                ("n_ratio_matches", C.c_int32), ("n_matches", C.c_int32), ("consensus", C.c_int32),
+                ("best_iteration", C.c_int32), ("iterations_run", C.c_int32),
+                ("mse", C.c_double), ("info_scale", C.c_double), ("T", C.c_double * 16)]
+
+
+RESULT_DTYPE = np.dtype([("ok", "<i4"), ("cam_from", "<i4"), ("cam_to", "<i4"), ("n_ratio_matches", "<i4"),
+                         ("n_matches", "<i4"), ("consensus", "<i4"), ("best_iteration", "<i4"),
+                         ("iterations_run", "<i4"), ("mse", "<f8"), ("info_scale", "<f8"), ("T", "<f8", (16,))])
+assert RESULT_DTYPE.itemsize == C.sizeof(EdgeResult) == 176
+
+
+def lib_path():
+    return _SO
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc", "uz_capi.cu")
+    deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    deps.append(os.path.join(_ROOT, "include", "uzliti_edge.h"))
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO, src]
+    subprocess.check_call(cmd)
+    return _SO
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise UzError(f"{_SO} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(_SO)
+    lib.uz_last_error.restype = C.c_char_p
+    lib.uz_version.restype = C.c_char_p
+    lib.uz_store_bytes.restype = C.c_int64
+    lib.uz_launch_count.restype = C.c_int64
+    lib.uz_destroy.restype = None
+    lib.uz_default_params.restype = None
+    for name in EXPORTED_SYMBOLS:
+        getattr(lib, name)
+    for name in ("uz_create", "uz_set_params", "uz_get_params", "uz_set_stream", "uz_store_add", "uz_store_add_bulk",
+                 "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
+                 "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
+                 "uz_set_debug", "uz_debug_pair", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
+                 "uz_microbench"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def features_array(cams, keep):
+    """list of camera dicts -> ctypes array of uz_features (borrowed pointers; `keep` holds the arrays)."""
+    arr = (Features * max(len(cams), 1))()
+    for i, c in enumerate(cams):
+        d, p, v = c["desc"], c["pos"], c["valid"]
+        if not (d.flags.c_contiguous or d.shape[0] <= 1) and d.strides[1] != 1:
+            d = np.ascontiguousarray(d)
+        if d.dtype != np.uint8:
+            d = np.ascontiguousarray(d, np.uint8)
+        if p.dtype != np.float64 or not p.flags.c_contiguous:
+            p = np.ascontiguousarray(p, np.float64)
+        if v.dtype != np.uint8 or not v.flags.c_contiguous:
+            v = np.ascontiguousarray(v, np.uint8)
+        keep += [d, p, v]
+        n = d.shape[0]
+        stride = d.strides[0] if n > 1 else 32
+        arr[i] = Features(d.ctypes.data, p.ctypes.data, v.ctypes.data, n, stride,
+                          int(c.get("feature_type", 2)), int(c.get("sensor_frame", 0)))
+    return arr
+
+
+class EdgeEstimator:
+    """One uz_context on one GPU.  Method names follow the reference class
+    (transformation_estimation/include/transformation_estimation/feature_transformation_estimator.h:33-58)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        st = self.lib.uz_create(int(device), C.byref(self.ctx))
+        if st != 0:
+            raise UzError(f"uz_create(device={device}) failed with status {st}: no usable sm_100 GPU "
+                          "(there is no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.lib.uz_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise UzError(f"status {st}: {self.lib.uz_last_error(self.ctx).decode()}")
+
+    # ---- config ---------------------------------------------------------------------------------
+    def get_params(self):
+        p = Params()
+        self._check(self.lib.uz_get_params(self.ctx, C.byref(p)))
+        return p
+
+    def setConfig(self, **kw):
+        p = self.get_params()
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        self._check(self.lib.uz_set_params(self.ctx, C.byref(p)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.uz_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- store ----------------------------------------------------------------------------------
+    def add_keyframe(self, cams):
+        keep = []
+        arr = features_array(cams, keep)
+        h = C.c_int32()
+        self._check(self.lib.uz_store_add(self.ctx, arr, len(cams), C.byref(h)))
+        return h.value
+
+    def add_keyframes(self, keyframes):
+        """keyframes: list of camera lists (or single camera dicts).  One bulk upload."""
+        keep, flat, counts = [], [], []
+        for kf in keyframes:
+            cams = kf if isinstance(kf, (list, tuple)) else [kf]
+            flat += list(cams)
+            counts.append(len(cams))
+        arr = features_array(flat, keep)
+        counts = np.array(counts, np.int32)
+        handles = np.empty(len(keyframes), np.int32)
+        self._check(self.lib.uz_store_add_bulk(self.ctx, arr, _p(counts), len(keyframes), _p(handles)))
+        return handles
+
+    def remove_keyframe(self, handle):
+        self._check(self.lib.uz_store_remove(self.ctx, int(handle)))
+
+    def clear(self):
+        self._check(self.lib.uz_store_clear(self.ctx))
+
+    def store_size(self):
+        return self.lib.uz_store_size(self.ctx)
+
+    def store_bytes(self):
+        return self.lib.uz_store_bytes(self.ctx)
+
+    # ---- stages ---------------------------------------------------------------------------------
+    def knnMatch(self, query, train):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) -> (idx[nq,2], dist[nq,2]) int32."""
+        query = np.asarray(query)
+        train = np.asarray(train)
+        if query.dtype != np.uint8 or (query.ndim == 2 and query.strides[1] != 1):
+            query = np.ascontiguousarray(query, np.uint8)
+        if train.dtype != np.uint8 or (train.ndim == 2 and train.strides[1] != 1):
+            train = np.ascontiguousarray(train, np.uint8)
+        nq, nt = query.shape[0], train.shape[0]
+        idx = np.full((nq, 2), -7, np.int32)
+        dist = np.full((nq, 2), -7, np.int32)
+        qs = query.strides[0] if nq > 1 else 32
+        ts = train.strides[0] if nt > 1 else 32
+        self._check(self.lib.uz_match_knn2(self.ctx, _p(query), nq, qs, _p(train), nt, ts, _p(idx), _p(dist)))
+        return idx, dist
+
+    def estimateSVD(self, P, Q, maxError, iterations, breakPercentage, do_prosac=True, samples=None):
+        P = np.ascontiguousarray(P, np.float64)
+        Q = np.ascontiguousarray(Q, np.float64)
+        M = P.shape[0]
+        T = np.empty(16, np.float64)
+        cons, bi, ir = C.c_int32(), C.c_int32(), C.c_int32()
+        mse = C.c_double()
+        mask = np.zeros(max(M, 1), np.uint8)
+        sp = None
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.int32)
+            sp = _p(samples)
+        self._check(self.lib.uz_estimate_svd(self.ctx, _p(P), _p(Q), M, C.c_double(maxError), int(iterations),
+                                             C.c_double(breakPercentage), int(bool(do_prosac)), sp, _p(T),
+                                             C.byref(cons), C.byref(mse), _p(mask), C.byref(bi), C.byref(ir)))
+        return dict(T=T.reshape(4, 4), consensus=cons.value, mse=mse.value, mask=mask[:M].astype(bool),
+                    best_iteration=bi.value, iterations_run=ir.value)
+
+    def consensus3D(self, P, Q, T, thresh):
+        P = np.ascontiguousarray(P, np.float64)
+        Q = np.ascontiguousarray(Q, np.float64)
+        T = np.ascontiguousarray(T, np.float64)
+        M = P.shape[0]
+        mask = np.zeros(max(M, 1), np.uint8)
+        cnt = C.c_int32()
+        self._check(self.lib.uz_consensus3d(self.ctx, _p(P), _p(Q), M, _p(T), C.c_double(thresh), _p(mask),
+                                            C.byref(cnt)))
+        return cnt.value, mask[:M].astype(bool)
+
+    def sample_list(self, M, iterations, do_prosac=True):
+        out = np.zeros((iterations, 3), np.int32)
+        self._check(self.lib.uz_sample_list(self.ctx, int(M), int(iterations), int(bool(do_prosac)), _p(out)))
+        return out
+
+    # ---- batched path ----------------------------------------------------------------------------
+    def estimateEdges(self, from_handles, to_handles):
+        """estimateEdge x n on stored keyframes -> structured array (RESULT_DTYPE)."""
+        f = np.ascontiguousarray(from_handles, np.int32)
+        t = np.ascontiguousarray(to_handles, np.int32)
+        res = np.zeros(len(f), RESULT_DTYPE)
+        self._check(self.lib.uz_estimate_edges(self.ctx, _p(f), _p(t), len(f), _p(res)))
+        return res
+
+    def estimateEdgesDevice(self, from_handles, to_handles, results_device_ptr):
+        f = np.ascontiguousarray(from_handles, np.int32)
+        t = np.ascontiguousarray(to_handles, np.int32)
+        self._check(self.lib.uz_estimate_edges_device(self.ctx, _p(f), _p(t), len(f),
+                                                      C.c_void_p(results_device_ptr)))
+
+    def estimateEdgesHost(self, pairs):
+        """pairs: list of (cams_from, cams_to) camera-dict lists: estimateEdgeDirect x n from host buffers."""
+        keep, ff, tt, nf, nt = [], [], [], [], []
+        for a, b in pairs:
+            a = a if isinstance(a, (list, tuple)) else [a]
+            b = b if isinstance(b, (list, tuple)) else [b]
+            ff += list(a); tt += list(b)
+            nf.append(len(a)); nt.append(len(b))
+        fa = features_array(ff, keep)
+        ta = features_array(tt, keep)
+        nf = np.array(nf, np.int32)
+        nt = np.array(nt, np.int32)
+        res = np.zeros(len(pairs), RESULT_DTYPE)
+        self._check(self.lib.uz_estimate_edges_host(self.ctx, fa, _p(nf), ta, _p(nt), len(pairs), _p(res)))
+        return res
+
+    def estimateEdgeDirect(self, cams_from, cams_to):
+        return self.estimateEdgesHost([(cams_from, cams_to)])[0]
+
+    def set_debug(self, on=True):
+        self._check(self.lib.uz_set_debug(self.ctx, int(bool(on))))
+
+    def debug_pair(self, pair_index, n_matches):
+        n = max(int(n_matches), 1)
+        m = np.zeros((n, 3), np.int32)
+        mask = np.zeros(n, np.uint8)
+        got = C.c_int32()
+        self._check(self.lib.uz_debug_pair(self.ctx, int(pair_index), _p(m), _p(mask), n, C.byref(got)))
+        return m[:n_matches], mask[:n_matches].astype(bool)
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def launch_count(self):
+        return self.lib.uz_launch_count(self.ctx)
+
+    def enable_timers(self, on=True):
+        self._check(self.lib.uz_enable_timers(self.ctx, int(bool(on))))
+
+    def reset_timers(self):
+        self._check(self.lib.uz_reset_timers(self.ctx))
+
+    def get_timers(self):
+        a, b = C.c_double(), C.c_double()
+        ml, sl, cmp_ = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.uz_get_timers(self.ctx, C.byref(a), C.byref(b), C.byref(ml), C.byref(sl), C.byref(cmp_)))
+        return dict(match_ms=a.value, solve_ms=b.value, match_launches=ml.value, solve_launches=sl.value,
+                    compares=cmp_.value)
+
+    def microbench(self, op):
+        g = C.c_double()
+        self._check(self.lib.uz_microbench(self.ctx, int(op), C.byref(g)))
+        return g.value

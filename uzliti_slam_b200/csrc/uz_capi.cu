@@ -1,0 +1,940 @@
+// uz_capi.cu — context, device-resident keyframe store and the C-ABI of include/uzliti_edge.h.
+//
+// Host side of the batched feature-edge path.  What the reference does per pair on one worker thread
+// (/root/reference/transformation_estimation/src/transformation_estimator.cpp:45-62: LIFO pop, impl,
+// callback, 1 ms sleep) becomes: enumerate the camera-pair matchings of all pairs on the host
+// (feature_transformation_estimator.cpp:40-49), one knn2 launch over every (matching, query tile), one
+// solve launch with a CTA per pair, one result copy.  No CPU compute fallback exists: without a
+// usable device every compute entry point returns UZ_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/uzliti_edge.h"
+#include "uz_knn2.cuh"
+#include "uz_samples.h"
+#include "uz_solve.cuh"
+
+using namespace uz;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Bump allocator over large device chunks (HBM3e: 180 GB — chunks are cheap, fragmentation is not an issue
+// for append-mostly keyframe maps).  Memory of removed keyframes is reclaimed by uz_store_clear().
+struct Arena {
+    struct Chunk { uint8_t* base; size_t size, used; };
+    std::vector<Chunk> chunks;
+    size_t chunk_bytes = (size_t)64 << 20;
+    size_t total = 0;
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        for (auto& c : chunks)
+            if (c.size - c.used >= bytes) { void* r = c.base + c.used; c.used += bytes; return r; }
+        size_t sz = std::max(chunk_bytes, bytes);
+        void* p = nullptr;
+        if (cudaMalloc(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        chunks.push_back(Chunk{(uint8_t*)p, sz, bytes});
+        total += sz;
+        return p;
+    }
+    void reset() { for (auto& c : chunks) c.used = 0; }
+    void release() { for (auto& c : chunks) cudaFree(c.base); chunks.clear(); total = 0; }
+};
+
+struct Cam {
+    uint32_t* raw = nullptr;   // n x 8 words, bytes as given
+    uint32_t* csa = nullptr;   // n x 8 words, CSA layout (uz_knn2.cuh)
+    double* pos = nullptr;     // 3 x n column-major
+    uint8_t* valid = nullptr;  // n
+    int32_t n = 0, feature_type = 0, sensor_frame = 0;
+};
+
+struct Keyframe {
+    std::vector<Cam> cams;
+    bool live = false;
+};
+
+struct PairRef { const Keyframe* from; const Keyframe* to; };
+
+}  // namespace
+
+struct uz_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    uz_params params;
+    std::string err;
+    int variant_csa = 1;
+    int sm_count = 148;
+
+    Arena store_arena, transient;
+    std::vector<Keyframe> kfs;
+    std::vector<int32_t> free_handles;
+    int32_t live = 0;
+    int32_t store_max_n = 0;
+
+    // sample table
+    DevBuf d_samples;
+    int samp_cap = -1, samp_iters = -1, samp_prosac = -1;
+
+    // per-launch buffers
+    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_misc;
+    PinBuf h_tasks, h_tiles, h_pair_tasks;
+
+    // parity taps
+    int debug = 0;
+    int dbg_cap = 0, dbg_pairs = 0;
+
+    // introspection
+    int64_t launches = 0;
+    int timers = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double match_ms = 0, solve_ms = 0;
+    int64_t match_launches = 0, solve_launches = 0, compares = 0;
+};
+
+namespace {
+
+uz_status fail(uz_context* ctx, uz_status st, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return st;
+}
+
+#define UZ_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            cudaGetLastError();                                                                         \
+            return fail((ctx), UZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+        }                                                                                               \
+    } while (0)
+
+int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+bool is_binary_type(int t) { return t >= UZ_FEATURE_BRIEF && t <= UZ_FEATURE_FREAK; }   // :54-57
+
+double thr_sq_star(double thr) {
+    // smallest double s with sqrt(s) >= thr (sqrt correctly rounded), so sqrt(s) < thr <=> s < s*
+    if (!(thr > 0.0)) return 0.0;
+    if (std::isinf(thr)) return thr;
+    double c = thr * thr;
+    while (c > 0.0 && std::sqrt(c) >= thr) c = std::nextafter(c, -INFINITY);
+    while (std::sqrt(std::nextafter(c, INFINITY)) < thr) c = std::nextafter(c, INFINITY);
+    return std::nextafter(c, INFINITY);
+}
+
+// ---- uploads -------------------------------------------------------------------------------------
+struct Span { const uint8_t* host; size_t bytes; uint8_t** dev_slot; };
+
+// Copies a set of host spans to the arena, merging host-contiguous spans into single transfers (a map
+// laid out as one big array on the host goes up in one DMA per field).  Identical host pointers share
+// one device copy.
+uz_status upload_spans(uz_context* ctx, Arena& arena, std::vector<Span>& spans) {
+    std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) {
+        return a.host != b.host ? a.host < b.host : a.bytes > b.bytes;
+    });
+    size_t i = 0;
+    while (i < spans.size()) {
+        size_t j = i;
+        const uint8_t* run_begin = spans[i].host;
+        const uint8_t* run_end = spans[i].host + spans[i].bytes;
+        while (j + 1 < spans.size() && spans[j + 1].host <= run_end &&
+               (spans[j + 1].host == run_end || spans[j + 1].host + spans[j + 1].bytes <= run_end ||
+                spans[j + 1].host == spans[j].host)) {
+            // contiguous continuation, a span nested in the run, or a duplicate
+            run_end = std::max(run_end, spans[j + 1].host + spans[j + 1].bytes);
+            ++j;
+        }
+        const size_t bytes = (size_t)(run_end - run_begin);
+        uint8_t* d = (uint8_t*)arena.alloc(bytes);
+        if (!d) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        if (bytes) UZ_CUDA(ctx, cudaMemcpyAsync(d, run_begin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t k = i; k <= j; ++k) *spans[k].dev_slot = d + (spans[k].host - run_begin);
+        i = j + 1;
+    }
+    return UZ_OK;
+}
+
+uz_status validate_features(uz_context* ctx, const uz_features* f) {
+    if (f->n < 0 || f->n > UZ_MAX_FEATURES) return fail(ctx, UZ_ERR_INVALID, "feature count out of range (0..UZ_MAX_FEATURES)");
+    if (f->n > 0 && (!f->descriptors || !f->positions || !f->valid_3d)) return fail(ctx, UZ_ERR_INVALID, "null feature buffer");
+    if (f->n > 0 && f->desc_stride < UZ_DESC_BYTES) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor stride < 32 bytes (only 256-bit binary descriptors)");
+    return UZ_OK;
+}
+
+// Uploads cameras (descriptors, positions, valid) and builds both descriptor layouts on the device.
+uz_status upload_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_features*>& feats,
+                      std::vector<Cam>& out) {
+    out.assign(feats.size(), Cam());
+    std::vector<Span> dspans, pspans, vspans;
+    std::vector<uint8_t*> d_raw(feats.size(), nullptr), d_pos(feats.size(), nullptr), d_val(feats.size(), nullptr);
+    std::vector<size_t> strided;
+    for (size_t i = 0; i < feats.size(); ++i) {
+        const uz_features* f = feats[i];
+        uz_status st = validate_features(ctx, f);
+        if (st != UZ_OK) return st;
+        out[i].n = f->n; out[i].feature_type = f->feature_type; out[i].sensor_frame = f->sensor_frame;
+        if (f->n == 0) continue;
+        if (f->desc_stride == UZ_DESC_BYTES) dspans.push_back(Span{f->descriptors, (size_t)f->n * 32, &d_raw[i]});
+        else strided.push_back(i);
+        pspans.push_back(Span{(const uint8_t*)f->positions, (size_t)f->n * 24, &d_pos[i]});
+        vspans.push_back(Span{f->valid_3d, (size_t)f->n, &d_val[i]});
+    }
+    uz_status st;
+    if ((st = upload_spans(ctx, arena, dspans)) != UZ_OK) return st;
+    if ((st = upload_spans(ctx, arena, pspans)) != UZ_OK) return st;
+    if ((st = upload_spans(ctx, arena, vspans)) != UZ_OK) return st;
+    for (size_t i : strided) {   // padded cv::Mat rows: pitch copy into packed rows
+        const uz_features* f = feats[i];
+        d_raw[i] = (uint8_t*)arena.alloc((size_t)f->n * 32);
+        if (!d_raw[i]) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        UZ_CUDA(ctx, cudaMemcpy2DAsync(d_raw[i], 32, f->descriptors, f->desc_stride, 32, f->n,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // CSA layout: one pack launch per device-contiguous run of raw rows
+    std::vector<size_t> order;
+    for (size_t i = 0; i < feats.size(); ++i) if (feats[i]->n > 0) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return d_raw[a] < d_raw[b]; });
+    size_t i = 0;
+    while (i < order.size()) {
+        size_t j = i;
+        uint8_t* b0 = d_raw[order[i]];
+        uint8_t* e0 = b0 + (size_t)feats[order[i]]->n * 32;
+        while (j + 1 < order.size() && d_raw[order[j + 1]] <= e0) {
+            e0 = std::max(e0, d_raw[order[j + 1]] + (size_t)feats[order[j + 1]]->n * 32);
+            ++j;
+        }
+        const size_t rows = (size_t)(e0 - b0) / 32;
+        uint8_t* csa = (uint8_t*)arena.alloc(rows * 32);
+        if (!csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        pack_descriptors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
+            b0, (int)rows, 32, (uint32_t*)b0, (uint32_t*)csa);
+        ctx->launches++;
+        for (size_t k = i; k <= j; ++k) {
+            Cam& c = out[order[k]];
+            c.raw = (uint32_t*)d_raw[order[k]];
+            c.csa = (uint32_t*)(csa + (d_raw[order[k]] - b0));
+        }
+        i = j + 1;
+    }
+    UZ_CUDA(ctx, cudaGetLastError());
+    for (size_t k = 0; k < feats.size(); ++k) { out[k].pos = (double*)d_pos[k]; out[k].valid = d_val[k]; }
+    return UZ_OK;
+}
+
+// ---- sample table --------------------------------------------------------------------------------
+uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max_m) {
+    if (ctx->samp_iters == iterations && ctx->samp_prosac == do_prosac && ctx->samp_cap >= max_m) return UZ_OK;
+    int cap = std::max(256, (max_m + 255) & ~255);
+    if (ctx->samp_iters == iterations && ctx->samp_prosac == do_prosac) cap = std::max(cap, ctx->samp_cap);
+    std::vector<uint16_t> table;
+    build_sample_table(iterations, do_prosac != 0, cap, table);
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // previous launches may still read the old table
+    UZ_CUDA(ctx, ctx->d_samples.ensure(table.size() * sizeof(uint16_t)));
+    UZ_CUDA(ctx, cudaMemcpy(ctx->d_samples.p, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ctx->samp_cap = cap; ctx->samp_iters = iterations; ctx->samp_prosac = do_prosac;
+    return UZ_OK;
+}
+
+// ---- launches --------------------------------------------------------------------------------------
+template <int THREADS, int QPT>
+void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys) {
+    if (ctx->variant_csa)
+        knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+    else
+        knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+}
+
+struct KnnConfig { int threads, qpt; };
+const KnnConfig kKnnConfigs[3] = {{256, 4}, {128, 4}, {64, 2}};
+
+// Runs K1 (+ optionally K2..K5) for a list of pairs whose cameras are already on the device.
+uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_results) {
+    const uz_params prm = ctx->params;     // snapshot (setConfig may race with a batch in the reference)
+    const int n_pairs = (int)pairs.size();
+    if (n_pairs == 0) return UZ_OK;
+
+    // 1. enumerate matchings (:40-49) and pick the tile shape
+    size_t max_tasks = 0;
+    for (const PairRef& p : pairs) max_tasks += p.from->cams.size() * p.to->cams.size();
+    UZ_CUDA(ctx, ctx->h_tasks.ensure(std::max<size_t>(max_tasks, 1) * sizeof(MatchTask)));
+    UZ_CUDA(ctx, ctx->h_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
+    MatchTask* tasks = (MatchTask*)ctx->h_tasks.p;
+    int2* pair_tasks = (int2*)ctx->h_pair_tasks.p;
+    size_t n_tasks = 0, key_rows = 0;
+    int max_nq = 0;
+    int64_t compares = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int first = (int)n_tasks;
+        const auto& fc = pairs[i].from->cams;
+        const auto& tc = pairs[i].to->cams;
+        for (size_t a = 0; a < fc.size(); ++a)
+            for (size_t b = 0; b < tc.size(); ++b) {
+                const Cam& F = fc[a];
+                const Cam& T = tc[b];
+                if (F.n >= prm.min_keypoints && T.n >= prm.min_keypoints && F.feature_type == T.feature_type &&
+                    F.sensor_frame == T.sensor_frame) {
+                    MatchTask& tk = tasks[n_tasks++];
+                    const bool bin = is_binary_type(F.feature_type);   // unknown type: empty matches (:60-62)
+                    tk.q_desc = ctx->variant_csa ? T.csa : T.raw;
+                    tk.t_desc = ctx->variant_csa ? F.csa : F.raw;
+                    tk.nq = bin ? T.n : 0; tk.nt = F.n;
+                    tk.key_off = (uint32_t)key_rows; tk.pair = i;
+                    tk.q_pos = T.pos; tk.q_valid = T.valid; tk.t_pos = F.pos; tk.t_valid = F.valid;
+                    tk.cam_from = (int)a; tk.cam_to = (int)b;
+                    key_rows += (size_t)tk.nq;
+                    max_nq = std::max(max_nq, tk.nq);
+                    compares += (int64_t)tk.nq * tk.nt;
+                }
+            }
+        pair_tasks[i] = make_int2(first, (int)n_tasks - first);
+    }
+    if (key_rows >= ((size_t)1 << 32)) return fail(ctx, UZ_ERR_INVALID, "batch too large: split it (key scratch > 2^32 rows)");
+
+    int best_cfg = 0;
+    double best_cost = 1e300;
+    for (int c = 0; c < 3; ++c) {
+        const int tile = kKnnConfigs[c].threads * kKnnConfigs[c].qpt;
+        double padded = 0; size_t tiles = 0;
+        for (size_t t = 0; t < n_tasks; ++t) {
+            const size_t nt = ((size_t)tasks[t].nq + tile - 1) / tile;
+            tiles += nt; padded += (double)nt * tile * tasks[t].nt;
+        }
+        // a launch that cannot fill the chip twice pays for its idle SMs
+        const double fill = std::min(1.0, (double)tiles * kKnnConfigs[c].threads / (2.0 * ctx->sm_count * 512));
+        const double cost = padded / std::max(fill, 1e-3);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_cfg = c; }
+    }
+    const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
+    size_t n_tiles = 0;
+    for (size_t t = 0; t < n_tasks; ++t) n_tiles += ((size_t)tasks[t].nq + tile_rows - 1) / tile_rows;
+    UZ_CUDA(ctx, ctx->h_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    int2* tiles = (int2*)ctx->h_tiles.p;
+    {
+        size_t k = 0;
+        for (size_t t = 0; t < n_tasks; ++t)
+            for (int q0 = 0; q0 < tasks[t].nq; q0 += tile_rows) tiles[k++] = make_int2((int)t, q0);
+    }
+
+    // 2. device buffers
+    UZ_CUDA(ctx, ctx->d_tasks.ensure(std::max<size_t>(n_tasks, 1) * sizeof(MatchTask)));
+    UZ_CUDA(ctx, ctx->d_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    UZ_CUDA(ctx, ctx->d_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
+    UZ_CUDA(ctx, ctx->d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
+    if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+
+    // 3. K1
+    if (ctx->timers) cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (n_tiles) {
+        switch (best_cfg) {
+            case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
+            case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
+            default: launch_knn2<64, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
+        }
+        ctx->launches++;
+        UZ_CUDA(ctx, cudaGetLastError());
+    }
+    if (ctx->timers) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (!d_results) {        // matching only (uz_match_knn2)
+        if (ctx->timers) {
+            UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            ctx->match_ms += ms; ctx->match_launches += n_tiles ? 1 : 0; ctx->compares += compares;
+        }
+        return UZ_OK;
+    }
+
+    // 4. K2..K5
+    const int cap = std::max(128, pow2ceil(std::max(max_nq, 1)));
+    uz_status st = ensure_samples(ctx, prm.ransac_iterations, prm.do_prosac, max_nq);
+    if (st != UZ_OK) return st;
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.thr = prm.ransac_threshold; sp.thr_sq_star = thr_sq_star(prm.ransac_threshold);
+    sp.break_pct = prm.break_percentage; sp.iterations = prm.ransac_iterations;
+    sp.ratio_num = prm.ratio_num; sp.ratio_den = prm.ratio_den; sp.cap = cap;
+    sp.samples = (const uint16_t*)ctx->d_samples.p; sp.samples_by_m = 1;
+    ctx->dbg_pairs = 0;
+    if (ctx->debug) {
+        UZ_CUDA(ctx, ctx->d_dbg_matches.ensure((size_t)n_pairs * cap * 3 * sizeof(int32_t)));
+        UZ_CUDA(ctx, ctx->d_dbg_mask.ensure((size_t)n_pairs * cap));
+        sp.dbg_matches = (int32_t*)ctx->d_dbg_matches.p; sp.dbg_mask = (uint8_t*)ctx->d_dbg_mask.p;
+        ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs;
+    }
+    solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
+        (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_pair_tasks.p, (const uint2*)ctx->d_keys.p, sp, d_results);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    if (ctx->timers) {
+        cudaEventRecord(ctx->ev[2], ctx->stream);
+        UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        ctx->match_ms += a; ctx->solve_ms += b;
+        ctx->match_launches += n_tiles ? 1 : 0; ctx->solve_launches += 1; ctx->compares += compares;
+    }
+    return UZ_OK;
+}
+
+uz_status check_ctx(uz_context* ctx) {
+    if (!ctx) return UZ_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, UZ_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return UZ_OK;
+}
+
+uz_status validate_params(uz_context* ctx, const uz_params* p) {
+    if (p->ransac_iterations < 1 || p->ransac_iterations > UZ_MAX_ITERATIONS) return fail(ctx, UZ_ERR_INVALID, "ransac_iterations out of range");
+    if (p->ratio_den <= 0 || p->ratio_num < 0 || p->ratio_den > 4096 || p->ratio_num > 4096) return fail(ctx, UZ_ERR_INVALID, "ratio out of range");
+    if (p->cross_check) return fail(ctx, UZ_ERR_UNSUPPORTED, "cross_check is not implemented yet (the reference has none)");
+    if (p->min_keypoints < 0) return fail(ctx, UZ_ERR_INVALID, "min_keypoints < 0");
+    return UZ_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* uz_version(void) { return "uzliti_edge_b200 0.1 (sm_100a)"; }
+
+void uz_default_params(uz_params* p) {
+    if (!p) return;
+    p->ransac_threshold = 0.1;     // iti_slam_launch/yaml/slam.yaml:35
+    p->break_percentage = 0.6;     // cfg/FeatureLinkEstimation.cfg:12
+    p->ransac_iterations = 100;    // slam.yaml:36
+    p->do_prosac = 1;
+    p->ratio_num = 99; p->ratio_den = 100;   // feature_transformation_estimator.cpp:67
+    p->min_keypoints = 7;          // :47
+    p->cross_check = 0;
+}
+
+uz_status uz_create(int32_t device, uz_context** out) {
+    if (!out) return UZ_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return UZ_ERR_CUDA; }
+    if (device < 0 || device >= count) return UZ_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return UZ_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return UZ_ERR_CUDA; }
+    if (prop.major != 10) return UZ_ERR_CUDA;     // sm_100a cubins only
+    uz_context* ctx = new uz_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    uz_default_params(&ctx->params);
+    const char* v = getenv("UZ_KNN_VARIANT");
+    if (v && v[0] == '1') ctx->variant_csa = 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UZ_ERR_CUDA; }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)solve_smem_bytes(UZ_MAX_FEATURES)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); uz_destroy(ctx); return UZ_ERR_CUDA; }
+    *out = ctx;
+    return UZ_OK;
+}
+
+void uz_destroy(uz_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->store_arena.release(); ctx->transient.release();
+    ctx->d_samples.release(); ctx->d_tasks.release(); ctx->d_tiles.release(); ctx->d_pair_tasks.release();
+    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release();
+    ctx->d_misc.release();
+    ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* uz_last_error(const uz_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uz_status uz_set_params(uz_context* ctx, const uz_params* p) {
+    if (!ctx || !p) return UZ_ERR_INVALID;
+    uz_status st = validate_params(ctx, p);
+    if (st != UZ_OK) return st;
+    ctx->params = *p;
+    return UZ_OK;
+}
+
+uz_status uz_get_params(const uz_context* ctx, uz_params* p) {
+    if (!ctx || !p) return UZ_ERR_INVALID;
+    *p = ctx->params;
+    return UZ_OK;
+}
+
+uz_status uz_set_stream(uz_context* ctx, void* cuda_stream) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { UZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return UZ_OK;
+}
+
+// ---- store -------------------------------------------------------------------------------------------
+uz_status uz_store_add_bulk(uz_context* ctx, const uz_features* cams, const int32_t* cams_per_keyframe,
+                            int32_t n_keyframes, int32_t* handles_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_keyframes < 0 || (n_keyframes > 0 && (!cams_per_keyframe || !handles_out))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    size_t total = 0;
+    for (int i = 0; i < n_keyframes; ++i) {
+        if (cams_per_keyframe[i] < 0) return fail(ctx, UZ_ERR_INVALID, "negative camera count");
+        total += (size_t)cams_per_keyframe[i];
+    }
+    if (total > 0 && !cams) return fail(ctx, UZ_ERR_INVALID, "null camera array");
+    std::vector<const uz_features*> feats(total);
+    for (size_t i = 0; i < total; ++i) feats[i] = cams + i;
+    std::vector<Cam> up;
+    st = upload_cams(ctx, ctx->store_arena, feats, up);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host buffers are borrowed only for the call
+    size_t k = 0;
+    for (int i = 0; i < n_keyframes; ++i) {
+        int32_t h;
+        if (!ctx->free_handles.empty()) { h = ctx->free_handles.back(); ctx->free_handles.pop_back(); }
+        else { h = (int32_t)ctx->kfs.size(); ctx->kfs.emplace_back(); }
+        Keyframe& kf = ctx->kfs[h];
+        kf.cams.assign(up.begin() + k, up.begin() + k + cams_per_keyframe[i]);
+        for (const Cam& c : kf.cams) ctx->store_max_n = std::max(ctx->store_max_n, c.n);
+        kf.live = true;
+        k += (size_t)cams_per_keyframe[i];
+        ctx->live++;
+        handles_out[i] = h;
+    }
+    return UZ_OK;
+}
+
+uz_status uz_store_add(uz_context* ctx, const uz_features* cams, int32_t n_cams, int32_t* handle_out) {
+    if (!handle_out) return UZ_ERR_INVALID;
+    return uz_store_add_bulk(ctx, cams, &n_cams, 1, handle_out);
+}
+
+uz_status uz_store_remove(uz_context* ctx, int32_t handle) {
+    if (!ctx) return UZ_ERR_INVALID;
+    if (handle < 0 || handle >= (int32_t)ctx->kfs.size() || !ctx->kfs[handle].live) return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle");
+    ctx->kfs[handle].live = false;
+    ctx->kfs[handle].cams.clear();
+    ctx->free_handles.push_back(handle);
+    ctx->live--;
+    return UZ_OK;
+}
+
+uz_status uz_store_clear(uz_context* ctx) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->kfs.clear(); ctx->free_handles.clear(); ctx->live = 0; ctx->store_max_n = 0;
+    ctx->store_arena.reset();
+    return UZ_OK;
+}
+
+int32_t uz_store_size(const uz_context* ctx) { return ctx ? ctx->live : 0; }
+
+int64_t uz_store_bytes(const uz_context* ctx) {
+    if (!ctx) return 0;
+    int64_t b = 0;
+    for (const auto& c : ctx->store_arena.chunks) b += (int64_t)c.used;
+    return b;
+}
+
+// ---- stage entry points ----------------------------------------------------------------------------
+uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32_t q_stride,
+                        const uint8_t* train, int32_t nt, int32_t t_stride, int32_t* idx_out, int32_t* dist_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (nq < 0 || nt < 0 || nq > 65535 || nt > 65535) return fail(ctx, UZ_ERR_INVALID, "nq/nt out of range (0..65535)");
+    if (nq == 0) return UZ_OK;
+    if (!query || !idx_out || !dist_out || (nt > 0 && !train)) return fail(ctx, UZ_ERR_INVALID, "null buffer");
+    if (q_stride < 32 || (nt > 0 && t_stride < 32)) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor stride < 32 bytes");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    // two position-less cameras
+    Keyframe kq, kt;
+    kq.cams.resize(1); kt.cams.resize(1);
+    auto up = [&](const uint8_t* h, int n, int stride, Cam& c) -> uz_status {
+        c.n = n; c.feature_type = UZ_FEATURE_ORB;
+        if (n == 0) return UZ_OK;
+        c.raw = (uint32_t*)ctx->transient.alloc((size_t)n * 32);
+        c.csa = (uint32_t*)ctx->transient.alloc((size_t)n * 32);
+        uint8_t* stage = (uint8_t*)ctx->transient.alloc((size_t)n * stride);
+        if (!c.raw || !c.csa || !stage) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        UZ_CUDA(ctx, cudaMemcpyAsync(stage, h, (size_t)(n - 1) * stride + 32, cudaMemcpyHostToDevice, ctx->stream));
+        pack_descriptors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(stage, n, stride, c.raw, c.csa);
+        ctx->launches++;
+        return UZ_OK;
+    };
+    if ((st = up(query, nq, q_stride, kq.cams[0])) != UZ_OK) return st;
+    if ((st = up(train, nt, t_stride, kt.cams[0])) != UZ_OK) return st;
+    uz_params saved = ctx->params;
+    ctx->params.min_keypoints = 0;
+    std::vector<PairRef> pairs(1, PairRef{&kt, &kq});
+    st = run_pairs(ctx, pairs, nullptr);
+    ctx->params = saved;
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, ctx->d_misc.ensure((size_t)nq * 16));
+    int32_t* d_idx = (int32_t*)ctx->d_misc.p;
+    int32_t* d_dist = d_idx + 2 * (size_t)nq;
+    unpack_keys_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)ctx->d_keys.p, nq, d_idx, d_dist);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    UZ_CUDA(ctx, cudaMemcpyAsync(idx_out, d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaMemcpyAsync(dist_out, d_dist, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
+uz_status uz_sample_list(uz_context* ctx, int32_t M, int32_t iterations, int32_t do_prosac, int32_t* out) {
+    if (!ctx || !out) return UZ_ERR_INVALID;
+    if (M < 0 || M > 65535 || iterations < 1 || iterations > UZ_MAX_ITERATIONS) return fail(ctx, UZ_ERR_INVALID, "M/iterations out of range");
+    std::vector<uint32_t> rnd;
+    glibc_rand_stream(1, (size_t)iterations * (size_t)std::max(M, 1), rnd);
+    std::vector<uint16_t> rows((size_t)(M + 1) * iterations * 3, 0);
+    build_sample_rows(iterations, do_prosac != 0, M, M + 1, rnd, rows.data());
+    const uint16_t* r = rows.data() + (size_t)M * iterations * 3;
+    for (int i = 0; i < iterations * 3; ++i) out[i] = r[i];
+    return UZ_OK;
+}
+
+uz_status uz_estimate_svd(uz_context* ctx, const double* P, const double* Q, int32_t M, double max_error,
+                          int32_t iterations, double break_percentage, int32_t do_prosac, const int32_t* samples,
+                          double* T16_out, int32_t* consensus_out, double* mse_out, uint8_t* inlier_mask_out,
+                          int32_t* best_iteration_out, int32_t* iterations_run_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (M < 0 || M > UZ_MAX_FEATURES) return fail(ctx, UZ_ERR_INVALID, "M out of range");
+    if (iterations < 1 || iterations > UZ_MAX_ITERATIONS) return fail(ctx, UZ_ERR_INVALID, "iterations out of range");
+    if ((M > 0 && (!P || !Q)) || !T16_out || !consensus_out || !mse_out) return fail(ctx, UZ_ERR_INVALID, "null buffer");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    const int cap = std::max(128, pow2ceil(std::max(M, 1)));
+    double* dP = (double*)ctx->transient.alloc((size_t)std::max(M, 1) * 24);
+    double* dQ = (double*)ctx->transient.alloc((size_t)std::max(M, 1) * 24);
+    uint8_t* dmask = (uint8_t*)ctx->transient.alloc((size_t)cap);
+    uz_edge_result* dres = (uz_edge_result*)ctx->transient.alloc(sizeof(uz_edge_result));
+    uint16_t* dsamp = nullptr;
+    if (!dP || !dQ || !dmask || !dres) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    if (M > 0) {
+        UZ_CUDA(ctx, cudaMemcpyAsync(dP, P, (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+        UZ_CUDA(ctx, cudaMemcpyAsync(dQ, Q, (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UZ_CUDA(ctx, cudaMemsetAsync(dmask, 0, cap, ctx->stream));
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    std::vector<uint16_t> s16;
+    if (samples) {
+        s16.resize((size_t)iterations * 3);
+        for (size_t i = 0; i < s16.size(); ++i) {
+            if (samples[i] < 0 || samples[i] >= std::max(M, 1)) return fail(ctx, UZ_ERR_INVALID, "sample index out of range");
+            s16[i] = (uint16_t)samples[i];
+        }
+        dsamp = (uint16_t*)ctx->transient.alloc(s16.size() * 2);
+        if (!dsamp) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        UZ_CUDA(ctx, cudaMemcpyAsync(dsamp, s16.data(), s16.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        sp.samples = dsamp; sp.samples_by_m = 0;
+    } else {
+        st = ensure_samples(ctx, iterations, do_prosac, M);
+        if (st != UZ_OK) return st;
+        sp.samples = (const uint16_t*)ctx->d_samples.p; sp.samples_by_m = 1;
+    }
+    sp.thr = max_error; sp.thr_sq_star = thr_sq_star(max_error); sp.break_pct = break_percentage;
+    sp.iterations = iterations; sp.ratio_num = 99; sp.ratio_den = 100; sp.cap = cap;
+    sp.direct_P = dP; sp.direct_Q = dQ; sp.direct_M = M;
+    sp.dbg_mask = dmask;
+    solve_kernel<kSolveThreads><<<1, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(nullptr, nullptr, nullptr, sp, dres);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    uz_edge_result r;
+    UZ_CUDA(ctx, cudaMemcpyAsync(&r, dres, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    if (inlier_mask_out && M > 0) UZ_CUDA(ctx, cudaMemcpyAsync(inlier_mask_out, dmask, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(T16_out, r.T, sizeof(r.T));
+    *consensus_out = r.consensus; *mse_out = r.mse;
+    if (best_iteration_out) *best_iteration_out = r.best_iteration;
+    if (iterations_run_out) *iterations_run_out = r.iterations_run;
+    return UZ_OK;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void consensus_kernel(const double* __restrict__ P, const double* __restrict__ Q, int M, const double* __restrict__ T16,
+                                 double thr_star, uint8_t* __restrict__ set, int32_t* __restrict__ count) {
+    double T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = T16[i];
+    int c = 0;
+    for (int base = 0; base < M; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool in = false;
+        if (i < M) {
+            in = residual_sq(T, P[3 * i], P[3 * i + 1], P[3 * i + 2], Q[3 * i], Q[3 * i + 1], Q[3 * i + 2]) < thr_star;
+            set[i] = in;
+        }
+        c += __syncthreads_count(in);
+    }
+    if (threadIdx.x == 0) *count = c;
+}
+}  // namespace
+
+extern "C" {
+
+uz_status uz_consensus3d(uz_context* ctx, const double* P, const double* Q, int32_t M, const double* T16,
+                         double thresh, uint8_t* set_out, int32_t* count_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (M < 0 || M > (1 << 24) || !T16 || !count_out || (M > 0 && (!P || !Q || !set_out))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    const size_t m1 = (size_t)std::max(M, 1);
+    double* dP = (double*)ctx->transient.alloc(m1 * 24);
+    double* dQ = (double*)ctx->transient.alloc(m1 * 24);
+    double* dT = (double*)ctx->transient.alloc(128);
+    uint8_t* dset = (uint8_t*)ctx->transient.alloc(m1);
+    int32_t* dcount = (int32_t*)ctx->transient.alloc(4);
+    if (!dP || !dQ || !dT || !dset || !dcount) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    if (M > 0) {
+        UZ_CUDA(ctx, cudaMemcpyAsync(dP, P, (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+        UZ_CUDA(ctx, cudaMemcpyAsync(dQ, Q, (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UZ_CUDA(ctx, cudaMemcpyAsync(dT, T16, 128, cudaMemcpyHostToDevice, ctx->stream));
+    consensus_kernel<<<1, 256, 0, ctx->stream>>>(dP, dQ, M, dT, thr_sq_star(thresh), dset, dcount);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    if (M > 0) UZ_CUDA(ctx, cudaMemcpyAsync(set_out, dset, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaMemcpyAsync(count_out, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
+// ---- the batched path ----------------------------------------------------------------------------------
+static uz_status pairs_from_handles(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
+                                    int32_t n_pairs, std::vector<PairRef>& pairs) {
+    if (n_pairs < 0 || (n_pairs > 0 && (!from_handles || !to_handles))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    pairs.resize((size_t)n_pairs);
+    const int32_t nk = (int32_t)ctx->kfs.size();
+    for (int i = 0; i < n_pairs; ++i) {
+        const int32_t a = from_handles[i], b = to_handles[i];
+        if (a < 0 || a >= nk || b < 0 || b >= nk || !ctx->kfs[a].live || !ctx->kfs[b].live)
+            return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle in pair list");
+        pairs[i] = PairRef{&ctx->kfs[a], &ctx->kfs[b]};
+    }
+    return UZ_OK;
+}
+
+uz_status uz_estimate_edges_device(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
+                                   int32_t n_pairs, void* results_device) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_pairs > 0 && !results_device) return fail(ctx, UZ_ERR_INVALID, "null results");
+    std::vector<PairRef> pairs;
+    st = pairs_from_handles(ctx, from_handles, to_handles, n_pairs, pairs);
+    if (st != UZ_OK) return st;
+    // the pinned task staging buffers are reused per call: the previous call's copies must have drained
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return run_pairs(ctx, pairs, (uz_edge_result*)results_device);
+}
+
+uz_status uz_estimate_edges(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
+                            int32_t n_pairs, uz_edge_result* results) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_pairs > 0 && !results) return fail(ctx, UZ_ERR_INVALID, "null results");
+    if (n_pairs <= 0) return n_pairs == 0 ? UZ_OK : fail(ctx, UZ_ERR_INVALID, "n_pairs < 0");
+    UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
+    st = uz_estimate_edges_device(ctx, from_handles, to_handles, n_pairs, ctx->d_results.p);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
+uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, const int32_t* n_from,
+                                 const uz_features* to_cams, const int32_t* n_to, int32_t n_pairs,
+                                 uz_edge_result* results) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_pairs < 0 || (n_pairs > 0 && (!n_from || !n_to || !results))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    if (n_pairs == 0) return UZ_OK;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    // unique cameras by (descriptor pointer, positions pointer, n): a keyframe that appears in many pairs
+    // (one query vs many candidates) is uploaded once
+    struct Key { const void* d; const void* p; int n; size_t slot; const uz_features* f; };
+    std::vector<Key> keys;
+    size_t tf = 0, tt = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (n_from[i] < 0 || n_to[i] < 0) return fail(ctx, UZ_ERR_INVALID, "negative camera count");
+        tf += (size_t)n_from[i]; tt += (size_t)n_to[i];
+    }
+    if ((tf && !from_cams) || (tt && !to_cams)) return fail(ctx, UZ_ERR_INVALID, "null camera array");
+    keys.reserve(tf + tt);
+    for (size_t i = 0; i < tf; ++i) keys.push_back(Key{from_cams[i].descriptors, from_cams[i].positions, from_cams[i].n, i, from_cams + i});
+    for (size_t i = 0; i < tt; ++i) keys.push_back(Key{to_cams[i].descriptors, to_cams[i].positions, to_cams[i].n, tf + i, to_cams + i});
+    std::vector<size_t> order(keys.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    auto less = [&](size_t a, size_t b) {
+        const Key& x = keys[a]; const Key& y = keys[b];
+        if (x.d != y.d) return x.d < y.d;
+        if (x.p != y.p) return x.p < y.p;
+        if (x.n != y.n) return x.n < y.n;
+        if (x.f->valid_3d != y.f->valid_3d) return x.f->valid_3d < y.f->valid_3d;
+        if (x.f->desc_stride != y.f->desc_stride) return x.f->desc_stride < y.f->desc_stride;
+        if (x.f->feature_type != y.f->feature_type) return x.f->feature_type < y.f->feature_type;
+        return x.f->sensor_frame < y.f->sensor_frame;
+    };
+    auto same = [&](size_t a, size_t b) { return !less(a, b) && !less(b, a); };
+    std::sort(order.begin(), order.end(), less);
+    std::vector<const uz_features*> uniq;
+    std::vector<size_t> slot_to_uniq(keys.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        if (i == 0 || !same(order[i - 1], order[i])) uniq.push_back(keys[order[i]].f);
+        slot_to_uniq[keys[order[i]].slot] = uniq.size() - 1;
+    }
+    std::vector<Cam> up;
+    st = upload_cams(ctx, ctx->transient, uniq, up);
+    if (st != UZ_OK) return st;
+    std::vector<Keyframe> kfs((size_t)n_pairs * 2);
+    std::vector<PairRef> pairs((size_t)n_pairs);
+    size_t cf = 0, ct = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        Keyframe& a = kfs[2 * (size_t)i];
+        Keyframe& b = kfs[2 * (size_t)i + 1];
+        a.cams.resize((size_t)n_from[i]); b.cams.resize((size_t)n_to[i]);
+        for (int k = 0; k < n_from[i]; ++k) a.cams[k] = up[slot_to_uniq[cf++]];
+        for (int k = 0; k < n_to[i]; ++k) b.cams[k] = up[slot_to_uniq[tf + ct++]];
+        pairs[i] = PairRef{&a, &b};
+    }
+    UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
+    st = run_pairs(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
+uz_status uz_set_debug(uz_context* ctx, int32_t enable) {
+    if (!ctx) return UZ_ERR_INVALID;
+    ctx->debug = enable ? 1 : 0;
+    if (!enable) ctx->dbg_pairs = 0;
+    return UZ_OK;
+}
+
+uz_status uz_debug_pair(uz_context* ctx, int32_t pair_index, int32_t* matches_out, uint8_t* inlier_mask_out,
+                        int32_t capacity, int32_t* n_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (pair_index < 0 || pair_index >= ctx->dbg_pairs) return fail(ctx, UZ_ERR_INVALID, "no debug data for that pair (uz_set_debug before the call)");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uz_edge_result r;
+    // n_matches of the pair lives in the caller's results; re-read M from the device result buffer if it is ours
+    (void)r;
+    const int cap = ctx->dbg_cap;
+    const int n = std::min(capacity, cap);
+    if (matches_out && n > 0)
+        UZ_CUDA(ctx, cudaMemcpy(matches_out, (int32_t*)ctx->d_dbg_matches.p + (size_t)pair_index * cap * 3, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    if (inlier_mask_out && n > 0)
+        UZ_CUDA(ctx, cudaMemcpy(inlier_mask_out, (uint8_t*)ctx->d_dbg_mask.p + (size_t)pair_index * cap, (size_t)n, cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    return UZ_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------------------
+int64_t uz_launch_count(const uz_context* ctx) { return ctx ? ctx->launches : 0; }
+
+uz_status uz_enable_timers(uz_context* ctx, int32_t enable) {
+    if (!ctx) return UZ_ERR_INVALID;
+    ctx->timers = enable ? 1 : 0;
+    return UZ_OK;
+}
+
+uz_status uz_reset_timers(uz_context* ctx) {
+    if (!ctx) return UZ_ERR_INVALID;
+    ctx->match_ms = ctx->solve_ms = 0; ctx->match_launches = ctx->solve_launches = ctx->compares = 0;
+    return UZ_OK;
+}
+
+uz_status uz_get_timers(uz_context* ctx, double* match_ms, double* solve_ms, int64_t* match_launches,
+                        int64_t* solve_launches, int64_t* descriptor_compares) {
+    if (!ctx) return UZ_ERR_INVALID;
+    if (match_ms) *match_ms = ctx->match_ms;
+    if (solve_ms) *solve_ms = ctx->solve_ms;
+    if (match_launches) *match_launches = ctx->match_launches;
+    if (solve_launches) *solve_launches = ctx->solve_launches;
+    if (descriptor_compares) *descriptor_compares = ctx->compares;
+    return UZ_OK;
+}
+
+uz_status uz_microbench(uz_context* ctx, int32_t op, double* gops_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (!gops_out || op < 0 || op > 3) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    UZ_CUDA(ctx, ctx->d_misc.ensure(256));
+    const int blocks = ctx->sm_count * 8, iters = 4096;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        switch (op) {
+            case 0: intpipe_bench_kernel<0><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_misc.p, 12345u + rep, iters); break;
+            case 1: intpipe_bench_kernel<1><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_misc.p, 12345u + rep, iters); break;
+            case 2: intpipe_bench_kernel<2><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_misc.p, 12345u + rep, iters); break;
+            default: intpipe_bench_kernel<3><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_misc.p, 12345u + rep, iters); break;
+        }
+        ctx->launches++;
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    const double ops = (double)blocks * 256.0 * iters * 32.0;
+    *gops_out = ops / (best * 1e-3) * 1e-9;
+    return UZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// uz_knn2.cuh — K1: brute-force Hamming kNN-2 over 256-bit descriptors on the sm_100a integer pipes.
+//
+// Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(query = to->features_, train = from->features_, k = 2)
+// (/root/reference/transformation_estimation/src/feature_transformation_estimator.cpp:38,58).
+// Output per query row: two packed keys  key = (distance << 16) | trainIdx,  m1 < m2, which is exactly
+// OpenCV's order by (distance, trainIdx); 0xFFFFFFFF marks a missing neighbour (nt < 2).
+//
+// Mapping: one CTA per (matching, query tile).  Every thread keeps QPT query descriptors in registers
+// (8 x u32 each); train descriptors stream through shared memory in 2-stage tiles filled by 1-D TMA
+// bulk copies (cp.async.bulk + mbarrier) and are read with warp-broadcast 128-bit loads, so one
+// LDS.128 pair feeds 32 x QPT compares.
+//
+// Arithmetic.  A 256-bit compare is 8 XOR + 8 POPC in the textbook form; POPC issues at a quarter of
+// the LOP3 rate, so the kernel trades POPCs for LOP3s with a carry-save adder tree.  Descriptors are
+// stored in a "CSA layout" (an invertible XOR transform done once at ingestion, see csa_pack):
+//   W0=w0  W1=w1  W2=w0^w1^w2  W3=w3  W4=w4  W5=w3^w4^w5  W6=w0^..^w6  W7=w7
+// With x_i = q_i ^ t_i, the XOR of two CSA-layout rows yields x0,x1,S1=x0^x1^x2,x3,x4,S2=x3^x4^x5,
+// S3=x0^..^x6,x7 directly, and the carries follow with one LOP3 each:
+//   C1=maj(x0,x1,x2)  C2=maj(x3,x4,x5)  C3=maj(S1,S2,x6)       (x2,x5,x6 are implied: lut 0xD4)
+//   S5=C1^C2^C3       C5=maj(C1,C2,C3)
+//   distance = popc(S3) + popc(x7) + 2 popc(S5) + 4 popc(C5)
+// = 13 LOP3 + 4 POPC + 4 IMAD (weights and the <<16 folded into the key build) + 3 VIMNMX (top-2).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uz {
+
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr int kTrainTileRows = 512;                 // 16 KB per stage
+constexpr int kStages = 2;
+constexpr int kKnnSmemBytes = kStages * kTrainTileRows * 32 + 64;
+
+struct MatchTask {
+    const uint32_t* q_desc;   // "to" camera descriptors (OpenCV query), layout per UZ variant, 32 B rows
+    const uint32_t* t_desc;   // "from" camera descriptors (OpenCV train)
+    int32_t nq, nt;
+    uint32_t key_off;         // first row of this matching in the keys scratch
+    int32_t pair;             // owning pair (index within the launch)
+    // solve-side views of the two cameras
+    const double* q_pos; const uint8_t* q_valid;   // to
+    const double* t_pos; const uint8_t* t_valid;   // from
+    int32_t cam_from, cam_to;
+};
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// raw 8 words -> CSA layout (also its own inverse is csa_unpack; both are XOR-linear)
+__host__ __device__ __forceinline__ void csa_pack(const uint32_t* w, uint32_t* o) {
+    const uint32_t s1 = w[0] ^ w[1] ^ w[2];
+    const uint32_t s2 = w[3] ^ w[4] ^ w[5];
+    o[0] = w[0]; o[1] = w[1]; o[2] = s1; o[3] = w[3]; o[4] = w[4]; o[5] = s2; o[6] = s1 ^ s2 ^ w[6]; o[7] = w[7];
+}
+
+// key = (hamming << 16) + jkey for two CSA-layout rows
+__device__ __forceinline__ uint32_t csa_key(const uint32_t (&U)[8], const uint4& a, const uint4& b, uint32_t jkey) {
+    const uint32_t x0 = U[0] ^ a.x, x1 = U[1] ^ a.y, S1 = U[2] ^ a.z;
+    const uint32_t C1 = lop3<0xD4>(x0, x1, S1);
+    const uint32_t x3 = U[3] ^ a.w, x4 = U[4] ^ b.x, S2 = U[5] ^ b.y;
+    const uint32_t C2 = lop3<0xD4>(x3, x4, S2);
+    const uint32_t S3 = U[6] ^ b.z;
+    const uint32_t C3 = lop3<0xD4>(S1, S2, S3);
+    const uint32_t x7 = U[7] ^ b.w;
+    const uint32_t S5 = lop3<0x96>(C1, C2, C3);
+    const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
+    uint32_t k = mad_u32(__popc(C5), 4u << 16, jkey);
+    k = mad_u32(__popc(S5), 2u << 16, k);
+    k = mad_u32(__popc(x7), 1u << 16, k);
+    k = mad_u32(__popc(S3), 1u << 16, k);
+    return k;
+}
+
+// textbook form on raw rows (8 XOR + 8 POPC) — kept as the measured alternative (UZ_KNN_VARIANT=1)
+__device__ __forceinline__ uint32_t plain_key(const uint32_t (&U)[8], const uint4& a, const uint4& b, uint32_t jkey) {
+    const uint32_t d0 = __popc(U[0] ^ a.x) + __popc(U[1] ^ a.y) + __popc(U[2] ^ a.z) + __popc(U[3] ^ a.w);
+    const uint32_t d1 = __popc(U[4] ^ b.x) + __popc(U[5] ^ b.y) + __popc(U[6] ^ b.z) + __popc(U[7] ^ b.w);
+    return mad_u32(d0 + d1, 1u << 16, jkey);
+}
+
+__device__ __forceinline__ void top2_update(uint32_t& m1, uint32_t& m2, uint32_t k) {
+    const uint32_t hi = max(m1, k);
+    m1 = min(m1, k);
+    m2 = min(m2, hi);
+}
+
+// ---- mbarrier / bulk-copy helpers (PTX) --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// tiles[blockIdx.x] = (task index, first query row of the tile)
+template <int THREADS, int QPT, bool CSA>
+__global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restrict__ tasks,
+                                                       const int2* __restrict__ tiles,
+                                                       uint2* __restrict__ keys) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kTrainTileRows * 32);
+
+    const int2 tile = tiles[blockIdx.x];
+    const MatchTask* tk = tasks + tile.x;
+    const uint32_t* __restrict__ qd = tk->q_desc;
+    const uint32_t* __restrict__ td = tk->t_desc;
+    const int nq = tk->nq, nt = tk->nt;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int ntiles = (nt + kTrainTileRows - 1) / kTrainTileRows;
+    if (tid == 0 && ntiles > 0) {
+        const uint32_t bytes = (uint32_t)min(nt, kTrainTileRows) * 32u;
+        mbar_expect_tx(&bars[0], bytes);
+        bulk_g2s(smem, td, bytes, &bars[0]);
+    }
+
+    // query rows of this thread: q0 + k*THREADS + tid (coalesced 32 B per thread)
+    uint32_t U[QPT][8];
+    uint32_t m1[QPT], m2[QPT];
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) {
+        const int q = tile.y + k * THREADS + tid;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (q < nq) {
+            const uint4* p = reinterpret_cast<const uint4*>(qd + (size_t)q * 8);
+            a = __ldg(p);
+            b = __ldg(p + 1);
+        }
+        U[k][0] = a.x; U[k][1] = a.y; U[k][2] = a.z; U[k][3] = a.w;
+        U[k][4] = b.x; U[k][5] = b.y; U[k][6] = b.z; U[k][7] = b.w;
+        m1[k] = kNoKey; m2[k] = kNoKey;
+    }
+
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int stage = ti & 1;
+        if (tid == 0 && ti + 1 < ntiles) {       // prefetch next tile into the other stage (freed by the
+            const int r0 = (ti + 1) * kTrainTileRows;   // __syncthreads that ended iteration ti-1)
+            const uint32_t bytes = (uint32_t)min(nt - r0, kTrainTileRows) * 32u;
+            mbar_expect_tx(&bars[stage ^ 1], bytes);
+            bulk_g2s(smem + (stage ^ 1) * kTrainTileRows * 32, td + (size_t)r0 * 8, bytes, &bars[stage ^ 1]);
+        }
+        mbar_wait(&bars[stage], (ti >> 1) & 1);
+        const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(smem + stage * kTrainTileRows * 32);
+        const int r0 = ti * kTrainTileRows;
+        const int nrows = min(nt - r0, kTrainTileRows);
+        int j = 0;
+#pragma unroll 1
+        for (; j + 4 <= nrows; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 a = rows[2 * (j + u)], b = rows[2 * (j + u) + 1];
+                const uint32_t jkey = (uint32_t)(r0 + j + u);
+#pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    const uint32_t key = CSA ? csa_key(U[k], a, b, jkey) : plain_key(U[k], a, b, jkey);
+                    top2_update(m1[k], m2[k], key);
+                }
+            }
+        }
+        for (; j < nrows; ++j) {
+            const uint4 a = rows[2 * j], b = rows[2 * j + 1];
+            const uint32_t jkey = (uint32_t)(r0 + j);
+#pragma unroll
+            for (int k = 0; k < QPT; ++k) {
+                const uint32_t key = CSA ? csa_key(U[k], a, b, jkey) : plain_key(U[k], a, b, jkey);
+                top2_update(m1[k], m2[k], key);
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) {
+        const int q = tile.y + k * THREADS + tid;
+        if (q < nq) keys[tk->key_off + q] = make_uint2(m1[k], m2[k]);
+    }
+}
+
+// raw descriptor rows (any byte stride) -> packed 8-word rows, raw and CSA layout
+__global__ void pack_descriptors_kernel(const uint8_t* __restrict__ src, int n, int stride,
+                                        uint32_t* __restrict__ raw, uint32_t* __restrict__ csa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = src + (size_t)i * stride;
+    uint32_t w[8], o[8];
+    if ((((uintptr_t)p) & 15) == 0) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                   ((uint32_t)p[4 * k + 3] << 24);
+    }
+    csa_pack(w, o);
+    uint4* r = reinterpret_cast<uint4*>(raw + (size_t)i * 8);
+    uint4* c = reinterpret_cast<uint4*>(csa + (size_t)i * 8);
+    r[0] = make_uint4(w[0], w[1], w[2], w[3]); r[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    c[0] = make_uint4(o[0], o[1], o[2], o[3]); c[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// keys -> (idx, dist) int32 pairs for uz_match_knn2
+__global__ void unpack_keys_kernel(const uint2* __restrict__ keys, int nq, int32_t* __restrict__ idx,
+                                   int32_t* __restrict__ dist) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint2 k = keys[q];
+    idx[2 * q] = k.x == kNoKey ? -1 : (int32_t)(k.x & 0xFFFFu);
+    dist[2 * q] = k.x == kNoKey ? -1 : (int32_t)(k.x >> 16);
+    idx[2 * q + 1] = k.y == kNoKey ? -1 : (int32_t)(k.y & 0xFFFFu);
+    dist[2 * q + 1] = k.y == kNoKey ? -1 : (int32_t)(k.y >> 16);
+}
+
+// ---- integer-pipe microbenchmarks (roofline denominators) ---------------------------------------
+// Each thread runs ITER iterations of 8 independent chains of one op; ops = grid*block*ITER*8.
+template <int OP>
+__global__ void __launch_bounds__(256) intpipe_bench_kernel(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u + blockIdx.x;
+    const uint32_t c1 = seed | 1u, c2 = seed ^ 0x5bd1e995u;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (OP == 0) {            // POPC (result fed back through the popc input to keep a chain)
+                    asm volatile("popc.b32 %0, %0;" : "+r"(v[i]));
+                } else if (OP == 1) {     // LOP3
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[i]) : "r"(c1), "r"(c2));
+                } else if (OP == 2) {     // IMAD
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[i]) : "r"(c1), "r"(c2));
+                } else if (OP == 3) {     // VIMNMX
+                    asm volatile("min.u32 %0, %0, %1;" : "+r"(v[i]) : "r"(c2 + i + r));
+                }
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 0x12345678u) out[0] = s;     // keep the chains live
+}
+
+}  // namespace uz
