@@ -150,6 +150,11 @@ uz_status uz_set_debug(uz_context* ctx, int32_t enable);
 uz_status uz_debug_pair(uz_context* ctx, int32_t pair_index, int32_t* matches_out, uint8_t* inlier_mask_out,
                         int32_t capacity, int32_t* n_out);
 
+/* Consensus count of every hypothesis the last call evaluated for that pair (iteration order; -1 = not
+ * evaluated because of the early break). */
+uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_out, int32_t capacity,
+                          int32_t* n_out);
+
 /* ---- introspection for the bench harness ----------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 int64_t   uz_launch_count(const uz_context* ctx);

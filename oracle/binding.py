@@ -144,12 +144,14 @@ def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac
     maxm = max([c["desc"].shape[0] for c in cams_to] + [1])
     matches = np.zeros((maxm, 3), np.int32)
     mask = np.zeros(maxm, np.uint8)
+    counts = np.full(iterations, -1, np.int32)
     lib().uzo_estimate_edge(fa, len(cams_from), ta, len(cams_to), C.c_double(thr), int(iterations),
                             C.c_double(bp), int(bool(do_prosac)), int(min_keypoints), C.byref(e),
-                            _p(matches) if want_debug else None, _p(mask) if want_debug else None, maxm)
+                            _p(matches) if want_debug else None, _p(mask) if want_debug else None, maxm,
+                            _p(counts))
     M = e.n_matches
     return dict(ok=bool(e.ok), cam_from=e.cam_from, cam_to=e.cam_to, n_ratio_matches=e.n_ratio_matches,
                 n_matches=M, consensus=e.consensus, best_iteration=e.best_iteration,
                 iterations_run=e.iterations_run, mse=e.mse, info_scale=e.info_scale,
                 T=np.array(e.T[:], np.float64).reshape(4, 4), matches=matches[:M].copy(),
-                inlier_mask=mask[:M].astype(bool))
+                inlier_mask=mask[:M].astype(bool), counts=counts)

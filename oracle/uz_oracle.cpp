@@ -292,7 +292,9 @@ struct ProsacOut {
 
 // prosac (:186-297) with minCorrespondenceCount = 3, on an explicit sample list.
 void prosac(const double* P, const double* Q, int M, const int32_t* samples, int iterations,
-            double thr, double breakPercentage, ProsacOut* out, uint8_t* inlier_mask /* M */) {
+            double thr, double breakPercentage, ProsacOut* out, uint8_t* inlier_mask /* M */,
+            int32_t* counts_out = nullptr /* iterations; -1 = not evaluated */) {
+    if (counts_out) for (int c = 0; c < iterations; ++c) counts_out[c] = -1;
     const int minCount = 3;
     int maxConsensus = 0;
     std::vector<uint8_t> set(M), maxSet(M, 0);
@@ -308,6 +310,7 @@ void prosac(const double* P, const double* Q, int M, const int32_t* samples, int
         }
         pose_svd(Pt, Qt, minCount, Ttemp);
         int consensus = consensus3d(P, Q, M, Ttemp, thr, set.data());
+        if (counts_out) counts_out[i] = consensus;
         if (consensus > maxConsensus) {
             maxConsensus = consensus;
             maxSet = set;
@@ -432,7 +435,8 @@ void uzo_estimate_svd(const double* P, const double* Q, int M, double thr, int i
 // trainIdx, distance — the sorted final_matches of :114) and inlier_mask (capacity max_matches).
 void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features* to, int n_to,
                        double thr, int iterations, double bp, int do_prosac, int min_keypoints,
-                       uzo_edge* edge, int32_t* matches_out, uint8_t* inlier_mask, int max_matches) {
+                       uzo_edge* edge, int32_t* matches_out, uint8_t* inlier_mask, int max_matches,
+                       int32_t* counts_out) {
     static const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     std::memset(edge, 0, sizeof(*edge));
     std::memcpy(edge->T, I4, sizeof(I4));
@@ -502,7 +506,7 @@ void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features*
         sample_list(M, iterations, do_prosac, samples.data());
         ProsacOut po;
         std::vector<uint8_t> mask(M);
-        prosac(Pd.data(), Xd.data(), M, samples.data(), iterations, thr, bp, &po, mask.data());   // :130
+        prosac(Pd.data(), Xd.data(), M, samples.data(), iterations, thr, bp, &po, mask.data(), counts_out);   // :130
         if (inlier_mask) std::memcpy(inlier_mask, mask.data(), std::min(M, max_matches));
         if (po.consensus > 0 && po.mse > 0) edge->info_scale = 0.1 * po.consensus / po.mse;      // :134-135
         std::memcpy(edge->T, po.T, sizeof(po.T));

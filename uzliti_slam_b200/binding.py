@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_remove", "uz_store_clear",
     "uz_store_size", "uz_store_bytes", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
-    "uz_set_debug", "uz_debug_pair", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
+    "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
     "uz_get_timers", "uz_microbench", "uz_version",
 ]
 
@@ -89,7 +89,7 @@ def load_library():
     for name in ("uz_create", "uz_set_params", "uz_get_params", "uz_set_stream", "uz_store_add", "uz_store_add_bulk",
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
-                 "uz_set_debug", "uz_debug_pair", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
+                 "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
                  "uz_microbench"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -130,8 +130,8 @@ class EdgeEstimator:
         self.ctx = C.c_void_p()
         st = self.lib.uz_create(int(device), C.byref(self.ctx))
         if st != 0:
-            raise UzError(f"uz_create(device={device}) failed with status {st}: no usable sm_100 GPU "
-                          "(there is no CPU fallback)")
+            raise UzError(f"uz_create(device={device}) failed with status {st}: "
+                          f"{self.lib.uz_last_error(None).decode()} (there is no CPU fallback)")
         self.device = device
 
     def close(self):
@@ -294,6 +294,13 @@ class EdgeEstimator:
         got = C.c_int32()
         self._check(self.lib.uz_debug_pair(self.ctx, int(pair_index), _p(m), _p(mask), n, C.byref(got)))
         return m[:n_matches], mask[:n_matches].astype(bool)
+
+    def debug_counts(self, pair_index):
+        n = self.get_params().ransac_iterations
+        out = np.full(n, -2, np.int32)
+        got = C.c_int32()
+        self._check(self.lib.uz_debug_counts(self.ctx, int(pair_index), _p(out), n, C.byref(got)))
+        return out[:got.value]
 
     # ---- introspection ---------------------------------------------------------------------------
     def launch_count(self):

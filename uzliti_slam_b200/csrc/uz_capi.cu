@@ -115,12 +115,12 @@ struct uz_context {
     int samp_cap = -1, samp_iters = -1, samp_prosac = -1;
 
     // per-launch buffers
-    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_misc;
+    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_misc;
     PinBuf h_tasks, h_tiles, h_pair_tasks;
 
     // parity taps
     int debug = 0;
-    int dbg_cap = 0, dbg_pairs = 0;
+    int dbg_cap = 0, dbg_pairs = 0, dbg_iters = 0;
 
     // introspection
     int64_t launches = 0;
@@ -132,8 +132,10 @@ struct uz_context {
 
 namespace {
 
+std::string g_create_err = "";   // why the last uz_create failed (uz_last_error(NULL))
+
 uz_status fail(uz_context* ctx, uz_status st, const std::string& msg) {
-    if (ctx) ctx->err = msg;
+    if (ctx) ctx->err = msg; else g_create_err = msg;
     return st;
 }
 
@@ -268,7 +270,10 @@ uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max
     build_sample_table(iterations, do_prosac != 0, cap, table);
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // previous launches may still read the old table
     UZ_CUDA(ctx, ctx->d_samples.ensure(table.size() * sizeof(uint16_t)));
-    UZ_CUDA(ctx, cudaMemcpy(ctx->d_samples.p, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    // stream-ordered: a plain cudaMemcpy from pageable memory runs on the legacy stream, which a
+    // non-blocking stream does not wait for
+    UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, table.data(), table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->samp_cap = cap; ctx->samp_iters = iterations; ctx->samp_prosac = do_prosac;
     return UZ_OK;
 }
@@ -397,8 +402,11 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     if (ctx->debug) {
         UZ_CUDA(ctx, ctx->d_dbg_matches.ensure((size_t)n_pairs * cap * 3 * sizeof(int32_t)));
         UZ_CUDA(ctx, ctx->d_dbg_mask.ensure((size_t)n_pairs * cap));
+        UZ_CUDA(ctx, ctx->d_dbg_counts.ensure((size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t)));
+        UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_counts.p, 0xFF, (size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t), ctx->stream));
         sp.dbg_matches = (int32_t*)ctx->d_dbg_matches.p; sp.dbg_mask = (uint8_t*)ctx->d_dbg_mask.p;
-        ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs;
+        sp.dbg_counts = (int32_t*)ctx->d_dbg_counts.p;
+        ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs; ctx->dbg_iters = prm.ransac_iterations;
     }
     solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
         (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_pair_tasks.p, (const uint2*)ctx->d_keys.p, sp, d_results);
@@ -454,24 +462,23 @@ uz_status uz_create(int32_t device, uz_context** out) {
     *out = nullptr;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return UZ_ERR_CUDA; }
-    if (device < 0 || device >= count) return UZ_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return UZ_ERR_CUDA; }
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return fail(nullptr, UZ_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+    if (device < 0 || device >= count) return fail(nullptr, UZ_ERR_INVALID, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return UZ_ERR_CUDA; }
-    if (prop.major != 10) return UZ_ERR_CUDA;     // sm_100a cubins only
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
+    if (prop.major != 10) return fail(nullptr, UZ_ERR_CUDA, "device is not sm_100 (this library carries sm_100a code only)");
     uz_context* ctx = new uz_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     uz_default_params(&ctx->params);
     const char* v = getenv("UZ_KNN_VARIANT");
     if (v && v[0] == '1') ctx->variant_csa = 0;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UZ_ERR_CUDA; }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
-    bool ok = true;
-    ok &= cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)solve_smem_bytes(UZ_MAX_FEATURES)) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); uz_destroy(ctx); return UZ_ERR_CUDA; }
+    e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)solve_smem_bytes(UZ_MAX_FEATURES));
+    if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
     *out = ctx;
     return UZ_OK;
 }
@@ -482,7 +489,7 @@ void uz_destroy(uz_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->store_arena.release(); ctx->transient.release();
     ctx->d_samples.release(); ctx->d_tasks.release(); ctx->d_tiles.release(); ctx->d_pair_tasks.release();
-    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release();
+    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release();
     ctx->d_misc.release();
     ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -490,7 +497,7 @@ void uz_destroy(uz_context* ctx) {
     delete ctx;
 }
 
-const char* uz_last_error(const uz_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* uz_last_error(const uz_context* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 uz_status uz_set_params(uz_context* ctx, const uz_params* p) {
     if (!ctx || !p) return UZ_ERR_INVALID;
@@ -871,15 +878,26 @@ uz_status uz_debug_pair(uz_context* ctx, int32_t pair_index, int32_t* matches_ou
     if (st != UZ_OK) return st;
     if (pair_index < 0 || pair_index >= ctx->dbg_pairs) return fail(ctx, UZ_ERR_INVALID, "no debug data for that pair (uz_set_debug before the call)");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    uz_edge_result r;
-    // n_matches of the pair lives in the caller's results; re-read M from the device result buffer if it is ours
-    (void)r;
     const int cap = ctx->dbg_cap;
     const int n = std::min(capacity, cap);
     if (matches_out && n > 0)
-        UZ_CUDA(ctx, cudaMemcpy(matches_out, (int32_t*)ctx->d_dbg_matches.p + (size_t)pair_index * cap * 3, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        UZ_CUDA(ctx, cudaMemcpyAsync(matches_out, (int32_t*)ctx->d_dbg_matches.p + (size_t)pair_index * cap * 3, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
     if (inlier_mask_out && n > 0)
-        UZ_CUDA(ctx, cudaMemcpy(inlier_mask_out, (uint8_t*)ctx->d_dbg_mask.p + (size_t)pair_index * cap, (size_t)n, cudaMemcpyDeviceToHost));
+        UZ_CUDA(ctx, cudaMemcpyAsync(inlier_mask_out, (uint8_t*)ctx->d_dbg_mask.p + (size_t)pair_index * cap, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = n;
+    return UZ_OK;
+}
+
+uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_out, int32_t capacity, int32_t* n_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (pair_index < 0 || pair_index >= ctx->dbg_pairs || !counts_out) return fail(ctx, UZ_ERR_INVALID, "no debug data for that pair (uz_set_debug before the call)");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n = std::min(capacity, ctx->dbg_iters);
+    if (n > 0)
+        UZ_CUDA(ctx, cudaMemcpyAsync(counts_out, (int32_t*)ctx->d_dbg_counts.p + (size_t)pair_index * ctx->dbg_iters, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_out) *n_out = n;
     return UZ_OK;
 }

@@ -35,15 +35,18 @@ struct SolveParams {
     // parity taps (may be null)
     int32_t* dbg_matches;    // [pair][cap][3]
     uint8_t* dbg_mask;       // [pair][cap]
+    int32_t* dbg_counts;     // [pair][iterations] consensus count of every evaluated hypothesis, -1 = not run
 };
 
 constexpr int kSolveThreads = 128;
 
-__host__ __device__ inline size_t solve_smem_bytes(int cap) {
-    return (size_t)cap * 48 /*P,Q*/ + (size_t)cap * 8 /*sort keys, later residual norms*/ +
+__host__ __device__ constexpr size_t solve_smem_bytes(int cap) {
+    return (size_t)cap * 48 /*P,Q (px is reused for the residual norms)*/ + (size_t)cap * 4 /*sort keys*/ +
            (size_t)kSolveThreads * 12 * 8 /*hypothesis transforms*/ + (size_t)kSolveThreads * 4 /*counts*/ +
            (size_t)cap /*mask*/ + 256 /*scalars*/;
 }
+
+static_assert(solve_smem_bytes(UZ_MAX_FEATURES) + 64 <= 232448, "solve kernel exceeds the 227 KB per-CTA shared memory of sm_100");
 
 __device__ __forceinline__ void write_identity(double* T16) {
 #pragma unroll
@@ -60,13 +63,13 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     double* px = reinterpret_cast<double*>(smem_raw);
     double* py = px + cap; double* pz = py + cap;
     double* qx = pz + cap; double* qy = qx + cap; double* qz = qy + cap;
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(qz + cap);
-    double* norms = reinterpret_cast<double*>(skeys);                 // aliases skeys after the gather
-    double* Th = reinterpret_cast<double*>(skeys) + cap;             // [THREADS][12]
-    int32_t* counts = reinterpret_cast<int32_t*>(Th + THREADS * 12); // [THREADS]
-    uint8_t* mask = reinterpret_cast<uint8_t*>(counts + THREADS);    // [cap]
-    double* Tbest = reinterpret_cast<double*>(mask + cap + ((16 - (cap & 15)) & 15));   // 12, 16B aligned
+    double* Th = qz + cap;                                            // [THREADS][12]
+    double* norms = px;                                               // norms[i] overwrites px[i] in place (K5)
+    double* Tbest = Th + THREADS * 12;                                // 12
     double* Tfin = Tbest + 12;                                        // 12
+    int32_t* counts = reinterpret_cast<int32_t*>(Tfin + 12);          // [THREADS]
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(counts + THREADS);  // [cap]
+    uint8_t* mask = reinterpret_cast<uint8_t*>(skeys + cap);          // [cap]
     __shared__ int s_best, s_maxc, s_break, s_run;
 
     const int tid = threadIdx.x;
@@ -219,15 +222,16 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
             s_maxc = maxc; s_best = best; s_break = brk; s_run = run;
         }
         __syncthreads();
+        if (prm.dbg_counts && tid < nh && h0 + tid < s_run) prm.dbg_counts[(size_t)pair * I + h0 + tid] = counts[tid];
         if (s_break) break;
     }
 
     const int maxc = s_maxc;
     if (maxc < 3) {              // :291-294 no hypothesis reached 3 inliers: T = I, consensus 0, still "true"
         if (tid == 0) {
-            res->ok = prm.direct_P ? 1 : 1; res->cam_from = cam_from; res->cam_to = cam_to;
+            res->ok = 1; res->cam_from = cam_from; res->cam_to = cam_to;
             res->n_ratio_matches = n_ratio; res->n_matches = M; res->consensus = 0;
-            res->best_iteration = -1; res->iterations_run = s_run; res->mse = 0.0; res->info_scale = 1.0;
+            res->best_iteration = s_best; res->iterations_run = s_run; res->mse = 0.0; res->info_scale = 1.0;
             write_identity(res->T);
         }
         if (prm.dbg_mask) for (int i = tid; i < M; i += THREADS) prm.dbg_mask[(size_t)pair * cap + i] = 0;
