@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — edge estimates/sec of the feature-edge path (Hamming kNN-2 + ratio + RANSAC rigid transform).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[3], SURVEY.md §8d "C4"): a 10 000-keyframe map, 1000 ORB-256 features per
+keyframe, K=20 loop-closure candidates per keyframe = 200 000 keyframe pairs, sharded over 8 GPUs.  One
+"step" = one pass of the hot path over one rank's shard of 25 000 pairs (weak scaling: the shard size is
+fixed, the map is replicated on every GPU, at N=8 the step is exactly C4).  Pairs are fully independent;
+the only exchange is the all-gather of the 176-byte per-pair edge records over NCCL.
+
+The JSON line carries:  value = whole-job edges/s with the keyframe store resident in HBM;  e2e = the same
+batch through uz_estimate_edges_host() from pinned HOST buffers (H2D of every referenced keyframe + D2H of
+the edge records inside the timed region);  roofline for the dominant kernel (knn2) against integer-pipe
+peaks microbenchmarked in this same run;  cpu_baseline = the oracle port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_KEYFRAMES = 10000
+N_FEATURES = 1000
+K_CAND = 20
+PAIRS_PER_GPU = 25000          # 200 000 / 8
+METRIC = "edge estimates/sec (Hamming kNN-2 + ratio + RANSAC)"
+UNIT = "edges/s"
+WORKLOAD = ("C4 loop-closure screening: 10000-keyframe map x 1000 ORB-256 features, K=20 candidates/keyframe, "
+            "25000 keyframe pairs per GPU (200000 pairs at 8 GPUs), 100 RANSAC hypotheses/pair, thr 0.1 m, break 0.6")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_map(n_keyframes, out=None):
+    from uzliti_slam_b200 import synthetic as S
+    t0 = time.time()
+    kfs, pairs, poses = S.make_map(n_keyframes, n_features=N_FEATURES, cluster=25, pool=1000, n_shared=600,
+                                   k_candidates=K_CAND, cross_cluster=4, seed=4, out=out)
+    log(f"[bench] synthetic map: {n_keyframes} keyframes, {len(pairs)} candidate pairs in {time.time() - t0:.1f}s")
+    return kfs, pairs, poses
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores (processes, because the oracle replays glibc rand())
+# ----------------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _cpu_worker(args):
+    lo, hi = args
+    from oracle import binding as O
+    kfs, pairs = _G["kfs"], _G["pairs"]
+    cons = 0
+    for i in range(lo, hi):
+        a, b = pairs[i]
+        r = O.estimate_edge([kfs[a]], [kfs[b]], want_debug=False)
+        cons += r["consensus"]
+    return hi - lo, cons
+
+
+def cpu_pass(kfs, pairs, pool, ncores, chunk=8):
+    """one bounded CPU pass over `pairs`; returns (pairs done, seconds)"""
+    _G["kfs"], _G["pairs"] = kfs, pairs
+    jobs = [(i, min(i + chunk, len(pairs))) for i in range(0, len(pairs), chunk)]
+    t0 = time.perf_counter()
+    done = sum(n for n, _ in pool.map(_cpu_worker, jobs))
+    return done, time.perf_counter() - t0
+
+
+def make_pool(kfs, pairs, ncores):
+    import multiprocessing as mp
+    _G["kfs"], _G["pairs"] = kfs, pairs
+    from oracle import binding as O
+    O.lib()
+    return mp.get_context("fork").Pool(ncores)
+
+
+def cpu_baseline(kfs, pairs, budget_s=12.0):
+    """oracle port on every host core for ~budget_s seconds of a fixed pseudo-random subsample"""
+    ncores = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(1)
+    sample = pairs[rng.permutation(len(pairs))]
+    pool = make_pool(kfs, sample, ncores)
+    try:
+        n0 = ncores * 8
+        cpu_pass(kfs, sample[:n0], pool, ncores)                       # warm-up (page-in, pool start)
+        _G["pairs"] = sample
+        done, secs, pos = 0, 0.0, 0
+        n = ncores * 32
+        while secs < budget_s and pos < len(sample):
+            jobs = [(i, min(i + 8, pos + n, len(sample))) for i in range(pos, min(pos + n, len(sample)), 8)]
+            t0 = time.perf_counter()
+            done += sum(k for k, _ in pool.map(_cpu_worker, jobs))
+            secs += time.perf_counter() - t0
+            pos += n
+    finally:
+        pool.close()
+        pool.join()
+    val = done / secs
+    extra = {}
+    try:   # context only: the OpenCV matcher the reference links, single thread, same 1000x1000 shape
+        import cv2
+        cv2.setNumThreads(1)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        a, b = sample[0]
+        t0 = time.perf_counter()
+        for _ in range(5):
+            bf.knnMatch(kfs[b]["desc"], kfs[a]["desc"], k=2)
+        extra["cv2_knnmatch_ms_1thread"] = round((time.perf_counter() - t0) / 5 * 1e3, 2)
+        extra["cv2_version"] = cv2.__version__
+    except Exception:
+        pass
+    return dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port",
+                sample=f"{done} pairs of the same workload (fixed random subsample of the 200000), oracle port "
+                       f"(oracle/uz_oracle.cpp, g++ -O3 x86-64-v3), one process per core, {secs:.1f}s", **extra)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_kf = min(N_KEYFRAMES, 2000)      # the sample below never touches more keyframes than this
+    kfs, pairs, _ = build_map(n_kf)
+    ncores = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(1)
+    sample = pairs[rng.permutation(len(pairs))]
+    per_step = ncores * 48
+    pool = make_pool(kfs, sample, ncores)
+    try:
+        _G["pairs"] = sample
+        pos = 0
+
+        def step():
+            nonlocal pos
+            lo = pos % max(1, len(sample) - per_step)
+            jobs = [(i, min(i + 8, lo + per_step)) for i in range(lo, lo + per_step, 8)]
+            t0 = time.perf_counter()
+            d = sum(k for k, _ in pool.map(_cpu_worker, jobs))
+            pos += per_step
+            return d, time.perf_counter() - t0
+        for _ in range(args.warmup):
+            step()
+        done, secs = 0, 0.0
+        for _ in range(args.steps):
+            d, s = step()
+            done += d
+            secs += s
+    finally:
+        pool.close()
+        pool.join()
+    val = done / secs
+    sample_desc = (f"each step = {per_step} pairs of the C4 workload (fixed random subsample), oracle port on "
+                   f"{ncores} host processes")
+    line = dict(impl="reference", metric=METRIC, value=round(val, 2), unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(secs / args.steps * 1e3, 3), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="u32", data="synthetic",
+                config=dict(workload=WORKLOAD, l2="n/a (CPU)", sample=sample_desc),
+                cpu_baseline=dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port", sample=sample_desc),
+                e2e=dict(value=round(val, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            log(f"[bench] --gpus {args.gpus} needs torchrun (one process per GPU); re-launching")
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+
+    n_kf = args.keyframes
+    pairs_per_gpu = args.pairs_per_gpu
+
+    # ---- data (host, pageable first: the CPU baseline forks before CUDA is touched) ----------------
+    desc = np.empty((n_kf, N_FEATURES, 32), np.uint8)
+    pos = np.empty((n_kf, N_FEATURES, 3), np.float64)
+    valid = np.empty((n_kf, N_FEATURES), np.uint8)
+    kfs, pairs, poses = build_map(n_kf, out=(desc, pos, valid))
+    total_pairs = len(pairs)
+    # rank r owns a contiguous chunk of the (from-sorted) pair list; cycle if the map is smaller than the job
+    lo = (rank * pairs_per_gpu) % total_pairs
+    sel = (lo + np.arange(pairs_per_gpu)) % total_pairs
+    my_pairs = pairs[sel]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(kfs, pairs, budget_s=args.cpu_seconds)
+        log(f"[bench] cpu_baseline: {cpu['value']} {UNIT} on {cpu['cores']} cores")
+
+    import torch
+    import torch.distributed as dist
+    from uzliti_slam_b200 import EdgeEstimator
+    from uzliti_slam_b200.binding import RESULT_DTYPE
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # pinned host copy of the map (the e2e leg DMAs straight out of it)
+    t_desc = torch.from_numpy(desc).pin_memory()
+    t_pos = torch.from_numpy(pos).pin_memory()
+    t_valid = torch.from_numpy(valid).pin_memory()
+    pd, pp, pv = t_desc.numpy(), t_pos.numpy(), t_valid.numpy()
+    pinned_kfs = [dict(kf, desc=pd[i], pos=pp[i], valid=pv[i]) for i, kf in enumerate(kfs)]
+
+    est = EdgeEstimator(local_rank)
+    stream = torch.cuda.current_stream()
+    est.set_stream(stream.cuda_stream)
+
+    # integer-pipe peaks, measured here and now (roofline denominators)
+    peaks = {name: est.microbench(op) for op, name in enumerate(["popc", "lop3", "imad", "vimnmx"])}
+
+    t0 = time.time()
+    handles = est.add_keyframes(pinned_kfs)
+    torch.cuda.synchronize()
+    log(f"[bench] rank {rank}: store resident, {est.store_bytes() / 1e6:.0f} MB in {time.time() - t0:.2f}s")
+    hf = np.ascontiguousarray(handles[my_pairs[:, 0]])
+    ht = np.ascontiguousarray(handles[my_pairs[:, 1]])
+    rec = RESULT_DTYPE.itemsize
+    res_local = torch.empty(pairs_per_gpu * rec, dtype=torch.uint8, device=dev)
+    res_all = torch.empty(world * pairs_per_gpu * rec, dtype=torch.uint8, device=dev) if world > 1 else res_local
+
+    def step():
+        est.estimateEdgesDevice(hf, ht, res_local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(res_all, res_local)      # per-pair best edges over NCCL/NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    est.enable_timers(True)
+    est.reset_timers()
+    launches0 = est.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = est.launch_count() - launches0
+    tm = est.get_timers()
+    est.enable_timers(False)
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        launches = int(t[1])
+    value = world * pairs_per_gpu * args.steps / (ms * 1e-3)
+
+    # sanity on the last step's records (not timed): true candidates found, false ones rejected
+    out = np.frombuffer(res_local.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    same = (my_pairs[:, 0] // 25) == (my_pairs[:, 1] // 25)
+    sanity = dict(ok_frac=float((out["ok"] == 1).mean()), median_consensus_true=float(np.median(out["consensus"][same])),
+                  max_consensus_false=int(out["consensus"][~same].max()) if (~same).any() else 0,
+                  mean_matches=float(out["n_matches"].mean()))
+
+    # ---- e2e: the same batch from pinned host buffers through uz_estimate_edges_host ------------------
+    prep = est.prepare_host_pairs([([pinned_kfs[a]], [pinned_kfs[b]]) for a, b in my_pairs])
+    uniq = np.unique(my_pairs)
+    h2d = int(len(uniq)) * N_FEATURES * (32 + 24 + 1)
+    d2h = pairs_per_gpu * rec
+    e2e_steps = max(2, min(args.steps, 5))
+    est.estimateEdgesHostPrepared(prep)
+    est.estimateEdgesHostPrepared(prep)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        est.estimateEdgesHostPrepared(prep)       # blocks until the edge records are back in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_val = world * pairs_per_gpu * e2e_steps / e2e_s
+    assert prep["res"].tobytes() == out.tobytes(), "host path and store path disagree"
+
+    if rank == 0:
+        cmp_per_launch = tm["compares"] / max(tm["match_launches"], 1)
+        knn_ms = tm["match_ms"] / max(tm["match_launches"], 1)
+        solve_ms = tm["solve_ms"] / max(tm["solve_launches"], 1)
+        gcmp = cmp_per_launch / (knn_ms * 1e-3) * 1e-9
+        # per compare the kernel issues 13 LOP3 + 1 LEA (ALU), 3 VIMNMX, 4 POPC, 3 IMAD (SASS, profiles/)
+        alu_limit = 1.0 / (14.0 / peaks["lop3"] + 3.0 / peaks["vimnmx"])
+        popc_limit = peaks["popc"] / 4.0
+        peak = min(alu_limit, popc_limit)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "knn2_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        alg_bytes = pairs_per_gpu * (2 * N_FEATURES * 32 + N_FEATURES * 8)
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = mp.get("hbm_gbs", 6650.0)
+        line = dict(
+            metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="u32", data="synthetic",
+            config=dict(workload=WORKLOAD, keyframes=n_kf, features=N_FEATURES, pairs_per_gpu=pairs_per_gpu,
+                        l2="inputs larger than L2: every step streams the 10000-keyframe store "
+                           f"({est.store_bytes() / 1e6:.0f} MB resident per GPU) through the match kernel; no flush",
+                        parallelism=f"pair-list sharding x{world}, store replicated, all-gather of 176 B edge records"),
+            g_descriptor_cmp_per_s=round(world * cmp_per_launch / (ms / args.steps * 1e-3) * 1e-9, 2),
+            roofline=dict(bound="int", kernel="knn2_kernel", achieved=round(gcmp, 2), peak=round(peak, 2), unit="Gcmp/s",
+                          frac=round(gcmp / peak, 4), traffic=traffic,
+                          peak_source="min(ALU, POPC) limit of the kernel's own SASS mix (14 ALU-class LOP3/LEA + 3 VIMNMX + "
+                                      "4 POPC per 256-bit compare) from pipe rates microbenchmarked in this run",
+                          pipe_peaks_gops={k: round(v, 1) for k, v in peaks.items()},
+                          textbook_peak_8popc=round(peaks["popc"] / 8.0, 2), frac_of_textbook=round(gcmp / (peaks["popc"] / 8.0), 4),
+                          knn2_ms_per_launch=round(knn_ms, 3), solve_ms_per_launch=round(solve_ms, 3),
+                          compares_per_launch=int(cmp_per_launch),
+                          hbm=dict(achieved_gbs=round(alg_bytes / (knn_ms * 1e-3) * 1e-9, 2), peak_gbs=hbm_peak,
+                                   frac=round(alg_bytes / (knn_ms * 1e-3) * 1e-9 / hbm_peak, 5),
+                                   peak_source="MEASURED_PEAKS.json" if mp else "fallback")),
+            cpu_baseline=cpu,
+            e2e=dict(value=round(e2e_val, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                     api="uz_estimate_edges_host (pinned host FeatureData in, host edge records out)"),
+            gpu_launches=launches, clocks=clocks, sanity=sanity)
+        print(json.dumps(line), flush=True)
+    est.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--keyframes", type=int, default=N_KEYFRAMES)
+    ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

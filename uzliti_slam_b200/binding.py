@@ -281,6 +281,25 @@ class EdgeEstimator:
         self._check(self.lib.uz_estimate_edges_host(self.ctx, fa, _p(nf), ta, _p(nt), len(pairs), _p(res)))
         return res
 
+    def prepare_host_pairs(self, pairs):
+        """Build the uz_features views of a host batch once (pointer structs only, no data is copied), so a
+        caller can time estimateEdgesHostPrepared() without Python marshalling in the loop."""
+        keep, ff, tt, nf, nt = [], [], [], [], []
+        for a, b in pairs:
+            a = a if isinstance(a, (list, tuple)) else [a]
+            b = b if isinstance(b, (list, tuple)) else [b]
+            ff += list(a); tt += list(b)
+            nf.append(len(a)); nt.append(len(b))
+        fa = features_array(ff, keep)
+        ta = features_array(tt, keep)
+        return dict(fa=fa, ta=ta, nf=np.array(nf, np.int32), nt=np.array(nt, np.int32), n=len(pairs), keep=keep,
+                    res=np.zeros(len(pairs), RESULT_DTYPE))
+
+    def estimateEdgesHostPrepared(self, prep):
+        self._check(self.lib.uz_estimate_edges_host(self.ctx, prep["fa"], _p(prep["nf"]), prep["ta"], _p(prep["nt"]),
+                                                    prep["n"], _p(prep["res"])))
+        return prep["res"]
+
     def estimateEdgeDirect(self, cams_from, cams_to):
         return self.estimateEdgesHost([(cams_from, cams_to)])[0]
 

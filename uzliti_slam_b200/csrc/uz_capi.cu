@@ -128,6 +128,17 @@ struct uz_context {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double match_ms = 0, solve_ms = 0;
     int64_t match_launches = 0, solve_launches = 0, compares = 0;
+    // lazily resolved event triples (start, after K1, after solve): recording costs ~1 us and no sync,
+    // so the timers can stay on inside a timed region; uz_get_timers() synchronises and folds them in
+    struct Timed { cudaEvent_t e[3]; bool has_solve; };
+    std::vector<Timed> pending;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
 };
 
 namespace {
@@ -368,7 +379,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
     // 3. K1
-    if (ctx->timers) cudaEventRecord(ctx->ev[0], ctx->stream);
+    uz_context::Timed tm;
+    tm.e[0] = tm.e[1] = tm.e[2] = nullptr; tm.has_solve = false;
+    if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
     if (n_tiles) {
         switch (best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
@@ -378,13 +391,12 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());
     }
-    if (ctx->timers) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (ctx->timers) {
+        cudaEventRecord(tm.e[1], ctx->stream);
+        ctx->match_launches += n_tiles ? 1 : 0; ctx->compares += compares;
+    }
     if (!d_results) {        // matching only (uz_match_knn2)
-        if (ctx->timers) {
-            UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-            ctx->match_ms += ms; ctx->match_launches += n_tiles ? 1 : 0; ctx->compares += compares;
-        }
+        if (ctx->timers) ctx->pending.push_back(tm);
         return UZ_OK;
     }
 
@@ -413,14 +425,25 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     if (ctx->timers) {
-        cudaEventRecord(ctx->ev[2], ctx->stream);
-        UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-        ctx->match_ms += a; ctx->solve_ms += b;
-        ctx->match_launches += n_tiles ? 1 : 0; ctx->solve_launches += 1; ctx->compares += compares;
+        tm.e[2] = ctx->get_event(); tm.has_solve = true;
+        cudaEventRecord(tm.e[2], ctx->stream);
+        ctx->solve_launches += 1;
+        ctx->pending.push_back(tm);
     }
+    return UZ_OK;
+}
+
+uz_status resolve_timers(uz_context* ctx) {
+    if (ctx->pending.empty()) return UZ_OK;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& t : ctx->pending) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, t.e[0], t.e[1]);
+        ctx->match_ms += a;
+        if (t.has_solve) { cudaEventElapsedTime(&b, t.e[1], t.e[2]); ctx->solve_ms += b; }
+        for (int i = 0; i < 3; ++i) if (t.e[i]) ctx->event_pool.push_back(t.e[i]);
+    }
+    ctx->pending.clear();
     return UZ_OK;
 }
 
@@ -493,6 +516,8 @@ void uz_destroy(uz_context* ctx) {
     ctx->d_misc.release();
     ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& t : ctx->pending) for (int i = 0; i < 3; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -913,6 +938,8 @@ uz_status uz_enable_timers(uz_context* ctx, int32_t enable) {
 
 uz_status uz_reset_timers(uz_context* ctx) {
     if (!ctx) return UZ_ERR_INVALID;
+    uz_status st = resolve_timers(ctx);
+    if (st != UZ_OK) return st;
     ctx->match_ms = ctx->solve_ms = 0; ctx->match_launches = ctx->solve_launches = ctx->compares = 0;
     return UZ_OK;
 }
@@ -920,6 +947,8 @@ uz_status uz_reset_timers(uz_context* ctx) {
 uz_status uz_get_timers(uz_context* ctx, double* match_ms, double* solve_ms, int64_t* match_launches,
                         int64_t* solve_launches, int64_t* descriptor_compares) {
     if (!ctx) return UZ_ERR_INVALID;
+    uz_status st = resolve_timers(ctx);
+    if (st != UZ_OK) return st;
     if (match_ms) *match_ms = ctx->match_ms;
     if (solve_ms) *solve_ms = ctx->solve_ms;
     if (match_launches) *match_launches = ctx->match_launches;

@@ -104,7 +104,7 @@ def make_pair(n_from, n_to=None, seed=0, rho=0.5, invalid_frac=0.15, gross_outli
 
 
 def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, k_candidates=20,
-             cross_cluster=4, seed=0, invalid_frac=0.15):
+             cross_cluster=4, seed=0, invalid_frac=0.15, out=None):
     """A keyframe map with loop-closure candidates (configs C3/C4 of BASELINE.json).
 
     Keyframes come in clusters that share a pool of landmarks: each keyframe observes n_shared pool
@@ -112,6 +112,9 @@ def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, 
     the reference's 30 deg / 1.5 m gates) plus fresh ones.  Every keyframe gets k_candidates candidate
     partners: k_candidates - cross_cluster from its own cluster (true loop closures) and
     cross_cluster from random other clusters (place-recognition false positives).
+
+    `out` = (desc uint8[n,N,32], pos float64[n,N,3], valid uint8[n,N]) optionally receives the keyframes
+    as slices of three big arrays (e.g. pinned host memory), so the whole map is contiguous per field.
 
     Returns (keyframes list, pairs int32[n_pairs,2] (from,to), poses float64[n,4,4] (cluster->keyframe)).
     """
@@ -130,6 +133,10 @@ def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, 
             D = np.concatenate([_flip(rng, Dp[sel]),
                                 rng.integers(0, 256, (n_features - n_shared, 32), dtype=np.uint8)])
             kf, _ = _finish(rng, D, _observe(rng, X), invalid_frac, False, 0)
+            if out is not None:
+                k = len(kfs)
+                out[0][k] = kf["desc"]; out[1][k] = kf["pos"]; out[2][k] = kf["valid"]
+                kf = dict(kf, desc=out[0][k], pos=out[1][k], valid=out[2][k])
             kfs.append(kf)
             poses.append(G)
             cluster_of.append(c0 // cluster)
