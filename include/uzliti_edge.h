@@ -155,6 +155,10 @@ uz_status uz_debug_pair(uz_context* ctx, int32_t pair_index, int32_t* matches_ou
 uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_out, int32_t capacity,
                           int32_t* n_out);
 
+/* clock64() of the pair's solve CTA at its 8 phase boundaries (start, keys built, sorted, gathered,
+ * hypotheses solved, winner known, refit done, end); profiling tap, debug mode only. */
+uz_status uz_debug_phases(uz_context* ctx, int32_t pair_index, int64_t* clocks8_out);
+
 /* ---- introspection for the bench harness ----------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 int64_t   uz_launch_count(const uz_context* ctx);

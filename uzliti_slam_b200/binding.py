@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_remove", "uz_store_clear",
     "uz_store_size", "uz_store_bytes", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
-    "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
+    "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
     "uz_get_timers", "uz_microbench", "uz_version",
 ]
 
@@ -89,7 +89,7 @@ def load_library():
     for name in ("uz_create", "uz_set_params", "uz_get_params", "uz_set_stream", "uz_store_add", "uz_store_add_bulk",
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
-                 "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
+                 "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
                  "uz_microbench"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -320,6 +320,11 @@ class EdgeEstimator:
         got = C.c_int32()
         self._check(self.lib.uz_debug_counts(self.ctx, int(pair_index), _p(out), n, C.byref(got)))
         return out[:got.value]
+
+    def debug_phases(self, pair_index):
+        out = np.zeros(8, np.int64)
+        self._check(self.lib.uz_debug_phases(self.ctx, int(pair_index), _p(out)))
+        return out
 
     # ---- introspection ---------------------------------------------------------------------------
     def launch_count(self):

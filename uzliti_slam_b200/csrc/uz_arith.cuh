@@ -101,7 +101,8 @@ UZ_HD Rot make_jacobi(float x, float y, float z) {
 }
 
 // x' = c*x + s*y ; y' = -s*x + c*y on rows p,q (stride 3 between row elements is 1) of a row-major 3x3
-UZ_HD void rot_rows(float* m, int p, int q, Rot j) {
+template <int p, int q>
+UZ_HD void rot_rows(float* m, Rot j) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float x = m[3 * p + k], y = m[3 * q + k];
@@ -109,7 +110,8 @@ UZ_HD void rot_rows(float* m, int p, int q, Rot j) {
         m[3 * q + k] = UZ_FADD(UZ_FMUL(-j.s, x), UZ_FMUL(j.c, y));
     }
 }
-UZ_HD void rot_cols(float* m, int p, int q, Rot j) {
+template <int p, int q>
+UZ_HD void rot_cols(float* m, Rot j) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float x = m[3 * k + p], y = m[3 * k + q];
@@ -119,7 +121,8 @@ UZ_HD void rot_cols(float* m, int p, int q, Rot j) {
 }
 
 // One (p,q) step of the JacobiSVD sweep; returns true if a rotation was applied.
-UZ_HD bool jacobi_step(float* W, float* U, float* V, int p, int q) {
+template <int p, int q>
+UZ_HD bool jacobi_step(float* W, float* U, float* V) {
     const float precision = 2.f * 1.1920928955078125e-07f;      // 2 * FLT_EPSILON
     const float considerAsZero = 2.f * 1.401298464324817e-45f;  // 2 * denorm_min
     const float wpp = W[3 * p + p], wqq = W[3 * q + q], wpq = W[3 * p + q], wqp = W[3 * q + p];
@@ -144,10 +147,10 @@ UZ_HD bool jacobi_step(float* W, float* U, float* V, int p, int q) {
     Rot jl;
     jl.c = UZ_FSUB(UZ_FMUL(rot1.c, jrt.c), UZ_FMUL(rot1.s, jrt.s));
     jl.s = UZ_FADD(UZ_FMUL(rot1.c, jrt.s), UZ_FMUL(rot1.s, jrt.c));
-    rot_rows(W, p, q, jl);
-    rot_cols(U, p, q, jl);
-    rot_cols(W, p, q, jrt);
-    rot_cols(V, p, q, jrt);
+    rot_rows<p, q>(W, jl);
+    rot_cols<p, q>(U, jl);
+    rot_cols<p, q>(W, jrt);
+    rot_cols<p, q>(V, jrt);
     return true;
 }
 
@@ -158,7 +161,7 @@ UZ_HD float det3(const float* m) {
     return UZ_FADD(UZ_FSUB(a, b), c);
 }
 
-UZ_HD void swap_cols(float* m, int a, int b) {
+UZ_HD void swap_cols(float* m, int a, int b) {   // a, b are compile-time at every call site after inlining
 #pragma unroll
     for (int r = 0; r < 3; ++r) { const float t = m[3 * r + a]; m[3 * r + a] = m[3 * r + b]; m[3 * r + b] = t; }
 }
@@ -174,9 +177,9 @@ UZ_HD void pose_finish(const PoseAcc& s, double* T12) {
     V[0] = V[4] = V[8] = 1.f;
     for (int sweep = 0; sweep < 64; ++sweep) {
         bool any = false;
-        any |= jacobi_step(W, U, V, 1, 0);
-        any |= jacobi_step(W, U, V, 2, 0);
-        any |= jacobi_step(W, U, V, 2, 1);
+        any |= jacobi_step<1, 0>(W, U, V);
+        any |= jacobi_step<2, 0>(W, U, V);
+        any |= jacobi_step<2, 1>(W, U, V);
         if (!any) break;
     }
 #pragma unroll
@@ -196,7 +199,8 @@ UZ_HD void pose_finish(const PoseAcc& s, double* T12) {
         if (sv[1] > best) { best = sv[1]; pos = 1; }
         if (sv[2] > best) { best = sv[2]; pos = 2; }
         if (best != 0.f) {
-            if (pos) { const float t = sv[0]; sv[0] = sv[pos]; sv[pos] = t; swap_cols(U, 0, pos); swap_cols(V, 0, pos); }
+            if (pos == 1) { const float t = sv[0]; sv[0] = sv[1]; sv[1] = t; swap_cols(U, 0, 1); swap_cols(V, 0, 1); }
+            else if (pos == 2) { const float t = sv[0]; sv[0] = sv[2]; sv[2] = t; swap_cols(U, 0, 2); swap_cols(V, 0, 2); }
             if (sv[2] > sv[1]) {
                 const float t = sv[1]; sv[1] = sv[2]; sv[2] = t; swap_cols(U, 1, 2); swap_cols(V, 1, 2);
             }

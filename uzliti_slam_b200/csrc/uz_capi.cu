@@ -115,7 +115,7 @@ struct uz_context {
     int samp_cap = -1, samp_iters = -1, samp_prosac = -1;
 
     // per-launch buffers
-    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_misc;
+    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
     PinBuf h_tasks, h_tiles, h_pair_tasks;
 
     // parity taps
@@ -418,6 +418,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_counts.p, 0xFF, (size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t), ctx->stream));
         sp.dbg_matches = (int32_t*)ctx->d_dbg_matches.p; sp.dbg_mask = (uint8_t*)ctx->d_dbg_mask.p;
         sp.dbg_counts = (int32_t*)ctx->d_dbg_counts.p;
+        UZ_CUDA(ctx, ctx->d_dbg_phase.ensure((size_t)n_pairs * 8 * sizeof(long long)));
+        UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_phase.p, 0, (size_t)n_pairs * 8 * sizeof(long long), ctx->stream));
+        sp.dbg_phase = (long long*)ctx->d_dbg_phase.p;
         ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs; ctx->dbg_iters = prm.ransac_iterations;
     }
     solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
@@ -512,7 +515,7 @@ void uz_destroy(uz_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->store_arena.release(); ctx->transient.release();
     ctx->d_samples.release(); ctx->d_tasks.release(); ctx->d_tiles.release(); ctx->d_pair_tasks.release();
-    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release();
+    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release();
     ctx->d_misc.release();
     ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -924,6 +927,15 @@ uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_o
         UZ_CUDA(ctx, cudaMemcpyAsync(counts_out, (int32_t*)ctx->d_dbg_counts.p + (size_t)pair_index * ctx->dbg_iters, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_out) *n_out = n;
+    return UZ_OK;
+}
+
+uz_status uz_debug_phases(uz_context* ctx, int32_t pair_index, int64_t* clocks8_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (pair_index < 0 || pair_index >= ctx->dbg_pairs || !clocks8_out) return fail(ctx, UZ_ERR_INVALID, "no debug data for that pair (uz_set_debug before the call)");
+    UZ_CUDA(ctx, cudaMemcpyAsync(clocks8_out, (long long*)ctx->d_dbg_phase.p + (size_t)pair_index * 8, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UZ_OK;
 }
 

@@ -36,6 +36,7 @@ struct SolveParams {
     int32_t* dbg_matches;    // [pair][cap][3]
     uint8_t* dbg_mask;       // [pair][cap]
     int32_t* dbg_counts;     // [pair][iterations] consensus count of every evaluated hypothesis, -1 = not run
+    long long* dbg_phase;    // [pair][8] clock64() at the phase boundaries of the CTA (profiling tap)
 };
 
 constexpr int kSolveThreads = 128;
@@ -75,6 +76,8 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     const int tid = threadIdx.x;
     const int pair = blockIdx.x;
     uz_edge_result* res = results + pair;
+#define UZ_PHASE(k) do { if (prm.dbg_phase && tid == 0) prm.dbg_phase[(size_t)pair * 8 + (k)] = clock64(); } while (0)
+    UZ_PHASE(0);
     int M = 0;
     int n_ratio = 0, cam_from = -1, cam_to = -1;
 
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
             skeys[i] = key;
         }
         __syncthreads();
+        UZ_PHASE(1);
         // bitonic sort ascending: (distance, queryIdx); kNoKey sinks to the end
         for (int kk = 2; kk <= cap; kk <<= 1) {
             for (int j = kk >> 1; j > 0; j >>= 1) {
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
                 __syncthreads();
             }
         }
+        UZ_PHASE(2);
         for (int base = 0; base < cap; base += THREADS)
             M += __syncthreads_count(skeys[base + tid] != kNoKey);
         const double* __restrict__ pq = tk->q_pos;
@@ -159,6 +164,7 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     }
     if (tid == 0) { s_best = -1; s_maxc = 0; s_break = 0; s_run = 0; }
     __syncthreads();
+    UZ_PHASE(3);
 
     if (M < 3) {                 // :118/:158 not enough depth-valid matches
         if (tid == 0) {
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
             pose_finish(acc, Th + tid * 12);
         }
         __syncthreads();
+        if (h0 == 0) UZ_PHASE(4);
         // each warp scores two hypotheses per pass over the points
         for (int h = warp * 2; h < nh; h += NW * 2) {
             const bool two = (h + 1) < nh;
@@ -239,18 +246,58 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     }
 
     // ---------------- K5: refit on the winner's inliers, recount, mse -------------------------------
-    for (int i = tid; i < M; i += THREADS)
-        mask[i] = residual_sq(Tbest, px[i], py[i], pz[i], qx[i], qy[i], qz[i]) < prm.thr_sq_star;
-    __syncthreads();
-    if (tid == 0) {              // float32 recurrence in inlier order: inherently sequential (:247-257)
-        PoseAcc acc;
-        pose_reset(acc);
-#pragma unroll 1
-        for (int i = 0; i < M; ++i)
-            if (mask[i]) pose_add(acc, (float)px[i], (float)py[i], (float)pz[i], (float)qx[i], (float)qy[i], (float)qz[i]);
-        pose_finish(acc, Tfin);
+    UZ_PHASE(5);
+    // (a) the winner's consensus set, compacted in index order (the refit recurrence is order dependent)
+    uint16_t* ilist = reinterpret_cast<uint16_t*>(skeys);
+    __shared__ int s_wcnt[NW];
+    int n_in = 0;
+    for (int base = 0; base < M; base += THREADS) {
+        const int i = base + tid;
+        const bool in = (i < M) && (residual_sq(Tbest, px[i], py[i], pz[i], qx[i], qy[i], qz[i]) < prm.thr_sq_star);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = n_in, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { if (w < warp) off += s_wcnt[w]; tot += s_wcnt[w]; }
+        if (in) ilist[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+        n_in += tot;
+        __syncthreads();
+    }
+    // (b) pcl::TransformationFromCorrespondences::add over the inliers in order (:247-257).  The float32
+    // recurrence is sequential in the points but its 15 state scalars are independent of each other:
+    // lane l < 9 carries covariance element (r,c) = (l/3, l%3) together with the two means it needs, every
+    // lane executing exactly the scalar operation sequence of uz::pose_add for its element.
+    if (warp == 0) {
+        const int e = lane % 9, r = e / 3, c = e % 3;
+        const double* __restrict__ Pc = px + (size_t)c * cap;
+        const double* __restrict__ Qr = qx + (size_t)r * cap;
+        float acc = 0.f, m1 = 0.f, m2 = 0.f, cv = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < n_in; ++k) {
+            const int i = ilist[k];
+            const float p = (float)Pc[i], q = (float)Qr[i];
+            acc = UZ_FADD(acc, 1.0f);
+            const float alpha = UZ_FDIV(1.0f, acc);
+            const float oma = UZ_FSUB(1.0f, alpha);
+            const float d1 = UZ_FSUB(p, m1), d2 = UZ_FSUB(q, m2);
+            cv = UZ_FMUL(oma, UZ_FADD(cv, UZ_FMUL(alpha, UZ_FMUL(d2, d1))));
+            m1 = UZ_FADD(m1, UZ_FMUL(alpha, d1));
+            m2 = UZ_FADD(m2, UZ_FMUL(alpha, d2));
+        }
+        PoseAcc A;
+        A.acc = acc;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A.c[k] = __shfl_sync(0xffffffffu, cv, k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            A.m1[k] = __shfl_sync(0xffffffffu, m1, k);          // lane k: (r,c) = (0,k)
+            A.m2[k] = __shfl_sync(0xffffffffu, m2, 3 * k);      // lane 3k: (r,c) = (k,0)
+        }
+        if (lane == 0) pose_finish(A, Tfin);
     }
     __syncthreads();
+    UZ_PHASE(6);
     int consensus = 0;
     for (int base = 0; base < M; base += THREADS) {
         const int i = base + tid;
@@ -258,17 +305,15 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
         if (i < M) {
             const double s = residual_sq(Tfin, px[i], py[i], pz[i], qx[i], qy[i], qz[i]);
             in = s < prm.thr_sq_star;
-            norms[i] = in ? UZ_DSQRT(s) : 0.0;
-            mask[i] = in;
+            norms[i] = in ? UZ_DSQRT(s) : 0.0;      // overwrites px[i]: P is dead after this pass
             if (prm.dbg_mask) prm.dbg_mask[(size_t)pair * cap + i] = in;
         }
         consensus += __syncthreads_count(in);
     }
     if (tid == 0) {
         double mse = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < M; ++i)
-            if (mask[i]) mse = UZ_DADD(mse, norms[i]);                    // :285-289 in index order
+#pragma unroll 4
+        for (int i = 0; i < M; ++i) mse = UZ_DADD(mse, norms[i]);          // :285-289 in index order (+0.0 is exact)
         mse = UZ_DDIV(mse, (double)consensus);                            // :290 (NaN when consensus == 0)
         double info = 1.0;
         if (consensus > 0 && mse > 0) info = UZ_DDIV(UZ_DMUL(0.1, (double)consensus), mse);   // :134-135
@@ -279,6 +324,8 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
         for (int e = 0; e < 12; ++e) res->T[e] = Tfin[e];
         res->T[12] = 0.0; res->T[13] = 0.0; res->T[14] = 0.0; res->T[15] = 1.0;
     }
+    UZ_PHASE(7);
+#undef UZ_PHASE
 }
 
 }  // namespace uz
