@@ -268,7 +268,10 @@ def run_gpu(args):
     pinned_kfs = [dict(kf, desc=pd[i], pos=pp[i], valid=pv[i]) for i, kf in enumerate(kfs)]
 
     est = EdgeEstimator(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the library launches on it, torch events and NCCL see the same queue
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     est.set_stream(stream.cuda_stream)
 
     # integer-pipe peaks, measured here and now (roofline denominators)

@@ -55,6 +55,12 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) 
     return d;
 }
 
+// Popcount weights (<<16 folded in).  They live in constant memory on purpose: with immediate powers of two
+// ptxas strength-reduces one of the four multiply-adds into an ALU-pipe LEA, and the ALU pipe is this
+// kernel's binding unit (13 LOP3 + 3 VIMNMX per compare); a constant-bank operand keeps all four on the
+// otherwise idle FMA pipe as IMAD.
+__constant__ uint32_t kPopcWeight[3] = {1u << 16, 2u << 16, 4u << 16};
+
 // raw 8 words -> CSA layout (also its own inverse is csa_unpack; both are XOR-linear)
 __host__ __device__ __forceinline__ void csa_pack(const uint32_t* w, uint32_t* o) {
     const uint32_t s1 = w[0] ^ w[1] ^ w[2];
@@ -73,10 +79,10 @@ __device__ __forceinline__ uint32_t csa_key(const uint32_t (&U)[8], const uint4&
     const uint32_t x7 = U[7] ^ b.w;
     const uint32_t S5 = lop3<0x96>(C1, C2, C3);
     const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
-    uint32_t k = mad_u32(__popc(C5), 4u << 16, jkey);
-    k = mad_u32(__popc(S5), 2u << 16, k);
-    k = mad_u32(__popc(x7), 1u << 16, k);
-    k = mad_u32(__popc(S3), 1u << 16, k);
+    uint32_t k = mad_u32(__popc(C5), kPopcWeight[2], jkey);
+    k = mad_u32(__popc(S5), kPopcWeight[1], k);
+    k = mad_u32(__popc(x7), kPopcWeight[0], k);
+    k = mad_u32(__popc(S3), kPopcWeight[0], k);
     return k;
 }
 
@@ -91,6 +97,13 @@ __device__ __forceinline__ void top2_update(uint32_t& m1, uint32_t& m2, uint32_t
     const uint32_t hi = max(m1, k);
     m1 = min(m1, k);
     m2 = min(m2, hi);
+}
+// two new keys at once: 5 min/max (one of them a 3-input VIMNMX3) instead of 6
+__device__ __forceinline__ void top2_update2(uint32_t& m1, uint32_t& m2, uint32_t ka, uint32_t kb) {
+    const uint32_t lo = min(ka, kb), hi = max(ka, kb);
+    const uint32_t t = max(m1, lo);
+    m1 = min(m1, lo);
+    m2 = min(min(m2, t), hi);
 }
 
 // ---- mbarrier / bulk-copy helpers (PTX) --------------------------------------------------------
@@ -179,13 +192,15 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restri
 #pragma unroll 1
         for (; j + 4 <= nrows; j += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint4 a = rows[2 * (j + u)], b = rows[2 * (j + u) + 1];
+            for (int u = 0; u < 4; u += 2) {
+                const uint4 a0 = rows[2 * (j + u)], b0 = rows[2 * (j + u) + 1];
+                const uint4 a1 = rows[2 * (j + u) + 2], b1 = rows[2 * (j + u) + 3];
                 const uint32_t jkey = (uint32_t)(r0 + j + u);
 #pragma unroll
                 for (int k = 0; k < QPT; ++k) {
-                    const uint32_t key = CSA ? csa_key(U[k], a, b, jkey) : plain_key(U[k], a, b, jkey);
-                    top2_update(m1[k], m2[k], key);
+                    const uint32_t k0 = CSA ? csa_key(U[k], a0, b0, jkey) : plain_key(U[k], a0, b0, jkey);
+                    const uint32_t k1 = CSA ? csa_key(U[k], a1, b1, jkey + 1) : plain_key(U[k], a1, b1, jkey + 1);
+                    top2_update2(m1[k], m2[k], k0, k1);
                 }
             }
         }

@@ -42,9 +42,9 @@ struct SolveParams {
 constexpr int kSolveThreads = 128;
 
 __host__ __device__ constexpr size_t solve_smem_bytes(int cap) {
-    return (size_t)cap * 48 /*P,Q (px is reused for the residual norms)*/ + (size_t)cap * 4 /*sort keys*/ +
+    return (size_t)cap * 48 /*P,Q (px also hosts the unsorted keys, later the residual norms)*/ + (size_t)cap * 4 /*sorted keys*/ +
            (size_t)kSolveThreads * 12 * 8 /*hypothesis transforms*/ + (size_t)kSolveThreads * 4 /*counts*/ +
-           (size_t)cap /*mask*/ + 256 /*scalars*/;
+           256 /*Tbest, Tfin*/;
 }
 
 static_assert(solve_smem_bytes(UZ_MAX_FEATURES) + 64 <= 232448, "solve kernel exceeds the 227 KB per-CTA shared memory of sm_100");
@@ -54,8 +54,50 @@ __device__ __forceinline__ void write_identity(double* T16) {
     for (int i = 0; i < 16; ++i) T16[i] = (i % 5 == 0) ? 1.0 : 0.0;
 }
 
+// ---- K2 helpers -----------------------------------------------------------------------------------
+// Rank sort of M unique keys (M <= E*THREADS): every thread keeps E keys in registers and counts, over
+// one broadcast pass through shared memory, how many keys are smaller — the count is the final slot.
+template <int THREADS, int E>
+__device__ __forceinline__ void rank_sort(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int M, int tid) {
+    uint32_t mine[E];
+    int rank[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const int i = tid + e * THREADS; mine[e] = i < M ? in[i] : kNoKey; rank[e] = 0; }
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    const int M4 = M >> 2;
+    for (int j = 0; j < M4; ++j) {
+        const uint4 k = in4[j];
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            rank[e] += (int)(k.x < mine[e]) + (int)(k.y < mine[e]) + (int)(k.z < mine[e]) + (int)(k.w < mine[e]);
+    }
+    for (int j = M4 << 2; j < M; ++j) {
+        const uint32_t k = in[j];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rank[e] += (int)(k < mine[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (tid + e * THREADS < M) out[rank[e]] = mine[e];
+}
+
+// ---- K4 helper: float32 pre-screen of the consensus test ---------------------------------------------
+// The reference test is  sqrt_d(s_d) < thr  with s_d evaluated in double (uz::residual_sq).  Evaluating the
+// same residual in float32 (FMA allowed) from float-rounded points gives s_f with, per component,
+//   |d_f - d| <= u (4 L1(p) + 3 |t|_inf + |q|_inf + |d|),  u = 2^-24,
+// hence | sqrt(s_f) - ||d|| | <= m := K (4.5 L1(p) + 1.5 L1(q) + 3.5 L1(t)),  K = 1.2e-7 > sqrt(3) u (1 + slack).
+// A point is a certain inlier if sqrt(s_f) < thr(1-1e-6) - m and a certain outlier if sqrt(s_f) > thr(1+1e-6) + m;
+// everything else (about 1e-6 of the evaluations, and any NaN) is re-evaluated exactly in double.  The
+// result is therefore bit-identical to the double-only evaluation at ~1/3 of its pipe time.
+constexpr float kScreenK = 1.2e-7f;
+
+// Rare path of the pre-screen, deliberately not inlined: it must not drag the double-precision transforms
+// into registers inside the float loop.
+__device__ __noinline__ int exact_inlier(const double* T12, const double* px, int cap, int i, double thr_sq_star) {
+    return residual_sq(T12, px[i], px[cap + i], px[2 * cap + i], px[3 * cap + i], px[4 * cap + i], px[5 * cap + i]) < thr_sq_star;
+}
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restrict__ tasks,
+__global__ void __launch_bounds__(THREADS, 3) solve_kernel(const MatchTask* __restrict__ tasks,
                                                         const int2* __restrict__ pair_tasks,
                                                         const uint2* __restrict__ keys, SolveParams prm,
                                                         uz_edge_result* __restrict__ results) {
@@ -69,11 +111,14 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     double* Tbest = Th + THREADS * 12;                                // 12
     double* Tfin = Tbest + 12;                                        // 12
     int32_t* counts = reinterpret_cast<int32_t*>(Tfin + 12);          // [THREADS]
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(counts + THREADS);  // [cap]
-    uint8_t* mask = reinterpret_cast<uint8_t*>(skeys + cap);          // [cap]
-    __shared__ int s_best, s_maxc, s_break, s_run;
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(counts + THREADS);  // [cap] sorted keys, later the inlier list
+    uint32_t* vkeys = reinterpret_cast<uint32_t*>(px);                // [cap] unsorted valid keys: aliases P, dead before the gather
+    __shared__ int s_best, s_maxc, s_break, s_run, s_nvalid, s_nratio;
+    constexpr int NW = THREADS / 32;
+    __shared__ int s_wcnt[NW];
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.x;
     uz_edge_result* res = results + pair;
 #define UZ_PHASE(k) do { if (prm.dbg_phase && tid == 0) prm.dbg_phase[(size_t)pair * 8 + (k)] = clock64(); } while (0)
@@ -84,21 +129,24 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     if (prm.direct_P == nullptr) {
         // ---------------- K2: best camera pair, filter, sort, gather -------------------------------
         const int2 pt = pair_tasks[pair];
-        int best = -1, best_score = -1;
-        for (int t = 0; t < pt.y; ++t) {
-            const MatchTask* tk = tasks + pt.x + t;
-            const uint2* k = keys + tk->key_off;
-            int cnt = 0;
-            for (int base = 0; base < tk->nq; base += THREADS) {
-                const int q = base + tid;
-                bool pass = false;
-                if (q < tk->nq) {
-                    const uint2 m = k[q];
-                    pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
+        int best = pt.y == 1 ? 0 : -1;
+        if (pt.y > 1) {          // rigs: score every same-frame camera pair first (:74-86)
+            int best_score = -1;
+            for (int t = 0; t < pt.y; ++t) {
+                const MatchTask* tk = tasks + pt.x + t;
+                const uint2* k = keys + tk->key_off;
+                int cnt = 0;
+                for (int base = 0; base < tk->nq; base += THREADS) {
+                    const int q = base + tid;
+                    bool pass = false;
+                    if (q < tk->nq) {
+                        const uint2 m = k[q];
+                        pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
+                    }
+                    cnt += __syncthreads_count(pass);
                 }
-                cnt += __syncthreads_count(pass);
+                if (cnt > best_score) { best_score = cnt; best = t; }   // :81 strict '>' keeps the first
             }
-            if (cnt > best_score) { best_score = cnt; best = t; }   // :81 strict '>' keeps the first
         }
         if (best < 0) {          // :93-95 no comparable camera pair
             if (tid == 0) {
@@ -109,39 +157,53 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
             return;
         }
         const MatchTask* tk = tasks + pt.x + best;
-        const uint2* k = keys + tk->key_off;
+        const uint2* __restrict__ k = keys + tk->key_off;
         const int nq = tk->nq;
-        n_ratio = best_score; cam_from = tk->cam_from; cam_to = tk->cam_to;
+        cam_from = tk->cam_from; cam_to = tk->cam_to;
         const uint8_t* __restrict__ vq = tk->q_valid;
         const uint8_t* __restrict__ vt = tk->t_valid;
-        for (int i = tid; i < cap; i += THREADS) {
-            uint32_t key = kNoKey;
-            if (i < nq) {
-                const uint2 m = k[i];
-                const bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
-                if (pass && vq[i] && vt[m.x & 0xFFFFu]) key = (m.x & 0xFFFF0000u) | (uint32_t)i;
+        if (tid == 0) { s_nvalid = 0; s_nratio = 0; }
+        __syncthreads();
+        // ratio test (:65-71) + valid_3d filter (:103-112); survivors are appended unordered
+        for (int i = tid; i < nq; i += THREADS) {
+            const uint2 m = k[i];
+            const bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
+            if (pass) {
+                atomicAdd(&s_nratio, 1);
+                if (vq[i] && vt[m.x & 0xFFFFu]) vkeys[atomicAdd(&s_nvalid, 1)] = (m.x & 0xFFFF0000u) | (uint32_t)i;
             }
-            skeys[i] = key;
         }
         __syncthreads();
+        M = s_nvalid;
+        n_ratio = s_nratio;
         UZ_PHASE(1);
-        // bitonic sort ascending: (distance, queryIdx); kNoKey sinks to the end
-        for (int kk = 2; kk <= cap; kk <<= 1) {
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < cap; i += THREADS) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint32_t a = skeys[i], b = skeys[ixj];
-                        const bool asc = (i & kk) == 0;
-                        if ((a > b) == asc) { skeys[i] = b; skeys[ixj] = a; }
+        // :114 sort by (distance, queryIdx)
+        if (M <= THREADS) rank_sort<THREADS, 1>(vkeys, skeys, M, tid);
+        else if (M <= 2 * THREADS) rank_sort<THREADS, 2>(vkeys, skeys, M, tid);
+        else if (M <= 4 * THREADS) rank_sort<THREADS, 4>(vkeys, skeys, M, tid);
+        else if (M <= 8 * THREADS) rank_sort<THREADS, 8>(vkeys, skeys, M, tid);
+        else {                   // large M: in-place bitonic network on the padded list
+            int n2 = 1;
+            while (n2 < M) n2 <<= 1;
+            for (int i = M + tid; i < n2; i += THREADS) vkeys[i] = kNoKey;
+            __syncthreads();
+            for (int kk = 2; kk <= n2; kk <<= 1) {
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < n2; i += THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint32_t a = vkeys[i], b = vkeys[ixj];
+                            const bool asc = (i & kk) == 0;
+                            if ((a > b) == asc) { vkeys[i] = b; vkeys[ixj] = a; }
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
+            for (int i = tid; i < M; i += THREADS) skeys[i] = vkeys[i];
         }
+        __syncthreads();
         UZ_PHASE(2);
-        for (int base = 0; base < cap; base += THREADS)
-            M += __syncthreads_count(skeys[base + tid] != kNoKey);
         const double* __restrict__ pq = tk->q_pos;
         const double* __restrict__ pt3 = tk->t_pos;
         for (int i = tid; i < M; i += THREADS) {
@@ -179,8 +241,9 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     // ---------------- K3/K4: hypotheses, consensus counts, sequential-semantics winner -------------
     const int I = prm.iterations;
     const uint16_t* __restrict__ samp = prm.samples + (prm.samples_by_m ? (size_t)M * I * 3 : 0);
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = THREADS / 32;
+    const float thr_dn = __double2float_rd(prm.thr * (1.0 - 1e-6));
+    const float thr_up = __double2float_ru(prm.thr * (1.0 + 1e-6));
+    constexpr int H = 4;         // hypotheses scored per pass over the points
     for (int h0 = 0; h0 < I; h0 += THREADS) {
         const int nh = min(THREADS, I - h0);
         if (tid < nh) {
@@ -195,24 +258,45 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
         }
         __syncthreads();
         if (h0 == 0) UZ_PHASE(4);
-        // each warp scores two hypotheses per pass over the points
-        for (int h = warp * 2; h < nh; h += NW * 2) {
-            const bool two = (h + 1) < nh;
-            double Ta[12], Tb[12];
+        for (int hb = warp * H; hb < nh; hb += NW * H) {
+            float T[H][12], kt[H];
+            int cnt[H];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) { Ta[e] = Th[h * 12 + e]; Tb[e] = Th[(two ? h + 1 : h) * 12 + e]; }
-            int ca = 0, cb = 0;
+            for (int a = 0; a < H; ++a) {
+                const int h = min(hb + a, nh - 1);          // tail: duplicates, their counts are discarded
+#pragma unroll
+                for (int e = 0; e < 12; ++e) T[a][e] = (float)Th[h * 12 + e];   // exact: T holds float32 values
+                kt[a] = kScreenK * 3.5f * (fabsf(T[a][3]) + fabsf(T[a][7]) + fabsf(T[a][11]));
+                cnt[a] = 0;
+            }
             for (int i = lane; i < M; i += 32) {
-                const double x = px[i], y = py[i], z = pz[i], u = qx[i], v = qy[i], w = qz[i];
-                ca += residual_sq(Ta, x, y, z, u, v, w) < prm.thr_sq_star;
-                cb += residual_sq(Tb, x, y, z, u, v, w) < prm.thr_sq_star;
+                const float x = (float)px[i], y = (float)py[i], z = (float)pz[i];
+                const float u = (float)qx[i], v = (float)qy[i], w = (float)qz[i];
+                const float kp = kScreenK * (4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
+#pragma unroll
+                for (int a = 0; a < H; ++a) {
+                    const float dx = fmaf(T[a][0], x, fmaf(T[a][1], y, fmaf(T[a][2], z, T[a][3]))) - u;
+                    const float dy = fmaf(T[a][4], x, fmaf(T[a][5], y, fmaf(T[a][6], z, T[a][7]))) - v;
+                    const float dz = fmaf(T[a][8], x, fmaf(T[a][9], y, fmaf(T[a][10], z, T[a][11]))) - w;
+                    const float sf = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    const float m = kp + kt[a];
+                    const float lo = thr_dn - m, hi = thr_up + m;
+                    const bool inl = (lo > 0.f) && (sf < lo * lo);
+                    const bool out = sf > hi * hi;
+                    if (inl) {
+                        cnt[a]++;
+                    } else if (!out) {   // borderline (or NaN): exact double evaluation, as the reference
+                        cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, px, cap, i, prm.thr_sq_star);
+                    }
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ca += __shfl_xor_sync(0xffffffffu, ca, o);
-                cb += __shfl_xor_sync(0xffffffffu, cb, o);
+            for (int a = 0; a < H; ++a) {
+                int c = cnt[a];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == 0 && hb + a < nh) counts[hb + a] = c;
             }
-            if (lane == 0) { counts[h] = ca; if (two) counts[h + 1] = cb; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -249,7 +333,6 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     UZ_PHASE(5);
     // (a) the winner's consensus set, compacted in index order (the refit recurrence is order dependent)
     uint16_t* ilist = reinterpret_cast<uint16_t*>(skeys);
-    __shared__ int s_wcnt[NW];
     int n_in = 0;
     for (int base = 0; base < M; base += THREADS) {
         const int i = base + tid;
@@ -267,34 +350,51 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const MatchTask* __restr
     // (b) pcl::TransformationFromCorrespondences::add over the inliers in order (:247-257).  The float32
     // recurrence is sequential in the points but its 15 state scalars are independent of each other:
     // lane l < 9 carries covariance element (r,c) = (l/3, l%3) together with the two means it needs, every
-    // lane executing exactly the scalar operation sequence of uz::pose_add for its element.
-    if (warp == 0) {
-        const int e = lane % 9, r = e / 3, c = e % 3;
-        const double* __restrict__ Pc = px + (size_t)c * cap;
-        const double* __restrict__ Qr = qx + (size_t)r * cap;
-        float acc = 0.f, m1 = 0.f, m2 = 0.f, cv = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < n_in; ++k) {
-            const int i = ilist[k];
-            const float p = (float)Pc[i], q = (float)Qr[i];
-            acc = UZ_FADD(acc, 1.0f);
-            const float alpha = UZ_FDIV(1.0f, acc);
-            const float oma = UZ_FSUB(1.0f, alpha);
-            const float d1 = UZ_FSUB(p, m1), d2 = UZ_FSUB(q, m2);
-            cv = UZ_FMUL(oma, UZ_FADD(cv, UZ_FMUL(alpha, UZ_FMUL(d2, d1))));
-            m1 = UZ_FADD(m1, UZ_FMUL(alpha, d1));
-            m2 = UZ_FADD(m2, UZ_FMUL(alpha, d2));
+    // lane executing exactly the scalar operation sequence of uz::pose_add for its element.  The operands
+    // (float-rounded points, alpha = 1/n, 1-alpha) are staged by all threads, chunk by chunk, into the
+    // hypothesis buffer (dead by now) so that the sequential loop is loads at known addresses + 10 flops.
+    {
+        float* fb = reinterpret_cast<float*>(Th);
+        constexpr int CH = THREADS * 12 * 8 / (8 * 4);       // floats per staged array
+        const int e9 = lane % 9, r = e9 / 3, c = e9 % 3;
+        float m1 = 0.f, m2 = 0.f, cv = 0.f;
+        for (int c0 = 0; c0 < n_in; c0 += CH) {
+            const int nch = min(CH, n_in - c0);
+            for (int k = tid; k < nch; k += THREADS) {
+                const int i = ilist[c0 + k];
+                fb[0 * CH + k] = (float)px[i]; fb[1 * CH + k] = (float)py[i]; fb[2 * CH + k] = (float)pz[i];
+                fb[3 * CH + k] = (float)qx[i]; fb[4 * CH + k] = (float)qy[i]; fb[5 * CH + k] = (float)qz[i];
+                const float alpha = UZ_FDIV(1.0f, (float)(c0 + k + 1));     // accumulated weight == n exactly
+                fb[6 * CH + k] = alpha;
+                fb[7 * CH + k] = UZ_FSUB(1.0f, alpha);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const float* __restrict__ Pc = fb + c * CH;
+                const float* __restrict__ Qr = fb + (3 + r) * CH;
+#pragma unroll 4
+                for (int k = 0; k < nch; ++k) {
+                    const float alpha = fb[6 * CH + k], oma = fb[7 * CH + k];
+                    const float d1 = UZ_FSUB(Pc[k], m1), d2 = UZ_FSUB(Qr[k], m2);
+                    cv = UZ_FMUL(oma, UZ_FADD(cv, UZ_FMUL(alpha, UZ_FMUL(d2, d1))));
+                    m1 = UZ_FADD(m1, UZ_FMUL(alpha, d1));
+                    m2 = UZ_FADD(m2, UZ_FMUL(alpha, d2));
+                }
+            }
+            __syncthreads();
         }
-        PoseAcc A;
-        A.acc = acc;
+        if (warp == 0) {
+            PoseAcc A;
+            A.acc = (float)n_in;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) A.c[k] = __shfl_sync(0xffffffffu, cv, k);
+            for (int k = 0; k < 9; ++k) A.c[k] = __shfl_sync(0xffffffffu, cv, k);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            A.m1[k] = __shfl_sync(0xffffffffu, m1, k);          // lane k: (r,c) = (0,k)
-            A.m2[k] = __shfl_sync(0xffffffffu, m2, 3 * k);      // lane 3k: (r,c) = (k,0)
+            for (int k = 0; k < 3; ++k) {
+                A.m1[k] = __shfl_sync(0xffffffffu, m1, k);          // lane k: (r,c) = (0,k)
+                A.m2[k] = __shfl_sync(0xffffffffu, m2, 3 * k);      // lane 3k: (r,c) = (k,0)
+            }
+            if (lane == 0) pose_finish(A, Tfin);
         }
-        if (lane == 0) pose_finish(A, Tfin);
     }
     __syncthreads();
     UZ_PHASE(6);
