@@ -242,8 +242,9 @@ def run_gpu(args):
     kfs, pairs, poses = build_map(n_kf, out=(desc, pos, valid))
     total_pairs = len(pairs)
     # rank r owns a contiguous chunk of the (from-sorted) pair list; cycle if the map is smaller than the job
-    lo = (rank * pairs_per_gpu) % total_pairs
-    sel = (lo + np.arange(pairs_per_gpu)) % total_pairs
+    from uzliti_slam_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(world * pairs_per_gpu, world, rank)
+    sel = np.arange(lo, hi) % total_pairs
     my_pairs = pairs[sel]
 
     cpu = None

@@ -99,6 +99,9 @@ struct uz_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t side = nullptr;     // high-priority stream the solve kernels of a chunked batch run on
+    int overlap_chunks = 1;          // UZ_OVERLAP_CHUNKS > 1: chunked 2-stream pipeline (measured: no gain on B200)
+    int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
     uz_params params;
     std::string err;
     int variant_csa = 1;
@@ -130,7 +133,7 @@ struct uz_context {
     int64_t match_launches = 0, solve_launches = 0, compares = 0;
     // lazily resolved event triples (start, after K1, after solve): recording costs ~1 us and no sync,
     // so the timers can stay on inside a timed region; uz_get_timers() synchronises and folds them in
-    struct Timed { cudaEvent_t e[3]; bool has_solve; };
+    struct Timed { cudaEvent_t e[4]; bool has_solve; };   // knn2 begin/end, solve begin/end
     std::vector<Timed> pending;
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t get_event() {
@@ -299,7 +302,7 @@ void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles,
 }
 
 struct KnnConfig { int threads, qpt; };
-const KnnConfig kKnnConfigs[3] = {{256, 4}, {128, 4}, {64, 2}};
+const KnnConfig kKnnConfigs[5] = {{256, 4}, {128, 4}, {64, 2}, {256, 2}, {128, 2}};
 
 // Runs K1 (+ optionally K2..K5) for a list of pairs whose cameras are already on the device.
 uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_results) {
@@ -358,6 +361,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         const double cost = padded / std::max(fill, 1e-3);
         if (cost < best_cost * 0.999) { best_cost = cost; best_cfg = c; }
     }
+    if (ctx->force_cfg >= 0 && ctx->force_cfg < 5) best_cfg = ctx->force_cfg;
     const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
     size_t n_tiles = 0;
     for (size_t t = 0; t < n_tasks; ++t) n_tiles += ((size_t)tasks[t].nq + tile_rows - 1) / tile_rows;
@@ -378,60 +382,95 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
-    // 3. K1
-    uz_context::Timed tm;
-    tm.e[0] = tm.e[1] = tm.e[2] = nullptr; tm.has_solve = false;
-    if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
-    if (n_tiles) {
-        switch (best_cfg) {
-            case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
-            case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
-            default: launch_knn2<64, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_tiles.p, (int)n_tiles, (uint2*)ctx->d_keys.p); break;
+    // 3. launch geometry: one launch pair per chunk of pairs; the solve of chunk c runs on the side stream and
+    // overlaps the knn2 of chunk c+1 (INT pipes vs FP32/FP64 pipes of the same SMs)
+    const bool with_solve = d_results != nullptr;
+    int n_chunks = 1;
+    if (with_solve && ctx->overlap_chunks > 1 && n_pairs >= 64 * ctx->sm_count) n_chunks = std::min(ctx->overlap_chunks, n_pairs / (16 * ctx->sm_count));
+    n_chunks = std::max(n_chunks, 1);
+    std::vector<int> chunk_pair(n_chunks + 1), chunk_tile(n_chunks + 1);
+    for (int c = 0; c <= n_chunks; ++c) chunk_pair[c] = (int)((int64_t)n_pairs * c / n_chunks);
+    {
+        int c = 0;
+        chunk_tile[0] = 0;
+        for (size_t k = 0; k < n_tiles; ++k) {
+            const int pr = tasks[tiles[k].x].pair;
+            while (c + 1 <= n_chunks && pr >= chunk_pair[c + 1]) chunk_tile[++c] = (int)k;
         }
-        ctx->launches++;
-        UZ_CUDA(ctx, cudaGetLastError());
-    }
-    if (ctx->timers) {
-        cudaEventRecord(tm.e[1], ctx->stream);
-        ctx->match_launches += n_tiles ? 1 : 0; ctx->compares += compares;
-    }
-    if (!d_results) {        // matching only (uz_match_knn2)
-        if (ctx->timers) ctx->pending.push_back(tm);
-        return UZ_OK;
+        while (c < n_chunks) chunk_tile[++c] = (int)n_tiles;
     }
 
-    // 4. K2..K5
-    const int cap = std::max(128, pow2ceil(std::max(max_nq, 1)));
-    uz_status st = ensure_samples(ctx, prm.ransac_iterations, prm.do_prosac, max_nq);
-    if (st != UZ_OK) return st;
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.thr = prm.ransac_threshold; sp.thr_sq_star = thr_sq_star(prm.ransac_threshold);
-    sp.break_pct = prm.break_percentage; sp.iterations = prm.ransac_iterations;
-    sp.ratio_num = prm.ratio_num; sp.ratio_den = prm.ratio_den; sp.cap = cap;
-    sp.samples = (const uint16_t*)ctx->d_samples.p; sp.samples_by_m = 1;
-    ctx->dbg_pairs = 0;
-    if (ctx->debug) {
-        UZ_CUDA(ctx, ctx->d_dbg_matches.ensure((size_t)n_pairs * cap * 3 * sizeof(int32_t)));
-        UZ_CUDA(ctx, ctx->d_dbg_mask.ensure((size_t)n_pairs * cap));
-        UZ_CUDA(ctx, ctx->d_dbg_counts.ensure((size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t)));
-        UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_counts.p, 0xFF, (size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t), ctx->stream));
-        sp.dbg_matches = (int32_t*)ctx->d_dbg_matches.p; sp.dbg_mask = (uint8_t*)ctx->d_dbg_mask.p;
-        sp.dbg_counts = (int32_t*)ctx->d_dbg_counts.p;
-        UZ_CUDA(ctx, ctx->d_dbg_phase.ensure((size_t)n_pairs * 8 * sizeof(long long)));
-        UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_phase.p, 0, (size_t)n_pairs * 8 * sizeof(long long), ctx->stream));
-        sp.dbg_phase = (long long*)ctx->d_dbg_phase.p;
-        ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs; ctx->dbg_iters = prm.ransac_iterations;
+    int cap = 0;
+    if (with_solve) {
+        cap = std::max(128, pow2ceil(std::max(max_nq, 1)));
+        uz_status st = ensure_samples(ctx, prm.ransac_iterations, prm.do_prosac, max_nq);
+        if (st != UZ_OK) return st;
+        sp.thr = prm.ransac_threshold; sp.thr_sq_star = thr_sq_star(prm.ransac_threshold);
+        sp.break_pct = prm.break_percentage; sp.iterations = prm.ransac_iterations;
+        sp.ratio_num = prm.ratio_num; sp.ratio_den = prm.ratio_den; sp.cap = cap;
+        sp.samples = (const uint16_t*)ctx->d_samples.p; sp.samples_by_m = 1;
+        ctx->dbg_pairs = 0;
+        if (ctx->debug) {
+            UZ_CUDA(ctx, ctx->d_dbg_matches.ensure((size_t)n_pairs * cap * 3 * sizeof(int32_t)));
+            UZ_CUDA(ctx, ctx->d_dbg_mask.ensure((size_t)n_pairs * cap));
+            UZ_CUDA(ctx, ctx->d_dbg_counts.ensure((size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t)));
+            UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_counts.p, 0xFF, (size_t)n_pairs * prm.ransac_iterations * sizeof(int32_t), ctx->stream));
+            sp.dbg_matches = (int32_t*)ctx->d_dbg_matches.p; sp.dbg_mask = (uint8_t*)ctx->d_dbg_mask.p;
+            sp.dbg_counts = (int32_t*)ctx->d_dbg_counts.p;
+            UZ_CUDA(ctx, ctx->d_dbg_phase.ensure((size_t)n_pairs * 8 * sizeof(long long)));
+            UZ_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_phase.p, 0, (size_t)n_pairs * 8 * sizeof(long long), ctx->stream));
+            sp.dbg_phase = (long long*)ctx->d_dbg_phase.p;
+            ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs; ctx->dbg_iters = prm.ransac_iterations;
+        }
     }
-    solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
-        (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_pair_tasks.p, (const uint2*)ctx->d_keys.p, sp, d_results);
-    ctx->launches++;
-    UZ_CUDA(ctx, cudaGetLastError());
-    if (ctx->timers) {
-        tm.e[2] = ctx->get_event(); tm.has_solve = true;
-        cudaEventRecord(tm.e[2], ctx->stream);
-        ctx->solve_launches += 1;
-        ctx->pending.push_back(tm);
+    const bool two_streams = with_solve && n_chunks > 1;
+    cudaStream_t sB = two_streams ? ctx->side : ctx->stream;
+    if (ctx->timers) ctx->compares += compares;
+
+    for (int c = 0; c < n_chunks; ++c) {
+        uz_context::Timed tm;
+        tm.e[0] = tm.e[1] = tm.e[2] = tm.e[3] = nullptr; tm.has_solve = false;
+        const int t0 = chunk_tile[c], nt_c = chunk_tile[c + 1] - chunk_tile[c];
+        const int p0 = chunk_pair[c], np_c = chunk_pair[c + 1] - chunk_pair[c];
+        if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
+        if (nt_c > 0) {
+            const int2* d_t = (const int2*)ctx->d_tiles.p + t0;
+            switch (best_cfg) {
+                case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+                case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+                case 2: launch_knn2<64, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+                case 3: launch_knn2<256, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+                default: launch_knn2<128, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+            }
+            ctx->launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
+            if (ctx->timers) ctx->match_launches++;
+        }
+        if (ctx->timers) cudaEventRecord(tm.e[1], ctx->stream);
+        if (with_solve && np_c > 0) {
+            if (two_streams) {
+                cudaEvent_t ev = ctx->get_event();
+                UZ_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+                UZ_CUDA(ctx, cudaStreamWaitEvent(sB, ev, 0));
+                ctx->event_pool.push_back(ev);        // safe to recycle: the wait has captured it
+            }
+            if (ctx->timers) { tm.e[2] = ctx->get_event(); tm.e[3] = ctx->get_event(); tm.has_solve = true; cudaEventRecord(tm.e[2], sB); }
+            sp.pair_base = p0;
+            solve_kernel<kSolveThreads><<<np_c, kSolveThreads, solve_smem_bytes(cap), sB>>>(
+                (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_pair_tasks.p, (const uint2*)ctx->d_keys.p, sp, d_results);
+            ctx->launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
+            if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
+        }
+        if (ctx->timers) ctx->pending.push_back(tm);
+    }
+    if (two_streams) {           // rejoin: everything the caller enqueues next on its stream sees the results
+        cudaEvent_t ev = ctx->get_event();
+        UZ_CUDA(ctx, cudaEventRecord(ev, sB));
+        UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+        ctx->event_pool.push_back(ev);
     }
     return UZ_OK;
 }
@@ -439,12 +478,13 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
 uz_status resolve_timers(uz_context* ctx) {
     if (ctx->pending.empty()) return UZ_OK;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->side) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->side));
     for (auto& t : ctx->pending) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, t.e[0], t.e[1]);
         ctx->match_ms += a;
-        if (t.has_solve) { cudaEventElapsedTime(&b, t.e[1], t.e[2]); ctx->solve_ms += b; }
-        for (int i = 0; i < 3; ++i) if (t.e[i]) ctx->event_pool.push_back(t.e[i]);
+        if (t.has_solve) { cudaEventElapsedTime(&b, t.e[2], t.e[3]); ctx->solve_ms += b; }
+        for (int i = 0; i < 4; ++i) if (t.e[i]) ctx->event_pool.push_back(t.e[i]);
     }
     ctx->pending.clear();
     return UZ_OK;
@@ -502,6 +542,15 @@ uz_status uz_create(int32_t device, uz_context** out) {
     if (v && v[0] == '1') ctx->variant_csa = 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(e)); }
+        const char* oc = getenv("UZ_OVERLAP_CHUNKS");
+        if (oc && atoi(oc) >= 1) ctx->overlap_chunks = atoi(oc);
+        const char* fc = getenv("UZ_KNN_CFG");
+        if (fc) ctx->force_cfg = atoi(fc);
+    }
     e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)solve_smem_bytes(UZ_MAX_FEATURES));
     if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
@@ -519,7 +568,8 @@ void uz_destroy(uz_context* ctx) {
     ctx->d_misc.release();
     ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (auto& t : ctx->pending) for (int i = 0; i < 3; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
+    for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

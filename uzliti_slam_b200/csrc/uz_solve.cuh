@@ -37,6 +37,7 @@ struct SolveParams {
     uint8_t* dbg_mask;       // [pair][cap]
     int32_t* dbg_counts;     // [pair][iterations] consensus count of every evaluated hypothesis, -1 = not run
     long long* dbg_phase;    // [pair][8] clock64() at the phase boundaries of the CTA (profiling tap)
+    int32_t pair_base;       // index of this launch's first pair inside the batch (chunked launches)
 };
 
 constexpr int kSolveThreads = 128;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 3) solve_kernel(const MatchTask* __re
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int pair = blockIdx.x;
+    const int pair = prm.pair_base + blockIdx.x;       // batch-wide index; pair_tasks/results are indexed by it
     uz_edge_result* res = results + pair;
 #define UZ_PHASE(k) do { if (prm.dbg_phase && tid == 0) prm.dbg_phase[(size_t)pair * 8 + (k)] = clock64(); } while (0)
     UZ_PHASE(0);
