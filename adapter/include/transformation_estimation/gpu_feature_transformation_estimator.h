@@ -1,0 +1,88 @@
+// gpu_feature_transformation_estimator.h — host-side mirror of the reference's estimator interface for the
+// feature-edge path, on top of the C-ABI (include/uzliti_edge.h).
+//
+//   class TransformationEstimator            <- transformation_estimation/include/transformation_estimation/
+//                                               transformation_estimator.h:45-67 (+ .cpp:22-62)
+//   class GpuFeatureTransformationEstimator  <- .../feature_transformation_estimator.h:33-58
+//
+// Same class shape, method names, argument meaning and failure convention (estimateEdgeImpl returns bool;
+// on false the worker zeroes matching_score_ and STILL fires the callback, transformation_estimator.cpp:53-56).
+// What changes is the execution model: the reference pops ONE pair per 1 ms tick on its worker thread; here
+// the worker drains the whole queue and hands it to the GPU as one batch (estimateEdgeBatch), with the
+// nodes' FeatureData cached in the device-resident keyframe store.  Callbacks are fired from the worker
+// thread, never while the caller of estimateEdge() is on the stack (the reference's callers hold graph_mutex_).
+#pragma once
+#ifdef UZ_ADAPTER_REAL_HEADERS
+#include <graph_slam_common/slam_node.h>
+#include <transformation_estimation/FeatureLinkEstimationConfig.h>
+#else
+#include <graph_slam_common/shim_types.h>
+#endif
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+
+#include "uzliti_edge.h"
+
+class TransformationEstimator {
+public:
+    TransformationEstimator(boost::function<void(SlamEdge)> callback);
+    virtual ~TransformationEstimator();
+
+    void estimateEdge(SlamNode& from, SlamNode& to);                                   // transformation_estimator.h:52
+    virtual bool estimateEdgeImpl(SlamNode& from, SlamNode& to, SlamEdge& edge) = 0;   // :54
+    // batch hook: default = one estimateEdgeImpl per pair; the GPU estimator overrides it
+    virtual void estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
+                                   std::vector<char>& ok);
+
+    std::map<std::string, Eigen::Isometry3d> sensor_transforms_;                       // :56 (unused by this path)
+
+    void waitIdle();                                  // test helper: block until the queue is drained and delivered
+
+protected:
+    void startThread();                               // called by the most-derived constructor
+    void stopThread();
+    void estimationThread();
+
+    std::thread estimation_thread_;
+    std::mutex estimation_mutex_;
+    std::condition_variable cv_;
+    bool running_ = false;
+    bool busy_ = false;
+    std::vector<std::pair<SlamNode, SlamNode> > est_queue_;
+    boost::function<void(SlamEdge)> callback_;
+};
+
+class GpuFeatureTransformationEstimator : public TransformationEstimator {
+public:
+    GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, int device = 0);
+    ~GpuFeatureTransformationEstimator();
+
+    bool estimateEdgeImpl(SlamNode& from, SlamNode& to, SlamEdge& edge);                                  // :38
+    void setConfig(transformation_estimation::FeatureLinkEstimationConfig config);                         // :40
+    bool estimateEdgeDirect(std::vector<SensorDataPtr> from, std::vector<SensorDataPtr> to, SlamEdge& edge);   // :42
+    void estimateSVD(Eigen::MatrixXd P, Eigen::MatrixXd Q, Eigen::Isometry3d& T, int& consensus, double& mse,
+                     double maxError, int iterations, double breakPercentage, bool do_prosac = true);      // :45
+    int consensus3D(Eigen::MatrixXd P, Eigen::MatrixXd Q, Eigen::Isometry3d T, double thresh,
+                    Eigen::Array<bool, 1, Eigen::Dynamic>& consensusSet);                                   // :53
+    void estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
+                           std::vector<char>& ok);
+
+    // device-resident keyframe store: nodes are uploaded once and addressed by id_ afterwards
+    void forgetNode(const std::string& id);
+    size_t residentNodes() const { return handles_.size(); }
+    const char* lastError() const;
+
+protected:
+    struct Resident { int32_t handle; std::vector<FeatureDataPtr> cams; };
+    bool ensureResident(const SlamNode& node, Resident** out);
+    void fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to, SlamEdge& edge) const;
+    int internFrame(const std::string& frame);
+
+    uz_context* ctx_ = nullptr;
+    transformation_estimation::FeatureLinkEstimationConfig config_;
+    std::unordered_map<std::string, Resident> handles_;
+    std::unordered_map<std::string, int> frames_;
+    std::mutex gpu_mutex_;
+};

@@ -1,0 +1,272 @@
+// gpu_feature_transformation_estimator.cpp — see the header.  Follows
+// transformation_estimation/src/transformation_estimator.cpp:22-62 and
+// transformation_estimation/src/feature_transformation_estimator.cpp:32-171,178-184,337-353.
+#include <transformation_estimation/gpu_feature_transformation_estimator.h>
+
+#include <cstdio>
+#include <stdexcept>
+
+// ---------------------------------------------------------------------------------------------------------
+// TransformationEstimator: queue + worker thread (transformation_estimator.cpp:22-62)
+// ---------------------------------------------------------------------------------------------------------
+TransformationEstimator::TransformationEstimator(boost::function<void(SlamEdge)> callback) : callback_(callback) {}
+
+TransformationEstimator::~TransformationEstimator() { stopThread(); }
+
+void TransformationEstimator::startThread() {
+    running_ = true;
+    estimation_thread_ = std::thread(&TransformationEstimator::estimationThread, this);
+}
+
+void TransformationEstimator::stopThread() {
+    {
+        std::lock_guard<std::mutex> lk(estimation_mutex_);
+        if (!running_) return;
+        running_ = false;
+    }
+    cv_.notify_all();
+    if (estimation_thread_.joinable()) estimation_thread_.join();
+}
+
+void TransformationEstimator::estimateEdge(SlamNode& from, SlamNode& to) {
+    {   // cheap and non-blocking: callers hold graph_mutex_ (graph_slam_node.cpp:207,448)
+        std::lock_guard<std::mutex> lk(estimation_mutex_);
+        est_queue_.push_back(std::make_pair(from, to));   // copies the nodes; FeatureData is shared (shared_ptr)
+    }
+    cv_.notify_one();
+}
+
+void TransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs,
+                                                std::vector<SlamEdge>& edges, std::vector<char>& ok) {
+    edges.assign(pairs.size(), SlamEdge());
+    ok.assign(pairs.size(), 0);
+    for (size_t i = 0; i < pairs.size(); ++i) ok[i] = estimateEdgeImpl(pairs[i].first, pairs[i].second, edges[i]);
+}
+
+void TransformationEstimator::estimationThread() {
+    std::unique_lock<std::mutex> lk(estimation_mutex_);
+    while (running_) {
+        if (est_queue_.empty()) { cv_.wait(lk); continue; }
+        std::vector<std::pair<SlamNode, SlamNode> > batch;
+        batch.swap(est_queue_);
+        // the reference pops the NEWEST pair first (LIFO, :49-50): deliver in that order
+        std::vector<std::pair<SlamNode, SlamNode> > lifo(batch.rbegin(), batch.rend());
+        busy_ = true;
+        lk.unlock();
+        std::vector<SlamEdge> edges;
+        std::vector<char> ok;
+        estimateEdgeBatch(lifo, edges, ok);
+        for (size_t i = 0; i < edges.size(); ++i) {
+            if (!ok[i]) edges[i].matching_score_ = 0.;   // :53-55
+            callback_(edges[i]);                         // :56 — fired even on failure
+        }
+        lk.lock();
+        busy_ = false;
+        cv_.notify_all();
+    }
+}
+
+void TransformationEstimator::waitIdle() {
+    std::unique_lock<std::mutex> lk(estimation_mutex_);
+    cv_.wait(lk, [this] { return est_queue_.empty() && !busy_; });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GpuFeatureTransformationEstimator
+// ---------------------------------------------------------------------------------------------------------
+GpuFeatureTransformationEstimator::GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, int device)
+    : TransformationEstimator(callback) {
+    if (uz_create(device, &ctx_) != UZ_OK)
+        throw std::runtime_error(std::string("uz_create failed (no CPU fallback): ") + uz_last_error(nullptr));
+    setConfig(config_);
+    startThread();
+}
+
+GpuFeatureTransformationEstimator::~GpuFeatureTransformationEstimator() {
+    stopThread();
+    uz_destroy(ctx_);
+}
+
+const char* GpuFeatureTransformationEstimator::lastError() const { return uz_last_error(ctx_); }
+
+void GpuFeatureTransformationEstimator::setConfig(transformation_estimation::FeatureLinkEstimationConfig config) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    config_ = config;                                     // feature_transformation_estimator.cpp:350-353
+    uz_params p;
+    uz_default_params(&p);
+    p.ransac_threshold = config.ransac_threshold;
+    p.ransac_iterations = config.ransac_iteration;
+    p.break_percentage = config.ransac_break_percentage;
+    // link_covariance is unused by the live reference code (:138-144 commented out); use_epnp is ignored (:130)
+    if (uz_set_params(ctx_, &p) != UZ_OK) std::fprintf(stderr, "setConfig: %s\n", uz_last_error(ctx_));
+}
+
+int GpuFeatureTransformationEstimator::internFrame(const std::string& frame) {
+    auto it = frames_.find(frame);
+    if (it != frames_.end()) return it->second;
+    const int id = (int)frames_.size();
+    frames_[frame] = id;
+    return id;
+}
+
+static void feature_view(const FeatureData& f, int frame_tag, std::vector<uint8_t>& valid_bytes, uz_features* out) {
+    const int n = (int)f.feature_positions_.cols();
+    valid_bytes.resize((size_t)n);
+    for (int i = 0; i < n; ++i) valid_bytes[i] = f.valid_3d_[i] ? 1 : 0;     // std::vector<bool> -> bytes
+    out->descriptors = f.features_.data;
+    out->positions = f.feature_positions_.data();
+    out->valid_3d = valid_bytes.data();
+    out->n = n;
+    out->desc_stride = (int)f.features_.step;
+    out->feature_type = f.feature_type_;
+    out->sensor_frame = frame_tag;
+}
+
+bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Resident** out) {
+    auto it = handles_.find(node.id_);
+    if (it != handles_.end() && !node.id_.empty()) { *out = &it->second; return true; }
+    Resident r;
+    std::vector<uz_features> views;
+    std::vector<std::vector<uint8_t> > valid;
+    for (const SensorDataPtr& d : node.sensor_data_)
+        if (d->type_ == graph_slam_msgs::SensorData::SENSOR_TYPE_FEATURE) {           // :41,:43
+            FeatureDataPtr f = boost::dynamic_pointer_cast<FeatureData>(d);
+            if (f) r.cams.push_back(f);
+        }
+    views.resize(r.cams.size());
+    valid.resize(r.cams.size());
+    for (size_t i = 0; i < r.cams.size(); ++i) feature_view(*r.cams[i], internFrame(r.cams[i]->sensor_frame_), valid[i], &views[i]);
+    if (uz_store_add(ctx_, views.data(), (int32_t)views.size(), &r.handle) != UZ_OK) return false;
+    std::string key = node.id_.empty() ? "#anon" + std::to_string(handles_.size()) : node.id_;
+    auto ins = handles_.emplace(key, r);
+    *out = &ins.first->second;
+    return true;
+}
+
+void GpuFeatureTransformationEstimator::forgetNode(const std::string& id) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    auto it = handles_.find(id);
+    if (it == handles_.end()) return;
+    uz_store_remove(ctx_, it->second.handle);
+    handles_.erase(it);
+}
+
+void GpuFeatureTransformationEstimator::fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to,
+                                                 SlamEdge& edge) const {
+    if (!r.ok) return;                                   // on failure the edge keeps its default-constructed fields
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) edge.transform_(a, b) = r.T[4 * a + b];               // :147
+    edge.information_ = Eigen::MatrixXd::Identity(6, 6);
+    if (r.consensus > 0 && r.mse > 0) {                                                     // :134-137
+        edge.information_ *= r.info_scale;
+        for (int a = 3; a < 6; ++a)
+            for (int b = 3; b < 6; ++b) edge.information_(a, b) *= 100.;
+    }
+    edge.type_ = graph_slam_msgs::Edge::TYPE_3D_FULL;                                       // :149
+    const FeatureData& f = *from.cams[r.cam_from];
+    const FeatureData& t = *to.cams[r.cam_to];
+    edge.sensor_from_ = f.sensor_frame_;                                                    // :150-153
+    edge.sensor_to_ = t.sensor_frame_;
+    edge.displacement_from_ = f.displacement_;
+    edge.displacement_to_ = t.displacement_;
+    edge.matching_score_ = r.consensus;                                                     // :155
+}
+
+void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs,
+                                                          std::vector<SlamEdge>& edges, std::vector<char>& ok) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    const size_t n = pairs.size();
+    edges.assign(n, SlamEdge());
+    ok.assign(n, 0);
+    std::vector<int32_t> hf(n), ht(n);
+    std::vector<Resident*> rf(n), rt(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (!ensureResident(pairs[i].first, &rf[i]) || !ensureResident(pairs[i].second, &rt[i])) {
+            std::fprintf(stderr, "estimateEdgeBatch: %s\n", uz_last_error(ctx_));
+            for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
+            return;
+        }
+        hf[i] = rf[i]->handle;
+        ht[i] = rt[i]->handle;
+    }
+    std::vector<uz_edge_result> res(n);
+    const uz_status st = uz_estimate_edges(ctx_, hf.data(), ht.data(), (int32_t)n, res.data());
+    for (size_t i = 0; i < n; ++i) {
+        if (st == UZ_OK) { fillEdge(res[i], *rf[i], *rt[i], edges[i]); ok[i] = res[i].ok ? 1 : 0; }
+        edges[i].id_from_ = pairs[i].first.id_;          // :168-169, set even on failure
+        edges[i].id_to_ = pairs[i].second.id_;
+    }
+    if (st != UZ_OK) std::fprintf(stderr, "uz_estimate_edges: %s\n", uz_last_error(ctx_));
+}
+
+bool GpuFeatureTransformationEstimator::estimateEdgeImpl(SlamNode& from, SlamNode& to, SlamEdge& edge) {
+    std::vector<std::pair<SlamNode, SlamNode> > one(1, std::make_pair(from, to));
+    std::vector<SlamEdge> edges;
+    std::vector<char> ok;
+    estimateEdgeBatch(one, edges, ok);
+    edge = edges[0];
+    return ok[0] != 0;
+}
+
+bool GpuFeatureTransformationEstimator::estimateEdgeDirect(std::vector<SensorDataPtr> from, std::vector<SensorDataPtr> to,
+                                                           SlamEdge& edge) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    Resident rf, rt;
+    std::vector<uz_features> vf, vt;
+    std::vector<std::vector<uint8_t> > valf, valt;
+    auto collect = [this](const std::vector<SensorDataPtr>& in, Resident& r, std::vector<uz_features>& v,
+                          std::vector<std::vector<uint8_t> >& val) {
+        for (const SensorDataPtr& d : in)
+            if (d->type_ == graph_slam_msgs::SensorData::SENSOR_TYPE_FEATURE) {
+                FeatureDataPtr f = boost::dynamic_pointer_cast<FeatureData>(d);
+                if (f) r.cams.push_back(f);
+            }
+        v.resize(r.cams.size());
+        val.resize(r.cams.size());
+        for (size_t i = 0; i < r.cams.size(); ++i) feature_view(*r.cams[i], internFrame(r.cams[i]->sensor_frame_), val[i], &v[i]);
+    };
+    collect(from, rf, vf, valf);
+    collect(to, rt, vt, valt);
+    const int32_t nf = (int32_t)vf.size(), nt = (int32_t)vt.size();
+    uz_edge_result r;
+    if (uz_estimate_edges_host(ctx_, vf.data(), &nf, vt.data(), &nt, 1, &r) != UZ_OK) {
+        std::fprintf(stderr, "estimateEdgeDirect: %s\n", uz_last_error(ctx_));
+        return false;
+    }
+    fillEdge(r, rf, rt, edge);
+    return r.ok != 0;
+}
+
+void GpuFeatureTransformationEstimator::estimateSVD(Eigen::MatrixXd P, Eigen::MatrixXd Q, Eigen::Isometry3d& T, int& consensus,
+                                                    double& mse, double maxError, int iterations, double breakPercentage,
+                                                    bool do_prosac) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    double T16[16];
+    int32_t c = 0;
+    consensus = 0; mse = 0.; T = Eigen::Isometry3d::Identity();
+    if (uz_estimate_svd(ctx_, P.data(), Q.data(), P.cols(), maxError, iterations, breakPercentage, do_prosac ? 1 : 0, nullptr,
+                        T16, &c, &mse, nullptr, nullptr, nullptr) != UZ_OK) {
+        std::fprintf(stderr, "estimateSVD: %s\n", uz_last_error(ctx_));
+        return;
+    }
+    consensus = c;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) T(a, b) = T16[4 * a + b];
+}
+
+int GpuFeatureTransformationEstimator::consensus3D(Eigen::MatrixXd P, Eigen::MatrixXd Q, Eigen::Isometry3d T, double thresh,
+                                                   Eigen::Array<bool, 1, Eigen::Dynamic>& consensusSet) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    double T16[16];
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) T16[4 * a + b] = T(a, b);
+    std::vector<uint8_t> set((size_t)std::max(P.cols(), 1));
+    int32_t count = 0;
+    consensusSet.resize(P.cols());
+    if (uz_consensus3d(ctx_, P.data(), Q.data(), P.cols(), T16, thresh, set.data(), &count) != UZ_OK) {
+        std::fprintf(stderr, "consensus3D: %s\n", uz_last_error(ctx_));
+        return 0;
+    }
+    for (int i = 0; i < P.cols(); ++i) consensusSet[i] = set[i] != 0;
+    return count;
+}

@@ -1,0 +1,140 @@
+// test_adapter.cpp — drives the adapter the way GraphSlamNode drives the reference estimator
+// (graph_slam/src/graph_slam_node.cpp:48 construction with a callback, :266/:284 estimateEdge per candidate,
+// :779-829 newEdgeCallback).  Needs a B200; run by tests/test_adapter.py (-m gpu).
+#include <transformation_estimation/gpu_feature_transformation_estimator.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static uint64_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
+static double uni() { return (rnd() >> 11) * (1.0 / 9007199254740992.0); }
+
+struct Pose { double R[9], t[3]; };
+static Pose small_pose(double ang, double tr) {
+    Pose p;
+    double ax[3] = {uni() - .5, uni() - .5, uni() - .5};
+    double n = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    for (double& a : ax) a /= n;
+    double c = std::cos(ang), s = std::sin(ang), C = 1 - c;
+    double R[9] = {c + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * s, ax[0] * ax[2] * C + ax[1] * s,
+                   ax[1] * ax[0] * C + ax[2] * s, c + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * s,
+                   ax[2] * ax[0] * C - ax[1] * s, ax[2] * ax[1] * C + ax[0] * s, c + ax[2] * ax[2] * C};
+    for (int i = 0; i < 9; ++i) p.R[i] = R[i];
+    for (int i = 0; i < 3; ++i) p.t[i] = (uni() - .5) * tr;
+    return p;
+}
+
+// n landmarks shared by both nodes (+ n fresh each); node B observes them through pose G: p_b = G * x
+static void make_pair_nodes(int n, const Pose& G, SlamNode& a, SlamNode& b, const std::string& ida, const std::string& idb,
+                            const std::string& frame) {
+    FeatureDataPtr fa(new FeatureData()), fb(new FeatureData());
+    for (FeatureDataPtr f : {fa, fb}) {
+        f->feature_type_ = graph_slam_msgs::Features::ORB;
+        f->sensor_frame_ = frame;
+        f->features_.create(2 * n, 32, CV_8U);
+        f->feature_positions_.resize(3, 2 * n);
+        f->valid_3d_.assign(2 * n, true);
+    }
+    for (int i = 0; i < 2 * n; ++i) {
+        double z = 0.5 + 6.5 * uni(), x = (uni() * 640 - 319.5) * z / 525., y = (uni() * 480 - 239.5) * z / 525.;
+        for (int k = 0; k < 32; ++k) fa->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
+        fa->feature_positions_(0, i) = x; fa->feature_positions_(1, i) = y; fa->feature_positions_(2, i) = z;
+        if (i < n) {           // shared landmark: same descriptor with a few flipped bits, transformed position
+            for (int k = 0; k < 32; ++k) {
+                unsigned char m = (unsigned char)(rnd() & rnd() & rnd() & rnd());
+                fb->features_.at<unsigned char>(i, k) = fa->features_.at<unsigned char>(i, k) ^ m;
+            }
+            fb->feature_positions_(0, i) = G.R[0] * x + G.R[1] * y + G.R[2] * z + G.t[0] + (uni() - .5) * 0.004;
+            fb->feature_positions_(1, i) = G.R[3] * x + G.R[4] * y + G.R[5] * z + G.t[1] + (uni() - .5) * 0.004;
+            fb->feature_positions_(2, i) = G.R[6] * x + G.R[7] * y + G.R[8] * z + G.t[2] + (uni() - .5) * 0.004;
+        } else {
+            for (int k = 0; k < 32; ++k) fb->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
+            double z2 = 0.5 + 6.5 * uni();
+            fb->feature_positions_(0, i) = (uni() * 640 - 319.5) * z2 / 525.;
+            fb->feature_positions_(1, i) = (uni() * 480 - 239.5) * z2 / 525.;
+            fb->feature_positions_(2, i) = z2;
+        }
+        if (i % 9 == 0) { fb->valid_3d_[i] = false; fb->feature_positions_(2, i) = -1; }
+    }
+    a = SlamNode(); b = SlamNode();
+    a.id_ = ida; b.id_ = idb;
+    a.addSensorData(fa); b.addSensorData(fb);
+}
+
+#define CHECK(c) do { if (!(c)) { std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main() {
+    std::mutex m;
+    std::map<std::string, SlamEdge> got;          // keyed by id_from|id_to
+    GpuFeatureTransformationEstimator est([&](SlamEdge e) { std::lock_guard<std::mutex> lk(m); got[e.id_from_ + "|" + e.id_to_] = e; });
+    transformation_estimation::FeatureLinkEstimationConfig cfg;
+    cfg.ransac_threshold = 0.1; cfg.ransac_iteration = 100; cfg.ransac_break_percentage = 0.6;    // slam.yaml:35-36
+    est.setConfig(cfg);
+
+    // 1. queue interface: many pairs, callbacks for all of them, same answers as the direct call
+    const int NP = 24;
+    std::vector<SlamNode> A(NP), B(NP);
+    std::vector<Pose> G(NP);
+    for (int i = 0; i < NP; ++i) {
+        G[i] = small_pose(0.3 * uni(), 1.0);
+        make_pair_nodes(250, G[i], A[i], B[i], "a" + std::to_string(i), "b" + std::to_string(i), "/camera_rgb_optical_frame");
+        est.estimateEdge(A[i], B[i]);
+    }
+    est.waitIdle();
+    CHECK((int)got.size() == NP);
+    CHECK(est.residentNodes() == (size_t)2 * NP);
+    for (int i = 0; i < NP; ++i) {
+        const SlamEdge& e = got["a" + std::to_string(i) + "|b" + std::to_string(i)];
+        CHECK(e.matching_score_ >= 100);                                  // ~250 planted correspondences, 1/9 without depth
+        CHECK(e.type_ == graph_slam_msgs::Edge::TYPE_3D_FULL);
+        CHECK(e.sensor_from_ == "/camera_rgb_optical_frame");
+        // transform_ maps to-frame (B) points into the from-frame (A): inverse of G
+        double err = 0;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) err = std::fmax(err, std::fabs(e.transform_(r, c) - G[i].R[3 * c + r]));
+        CHECK(err < 2e-3);
+        CHECK(e.information_(0, 0) > 1.0 && std::fabs(e.information_(3, 3) - 100. * e.information_(0, 0)) < 1e-6 * e.information_(3, 3));
+        SlamEdge d;
+        CHECK(est.estimateEdgeDirect(A[i].sensor_data_, B[i].sensor_data_, d));
+        CHECK(d.matching_score_ == e.matching_score_);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) CHECK(d.transform_(r, c) == e.transform_(r, c));
+    }
+
+    // 2. failure convention: different sensor frames -> no comparable pair -> score 0, callback still fires
+    got.clear();
+    SlamNode X, Y;
+    make_pair_nodes(100, G[0], X, Y, "x", "y", "/cam0");
+    boost::dynamic_pointer_cast<FeatureData>(Y.sensor_data_[0])->sensor_frame_ = "/cam1";
+    est.estimateEdge(X, Y);
+    est.waitIdle();
+    CHECK(got.size() == 1 && got["x|y"].matching_score_ == 0. && got["x|y"].type_ == 0);
+    SlamEdge fe;
+    CHECK(!est.estimateEdgeImpl(X, Y, fe) && fe.id_from_ == "x" && fe.id_to_ == "y");
+
+    // 3. estimateSVD / consensus3D, the TransformationFilter call shape (transformation_filter.cpp:272,275)
+    Eigen::MatrixXd P(3, 80), Q(3, 80);
+    for (int i = 0; i < 80; ++i) {
+        double x = uni() * 4, y = uni() * 4, z = uni() * 4;
+        P(0, i) = x; P(1, i) = y; P(2, i) = z;
+        Q(0, i) = G[1].R[0] * x + G[1].R[1] * y + G[1].R[2] * z + G[1].t[0];
+        Q(1, i) = G[1].R[3] * x + G[1].R[4] * y + G[1].R[5] * z + G[1].t[1];
+        Q(2, i) = G[1].R[6] * x + G[1].R[7] * y + G[1].R[8] * z + G[1].t[2];
+        if (i % 4 == 0) Q(0, i) += 2.0;
+    }
+    Eigen::Isometry3d T;
+    int consensus = 0;
+    double mse = 0;
+    est.estimateSVD(P, Q, T, consensus, mse, 0.3, 200, 1.0, false);
+    CHECK(consensus == 60 && mse < 1e-3);
+    Eigen::Array<bool, 1, Eigen::Dynamic> set;
+    CHECK(est.consensus3D(P, Q, T, 0.3, set) == 60 && set.count() == 60 && !set[0] && set[1]);
+
+    est.forgetNode("a0");
+    CHECK(est.residentNodes() == (size_t)2 * NP + 2 - 1);
+    std::printf("ADAPTER OK: %d queued pairs, callbacks delivered, direct/batch identical\n", NP);
+    return 0;
+}

@@ -1,0 +1,37 @@
+"""The C++ host-side mirror of the reference interface (adapter/): builds on CPU, runs on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ADAPTER = os.path.join(ROOT, "adapter")
+
+
+def _build():
+    if not os.path.exists(os.path.join(ADAPTER, "test_adapter")) or not os.path.exists(os.path.join(ADAPTER, "libuz_adapter.so")):
+        subprocess.check_call(["make", "-C", ADAPTER, "CXX=g++"])
+
+
+def test_adapter_builds_and_exposes_the_reference_interface(built):
+    _build()
+    syms = subprocess.check_output(["nm", "-DC", os.path.join(ADAPTER, "libuz_adapter.so")], text=True)
+    for name in ("TransformationEstimator::estimateEdge(SlamNode&, SlamNode&)",
+                 "GpuFeatureTransformationEstimator::estimateEdgeImpl(SlamNode&, SlamNode&, SlamEdge&)",
+                 "GpuFeatureTransformationEstimator::estimateEdgeDirect(",
+                 "GpuFeatureTransformationEstimator::estimateSVD(",
+                 "GpuFeatureTransformationEstimator::consensus3D(",
+                 "GpuFeatureTransformationEstimator::setConfig(",
+                 "GpuFeatureTransformationEstimator::estimateEdgeBatch("):
+        assert name in syms, name
+    # the adapter reaches the GPU only through the C-ABI
+    undefined = subprocess.check_output(["nm", "-Du", os.path.join(ADAPTER, "libuz_adapter.so")], text=True)
+    assert "uz_estimate_edges" in undefined and "cuda" not in undefined.lower()
+
+
+@pytest.mark.gpu
+def test_adapter_end_to_end_on_gpu(built):
+    _build()
+    out = subprocess.run([os.path.join(ADAPTER, "test_adapter")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ADAPTER OK" in out.stdout
