@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from uzliti_slam_b200 import EdgeEstimator, synthetic as S
 est = EdgeEstimator(0)
