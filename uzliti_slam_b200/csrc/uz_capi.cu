@@ -6,9 +6,11 @@
 // (feature_transformation_estimator.cpp:40-49), one knn2 launch over every (matching, query tile), one
 // solve launch with a CTA per pair, one result copy.  No CPU compute fallback exists: without a
 // usable device every compute entry point returns UZ_ERR_CUDA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -113,6 +115,14 @@ struct uz_context {
     int32_t live = 0;
     int32_t store_max_n = 0;
 
+    // pinned, device-mapped host ranges seen so far (host begin, host end, device address of begin)
+    struct MappedRange { uintptr_t hb, he, db; };
+    std::vector<MappedRange> mapped;
+    void* pfn_ptr_attr = nullptr;    // cuPointerGetAttribute via cudaGetDriverEntryPoint (no link-time libcuda)
+    int gather_upload = 1;           // UZ_GATHER_UPLOAD=0 forces the cudaMemcpyAsync path
+    DevBuf d_chunks;
+    PinBuf h_chunks;
+
     // sample table
     DevBuf d_samples;
     int samp_cap = -1, samp_iters = -1, samp_prosac = -1;
@@ -145,6 +155,20 @@ struct uz_context {
 };
 
 namespace {
+
+// UZ_TRACE=1: host-side stage times of the batched entry points on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char* name;
+    Trace(const char* n) : on(getenv("UZ_TRACE") != nullptr), name(n) { if (on) t0 = std::chrono::steady_clock::now(); }
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[uz trace] %s: %s %.3f ms\n", name, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 std::string g_create_err = "";   // why the last uz_create failed (uz_last_error(NULL))
 
@@ -179,13 +203,20 @@ double thr_sq_star(double thr) {
 // ---- uploads -------------------------------------------------------------------------------------
 struct Span { const uint8_t* host; size_t bytes; uint8_t** dev_slot; };
 
-// Copies a set of host spans to the arena, merging host-contiguous spans into single transfers (a map
-// laid out as one big array on the host goes up in one DMA per field).  Identical host pointers share
-// one device copy.
-uz_status upload_spans(uz_context* ctx, Arena& arena, std::vector<Span>& spans) {
+// A host-contiguous run of spans and where it goes on the device.
+struct Run { const uint8_t* host; size_t bytes; uint8_t* dev; };
+
+// Lays a set of host spans out in ONE device block, merging host-contiguous spans into runs (a map laid out
+// as one big array on the host becomes one run per field) and sharing one device copy between identical
+// host pointers.  No data moves here; the runs are appended to `runs` for flush_runs().
+uz_status plan_spans(uz_context* ctx, Arena& arena, std::vector<Span>& spans, std::vector<Run>& runs,
+                     uint8_t** block_out = nullptr, size_t* block_bytes_out = nullptr) {
     std::sort(spans.begin(), spans.end(), [](const Span& a, const Span& b) {
         return a.host != b.host ? a.host < b.host : a.bytes > b.bytes;
     });
+    struct Tmp { size_t first, last; const uint8_t* b; const uint8_t* e; size_t off; };
+    std::vector<Tmp> tmp;
+    size_t total = 0;
     size_t i = 0;
     while (i < spans.size()) {
         size_t j = i;
@@ -198,13 +229,88 @@ uz_status upload_spans(uz_context* ctx, Arena& arena, std::vector<Span>& spans) 
             run_end = std::max(run_end, spans[j + 1].host + spans[j + 1].bytes);
             ++j;
         }
-        const size_t bytes = (size_t)(run_end - run_begin);
-        uint8_t* d = (uint8_t*)arena.alloc(bytes);
-        if (!d) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
-        if (bytes) UZ_CUDA(ctx, cudaMemcpyAsync(d, run_begin, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        for (size_t k = i; k <= j; ++k) *spans[k].dev_slot = d + (spans[k].host - run_begin);
+        tmp.push_back(Tmp{i, j, run_begin, run_end, total});
+        total += ((size_t)(run_end - run_begin) + 31) & ~(size_t)31;      // runs stay 32 B aligned inside the block
         i = j + 1;
     }
+    uint8_t* block = (uint8_t*)arena.alloc(std::max<size_t>(total, 1));
+    if (!block) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    for (const Tmp& t : tmp) {
+        runs.push_back(Run{t.b, (size_t)(t.e - t.b), block + t.off});
+        for (size_t k = t.first; k <= t.last; ++k) *spans[k].dev_slot = block + t.off + (spans[k].host - t.b);
+    }
+    if (block_out) *block_out = block;
+    if (block_bytes_out) *block_bytes_out = total;
+    return UZ_OK;
+}
+
+// Device-side address of a pinned, device-mapped host range, or 0 if the range is not (entirely) mapped.
+uintptr_t mapped_device_address(uz_context* ctx, const uint8_t* host, size_t bytes) {
+    const uintptr_t h = (uintptr_t)host;
+    for (const auto& r : ctx->mapped)
+        if (h >= r.hb && h + bytes <= r.he) return r.db + (h - r.hb);
+    typedef CUresult (*attr_fn)(void*, CUpointer_attribute, CUdeviceptr);
+    if (!ctx->pfn_ptr_attr) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return 0;
+        }
+        ctx->pfn_ptr_attr = fn;
+    }
+    attr_fn get = (attr_fn)ctx->pfn_ptr_attr;
+    unsigned int mtype = 0;
+    CUdeviceptr start = 0, dptr = 0;
+    size_t size = 0;
+    if (get(&mtype, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)h) != CUDA_SUCCESS || mtype != CU_MEMORYTYPE_HOST) return 0;
+    if (get(&start, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)h) != CUDA_SUCCESS) return 0;
+    if (get(&size, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)h) != CUDA_SUCCESS) return 0;
+    if (get(&dptr, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)h) != CUDA_SUCCESS || !dptr) return 0;
+    uz_context::MappedRange r;
+    r.hb = (uintptr_t)start; r.he = r.hb + size; r.db = (uintptr_t)dptr - (h - r.hb);
+    if (ctx->mapped.size() < 4096) ctx->mapped.push_back(r);
+    if (h >= r.hb && h + bytes <= r.he) return r.db + (h - r.hb);
+    return 0;
+}
+
+// Moves the planned runs.  Pinned, device-mapped sources are pulled by ONE gather kernel; anything else
+// (pageable memory, or few large runs where the DMA engines are the better tool) goes through cudaMemcpyAsync.
+uz_status flush_runs(uz_context* ctx, const std::vector<Run>& runs) {
+    bool gather = ctx->gather_upload && runs.size() > 16;
+    std::vector<uintptr_t> dev_src;
+    if (gather) {
+        dev_src.resize(runs.size());
+        for (size_t i = 0; i < runs.size() && gather; ++i) {
+            dev_src[i] = runs[i].bytes ? mapped_device_address(ctx, runs[i].host, runs[i].bytes) : 1;
+            if (!dev_src[i]) gather = false;
+        }
+    }
+    if (!gather) {
+        for (const Run& r : runs)
+            if (r.bytes) UZ_CUDA(ctx, cudaMemcpyAsync(r.dev, r.host, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return UZ_OK;
+    }
+    const size_t kChunk = 16384;
+    size_t n_chunks = 0;
+    for (const Run& r : runs) n_chunks += (r.bytes + kChunk - 1) / kChunk;
+    if (n_chunks == 0) return UZ_OK;
+    UZ_CUDA(ctx, ctx->h_chunks.ensure(n_chunks * sizeof(CopyChunk)));
+    UZ_CUDA(ctx, ctx->d_chunks.ensure(n_chunks * sizeof(CopyChunk)));
+    CopyChunk* cc = (CopyChunk*)ctx->h_chunks.p;
+    size_t k = 0;
+    for (size_t i = 0; i < runs.size(); ++i)
+        for (size_t off = 0; off < runs[i].bytes; off += kChunk) {
+            cc[k].src = (const uint8_t*)(dev_src[i] + off);
+            cc[k].dst = runs[i].dev + off;
+            cc[k].bytes = (uint32_t)std::min(kChunk, runs[i].bytes - off);
+            cc[k].pad = 0;
+            ++k;
+        }
+    UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunks.p, cc, n_chunks * sizeof(CopyChunk), cudaMemcpyHostToDevice, ctx->stream));
+    gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>((const CopyChunk*)ctx->d_chunks.p);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
     return UZ_OK;
 }
 
@@ -234,41 +340,34 @@ uz_status upload_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_
         vspans.push_back(Span{f->valid_3d, (size_t)f->n, &d_val[i]});
     }
     uz_status st;
-    if ((st = upload_spans(ctx, arena, dspans)) != UZ_OK) return st;
-    if ((st = upload_spans(ctx, arena, pspans)) != UZ_OK) return st;
-    if ((st = upload_spans(ctx, arena, vspans)) != UZ_OK) return st;
-    for (size_t i : strided) {   // padded cv::Mat rows: pitch copy into packed rows
+    std::vector<Run> runs;
+    uint8_t* raw_block = nullptr;
+    size_t raw_bytes = 0;
+    if ((st = plan_spans(ctx, arena, dspans, runs, &raw_block, &raw_bytes)) != UZ_OK) return st;
+    if ((st = plan_spans(ctx, arena, pspans, runs)) != UZ_OK) return st;
+    if ((st = plan_spans(ctx, arena, vspans, runs)) != UZ_OK) return st;
+    if ((st = flush_runs(ctx, runs)) != UZ_OK) return st;
+    // CSA layout of the packed block: one launch, the CSA block mirrors the raw block row for row
+    if (raw_bytes) {
+        uint8_t* csa = (uint8_t*)arena.alloc(raw_bytes);
+        if (!csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        const size_t rows = raw_bytes / 32;
+        pack_descriptors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
+            raw_block, (int)rows, 32, (uint32_t*)raw_block, (uint32_t*)csa);
+        ctx->launches++;
+        for (size_t i = 0; i < feats.size(); ++i)
+            if (d_raw[i]) { out[i].raw = (uint32_t*)d_raw[i]; out[i].csa = (uint32_t*)(csa + (d_raw[i] - raw_block)); }
+    }
+    for (size_t i : strided) {   // padded cv::Mat rows: pitch copy into packed rows, then their own CSA pass
         const uz_features* f = feats[i];
         d_raw[i] = (uint8_t*)arena.alloc((size_t)f->n * 32);
-        if (!d_raw[i]) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        uint8_t* csa = (uint8_t*)arena.alloc((size_t)f->n * 32);
+        if (!d_raw[i] || !csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
         UZ_CUDA(ctx, cudaMemcpy2DAsync(d_raw[i], 32, f->descriptors, f->desc_stride, 32, f->n,
                                        cudaMemcpyHostToDevice, ctx->stream));
-    }
-    // CSA layout: one pack launch per device-contiguous run of raw rows
-    std::vector<size_t> order;
-    for (size_t i = 0; i < feats.size(); ++i) if (feats[i]->n > 0) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return d_raw[a] < d_raw[b]; });
-    size_t i = 0;
-    while (i < order.size()) {
-        size_t j = i;
-        uint8_t* b0 = d_raw[order[i]];
-        uint8_t* e0 = b0 + (size_t)feats[order[i]]->n * 32;
-        while (j + 1 < order.size() && d_raw[order[j + 1]] <= e0) {
-            e0 = std::max(e0, d_raw[order[j + 1]] + (size_t)feats[order[j + 1]]->n * 32);
-            ++j;
-        }
-        const size_t rows = (size_t)(e0 - b0) / 32;
-        uint8_t* csa = (uint8_t*)arena.alloc(rows * 32);
-        if (!csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
-        pack_descriptors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
-            b0, (int)rows, 32, (uint32_t*)b0, (uint32_t*)csa);
+        pack_descriptors_kernel<<<(f->n + 255) / 256, 256, 0, ctx->stream>>>(d_raw[i], f->n, 32, (uint32_t*)d_raw[i], (uint32_t*)csa);
         ctx->launches++;
-        for (size_t k = i; k <= j; ++k) {
-            Cam& c = out[order[k]];
-            c.raw = (uint32_t*)d_raw[order[k]];
-            c.csa = (uint32_t*)(csa + (d_raw[order[k]] - b0));
-        }
-        i = j + 1;
+        out[i].raw = (uint32_t*)d_raw[i]; out[i].csa = (uint32_t*)csa;
     }
     UZ_CUDA(ctx, cudaGetLastError());
     for (size_t k = 0; k < feats.size(); ++k) { out[k].pos = (double*)d_pos[k]; out[k].valid = d_val[k]; }
@@ -550,6 +649,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (oc && atoi(oc) >= 1) ctx->overlap_chunks = atoi(oc);
         const char* fc = getenv("UZ_KNN_CFG");
         if (fc) ctx->force_cfg = atoi(fc);
+        const char* gu = getenv("UZ_GATHER_UPLOAD");
+        if (gu) ctx->gather_upload = atoi(gu);
     }
     e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)solve_smem_bytes(UZ_MAX_FEATURES));
@@ -564,7 +665,7 @@ void uz_destroy(uz_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->store_arena.release(); ctx->transient.release();
     ctx->d_samples.release(); ctx->d_tasks.release(); ctx->d_tiles.release(); ctx->d_pair_tasks.release();
-    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release();
+    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release();
     ctx->d_misc.release();
     ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -886,6 +987,7 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     if (st != UZ_OK) return st;
     if (n_pairs < 0 || (n_pairs > 0 && (!n_from || !n_to || !results))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
     if (n_pairs == 0) return UZ_OK;
+    Trace tr("estimate_edges_host");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     // unique cameras by (descriptor pointer, positions pointer, n): a keyframe that appears in many pairs
@@ -921,9 +1023,11 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         if (i == 0 || !same(order[i - 1], order[i])) uniq.push_back(keys[order[i]].f);
         slot_to_uniq[keys[order[i]].slot] = uniq.size() - 1;
     }
+    tr.lap("dedupe");
     std::vector<Cam> up;
     st = upload_cams(ctx, ctx->transient, uniq, up);
     if (st != UZ_OK) return st;
+    tr.lap("upload_cams (enqueue)");
     std::vector<Keyframe> kfs((size_t)n_pairs * 2);
     std::vector<PairRef> pairs((size_t)n_pairs);
     size_t cf = 0, ct = 0;
@@ -935,11 +1039,14 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         for (int k = 0; k < n_to[i]; ++k) b.cams[k] = up[slot_to_uniq[tf + ct++]];
         pairs[i] = PairRef{&a, &b};
     }
+    tr.lap("pair refs");
     UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
     st = run_pairs(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
     if (st != UZ_OK) return st;
+    tr.lap("run_pairs (enqueue)");
     UZ_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tr.lap("wait GPU + D2H");
     return UZ_OK;
 }
 

@@ -98,7 +98,7 @@ __device__ __noinline__ int exact_inlier(const double* T12, const double* px, in
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 3) solve_kernel(const MatchTask* __restrict__ tasks,
+__global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __restrict__ tasks,
                                                         const int2* __restrict__ pair_tasks,
                                                         const uint2* __restrict__ keys, SolveParams prm,
                                                         uz_edge_result* __restrict__ results) {
