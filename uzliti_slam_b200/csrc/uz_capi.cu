@@ -127,9 +127,17 @@ struct uz_context {
     DevBuf d_samples;
     int samp_cap = -1, samp_iters = -1, samp_prosac = -1;
 
-    // per-launch buffers
-    DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
-    PinBuf h_tasks, h_tiles, h_pair_tasks;
+    // per-batch staging, double buffered: the host prepares batch i+1 (task/tile tables in pinned memory) while
+    // the GPU still works on batch i; a slot is reused once the event recorded behind its last kernel fired
+    struct Slot {
+        DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys;
+        PinBuf h_tasks, h_tiles, h_pair_tasks;
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    Slot slots[2];
+    int cur_slot = 0;
+    DevBuf d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
 
     // parity taps
     int debug = 0;
@@ -408,14 +416,18 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     const uz_params prm = ctx->params;     // snapshot (setConfig may race with a batch in the reference)
     const int n_pairs = (int)pairs.size();
     if (n_pairs == 0) return UZ_OK;
+    ctx->cur_slot ^= 1;
+    uz_context::Slot& sl = ctx->slots[ctx->cur_slot];
+    if (!sl.done) UZ_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    if (sl.used) UZ_CUDA(ctx, cudaEventSynchronize(sl.done));      // normally long complete
 
     // 1. enumerate matchings (:40-49) and pick the tile shape
     size_t max_tasks = 0;
     for (const PairRef& p : pairs) max_tasks += p.from->cams.size() * p.to->cams.size();
-    UZ_CUDA(ctx, ctx->h_tasks.ensure(std::max<size_t>(max_tasks, 1) * sizeof(MatchTask)));
-    UZ_CUDA(ctx, ctx->h_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
-    MatchTask* tasks = (MatchTask*)ctx->h_tasks.p;
-    int2* pair_tasks = (int2*)ctx->h_pair_tasks.p;
+    UZ_CUDA(ctx, sl.h_tasks.ensure(std::max<size_t>(max_tasks, 1) * sizeof(MatchTask)));
+    UZ_CUDA(ctx, sl.h_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
+    MatchTask* tasks = (MatchTask*)sl.h_tasks.p;
+    int2* pair_tasks = (int2*)sl.h_pair_tasks.p;
     size_t n_tasks = 0, key_rows = 0;
     int max_nq = 0;
     int64_t compares = 0;
@@ -464,8 +476,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
     size_t n_tiles = 0;
     for (size_t t = 0; t < n_tasks; ++t) n_tiles += ((size_t)tasks[t].nq + tile_rows - 1) / tile_rows;
-    UZ_CUDA(ctx, ctx->h_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
-    int2* tiles = (int2*)ctx->h_tiles.p;
+    UZ_CUDA(ctx, sl.h_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    int2* tiles = (int2*)sl.h_tiles.p;
     {
         size_t k = 0;
         for (size_t t = 0; t < n_tasks; ++t)
@@ -473,13 +485,13 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     }
 
     // 2. device buffers
-    UZ_CUDA(ctx, ctx->d_tasks.ensure(std::max<size_t>(n_tasks, 1) * sizeof(MatchTask)));
-    UZ_CUDA(ctx, ctx->d_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
-    UZ_CUDA(ctx, ctx->d_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
-    UZ_CUDA(ctx, ctx->d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
-    if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
-    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-    UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    UZ_CUDA(ctx, sl.d_tasks.ensure(std::max<size_t>(n_tasks, 1) * sizeof(MatchTask)));
+    UZ_CUDA(ctx, sl.d_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    UZ_CUDA(ctx, sl.d_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
+    UZ_CUDA(ctx, sl.d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
+    if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
     // 3. launch geometry: one launch pair per chunk of pairs; the solve of chunk c runs on the side stream and
     // overlaps the knn2 of chunk c+1 (INT pipes vs FP32/FP64 pipes of the same SMs)
@@ -535,13 +547,13 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         const int p0 = chunk_pair[c], np_c = chunk_pair[c + 1] - chunk_pair[c];
         if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
         if (nt_c > 0) {
-            const int2* d_t = (const int2*)ctx->d_tiles.p + t0;
+            const int2* d_t = (const int2*)sl.d_tiles.p + t0;
             switch (best_cfg) {
-                case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
-                case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
-                case 2: launch_knn2<64, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
-                case 3: launch_knn2<256, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
-                default: launch_knn2<128, 2>(ctx, (const MatchTask*)ctx->d_tasks.p, d_t, nt_c, (uint2*)ctx->d_keys.p); break;
+                case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
+                case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
+                case 2: launch_knn2<64, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
+                case 3: launch_knn2<256, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
+                default: launch_knn2<128, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
             }
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
@@ -558,7 +570,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             if (ctx->timers) { tm.e[2] = ctx->get_event(); tm.e[3] = ctx->get_event(); tm.has_solve = true; cudaEventRecord(tm.e[2], sB); }
             sp.pair_base = p0;
             solve_kernel<kSolveThreads><<<np_c, kSolveThreads, solve_smem_bytes(cap), sB>>>(
-                (const MatchTask*)ctx->d_tasks.p, (const int2*)ctx->d_pair_tasks.p, (const uint2*)ctx->d_keys.p, sp, d_results);
+                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
@@ -571,6 +583,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
         ctx->event_pool.push_back(ev);
     }
+    UZ_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+    sl.used = true;
     return UZ_OK;
 }
 
@@ -664,10 +678,13 @@ void uz_destroy(uz_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->store_arena.release(); ctx->transient.release();
-    ctx->d_samples.release(); ctx->d_tasks.release(); ctx->d_tiles.release(); ctx->d_pair_tasks.release();
-    ctx->d_keys.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release();
+    for (auto& sl : ctx->slots) {
+        sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release();
+        sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release();
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    ctx->d_samples.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release();
     ctx->d_misc.release();
-    ctx->h_tasks.release(); ctx->h_tiles.release(); ctx->h_pair_tasks.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
@@ -806,7 +823,7 @@ uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32
     UZ_CUDA(ctx, ctx->d_misc.ensure((size_t)nq * 16));
     int32_t* d_idx = (int32_t*)ctx->d_misc.p;
     int32_t* d_dist = d_idx + 2 * (size_t)nq;
-    unpack_keys_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)ctx->d_keys.p, nq, d_idx, d_dist);
+    unpack_keys_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)ctx->slots[ctx->cur_slot].d_keys.p, nq, d_idx, d_dist);
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     UZ_CUDA(ctx, cudaMemcpyAsync(idx_out, d_idx, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -961,9 +978,7 @@ uz_status uz_estimate_edges_device(uz_context* ctx, const int32_t* from_handles,
     std::vector<PairRef> pairs;
     st = pairs_from_handles(ctx, from_handles, to_handles, n_pairs, pairs);
     if (st != UZ_OK) return st;
-    // the pinned task staging buffers are reused per call: the previous call's copies must have drained
-    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return run_pairs(ctx, pairs, (uz_edge_result*)results_device);
+    return run_pairs(ctx, pairs, (uz_edge_result*)results_device);   // asynchronous: staging is double buffered
 }
 
 uz_status uz_estimate_edges(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,

@@ -43,7 +43,8 @@ struct SolveParams {
 constexpr int kSolveThreads = 128;
 
 __host__ __device__ constexpr size_t solve_smem_bytes(int cap) {
-    return (size_t)cap * 48 /*P,Q (px also hosts the unsorted keys, later the residual norms)*/ + (size_t)cap * 4 /*sorted keys*/ +
+    return (size_t)cap * 24 /*float32 copies of P,Q (also: unsorted keys, later the residual norms)*/ +
+           (size_t)cap * 4 /*sorted keys, then packed (trainIdx<<16)|queryIdx*/ + (size_t)cap * 2 /*ordered inlier list*/ +
            (size_t)kSolveThreads * 12 * 8 /*hypothesis transforms*/ + (size_t)kSolveThreads * 4 /*counts*/ +
            256 /*Tbest, Tfin*/;
 }
@@ -93,8 +94,10 @@ constexpr float kScreenK = 1.2e-7f;
 
 // Rare path of the pre-screen, deliberately not inlined: it must not drag the double-precision transforms
 // into registers inside the float loop.
-__device__ __noinline__ int exact_inlier(const double* T12, const double* px, int cap, int i, double thr_sq_star) {
-    return residual_sq(T12, px[i], px[cap + i], px[2 * cap + i], px[3 * cap + i], px[4 * cap + i], px[5 * cap + i]) < thr_sq_star;
+__device__ __noinline__ int exact_inlier(const double* T12, const double* gP, const double* gQ, uint32_t tq, double thr_sq_star) {
+    const double* p = gP + 3 * (tq & 0xFFFFu);
+    const double* q = gQ + 3 * (tq >> 16);
+    return residual_sq(T12, p[0], p[1], p[2], q[0], q[1], q[2]) < thr_sq_star;
 }
 
 template <int THREADS>
@@ -104,16 +107,23 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                                                         uz_edge_result* __restrict__ results) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int cap = prm.cap;
-    double* px = reinterpret_cast<double*>(smem_raw);
-    double* py = px + cap; double* pz = py + cap;
-    double* qx = pz + cap; double* qy = qx + cap; double* qz = qy + cap;
-    double* Th = qz + cap;                                            // [THREADS][12]
-    double* norms = px;                                               // norms[i] overwrites px[i] in place (K5)
+    // On-chip state of the pair.  Only float32 copies of the matched 3-D points live here (the scoring loop
+    // and the float32 pose recurrences read nothing else); the float64 originals stay in the keyframe store
+    // and are fetched through the packed (trainIdx<<16)|queryIdx list where exactness needs them.
+    double* Th = reinterpret_cast<double*>(smem_raw);                 // [THREADS][12] hypothesis transforms
     double* Tbest = Th + THREADS * 12;                                // 12
     double* Tfin = Tbest + 12;                                        // 12
-    int32_t* counts = reinterpret_cast<int32_t*>(Tfin + 12);          // [THREADS]
-    uint32_t* skeys = reinterpret_cast<uint32_t*>(counts + THREADS);  // [cap] sorted keys, later the inlier list
-    uint32_t* vkeys = reinterpret_cast<uint32_t*>(px);                // [cap] unsorted valid keys: aliases P, dead before the gather
+    float* pf = reinterpret_cast<float*>(Tfin + 12);                  // [6][cap]: px py pz (to) qx qy qz (from)
+    float* pxf = pf; float* pyf = pf + cap; float* pzf = pf + 2 * cap;
+    float* qxf = pf + 3 * cap; float* qyf = pf + 4 * cap; float* qzf = pf + 5 * cap;
+    double* norms = reinterpret_cast<double*>(pf);                    // residual norms reuse pf after the last pass
+    uint32_t* vkeys = reinterpret_cast<uint32_t*>(pf);                // unsorted valid keys: alias pf, dead before the gather
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(pf + 6 * cap);      // [cap] sorted keys -> (t<<16)|q -> inlier list
+    uint32_t* tq = skeys;
+    int32_t* counts = reinterpret_cast<int32_t*>(skeys + cap);        // [THREADS]
+    uint16_t* ilist = reinterpret_cast<uint16_t*>(counts + THREADS);  // [cap] winner's inliers in index order
+    const double* __restrict__ gP = nullptr;                          // float64 positions of the to-camera (by queryIdx)
+    const double* __restrict__ gQ = nullptr;                          // float64 positions of the from-camera (by trainIdx)
     __shared__ int s_best, s_maxc, s_break, s_run, s_nvalid, s_nratio;
     constexpr int NW = THREADS / 32;
     __shared__ int s_wcnt[NW];
@@ -205,14 +215,15 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         }
         __syncthreads();
         UZ_PHASE(2);
-        const double* __restrict__ pq = tk->q_pos;
-        const double* __restrict__ pt3 = tk->t_pos;
+        gP = tk->q_pos;
+        gQ = tk->t_pos;
         for (int i = tid; i < M; i += THREADS) {
             const uint32_t key = skeys[i];
             const int q = key & 0xFFFFu;
             const int t = k[q].x & 0xFFFFu;
-            px[i] = pq[3 * q]; py[i] = pq[3 * q + 1]; pz[i] = pq[3 * q + 2];
-            qx[i] = pt3[3 * t]; qy[i] = pt3[3 * t + 1]; qz[i] = pt3[3 * t + 2];
+            pxf[i] = (float)gP[3 * q]; pyf[i] = (float)gP[3 * q + 1]; pzf[i] = (float)gP[3 * q + 2];
+            qxf[i] = (float)gQ[3 * t]; qyf[i] = (float)gQ[3 * t + 1]; qzf[i] = (float)gQ[3 * t + 2];
+            tq[i] = ((uint32_t)t << 16) | (uint32_t)q;
             if (prm.dbg_matches) {
                 int32_t* d = prm.dbg_matches + ((size_t)pair * cap + i) * 3;
                 d[0] = q; d[1] = t; d[2] = (int)(key >> 16);
@@ -220,9 +231,12 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         }
     } else {
         M = prm.direct_M;
+        gP = prm.direct_P;
+        gQ = prm.direct_Q;
         for (int i = tid; i < M; i += THREADS) {
-            px[i] = prm.direct_P[3 * i]; py[i] = prm.direct_P[3 * i + 1]; pz[i] = prm.direct_P[3 * i + 2];
-            qx[i] = prm.direct_Q[3 * i]; qy[i] = prm.direct_Q[3 * i + 1]; qz[i] = prm.direct_Q[3 * i + 2];
+            pxf[i] = (float)gP[3 * i]; pyf[i] = (float)gP[3 * i + 1]; pzf[i] = (float)gP[3 * i + 2];
+            qxf[i] = (float)gQ[3 * i]; qyf[i] = (float)gQ[3 * i + 1]; qzf[i] = (float)gQ[3 * i + 2];
+            tq[i] = ((uint32_t)i << 16) | (uint32_t)i;
         }
     }
     if (tid == 0) { s_best = -1; s_maxc = 0; s_break = 0; s_run = 0; }
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
 #pragma unroll 1
             for (int j = 0; j < 3; ++j) {
                 const int s = samp[(size_t)(h0 + tid) * 3 + j];
-                pose_add(acc, (float)px[s], (float)py[s], (float)pz[s], (float)qx[s], (float)qy[s], (float)qz[s]);
+                pose_add(acc, pxf[s], pyf[s], pzf[s], qxf[s], qyf[s], qzf[s]);       // == (float) of the doubles (:303-304)
             }
             pose_finish(acc, Th + tid * 12);
         }
@@ -271,8 +285,8 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                 cnt[a] = 0;
             }
             for (int i = lane; i < M; i += 32) {
-                const float x = (float)px[i], y = (float)py[i], z = (float)pz[i];
-                const float u = (float)qx[i], v = (float)qy[i], w = (float)qz[i];
+                const float x = pxf[i], y = pyf[i], z = pzf[i];
+                const float u = qxf[i], v = qyf[i], w = qzf[i];
                 const float kp = kScreenK * (4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
 #pragma unroll
                 for (int a = 0; a < H; ++a) {
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                     if (inl) {
                         cnt[a]++;
                     } else if (!out) {   // borderline (or NaN): exact double evaluation, as the reference
-                        cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, px, cap, i, prm.thr_sq_star);
+                        cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, gP, gQ, tq[i], prm.thr_sq_star);
                     }
                 }
             }
@@ -333,11 +347,16 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     // ---------------- K5: refit on the winner's inliers, recount, mse -------------------------------
     UZ_PHASE(5);
     // (a) the winner's consensus set, compacted in index order (the refit recurrence is order dependent)
-    uint16_t* ilist = reinterpret_cast<uint16_t*>(skeys);
     int n_in = 0;
     for (int base = 0; base < M; base += THREADS) {
         const int i = base + tid;
-        const bool in = (i < M) && (residual_sq(Tbest, px[i], py[i], pz[i], qx[i], qy[i], qz[i]) < prm.thr_sq_star);
+        bool in = false;
+        if (i < M) {
+            const uint32_t e = tq[i];
+            const double* p = gP + 3 * (e & 0xFFFFu);
+            const double* q = gQ + 3 * (e >> 16);
+            in = residual_sq(Tbest, p[0], p[1], p[2], q[0], q[1], q[2]) < prm.thr_sq_star;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, in);
         if (lane == 0) s_wcnt[warp] = __popc(bal);
         __syncthreads();
@@ -363,8 +382,8 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
             const int nch = min(CH, n_in - c0);
             for (int k = tid; k < nch; k += THREADS) {
                 const int i = ilist[c0 + k];
-                fb[0 * CH + k] = (float)px[i]; fb[1 * CH + k] = (float)py[i]; fb[2 * CH + k] = (float)pz[i];
-                fb[3 * CH + k] = (float)qx[i]; fb[4 * CH + k] = (float)qy[i]; fb[5 * CH + k] = (float)qz[i];
+                fb[0 * CH + k] = pxf[i]; fb[1 * CH + k] = pyf[i]; fb[2 * CH + k] = pzf[i];
+                fb[3 * CH + k] = qxf[i]; fb[4 * CH + k] = qyf[i]; fb[5 * CH + k] = qzf[i];
                 const float alpha = UZ_FDIV(1.0f, (float)(c0 + k + 1));     // accumulated weight == n exactly
                 fb[6 * CH + k] = alpha;
                 fb[7 * CH + k] = UZ_FSUB(1.0f, alpha);
@@ -403,14 +422,20 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     for (int base = 0; base < M; base += THREADS) {
         const int i = base + tid;
         bool in = false;
+        double nrm = 0.0;
         if (i < M) {
-            const double s = residual_sq(Tfin, px[i], py[i], pz[i], qx[i], qy[i], qz[i]);
+            const uint32_t e = tq[i];
+            const double* p = gP + 3 * (e & 0xFFFFu);
+            const double* q = gQ + 3 * (e >> 16);
+            const double s = residual_sq(Tfin, p[0], p[1], p[2], q[0], q[1], q[2]);
             in = s < prm.thr_sq_star;
-            norms[i] = in ? UZ_DSQRT(s) : 0.0;      // overwrites px[i]: P is dead after this pass
+            nrm = in ? UZ_DSQRT(s) : 0.0;
             if (prm.dbg_mask) prm.dbg_mask[(size_t)pair * cap + i] = in;
         }
         consensus += __syncthreads_count(in);
+        if (i < M) norms[i] = nrm;              // pf is dead by now (the refit staged its operands already)
     }
+    __syncthreads();
     if (tid == 0) {
         double mse = 0.0;
 #pragma unroll 4
