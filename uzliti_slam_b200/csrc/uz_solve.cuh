@@ -86,7 +86,9 @@ __device__ __forceinline__ void rank_sort(const uint32_t* __restrict__ in, uint3
 // The reference test is  sqrt_d(s_d) < thr  with s_d evaluated in double (uz::residual_sq).  Evaluating the
 // same residual in float32 (FMA allowed) from float-rounded points gives s_f with, per component,
 //   |d_f - d| <= u (4 L1(p) + 3 |t|_inf + |q|_inf + |d|),  u = 2^-24,
-// hence | sqrt(s_f) - ||d|| | <= m := K (4.5 L1(p) + 1.5 L1(q) + 3.5 L1(t)),  K = 1.2e-7 > sqrt(3) u (1 + slack).
+// hence | sqrt(s_f) - ||d|| | <= m := K (4.5 L1(p) + 1.5 L1(q) + 3.5 L1(t)),  K = 1.2e-7 > sqrt(3) u (1 + slack);
+// the kernel uses ONE margin per hypothesis chunk (max over the pair's points + max over the chunk's
+// translations), so the loop compares against two CTA-uniform thresholds.
 // A point is a certain inlier if sqrt(s_f) < thr(1-1e-6) - m and a certain outlier if sqrt(s_f) > thr(1+1e-6) + m;
 // everything else (about 1e-6 of the evaluations, and any NaN) is re-evaluated exactly in double.  The
 // result is therefore bit-identical to the double-only evaluation at ~1/3 of its pipe time.
@@ -98,6 +100,20 @@ __device__ __noinline__ int exact_inlier(const double* T12, const double* gP, co
     const double* p = gP + 3 * (tq & 0xFFFFu);
     const double* q = gQ + 3 * (tq >> 16);
     return residual_sq(T12, p[0], p[1], p[2], q[0], q[1], q[2]) < thr_sq_star;
+}
+
+// block-wide maximum of a non-negative float (NaN contributions are ignored by fmaxf)
+template <int THREADS>
+__device__ __forceinline__ float block_max(float v, float* s_red /* [THREADS/32] */, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) r = fmaxf(r, s_red[w]);
+    return r;
 }
 
 template <int THREADS>
@@ -127,6 +143,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     __shared__ int s_best, s_maxc, s_break, s_run, s_nvalid, s_nratio;
     constexpr int NW = THREADS / 32;
     __shared__ int s_wcnt[NW];
+    __shared__ float s_red[NW];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -136,6 +153,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     UZ_PHASE(0);
     int M = 0;
     int n_ratio = 0, cam_from = -1, cam_to = -1;
+    float kp_local = 0.f;        // per-thread max of the point part of the pre-screen error bound
 
     if (prm.direct_P == nullptr) {
         // ---------------- K2: best camera pair, filter, sort, gather -------------------------------
@@ -221,8 +239,10 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
             const uint32_t key = skeys[i];
             const int q = key & 0xFFFFu;
             const int t = k[q].x & 0xFFFFu;
-            pxf[i] = (float)gP[3 * q]; pyf[i] = (float)gP[3 * q + 1]; pzf[i] = (float)gP[3 * q + 2];
-            qxf[i] = (float)gQ[3 * t]; qyf[i] = (float)gQ[3 * t + 1]; qzf[i] = (float)gQ[3 * t + 2];
+            const float x = (float)gP[3 * q], y = (float)gP[3 * q + 1], z = (float)gP[3 * q + 2];
+            const float u = (float)gQ[3 * t], v = (float)gQ[3 * t + 1], w = (float)gQ[3 * t + 2];
+            pxf[i] = x; pyf[i] = y; pzf[i] = z; qxf[i] = u; qyf[i] = v; qzf[i] = w;
+            kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
             tq[i] = ((uint32_t)t << 16) | (uint32_t)q;
             if (prm.dbg_matches) {
                 int32_t* d = prm.dbg_matches + ((size_t)pair * cap + i) * 3;
@@ -234,13 +254,15 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         gP = prm.direct_P;
         gQ = prm.direct_Q;
         for (int i = tid; i < M; i += THREADS) {
-            pxf[i] = (float)gP[3 * i]; pyf[i] = (float)gP[3 * i + 1]; pzf[i] = (float)gP[3 * i + 2];
-            qxf[i] = (float)gQ[3 * i]; qyf[i] = (float)gQ[3 * i + 1]; qzf[i] = (float)gQ[3 * i + 2];
+            const float x = (float)gP[3 * i], y = (float)gP[3 * i + 1], z = (float)gP[3 * i + 2];
+            const float u = (float)gQ[3 * i], v = (float)gQ[3 * i + 1], w = (float)gQ[3 * i + 2];
+            pxf[i] = x; pyf[i] = y; pzf[i] = z; qxf[i] = u; qyf[i] = v; qzf[i] = w;
+            kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
             tq[i] = ((uint32_t)i << 16) | (uint32_t)i;
         }
     }
     if (tid == 0) { s_best = -1; s_maxc = 0; s_break = 0; s_run = 0; }
-    __syncthreads();
+    const float kp_max = block_max<THREADS>(kp_local, s_red, tid);     // (also the barrier after the gather)
     UZ_PHASE(3);
 
     if (M < 3) {                 // :118/:158 not enough depth-valid matches
@@ -261,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     constexpr int H = 4;         // hypotheses scored per pass over the points
     for (int h0 = 0; h0 < I; h0 += THREADS) {
         const int nh = min(THREADS, I - h0);
+        float kt_local = 0.f;
         if (tid < nh) {
             PoseAcc acc;
             pose_reset(acc);
@@ -270,39 +293,46 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                 pose_add(acc, pxf[s], pyf[s], pzf[s], qxf[s], qyf[s], qzf[s]);       // == (float) of the doubles (:303-304)
             }
             pose_finish(acc, Th + tid * 12);
+            kt_local = 3.5f * (fabsf((float)Th[tid * 12 + 3]) + fabsf((float)Th[tid * 12 + 7]) + fabsf((float)Th[tid * 12 + 11]));
         }
-        __syncthreads();
+        // one screening margin for the whole chunk: the largest point bound plus the largest translation bound
+        const float m_scr = kScreenK * (kp_max + block_max<THREADS>(kt_local, s_red, tid));     // (barrier inside)
+        const float lo = thr_dn - m_scr, hi = thr_up + m_scr;
+        const float lo2 = lo > 0.f ? lo * lo : -1.f;      // sf < lo2  =>  certainly inside  (never if lo <= 0)
+        const float hi2 = hi * hi;                        // sf > hi2  =>  certainly outside
         if (h0 == 0) UZ_PHASE(4);
         for (int hb = warp * H; hb < nh; hb += NW * H) {
-            float T[H][12], kt[H];
+            float T[H][12];
             int cnt[H];
 #pragma unroll
             for (int a = 0; a < H; ++a) {
                 const int h = min(hb + a, nh - 1);          // tail: duplicates, their counts are discarded
 #pragma unroll
                 for (int e = 0; e < 12; ++e) T[a][e] = (float)Th[h * 12 + e];   // exact: T holds float32 values
-                kt[a] = kScreenK * 3.5f * (fabsf(T[a][3]) + fabsf(T[a][7]) + fabsf(T[a][11]));
                 cnt[a] = 0;
             }
-            for (int i = lane; i < M; i += 32) {
+            for (int base = 0; base < M; base += 32) {       // whole warp stays converged: branch-free common path
+                const bool live = base + lane < M;
+                const int i = live ? base + lane : M - 1;
                 const float x = pxf[i], y = pyf[i], z = pzf[i];
                 const float u = qxf[i], v = qyf[i], w = qzf[i];
-                const float kp = kScreenK * (4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
+                unsigned need = 0;
 #pragma unroll
                 for (int a = 0; a < H; ++a) {
                     const float dx = fmaf(T[a][0], x, fmaf(T[a][1], y, fmaf(T[a][2], z, T[a][3]))) - u;
                     const float dy = fmaf(T[a][4], x, fmaf(T[a][5], y, fmaf(T[a][6], z, T[a][7]))) - v;
                     const float dz = fmaf(T[a][8], x, fmaf(T[a][9], y, fmaf(T[a][10], z, T[a][11]))) - w;
                     const float sf = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    const float m = kp + kt[a];
-                    const float lo = thr_dn - m, hi = thr_up + m;
-                    const bool inl = (lo > 0.f) && (sf < lo * lo);
-                    const bool out = sf > hi * hi;
-                    if (inl) {
-                        cnt[a]++;
-                    } else if (!out) {   // borderline (or NaN): exact double evaluation, as the reference
-                        cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, gP, gQ, tq[i], prm.thr_sq_star);
-                    }
+                    const bool inl = sf < lo2;                 // certainly inside
+                    const bool und = !(inl || sf > hi2);       // neither certain (borderline or NaN)
+                    cnt[a] += (int)(inl && live);
+                    need |= (unsigned)(und && live) << a;
+                }
+                if (__any_sync(0xffffffffu, need != 0)) {     // ~1e-6 of the evaluations: exact double, as the reference
+#pragma unroll
+                    for (int a = 0; a < H; ++a)
+                        if ((need >> a) & 1u)
+                            cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, gP, gQ, tq[i], prm.thr_sq_star);
                 }
             }
 #pragma unroll
