@@ -2,7 +2,8 @@
 //
 // Follows /root/reference/transformation_estimation/src/feature_transformation_estimator.cpp:
 //   K2  :65-71 ratio test, :74-86 best camera pair (score = #ratio survivors, first strict max),
-//       :103-112 valid_3d filter, :114 sort (total order (distance, queryIdx)),
+//       :103-112 valid_3d filter, :114 sort (total order (distance, queryIdx); done as a
+//       stable counting sort by distance over the query-ordered matches),
 //       :118-124 gather of Pd (to) / Xd (from)
 //   K3  :214-227 hypotheses from the shared sample-index list, estimatePoseSVD :299-314 (uz_arith.cuh)
 //   K4  :230-241 consensus3D :337-347 per hypothesis, strict-'>' running maximum, early break
@@ -56,32 +57,6 @@ __device__ __forceinline__ void write_identity(double* T16) {
     for (int i = 0; i < 16; ++i) T16[i] = (i % 5 == 0) ? 1.0 : 0.0;
 }
 
-// ---- K2 helpers -----------------------------------------------------------------------------------
-// Rank sort of M unique keys (M <= E*THREADS): every thread keeps E keys in registers and counts, over
-// one broadcast pass through shared memory, how many keys are smaller — the count is the final slot.
-template <int THREADS, int E>
-__device__ __forceinline__ void rank_sort(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int M, int tid) {
-    uint32_t mine[E];
-    int rank[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) { const int i = tid + e * THREADS; mine[e] = i < M ? in[i] : kNoKey; rank[e] = 0; }
-    const uint4* in4 = reinterpret_cast<const uint4*>(in);
-    const int M4 = M >> 2;
-    for (int j = 0; j < M4; ++j) {
-        const uint4 k = in4[j];
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-            rank[e] += (int)(k.x < mine[e]) + (int)(k.y < mine[e]) + (int)(k.z < mine[e]) + (int)(k.w < mine[e]);
-    }
-    for (int j = M4 << 2; j < M; ++j) {
-        const uint32_t k = in[j];
-#pragma unroll
-        for (int e = 0; e < E; ++e) rank[e] += (int)(k < mine[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) if (tid + e * THREADS < M) out[rank[e]] = mine[e];
-}
-
 // ---- K4 helper: float32 pre-screen of the consensus test ---------------------------------------------
 // The reference test is  sqrt_d(s_d) < thr  with s_d evaluated in double (uz::residual_sq).  Evaluating the
 // same residual in float32 (FMA allowed) from float-rounded points gives s_f with, per component,
@@ -133,7 +108,6 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     float* pxf = pf; float* pyf = pf + cap; float* pzf = pf + 2 * cap;
     float* qxf = pf + 3 * cap; float* qyf = pf + 4 * cap; float* qzf = pf + 5 * cap;
     double* norms = reinterpret_cast<double*>(pf);                    // residual norms reuse pf after the last pass
-    uint32_t* vkeys = reinterpret_cast<uint32_t*>(pf);                // unsorted valid keys: alias pf, dead before the gather
     uint32_t* skeys = reinterpret_cast<uint32_t*>(pf + 6 * cap);      // [cap] sorted keys -> (t<<16)|q -> inlier list
     uint32_t* tq = skeys;
     int32_t* counts = reinterpret_cast<int32_t*>(skeys + cap);        // [THREADS]
@@ -191,47 +165,54 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         cam_from = tk->cam_from; cam_to = tk->cam_to;
         const uint8_t* __restrict__ vq = tk->q_valid;
         const uint8_t* __restrict__ vt = tk->t_valid;
+        // ratio test (:65-71) + valid_3d filter (:103-112) + the sort of :114 as a STABLE COUNTING SORT by
+        // distance: matches are produced in query order, so equal distances keep ascending queryIdx, which
+        // is exactly the (distance, queryIdx) order.  Pass 1 (all warps): per-query distance + histogram.
+        int* hist = reinterpret_cast<int*>(Th);                 // [288] bins; Th is not used before K3
+        uint16_t* dq = reinterpret_cast<uint16_t*>(pf);         // [cap] distance of query i, 0xFFFF = dropped
+        for (int bidx = tid; bidx < 288; bidx += THREADS) hist[bidx] = 0;
         if (tid == 0) { s_nvalid = 0; s_nratio = 0; }
         __syncthreads();
-        // ratio test (:65-71) + valid_3d filter (:103-112); survivors are appended unordered
         for (int i = tid; i < nq; i += THREADS) {
             const uint2 m = k[i];
             const bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
+            uint16_t d = 0xFFFFu;
             if (pass) {
                 atomicAdd(&s_nratio, 1);
-                if (vq[i] && vt[m.x & 0xFFFFu]) vkeys[atomicAdd(&s_nvalid, 1)] = (m.x & 0xFFFF0000u) | (uint32_t)i;
+                if (vq[i] && vt[m.x & 0xFFFFu]) { d = (uint16_t)(m.x >> 16); atomicAdd(&hist[d], 1); }
+            }
+            dq[i] = d;
+        }
+        __syncthreads();
+        n_ratio = s_nratio;
+        UZ_PHASE(1);
+        if (warp == 0) {
+            // exclusive prefix over the 257 bins: 9 consecutive bins per lane
+            int loc[9], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { loc[j] = hist[lane * 9 + j]; sum += loc[j]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            int run = inc - sum;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { hist[lane * 9 + j] = run; run += loc[j]; }
+            if (lane == 31) s_nvalid = inc;
+            __syncwarp();
+            // pass 2 (one warp, query order): slot = bin offset + rank among equal distances seen so far
+            for (int base = 0; base < nq; base += 32) {
+                const int q = base + lane;
+                const unsigned d = q < nq ? dq[q] : 0xFFFFu;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                if (d != 0xFFFFu) skeys[hist[d] + rank] = (d << 16) | (unsigned)q;
+                __syncwarp();
+                if (d != 0xFFFFu && rank == 0) hist[d] += __popc(peers);
+                __syncwarp();
             }
         }
         __syncthreads();
         M = s_nvalid;
-        n_ratio = s_nratio;
-        UZ_PHASE(1);
-        // :114 sort by (distance, queryIdx)
-        if (M <= THREADS) rank_sort<THREADS, 1>(vkeys, skeys, M, tid);
-        else if (M <= 2 * THREADS) rank_sort<THREADS, 2>(vkeys, skeys, M, tid);
-        else if (M <= 4 * THREADS) rank_sort<THREADS, 4>(vkeys, skeys, M, tid);
-        else if (M <= 8 * THREADS) rank_sort<THREADS, 8>(vkeys, skeys, M, tid);
-        else {                   // large M: in-place bitonic network on the padded list
-            int n2 = 1;
-            while (n2 < M) n2 <<= 1;
-            for (int i = M + tid; i < n2; i += THREADS) vkeys[i] = kNoKey;
-            __syncthreads();
-            for (int kk = 2; kk <= n2; kk <<= 1) {
-                for (int j = kk >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < n2; i += THREADS) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const uint32_t a = vkeys[i], b = vkeys[ixj];
-                            const bool asc = (i & kk) == 0;
-                            if ((a > b) == asc) { vkeys[i] = b; vkeys[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            for (int i = tid; i < M; i += THREADS) skeys[i] = vkeys[i];
-        }
-        __syncthreads();
         UZ_PHASE(2);
         gP = tk->q_pos;
         gQ = tk->t_pos;
