@@ -176,48 +176,110 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region.  NVML is polled from a thread every 10 ms
+    (started before the warm-up so the first sample never lands after the region); `mark()` brackets the
+    timed region and only samples taken inside it are reported.  nvidia-smi is the fallback when NVML is absent."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.lines = []
-        self.proc = None
+        self.samples = []          # (t, sm_mhz, max_mhz, power_w, reasons-bitmask)
+        self.t_begin = self.t_end = None
+        self._stop = False
+        self._thread = None
+        self.source = None
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+    def _nvml_loop(self):
+        import pynvml as N
+        N.nvmlInit()
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        idx = self.device
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.device])
+            except Exception:
+                idx = self.device
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        self.source = "nvml"
+        while not self._stop:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = N.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                 "-i", str(self.device), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+        self._proc = proc
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        bits = (0x8, 0x40, 0x20, 0x4)
+        for ln in proc.stdout:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                mask = 0
+                for b, v in zip(bits, f[5:9]):
+                    if v.lower().startswith("active"):
+                        mask |= b
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]), mask))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
-                    samples=len(sm), reasons=sorted(reasons))
+            if self._stop:
+                break
+        proc.terminate()
+
+    def start(self):
+        def run():
+            try:
+                self._nvml_loop()
+            except Exception:
+                try:
+                    self._smi_loop()
+                except Exception:
+                    self.source = None
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+        t0 = time.time()
+        while not self.samples and time.time() - t0 < 5.0:      # first sample before anything is timed
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
+    def stop(self):
+        self._stop = True
+        if getattr(self, "_proc", None):
+            self._proc.terminate()
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"], source=self.source)
+        inside = [s for s in self.samples if self.t_begin is not None and self.t_begin <= s[0] <= (self.t_end or 1e300)]
+        window = "timed region"
+        if not inside:                       # region shorter than one sampling period: nearest samples around it
+            window = "nearest samples around the timed region"
+            mid = 0.5 * ((self.t_begin or 0) + (self.t_end or 0))
+            inside = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]
+        mask = 0
+        for s in inside:
+            mask |= s[4]
+        reasons = [n for n, b in (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+                                  ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80)) if mask & b]
+        return dict(sm_mhz=float(np.median([s[1] for s in inside])), sm_max_mhz=float(max(s[2] for s in inside)),
+                    power_w_max=float(max(s[3] for s in inside)), samples=len(inside), window=window,
+                    source=self.source, reasons=reasons)
 
 
 def run_gpu(args):
@@ -298,22 +360,24 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     est.enable_timers(True)
     est.reset_timers()
     launches0 = est.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = est.launch_count() - launches0

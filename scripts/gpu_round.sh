@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench, ncu launch list, ncu --set full of the two kernels.
+# Usage (from the repo root, via gpurun): bash scripts/gpu_round.sh <tag>
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
+tail -3 gpurun_out/pytest_$TAG.log
+timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
+cat gpurun_out/bench_$TAG.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_ref_$TAG.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 3 -c 1 -f -o gpurun_out/knn2_full_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 3 -c 1 -f -o gpurun_out/solve_full_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out
