@@ -53,7 +53,9 @@ typedef struct {
     int32_t do_prosac;             /* estimateSVD(..., do_prosac): 1 = growing-prefix shuffle     */
     int32_t ratio_num, ratio_den;  /* keep best iff ratio_den*d0 < ratio_num*d1   (99/100 == :67) */
     int32_t min_keypoints;         /* :47 (7)                                                    */
-    int32_t cross_check;           /* opt-in mutual-nearest filter; the reference has none (0)    */
+    int32_t cross_check;           /* opt-in (reference: none, 0): keep a ratio survivor (q,t) only if q is also the
+                                      nearest query row of t, lowest index on ties == cv::BFMatcher(crossCheck=true);
+                                      runs every matching a second time, reversed                  */
 } uz_params;
 
 /* One FeatureData (graph_slam_common/include/graph_slam_common/sensor_data.h:49-70) as borrowed POD. */

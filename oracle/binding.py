@@ -62,6 +62,18 @@ def knn2(q, t):
     return idx, dist
 
 
+def cross_match(q, t):
+    """cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match(q, t) as (idx[nq], dist[nq]); -1 = query unmatched."""
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    nq = q.shape[0]
+    nb = q.shape[1]
+    idx = np.empty(nq, np.int32)
+    dist = np.empty(nq, np.int32)
+    lib().uzo_cross_match(_p(q), nq, nb, _p(t), t.shape[0], nb, nb, _p(idx), _p(dist))
+    return idx, dist
+
+
 def ratio_pass(d0, d1):
     return bool(lib().uzo_ratio_pass(int(d0), int(d1)))
 
@@ -136,7 +148,7 @@ def make_features(cams):
 
 
 def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac=True, min_keypoints=7,
-                  want_debug=True):
+                  want_debug=True, cross_check=False):
     """estimateEdgeDirect over two keyframes (lists of camera dicts)."""
     fa, k1 = make_features(cams_from)
     ta, k2 = make_features(cams_to)
@@ -148,7 +160,7 @@ def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac
     lib().uzo_estimate_edge(fa, len(cams_from), ta, len(cams_to), C.c_double(thr), int(iterations),
                             C.c_double(bp), int(bool(do_prosac)), int(min_keypoints), C.byref(e),
                             _p(matches) if want_debug else None, _p(mask) if want_debug else None, maxm,
-                            _p(counts))
+                            _p(counts), int(bool(cross_check)))
     M = e.n_matches
     return dict(ok=bool(e.ok), cam_from=e.cam_from, cam_to=e.cam_to, n_ratio_matches=e.n_ratio_matches,
                 n_matches=M, consensus=e.consensus, best_iteration=e.best_iteration,

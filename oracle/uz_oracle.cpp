@@ -86,6 +86,26 @@ inline bool ratio_pass(int d0, int d1) {
 
 struct Match { int q, t, d; };
 
+// Opt-in cross-check (uz_params.cross_check; NOT in the reference, which never enables it): what
+// cv::BFMatcher(normType, crossCheck=true).match(query, train) returns — mutual nearest neighbours: (q, t) with
+// t the nearest train row of q and q the nearest query row of t, both with lowest-index tie breaking.
+// idx/dist: nq entries, -1 = query unmatched.  Pinned against live cv2 4.13 in tests/test_oracle_matching.py.
+void cross_match(const uint8_t* q, int nq, int qstride, const uint8_t* t, int nt, int tstride, int nbytes,
+                 int32_t* idx, int32_t* dist) {
+    std::vector<int> best_q((size_t)nt, -1), best_qd((size_t)nt, INT32_MAX);
+    for (int i = 0; i < nq; ++i) { idx[i] = -1; dist[i] = INT32_MAX; }
+    for (int i = 0; i < nq; ++i) {
+        const uint8_t* qi = q + (size_t)i * qstride;
+        for (int j = 0; j < nt; ++j) {
+            int d = hamming(qi, t + (size_t)j * tstride, nbytes);
+            if (d < dist[i]) { dist[i] = d; idx[i] = j; }               // nearest train of q (lowest j on ties)
+            if (d < best_qd[j]) { best_qd[j] = d; best_q[j] = i; }      // nearest query of t (lowest i on ties)
+        }
+    }
+    for (int i = 0; i < nq; ++i)
+        if (idx[i] < 0 || best_q[idx[i]] != i) { idx[i] = -1; dist[i] = -1; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stage 3: pose from correspondences (:299-314) — PCL add()/getTransformation() in float32.
 // ---------------------------------------------------------------------------------------------
@@ -384,6 +404,12 @@ int uzo_knn2(const uint8_t* q, int nq, int qstride, const uint8_t* t, int nt, in
     return 0;
 }
 
+int uzo_cross_match(const uint8_t* q, int nq, int qstride, const uint8_t* t, int nt, int tstride, int nbytes,
+                    int32_t* idx, int32_t* dist) {
+    cross_match(q, nq, qstride, t, nt, tstride, nbytes, idx, dist);
+    return 0;
+}
+
 int uzo_ratio_pass(int d0, int d1) { return ratio_pass(d0, d1) ? 1 : 0; }
 
 void uzo_sample_list(int M, int iterations, int do_prosac, int32_t* out) {
@@ -436,7 +462,7 @@ void uzo_estimate_svd(const double* P, const double* Q, int M, double thr, int i
 void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features* to, int n_to,
                        double thr, int iterations, double bp, int do_prosac, int min_keypoints,
                        uzo_edge* edge, int32_t* matches_out, uint8_t* inlier_mask, int max_matches,
-                       int32_t* counts_out) {
+                       int32_t* counts_out, int cross_check) {
     static const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     std::memset(edge, 0, sizeof(*edge));
     std::memcpy(edge->T, I4, sizeof(I4));
@@ -459,9 +485,15 @@ void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features*
                     std::vector<int32_t> idx(2 * (size_t)Tt.n), dist(2 * (size_t)Tt.n);
                     knn2(Tt.descriptors, Tt.n, Tt.desc_stride, F.descriptors, F.n, F.desc_stride,
                          F.desc_bytes, idx.data(), dist.data());
+                    std::vector<int32_t> xidx, xdist;
+                    if (cross_check) {     // opt-in, not in the reference: keep (q, t) only if the crossCheck matcher returns it
+                        xidx.resize((size_t)Tt.n); xdist.resize((size_t)Tt.n);
+                        cross_match(Tt.descriptors, Tt.n, Tt.desc_stride, F.descriptors, F.n, F.desc_stride,
+                                    F.desc_bytes, xidx.data(), xdist.data());
+                    }
                     for (int q = 0; q < Tt.n; ++q) {
                         if (idx[2 * q] >= 0 && idx[2 * q + 1] >= 0) {                 // size() == 2
-                            if (ratio_pass(dist[2 * q], dist[2 * q + 1]))
+                            if (ratio_pass(dist[2 * q], dist[2 * q + 1]) && (!cross_check || xidx[q] == idx[2 * q]))
                                 matches.push_back(Match{q, idx[2 * q], dist[2 * q]});
                         }
                     }

@@ -284,6 +284,38 @@ def test_edge_params(est, oracle, params):
         est.setConfig(ransac_threshold=0.1, break_percentage=0.6, ransac_iterations=100, do_prosac=1)
 
 
+@pytest.mark.parametrize("n,seed,kw", [(500, 70, {}), (1000, 71, dict(tie_stress=True)), (300, 72, dict(rho=0.9)),
+                                       (1500, 73, dict(gross_outlier_frac=0.4))])
+def test_edge_cross_check(est, oracle, n, seed, kw):
+    """opt-in mutual filter (uz_params.cross_check): the reversed matching runs through the same kernel"""
+    f, t, _ = S.make_pair(n, seed=seed, **kw)
+    try:
+        est.setConfig(cross_check=1)
+        est.set_debug(True)
+        r = est.estimateEdgeDirect([f], [t])
+        o = oracle.estimate_edge([f], [t], cross_check=True)
+        _check_edge(r, o, f"cross n={n}")
+        m, mask = est.debug_pair(0, r["n_matches"])
+        assert np.array_equal(m, o["matches"])
+        if o["ok"]:
+            assert np.array_equal(mask, o["inlier_mask"])
+        plain = oracle.estimate_edge([f], [t])
+        assert o["n_ratio_matches"] <= plain["n_ratio_matches"]
+        # rigs + store path with the filter on
+        cams_f, cams_t = [], []
+        for cam in range(2):
+            a, b, _ = S.make_pair(300 + 100 * cam, seed=seed + 5 + cam, sensor_frame=cam)
+            cams_f.append(a); cams_t.append(b)
+        est.clear()
+        h = est.add_keyframes([cams_f, cams_t])
+        rr = est.estimateEdges([h[0]], [h[1]])[0]
+        _check_edge(rr, oracle.estimate_edge(cams_f, cams_t, cross_check=True), "cross rig")
+    finally:
+        est.set_debug(False)
+        est.setConfig(cross_check=0)
+        est.clear()
+
+
 def test_batch_is_order_independent_and_deterministic(est):
     kfs, pairs, _ = S.make_map(30, n_features=500, cluster=6, pool=500, n_shared=300, k_candidates=4,
                                cross_cluster=1, seed=9)

@@ -57,3 +57,38 @@ def test_ratio_predicate_equals_integer_form(oracle):
     for d1 in range(0, 257):
         for d0 in range(0, d1 + 1):
             assert oracle.ratio_pass(d0, d1) == (100 * d0 < 99 * d1), (d0, d1)
+
+
+def _cv2_cross(q, t):
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(q, t)
+    idx = np.full(len(q), -1, np.int32)
+    dist = np.full(len(q), -1, np.int32)
+    for d in m:
+        idx[d.queryIdx] = d.trainIdx
+        dist[d.queryIdx] = int(d.distance)
+    return idx, dist
+
+
+@pytest.mark.parametrize("nq,nt,keep", [(500, 500, 32), (300, 700, 32), (700, 300, 32), (400, 600, 2), (600, 400, 1),
+                                        (5, 1, 32), (1, 5, 32)])
+def test_oracle_cross_check_matches_cv2(oracle, nq, nt, keep):
+    """The opt-in cross-check (uz_params.cross_check) is OpenCV's crossCheck matcher, tie rules included."""
+    rng = np.random.default_rng(7 * nq + nt + keep)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q[:, keep:] = 0
+    t[:, keep:] = 0
+    oi, od = oracle.cross_match(q, t)
+    ci, cd = _cv2_cross(q, t)
+    assert np.array_equal(oi, ci) and np.array_equal(od, cd)
+
+
+def test_oracle_cross_check_edge_is_a_subset_filter(oracle):
+    """edge-level definition: a ratio survivor (q, t) stays iff the crossCheck matcher returns (q, t)"""
+    f, t, _ = S.make_pair(600, seed=77, tie_stress=True)
+    a = oracle.estimate_edge([f], [t])
+    b = oracle.estimate_edge([f], [t], cross_check=True)
+    ci, _ = _cv2_cross(t["desc"], f["desc"])
+    keep = [tuple(m) for m in a["matches"] if ci[m[0]] == m[1]]
+    assert 0 < len(keep) < len(a["matches"])
+    assert sorted(keep) == sorted(tuple(m) for m in b["matches"])

@@ -424,7 +424,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     // 1. enumerate matchings (:40-49) and pick the tile shape
     size_t max_tasks = 0;
     for (const PairRef& p : pairs) max_tasks += p.from->cams.size() * p.to->cams.size();
-    UZ_CUDA(ctx, sl.h_tasks.ensure(std::max<size_t>(max_tasks, 1) * sizeof(MatchTask)));
+    const bool cross = prm.cross_check != 0 && d_results != nullptr;
+    // with cross-check every matching is also run reversed; the reversed tasks live behind the forward ones
+    UZ_CUDA(ctx, sl.h_tasks.ensure(std::max<size_t>(max_tasks, 1) * (cross ? 2 : 1) * sizeof(MatchTask)));
     UZ_CUDA(ctx, sl.h_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
     MatchTask* tasks = (MatchTask*)sl.h_tasks.p;
     int2* pair_tasks = (int2*)sl.h_pair_tasks.p;
@@ -449,12 +451,29 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
                     tk.key_off = (uint32_t)key_rows; tk.pair = i;
                     tk.q_pos = T.pos; tk.q_valid = T.valid; tk.t_pos = F.pos; tk.t_valid = F.valid;
                     tk.cam_from = (int)a; tk.cam_to = (int)b;
+                    tk.rev_key_off = kNoRev; tk.pad_ = 0;
                     key_rows += (size_t)tk.nq;
                     max_nq = std::max(max_nq, tk.nq);
                     compares += (int64_t)tk.nq * tk.nt;
                 }
             }
         pair_tasks[i] = make_int2(first, (int)n_tasks - first);
+    }
+    const size_t n_fwd = n_tasks;
+    if (cross) {
+        for (size_t t = 0; t < n_fwd; ++t) {
+            MatchTask& f = tasks[t];
+            if (f.nq == 0) continue;                 // non-binary type: no matches to check
+            MatchTask& r = tasks[n_tasks];
+            r = f;
+            r.q_desc = f.t_desc; r.t_desc = f.q_desc; r.nq = f.nt; r.nt = f.nq;
+            r.key_off = (uint32_t)key_rows; r.rev_key_off = kNoRev;
+            f.rev_key_off = r.key_off;
+            key_rows += (size_t)r.nq;
+            compares += (int64_t)r.nq * r.nt;
+            f.pad_ = (uint32_t)n_tasks;              // index of the reversed task (host-side only)
+            ++n_tasks;
+        }
     }
     if (key_rows >= ((size_t)1 << 32)) return fail(ctx, UZ_ERR_INVALID, "batch too large: split it (key scratch > 2^32 rows)");
 
@@ -480,8 +499,13 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     int2* tiles = (int2*)sl.h_tiles.p;
     {
         size_t k = 0;
-        for (size_t t = 0; t < n_tasks; ++t)
+        for (size_t t = 0; t < n_fwd; ++t) {         // forward tiles, then the reversed tiles of the same matching
             for (int q0 = 0; q0 < tasks[t].nq; q0 += tile_rows) tiles[k++] = make_int2((int)t, q0);
+            if (tasks[t].rev_key_off != kNoRev) {
+                const int r = (int)tasks[t].pad_;
+                for (int q0 = 0; q0 < tasks[r].nq; q0 += tile_rows) tiles[k++] = make_int2(r, q0);
+            }
+        }
     }
 
     // 2. device buffers
@@ -613,7 +637,7 @@ uz_status check_ctx(uz_context* ctx) {
 uz_status validate_params(uz_context* ctx, const uz_params* p) {
     if (p->ransac_iterations < 1 || p->ransac_iterations > UZ_MAX_ITERATIONS) return fail(ctx, UZ_ERR_INVALID, "ransac_iterations out of range");
     if (p->ratio_den <= 0 || p->ratio_num < 0 || p->ratio_den > 4096 || p->ratio_num > 4096) return fail(ctx, UZ_ERR_INVALID, "ratio out of range");
-    if (p->cross_check) return fail(ctx, UZ_ERR_UNSUPPORTED, "cross_check is not implemented yet (the reference has none)");
+    if (p->cross_check != 0 && p->cross_check != 1) return fail(ctx, UZ_ERR_INVALID, "cross_check must be 0 or 1");
     if (p->min_keypoints < 0) return fail(ctx, UZ_ERR_INVALID, "min_keypoints < 0");
     return UZ_OK;
 }

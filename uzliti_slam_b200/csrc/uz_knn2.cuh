@@ -41,7 +41,10 @@ struct MatchTask {
     const double* q_pos; const uint8_t* q_valid;   // to
     const double* t_pos; const uint8_t* t_valid;   // from
     int32_t cam_from, cam_to;
+    uint32_t rev_key_off;     // cross-check: first keys row of the REVERSED matching (query = from, train = to), kNoRev = off
+    uint32_t pad_;
 };
+constexpr uint32_t kNoRev = 0xFFFFFFFFu;
 
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

@@ -91,6 +91,16 @@ __device__ __forceinline__ float block_max(float v, float* s_red /* [THREADS/32]
     return r;
 }
 
+// Ratio test (:65-71) of query row q, plus the opt-in cross-check (uz_params.cross_check; the reference has none):
+// the survivor (q, t = best train of q) is kept only if q is also the best query of t in the reversed matching,
+// ties by lowest index - i.e. (q, t) is what cv::BFMatcher(NORM_HAMMING, crossCheck=true).match() returns for q.
+__device__ __forceinline__ bool match_survives(const uint2 m, int q, int ratio_num, int ratio_den,
+                                               const uint2* __restrict__ keys, uint32_t rev_key_off) {
+    bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * ratio_den < (int)(m.y >> 16) * ratio_num);
+    if (pass && rev_key_off != kNoRev) pass = (int)(keys[rev_key_off + (m.x & 0xFFFFu)].x & 0xFFFFu) == q;
+    return pass;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __restrict__ tasks,
                                                         const int2* __restrict__ pair_tasks,
@@ -142,10 +152,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                 for (int base = 0; base < tk->nq; base += THREADS) {
                     const int q = base + tid;
                     bool pass = false;
-                    if (q < tk->nq) {
-                        const uint2 m = k[q];
-                        pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
-                    }
+                    if (q < tk->nq) pass = match_survives(k[q], q, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
                     cnt += __syncthreads_count(pass);
                 }
                 if (cnt > best_score) { best_score = cnt; best = t; }   // :81 strict '>' keeps the first
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         __syncthreads();
         for (int i = tid; i < nq; i += THREADS) {
             const uint2 m = k[i];
-            const bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * prm.ratio_den < (int)(m.y >> 16) * prm.ratio_num);
+            const bool pass = match_survives(m, i, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
             uint16_t d = 0xFFFFu;
             if (pass) {
                 atomicAdd(&s_nratio, 1);
