@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/uzliti_edge.h"
@@ -57,6 +58,30 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Bump pools for per-call scratch that several in-flight copies/kernels read (copy-chunk tables): blocks stay
+// alive until reset(), which the entry points call only when the stream is known to be idle.
+template <bool PINNED_HOST>
+struct BumpPool {
+    struct Block { uint8_t* base; size_t size, used; };
+    std::vector<Block> blocks;
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto& b : blocks)
+            if (b.size - b.used >= bytes) { void* r = b.base + b.used; b.used += bytes; return r; }
+        const size_t sz = std::max(bytes, (size_t)1 << 20);
+        void* p = nullptr;
+        const cudaError_t e = PINNED_HOST ? cudaMallocHost(&p, sz) : cudaMalloc(&p, sz);
+        if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        blocks.push_back(Block{(uint8_t*)p, sz, bytes});
+        return p;
+    }
+    void reset() { for (auto& b : blocks) b.used = 0; }
+    void release() {
+        for (auto& b : blocks) { if (PINNED_HOST) cudaFreeHost(b.base); else cudaFree(b.base); }
+        blocks.clear();
+    }
+};
+
 // Bump allocator over large device chunks (HBM3e: 180 GB — chunks are cheap, fragmentation is not an issue
 // for append-mostly keyframe maps).  Memory of removed keyframes is reclaimed by uz_store_clear().
 struct Arena {
@@ -93,7 +118,8 @@ struct Keyframe {
     bool live = false;
 };
 
-struct PairRef { const Keyframe* from; const Keyframe* to; };
+// one keyframe pair as two camera spans (store keyframes or transient uploads)
+struct PairRef { const Cam* from; int n_from; const Cam* to; int n_to; };
 
 }  // namespace
 
@@ -120,8 +146,12 @@ struct uz_context {
     std::vector<MappedRange> mapped;
     void* pfn_ptr_attr = nullptr;    // cuPointerGetAttribute via cudaGetDriverEntryPoint (no link-time libcuda)
     int gather_upload = 1;           // UZ_GATHER_UPLOAD=0 forces the cudaMemcpyAsync path
-    DevBuf d_chunks;
-    PinBuf h_chunks;
+    int copy_beside_compute = 0;     // set while uploads are enqueued that overlap the match kernel
+    int copy_ctas = 64;              // UZ_COPY_CTAS
+    int host_chunks = 0;             // UZ_HOST_CHUNKS: upload/compute pipeline depth of uz_estimate_edges_host (0 = auto)
+    BumpPool<false> d_chunks;
+    BumpPool<true> h_chunks;
+    PinBuf h_results;                // pinned landing zone of the edge records of uz_estimate_edges_host
 
     // sample table
     DevBuf d_samples;
@@ -303,9 +333,9 @@ uz_status flush_runs(uz_context* ctx, const std::vector<Run>& runs) {
     size_t n_chunks = 0;
     for (const Run& r : runs) n_chunks += (r.bytes + kChunk - 1) / kChunk;
     if (n_chunks == 0) return UZ_OK;
-    UZ_CUDA(ctx, ctx->h_chunks.ensure(n_chunks * sizeof(CopyChunk)));
-    UZ_CUDA(ctx, ctx->d_chunks.ensure(n_chunks * sizeof(CopyChunk)));
-    CopyChunk* cc = (CopyChunk*)ctx->h_chunks.p;
+    CopyChunk* cc = (CopyChunk*)ctx->h_chunks.alloc(n_chunks * sizeof(CopyChunk));
+    CopyChunk* d_cc = (CopyChunk*)ctx->d_chunks.alloc(n_chunks * sizeof(CopyChunk));
+    if (!cc || !d_cc) return fail(ctx, UZ_ERR_NOMEM, "copy-chunk table allocation failed");
     size_t k = 0;
     for (size_t i = 0; i < runs.size(); ++i)
         for (size_t off = 0; off < runs[i].bytes; off += kChunk) {
@@ -315,8 +345,11 @@ uz_status flush_runs(uz_context* ctx, const std::vector<Run>& runs) {
             cc[k].pad = 0;
             ++k;
         }
-    UZ_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunks.p, cc, n_chunks * sizeof(CopyChunk), cudaMemcpyHostToDevice, ctx->stream));
-    gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>((const CopyChunk*)ctx->d_chunks.p);
+    UZ_CUDA(ctx, cudaMemcpyAsync(d_cc, cc, n_chunks * sizeof(CopyChunk), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->copy_beside_compute)      // few small CTAs: they fit in the registers the match kernel leaves free
+        gather_copy_kernel<<<(unsigned)std::min<size_t>(n_chunks, (size_t)ctx->copy_ctas), 128, 0, ctx->stream>>>(d_cc, (int)n_chunks);
+    else
+        gather_copy_kernel<<<(unsigned)std::min<size_t>(n_chunks, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_cc, (int)n_chunks);
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     return UZ_OK;
@@ -423,7 +456,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
 
     // 1. enumerate matchings (:40-49) and pick the tile shape
     size_t max_tasks = 0;
-    for (const PairRef& p : pairs) max_tasks += p.from->cams.size() * p.to->cams.size();
+    for (const PairRef& p : pairs) max_tasks += (size_t)p.n_from * (size_t)p.n_to;
     const bool cross = prm.cross_check != 0 && d_results != nullptr;
     // with cross-check every matching is also run reversed; the reversed tasks live behind the forward ones
     UZ_CUDA(ctx, sl.h_tasks.ensure(std::max<size_t>(max_tasks, 1) * (cross ? 2 : 1) * sizeof(MatchTask)));
@@ -435,10 +468,10 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     int64_t compares = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const int first = (int)n_tasks;
-        const auto& fc = pairs[i].from->cams;
-        const auto& tc = pairs[i].to->cams;
-        for (size_t a = 0; a < fc.size(); ++a)
-            for (size_t b = 0; b < tc.size(); ++b) {
+        const Cam* fc = pairs[i].from;
+        const Cam* tc = pairs[i].to;
+        for (int a = 0; a < pairs[i].n_from; ++a)
+            for (int b = 0; b < pairs[i].n_to; ++b) {
                 const Cam& F = fc[a];
                 const Cam& T = tc[b];
                 if (F.n >= prm.min_keypoints && T.n >= prm.min_keypoints && F.feature_type == T.feature_type &&
@@ -689,6 +722,10 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (fc) ctx->force_cfg = atoi(fc);
         const char* gu = getenv("UZ_GATHER_UPLOAD");
         if (gu) ctx->gather_upload = atoi(gu);
+        const char* cc = getenv("UZ_COPY_CTAS");
+        if (cc && atoi(cc) > 0) ctx->copy_ctas = atoi(cc);
+        const char* hc = getenv("UZ_HOST_CHUNKS");
+        if (hc) ctx->host_chunks = atoi(hc);
     }
     e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)solve_smem_bytes(UZ_MAX_FEATURES));
@@ -707,7 +744,7 @@ void uz_destroy(uz_context* ctx) {
         sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release();
         if (sl.done) cudaEventDestroy(sl.done);
     }
-    ctx->d_samples.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release();
+    ctx->d_samples.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release(); ctx->h_results.release();
     ctx->d_misc.release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
@@ -758,6 +795,8 @@ uz_status uz_store_add_bulk(uz_context* ctx, const uz_features* cams, const int3
     std::vector<const uz_features*> feats(total);
     for (size_t i = 0; i < total; ++i) feats[i] = cams + i;
     std::vector<Cam> up;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
     st = upload_cams(ctx, ctx->store_arena, feats, up);
     if (st != UZ_OK) return st;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host buffers are borrowed only for the call
@@ -840,7 +879,7 @@ uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32
     if ((st = up(train, nt, t_stride, kt.cams[0])) != UZ_OK) return st;
     uz_params saved = ctx->params;
     ctx->params.min_keypoints = 0;
-    std::vector<PairRef> pairs(1, PairRef{&kt, &kq});
+    std::vector<PairRef> pairs(1, PairRef{kt.cams.data(), 1, kq.cams.data(), 1});
     st = run_pairs(ctx, pairs, nullptr);
     ctx->params = saved;
     if (st != UZ_OK) return st;
@@ -989,7 +1028,7 @@ static uz_status pairs_from_handles(uz_context* ctx, const int32_t* from_handles
         const int32_t a = from_handles[i], b = to_handles[i];
         if (a < 0 || a >= nk || b < 0 || b >= nk || !ctx->kfs[a].live || !ctx->kfs[b].live)
             return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle in pair list");
-        pairs[i] = PairRef{&ctx->kfs[a], &ctx->kfs[b]};
+        pairs[i] = PairRef{ctx->kfs[a].cams.data(), (int)ctx->kfs[a].cams.size(), ctx->kfs[b].cams.data(), (int)ctx->kfs[b].cams.size()};
     }
     return UZ_OK;
 }
@@ -1029,61 +1068,138 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     Trace tr("estimate_edges_host");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
-    // unique cameras by (descriptor pointer, positions pointer, n): a keyframe that appears in many pairs
-    // (one query vs many candidates) is uploaded once
-    struct Key { const void* d; const void* p; int n; size_t slot; const uz_features* f; };
-    std::vector<Key> keys;
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
     size_t tf = 0, tt = 0;
     for (int i = 0; i < n_pairs; ++i) {
         if (n_from[i] < 0 || n_to[i] < 0) return fail(ctx, UZ_ERR_INVALID, "negative camera count");
         tf += (size_t)n_from[i]; tt += (size_t)n_to[i];
     }
     if ((tf && !from_cams) || (tt && !to_cams)) return fail(ctx, UZ_ERR_INVALID, "null camera array");
-    keys.reserve(tf + tt);
-    for (size_t i = 0; i < tf; ++i) keys.push_back(Key{from_cams[i].descriptors, from_cams[i].positions, from_cams[i].n, i, from_cams + i});
-    for (size_t i = 0; i < tt; ++i) keys.push_back(Key{to_cams[i].descriptors, to_cams[i].positions, to_cams[i].n, tf + i, to_cams + i});
-    std::vector<size_t> order(keys.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-    auto less = [&](size_t a, size_t b) {
-        const Key& x = keys[a]; const Key& y = keys[b];
-        if (x.d != y.d) return x.d < y.d;
-        if (x.p != y.p) return x.p < y.p;
-        if (x.n != y.n) return x.n < y.n;
-        if (x.f->valid_3d != y.f->valid_3d) return x.f->valid_3d < y.f->valid_3d;
-        if (x.f->desc_stride != y.f->desc_stride) return x.f->desc_stride < y.f->desc_stride;
-        if (x.f->feature_type != y.f->feature_type) return x.f->feature_type < y.f->feature_type;
-        return x.f->sensor_frame < y.f->sensor_frame;
+
+    // The batch is cut into chunks of pairs.  Chunk c's cameras are uploaded on the high-priority side stream while
+    // chunk c-1 is matched and solved on the main stream, so only the first chunk's H2D time is exposed.
+    int n_chunks = ctx->host_chunks;
+    if (n_chunks <= 0) n_chunks = n_pairs >= 8192 ? 4 : (n_pairs >= 2048 ? 2 : 1);
+    n_chunks = std::max(1, std::min(n_chunks, n_pairs));
+    if (ctx->debug) n_chunks = 1;        // the parity taps describe ONE launch pair
+
+    // unique cameras (a keyframe that appears in many pairs - one query vs many candidates - is uploaded once),
+    // numbered in order of first use so that every chunk uploads exactly the cameras nobody before it needed
+    struct CamKey {
+        const void* d; const void* p; const void* v; int32_t n, stride, type, frame;
+        bool operator==(const CamKey& o) const {
+            return d == o.d && p == o.p && v == o.v && n == o.n && stride == o.stride && type == o.type && frame == o.frame;
+        }
     };
-    auto same = [&](size_t a, size_t b) { return !less(a, b) && !less(b, a); };
-    std::sort(order.begin(), order.end(), less);
+    struct CamKeyHash {
+        size_t operator()(const CamKey& k) const {
+            uint64_t h = (uint64_t)(uintptr_t)k.d * 0x9E3779B97F4A7C15ull;
+            h ^= ((uint64_t)(uintptr_t)k.p + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+            h ^= (uint64_t)(uint32_t)k.n * 0x165667B19E3779F9ull + (uint64_t)(uint32_t)k.frame;
+            return (size_t)(h ^ (h >> 29));
+        }
+    };
+    std::unordered_map<CamKey, uint32_t, CamKeyHash> seen;
+    seen.reserve((tf + tt) * 2);
     std::vector<const uz_features*> uniq;
-    std::vector<size_t> slot_to_uniq(keys.size());
-    for (size_t i = 0; i < order.size(); ++i) {
-        if (i == 0 || !same(order[i - 1], order[i])) uniq.push_back(keys[order[i]].f);
-        slot_to_uniq[keys[order[i]].slot] = uniq.size() - 1;
+    std::vector<uint32_t> from_u(tf), to_u(tt);
+    std::vector<size_t> chunk_uniq_end((size_t)n_chunks), chunk_pair_end((size_t)n_chunks);
+    auto intern = [&](const uz_features* f) -> uint32_t {
+        const CamKey k{f->descriptors, f->positions, f->valid_3d, f->n, f->desc_stride, f->feature_type, f->sensor_frame};
+        auto it = seen.find(k);
+        if (it != seen.end()) return it->second;
+        const uint32_t id = (uint32_t)uniq.size();
+        seen.emplace(k, id);
+        uniq.push_back(f);
+        return id;
+    };
+    {
+        size_t cf = 0, ct = 0;
+        int c = 0;
+        for (int i = 0; i < n_pairs; ++i) {
+            for (int k = 0; k < n_from[i]; ++k, ++cf) from_u[cf] = intern(from_cams + cf);
+            for (int k = 0; k < n_to[i]; ++k, ++ct) to_u[ct] = intern(to_cams + ct);
+            if (i + 1 == (int)((int64_t)n_pairs * (c + 1) / n_chunks)) {
+                chunk_uniq_end[c] = uniq.size(); chunk_pair_end[c] = (size_t)i + 1;
+                ++c;
+            }
+        }
     }
     tr.lap("dedupe");
-    std::vector<Cam> up;
-    st = upload_cams(ctx, ctx->transient, uniq, up);
-    if (st != UZ_OK) return st;
+
+    // enqueue every chunk's upload (+ CSA pass) on the side stream, one event behind each
+    cudaStream_t main_stream = ctx->stream;
+    const bool piped = n_chunks > 1 && ctx->side != nullptr;
+    std::vector<Cam> up(uniq.size());
+    std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr);
+    if (piped) {            // the side stream must not run ahead of work the caller queued on the main stream
+        cudaEvent_t ev = ctx->get_event();
+        UZ_CUDA(ctx, cudaEventRecord(ev, main_stream));
+        UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ev, 0));
+        ctx->event_pool.push_back(ev);
+        ctx->stream = ctx->side;
+    }
+    for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
+        const size_t u0 = c ? chunk_uniq_end[c - 1] : 0, u1 = chunk_uniq_end[c];
+        std::vector<const uz_features*> part(uniq.begin() + u0, uniq.begin() + u1);
+        std::vector<Cam> got;
+        ctx->copy_beside_compute = piped && c > 0;       // chunk 0 has the chip to itself
+        st = upload_cams(ctx, ctx->transient, part, got);
+        ctx->copy_beside_compute = 0;
+        if (st != UZ_OK) break;
+        std::copy(got.begin(), got.end(), up.begin() + u0);
+        if (piped) {
+            ready[c] = ctx->get_event();
+            if (cudaEventRecord(ready[c], ctx->stream) != cudaSuccess) { st = fail(ctx, UZ_ERR_CUDA, "cudaEventRecord failed"); break; }
+        }
+    }
+    ctx->stream = main_stream;
+    if (st != UZ_OK) { for (auto e : ready) if (e) ctx->event_pool.push_back(e); return st; }
     tr.lap("upload_cams (enqueue)");
-    std::vector<Keyframe> kfs((size_t)n_pairs * 2);
+
+    std::vector<Cam> fcams(tf), tcams(tt);
+    for (size_t i = 0; i < tf; ++i) fcams[i] = up[from_u[i]];
+    for (size_t i = 0; i < tt; ++i) tcams[i] = up[to_u[i]];
     std::vector<PairRef> pairs((size_t)n_pairs);
-    size_t cf = 0, ct = 0;
-    for (int i = 0; i < n_pairs; ++i) {
-        Keyframe& a = kfs[2 * (size_t)i];
-        Keyframe& b = kfs[2 * (size_t)i + 1];
-        a.cams.resize((size_t)n_from[i]); b.cams.resize((size_t)n_to[i]);
-        for (int k = 0; k < n_from[i]; ++k) a.cams[k] = up[slot_to_uniq[cf++]];
-        for (int k = 0; k < n_to[i]; ++k) b.cams[k] = up[slot_to_uniq[tf + ct++]];
-        pairs[i] = PairRef{&a, &b};
+    {
+        size_t cf = 0, ct = 0;
+        for (int i = 0; i < n_pairs; ++i) {
+            pairs[i] = PairRef{fcams.data() + cf, n_from[i], tcams.data() + ct, n_to[i]};
+            cf += (size_t)n_from[i]; ct += (size_t)n_to[i];
+        }
     }
     tr.lap("pair refs");
     UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
-    st = run_pairs(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
-    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, ctx->h_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
+    uz_edge_result* h_res = (uz_edge_result*)ctx->h_results.p;
+    std::vector<cudaEvent_t> home((size_t)n_chunks, nullptr);
+    for (int c = 0; c < n_chunks; ++c) {
+        const size_t p0 = c ? chunk_pair_end[c - 1] : 0, p1 = chunk_pair_end[c];
+        if (piped) {
+            cudaStreamWaitEvent(ctx->stream, ready[c], 0);
+            ctx->event_pool.push_back(ready[c]);
+            ready[c] = nullptr;
+        }
+        if (p1 > p0 && st == UZ_OK) {
+            std::vector<PairRef> part(pairs.begin() + p0, pairs.begin() + p1);
+            st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0);
+            // records come home chunk by chunk behind their solve kernel, into pinned memory (a pageable
+            // destination would make the copy synchronous and stall the enqueue of the next chunk)
+            if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
+                                               cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
+            if (st == UZ_OK) { home[c] = ctx->get_event(); cudaEventRecord(home[c], ctx->stream); }
+        }
+    }
     tr.lap("run_pairs (enqueue)");
-    UZ_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int c = 0; c < n_chunks; ++c) {
+        if (!home[c]) continue;
+        const size_t p0 = c ? chunk_pair_end[c - 1] : 0, p1 = chunk_pair_end[c];
+        if (st == UZ_OK && cudaEventSynchronize(home[c]) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "cudaEventSynchronize failed");
+        if (st == UZ_OK) memcpy(results + p0, h_res + p0, (p1 - p0) * sizeof(uz_edge_result));
+        ctx->event_pool.push_back(home[c]);
+    }
+    if (st != UZ_OK) { cudaStreamSynchronize(ctx->stream); cudaGetLastError(); return st; }
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tr.lap("wait GPU + D2H");
     return UZ_OK;

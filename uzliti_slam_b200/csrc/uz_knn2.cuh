@@ -254,34 +254,38 @@ __global__ void pack_descriptors_kernel(const uint8_t* __restrict__ src, int n, 
 // cudaMemcpyAsync calls (2 us of driver time each) when a batch references scattered keyframes.
 struct CopyChunk { const uint8_t* src; uint8_t* dst; uint32_t bytes; uint32_t pad; };
 
-__global__ void __launch_bounds__(256) gather_copy_kernel(const CopyChunk* __restrict__ chunks) {
-    const CopyChunk c = chunks[blockIdx.x];
-    const uintptr_t a = (uintptr_t)c.src | (uintptr_t)c.dst;
-    const int tid = threadIdx.x;
-    if ((a & 15) == 0) {
-        const uint4* __restrict__ s = reinterpret_cast<const uint4*>(c.src);
-        uint4* __restrict__ d = reinterpret_cast<uint4*>(c.dst);
-        const int n = (int)(c.bytes >> 4);
-        for (int i = tid; i < n; i += 1024) {          // four independent 16 B loads in flight per thread
-            uint4 v0, v1, v2, v3;
-            v0 = s[i];
-            if (i + 256 < n) v1 = s[i + 256];
-            if (i + 512 < n) v2 = s[i + 512];
-            if (i + 768 < n) v3 = s[i + 768];
-            d[i] = v0;
-            if (i + 256 < n) d[i + 256] = v1;
-            if (i + 512 < n) d[i + 512] = v2;
-            if (i + 768 < n) d[i + 768] = v3;
+__global__ void __launch_bounds__(256) gather_copy_kernel(const CopyChunk* __restrict__ chunks, int n_chunks) {
+    // grid-stride over the chunk table: a full-size grid when nothing else runs, a small persistent grid when the
+    // copy runs beside the match kernel (a PCIe pull needs ~200 KB in flight, not the whole chip)
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+        const CopyChunk c = chunks[ci];
+        const uintptr_t a = (uintptr_t)c.src | (uintptr_t)c.dst;
+        if ((a & 15) == 0) {
+            const uint4* __restrict__ s = reinterpret_cast<const uint4*>(c.src);
+            uint4* __restrict__ d = reinterpret_cast<uint4*>(c.dst);
+            const int n = (int)(c.bytes >> 4);
+            for (int i = tid; i < n; i += 4 * nth) {          // four independent 16 B loads in flight per thread
+                uint4 v0, v1, v2, v3;
+                v0 = s[i];
+                if (i + nth < n) v1 = s[i + nth];
+                if (i + 2 * nth < n) v2 = s[i + 2 * nth];
+                if (i + 3 * nth < n) v3 = s[i + 3 * nth];
+                d[i] = v0;
+                if (i + nth < n) d[i + nth] = v1;
+                if (i + 2 * nth < n) d[i + 2 * nth] = v2;
+                if (i + 3 * nth < n) d[i + 3 * nth] = v3;
+            }
+            for (int i = (n << 4) + tid; i < (int)c.bytes; i += nth) c.dst[i] = c.src[i];
+        } else if ((a & 7) == 0) {
+            const uint2* __restrict__ s = reinterpret_cast<const uint2*>(c.src);
+            uint2* __restrict__ d = reinterpret_cast<uint2*>(c.dst);
+            const int n = (int)(c.bytes >> 3);
+            for (int i = tid; i < n; i += nth) d[i] = s[i];
+            for (int i = (n << 3) + tid; i < (int)c.bytes; i += nth) c.dst[i] = c.src[i];
+        } else {
+            for (int i = tid; i < (int)c.bytes; i += nth) c.dst[i] = c.src[i];
         }
-        for (int i = (n << 4) + tid; i < (int)c.bytes; i += 256) c.dst[i] = c.src[i];
-    } else if ((a & 7) == 0) {
-        const uint2* __restrict__ s = reinterpret_cast<const uint2*>(c.src);
-        uint2* __restrict__ d = reinterpret_cast<uint2*>(c.dst);
-        const int n = (int)(c.bytes >> 3);
-        for (int i = tid; i < n; i += 256) d[i] = s[i];
-        for (int i = (n << 3) + tid; i < (int)c.bytes; i += 256) c.dst[i] = c.src[i];
-    } else {
-        for (int i = tid; i < (int)c.bytes; i += 256) c.dst[i] = c.src[i];
     }
 }
 
