@@ -161,6 +161,45 @@ uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_o
  * hypotheses solved, winner known, refit done, end); profiling tap, debug mode only. */
 uz_status uz_debug_phases(uz_context* ctx, int32_t pair_index, int64_t* clocks8_out);
 
+/* ---- candidate generation (the step before the path) --------------------------- */
+/* place_recognition: LshSetRecognizer (place_recognition/src/lsh_set_recognizer.cpp:46-94,96-165,188-305: 8 hash tables
+ * over descriptor bytes [4k,4k+4), one vote per bucket entry) behind PlaceRecognizer's filters
+ * (place_recognition/src/place_recognizer.cpp:64-118,154-190: live place, |dt| > 5 s, first k, checked_ set), on the
+ * device over keyframes already in the store.  A place's id IS its store handle; stamps are ros::Time in nanoseconds.
+ * Results are (from = recognised older keyframe, to = new keyframe) handle pairs, exactly the pairs the reference feeds
+ * to estimateEdge (graph_slam_node.cpp:512-530), so they can go straight into uz_estimate_edges. */
+typedef struct {
+    double  T;                     /* cfg/PlaceRecognizer.cfg:12; similarity = votes / 8 tables >= T      */
+    int32_t k_nearest_neighbors;   /* cfg/PlaceRecognizer.cfg:10                                          */
+    int32_t min_rows;              /* 150: only keyframes with more descriptors are inserted (:66,:108)   */
+    int32_t min_key_bits;          /* 12 = 3*key_width: matchAndAdd skips keys with popcount <= this (:239) */
+    int64_t min_gap_ns;            /* 5 s: neighbours closer in time are dropped (place_recognizer.cpp:94) */
+} uz_place_params;
+void      uz_default_place_params(uz_place_params* p);     /* iti_slam_launch/yaml/slam.yaml:45-48: k = 20, T = 2 */
+uz_status uz_places_set_params(uz_context* ctx, const uz_place_params* p);
+/* PlaceRecognizer::clear (place_recognizer.cpp:49-62); also forgets the checked_ pairs (handles are recycled). */
+uz_status uz_places_clear(uz_context* ctx);
+/* addNode + searchAndAddPlace for handles[0..n) IN ORDER (keyframe i sees every earlier place, including
+ * handles[0..i)), as one batch.  pairs_out: capacity x 2 int32 (from, to); *n_pairs_out = pairs found (may exceed
+ * capacity: only the first `capacity` are written).  pair_owner_out (optional, capacity): index i of the keyframe. */
+uz_status uz_places_search_and_add(uz_context* ctx, const int32_t* handles, const int64_t* stamps_ns, int32_t n,
+                                   int32_t* pairs_out, int32_t capacity, int32_t* n_pairs_out);
+/* addPlace (place_recognizer.cpp:120-147; resume path graph_slam_node.cpp:148-151): insert without searching,
+ * no popcount filter on the keys. */
+uz_status uz_places_add(uz_context* ctx, const int32_t* handles, const int64_t* stamps_ns, int32_t n);
+/* searchPlace (place_recognizer.cpp:154-190): query without inserting; each query sees every place. */
+uz_status uz_places_search(uz_context* ctx, const int32_t* handles, const int64_t* stamps_ns, int32_t n,
+                           int32_t* pairs_out, int32_t capacity, int32_t* n_pairs_out);
+/* removePlace (place_recognizer.cpp:198-206). */
+uz_status uz_places_remove(uz_context* ctx, int32_t handle);
+int32_t   uz_places_count(const uz_context* ctx);          /* place_count_ (removed places included) */
+/* Parity tap: FastLshSet::match votes of one stored camera against every place (votes_out: uz_places_count ints);
+ * filtered != 0 applies matchAndAdd's popcount filter to the query keys. */
+uz_status uz_places_votes(uz_context* ctx, int32_t handle, int32_t cam, int32_t filtered, int32_t* votes_out,
+                          int32_t capacity);
+/* Device time (ms) of the insert / vote / select kernels of the last uz_places_* call and its bucket-entry visits. */
+uz_status uz_places_last_timing(uz_context* ctx, double* insert_ms, double* vote_ms, double* select_ms);
+
 /* ---- introspection for the bench harness ----------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 int64_t   uz_launch_count(const uz_context* ctx);

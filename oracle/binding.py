@@ -167,3 +167,55 @@ def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac
                 iterations_run=e.iterations_run, mse=e.mse, info_scale=e.info_scale,
                 T=np.array(e.T[:], np.float64).reshape(4, 4), matches=matches[:M].copy(),
                 inlier_mask=mask[:M].astype(bool), counts=counts)
+
+
+class Places:
+    """Sequential CPU restatement of LshSetRecognizer behind PlaceRecognizer's filters (oracle/uz_oracle.cpp, 8f-1).
+    ids are arbitrary integers (the tests use store handles), stamps are nanoseconds."""
+
+    def __init__(self, T=2.0, k=20):
+        L = lib()
+        L.uzo_places_new.restype = C.c_void_p
+        L.uzo_places_free.restype = None
+        L.uzo_places_clear.restype = None
+        L.uzo_places_add.restype = None
+        L.uzo_places_remove.restype = None
+        L.uzo_places_votes.restype = None
+        self.h = C.c_void_p(L.uzo_places_new())
+        self.T, self.k = float(T), int(k)
+
+    def __del__(self):
+        try:
+            lib().uzo_places_free(self.h)
+        except Exception:
+            pass
+
+    def clear(self):
+        lib().uzo_places_clear(self.h)
+
+    def _pairs(self, fn, id_, stamp_ns, cams):
+        arr, keep = make_features(cams)
+        cap = self.k + 8
+        out = np.zeros((cap, 2), np.int64)
+        n = fn(self.h, C.c_longlong(int(id_)), C.c_longlong(int(stamp_ns)), arr, len(cams), C.c_double(self.T),
+               self.k, _p(out), cap)
+        return out[:n].copy()
+
+    def search_and_add(self, id_, stamp_ns, cams):
+        return self._pairs(lib().uzo_places_search_and_add, id_, stamp_ns, cams)
+
+    def search(self, id_, stamp_ns, cams):
+        return self._pairs(lib().uzo_places_search, id_, stamp_ns, cams)
+
+    def add(self, id_, stamp_ns, cams):
+        arr, keep = make_features(cams)
+        lib().uzo_places_add(self.h, C.c_longlong(int(id_)), C.c_longlong(int(stamp_ns)), arr, len(cams))
+
+    def remove(self, id_):
+        lib().uzo_places_remove(self.h, C.c_longlong(int(id_)))
+
+    def votes(self, cam, n_places, filtered=False):
+        arr, keep = make_features([cam])
+        out = np.zeros(max(n_places, 1), np.int32)
+        lib().uzo_places_votes(self.h, arr, int(bool(filtered)), _p(out))
+        return out[:n_places]

@@ -13,6 +13,9 @@
 //     :299-314 estimatePoseSVD     (pcl::TransformationFromCorrespondences, float32, weight==1 bug)
 //     :337-347 consensus3D         (double, strict '<')
 //   /root/reference/transformation_estimation/src/transformation_estimator.cpp:53-55 (score 0 on failure)
+// and of the step before the path (candidate generation):
+//   /root/reference/place_recognition/src/lsh_set_recognizer.cpp:46-94,96-165,188-305 (LshSetRecognizer, FastLshSet/Table)
+//   /root/reference/place_recognition/src/place_recognizer.cpp:73-118,140-190        (searchAndAddPlace / searchPlace filters)
 //
 // Third-party arithmetic restated here (sources are NOT under /root/reference):
 //   * OpenCV cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)  [ROS Indigo => OpenCV 2.4.8; checked live
@@ -40,6 +43,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -548,6 +555,189 @@ void uzo_estimate_edge(const uzo_features* from, int n_from, const uzo_features*
         edge->iterations_run = po.iterations_run;
         edge->ok = 1;
     }
+}
+
+}  // extern "C"
+
+
+// =================================================================================================
+// 8f-1: candidate generation — LshSetRecognizer + PlaceRecognizer filters, sequential restatement.
+// =================================================================================================
+namespace {
+
+// FastLshSet(4): 8 tables keyed by descriptor bytes [4k, 4k+4) (lsh_set_recognizer.cpp:262-268, :190-200);
+// a bucket is the list of place indices, one entry per descriptor row that carried the key (duplicates kept).
+struct PlacesOracle {
+    static const int kTables = 8, kKeyWidth = 4;
+    std::unordered_map<uint32_t, std::vector<int>> tables[kTables];
+    int place_count = 0;                                   // place_recognizer.h: place_count_
+    std::map<int, long long> left;                         // place_id_map_.left : place index -> id (live places)
+    std::map<long long, int> right;                        // place_id_map_.right: id -> place index
+    std::map<long long, long long> time_ns;                // pr_time_map_
+    std::set<std::pair<long long, long long>> checked;     // checked_
+
+    static uint32_t key_of(const uint8_t* d, int k) {
+        uint32_t v;
+        std::memcpy(&v, d + kKeyWidth * k, 4);             // index.b[i] = descriptor[start_byte_ + i] (little endian)
+        return v;
+    }
+    // FastLshSet::add (:276-284): no popcount filter
+    void add(const uint8_t* desc, int n, int stride, int id) {
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < kTables; ++k) tables[k][key_of(desc + (size_t)i * stride, k)].push_back(id);
+    }
+    // FastLshSet::match (:286-294)
+    void match(const uint8_t* desc, int n, int stride, std::vector<int>& votes) {
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < kTables; ++k) {
+                auto it = tables[k].find(key_of(desc + (size_t)i * stride, k));
+                if (it != tables[k].end())
+                    for (int ind : it->second) votes[ind]++;
+            }
+    }
+    // FastLshSet::matchAndAdd (:296-305) with FastLshTable::matchAndAdd's popcount filter (:231-246)
+    void match_and_add(const uint8_t* desc, int n, int stride, int id, std::vector<int>& votes) {
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < kTables; ++k) {
+                const uint32_t key = key_of(desc + (size_t)i * stride, k);
+                if (__builtin_popcount(key) > 3 * kKeyWidth) {
+                    auto& bucket = tables[k][key];
+                    for (int ind : bucket) votes[ind]++;
+                    bucket.push_back(id);
+                }
+            }
+    }
+    // "Get all matches that have more than T similarity" + sort (:72-90).  std::sort is unstable in the reference;
+    // the build fixes the order among equal similarities to ascending place index (stable sort of the ascending scan).
+    static void rank(const std::vector<int>& votes, double T, std::vector<int>& res) {
+        std::vector<std::pair<int, float>> matches;
+        for (int i = 0; i < (int)votes.size(); i++)
+            if (votes[i] > 0) {
+                float similarity = (float)votes[i] / (float)kTables;
+                if (similarity >= T) matches.push_back(std::make_pair(i, similarity));
+            }
+        std::stable_sort(matches.begin(), matches.end(),
+                         [](const std::pair<int, float>& l, const std::pair<int, float>& r) { return l.second > r.second; });
+        for (auto& m : matches) res.push_back(m.first);
+    }
+    // place_recognizer.cpp:91-116: drop unknown/removed places and |dt| <= 5 s, take k, then the checked_ filter
+    int filter(const std::vector<int>& neighbors, long long id, int k_nn, long long* pairs_out, int cap) {
+        std::vector<long long> mapped;
+        int pr_count = 0;
+        for (int nb : neighbors) {
+            auto it = left.find(nb);
+            if (it != left.end()) {
+                const long long dt = time_ns[it->second] - time_ns[id];
+                if ((dt < 0 ? -dt : dt) > 5000000000LL) {
+                    mapped.push_back(it->second);
+                    pr_count++;
+                    if (pr_count >= k_nn) break;
+                }
+            }
+        }
+        int n = 0;
+        for (long long m : mapped) {
+            auto pr = std::make_pair(m, id);
+            if (checked.find(pr) == checked.end()) {
+                if (n < cap) { pairs_out[2 * n] = m; pairs_out[2 * n + 1] = id; }
+                ++n;
+                checked.insert(pr);
+            }
+        }
+        return n;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* uzo_places_new() { return new PlacesOracle(); }
+void uzo_places_free(void* h) { delete (PlacesOracle*)h; }
+
+// PlaceRecognizer::clear (place_recognizer.cpp:49-62).  Like the product, this also forgets checked_ (the reference
+// keeps it; with recycled integer ids that would alias unrelated keyframes — recorded as a deliberate deviation).
+void uzo_places_clear(void* h) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    for (auto& t : o->tables) t.clear();
+    o->place_count = 0; o->left.clear(); o->right.clear(); o->time_ns.clear(); o->checked.clear();
+}
+
+// addNode's pr_time_map_ entry + searchAndAddPlace (place_recognizer.cpp:64-118) over LshSetRecognizer::
+// searchAndAddPlaceImpl (lsh_set_recognizer.cpp:46-94).  cams: the node's FEATURE sensors.  Returns the number of
+// (neighbor id, id) pairs; at most cap are written.
+int uzo_places_search_and_add(void* h, long long id, long long stamp_ns, const uzo_features* cams, int n_cams,
+                              double T, int k_nn, long long* pairs_out, int cap) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    o->time_ns[id] = stamp_ns;
+    if (o->right.find(id) != o->right.end()) return 0;                    // "tried to add existing place"
+    std::vector<int> neighbors;
+    for (int c = 0; c < n_cams; ++c) {
+        std::vector<int> votes(o->place_count + 1, 0);
+        if (cams[c].n > 150) o->match_and_add(cams[c].descriptors, cams[c].n, cams[c].desc_stride, o->place_count, votes);
+        else o->match(cams[c].descriptors, cams[c].n, cams[c].desc_stride, votes);
+        PlacesOracle::rank(votes, T, neighbors);
+    }
+    o->left[o->place_count] = id; o->right[id] = o->place_count;
+    o->place_count++;
+    return o->filter(neighbors, id, k_nn, pairs_out, cap);
+}
+
+// addPlace (place_recognizer.cpp:120-147) over addPlaceImpl (lsh_set_recognizer.cpp:96-119)
+void uzo_places_add(void* h, long long id, long long stamp_ns, const uzo_features* cams, int n_cams) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    o->time_ns[id] = stamp_ns;
+    if (o->right.find(id) != o->right.end()) return;
+    for (int c = 0; c < n_cams; ++c)
+        if (cams[c].n > 150) o->add(cams[c].descriptors, cams[c].n, cams[c].desc_stride, o->place_count);
+    o->left[o->place_count] = id; o->right[id] = o->place_count;
+    o->place_count++;
+}
+
+// searchPlace (place_recognizer.cpp:154-190) over searchImpl (lsh_set_recognizer.cpp:121-165).  The caller's stamp is
+// used for the time filter without being recorded (searchPlace reads pr_time_map_[id]; callers set it beforehand).
+int uzo_places_search(void* h, long long id, long long stamp_ns, const uzo_features* cams, int n_cams, double T, int k_nn,
+                      long long* pairs_out, int cap) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    if (o->left.empty()) return 0;
+    o->time_ns[id] = stamp_ns;
+    std::vector<int> neighbors;
+    for (int c = 0; c < n_cams; ++c) {
+        std::vector<int> votes(o->place_count, 0);
+        o->match(cams[c].descriptors, cams[c].n, cams[c].desc_stride, votes);
+        PlacesOracle::rank(votes, T, neighbors);
+    }
+    return o->filter(neighbors, id, k_nn, pairs_out, cap);
+}
+
+// removePlace (place_recognizer.cpp:198-206).  The bucket entries are left in place: a removed place index is never
+// reported again because filter() looks it up in place_id_map_.left first, which is all removePlaceImpl's erase achieves.
+void uzo_places_remove(void* h, long long id) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    auto it = o->right.find(id);
+    if (it == o->right.end()) return;
+    o->left.erase(it->second);
+    o->right.erase(it);
+    o->time_ns.erase(id);
+}
+
+// votes of one descriptor set against the current tables (FastLshSet::match), for parity taps
+void uzo_places_votes(void* h, const uzo_features* cam, int filtered, int32_t* votes_out /* place_count */) {
+    PlacesOracle* o = (PlacesOracle*)h;
+    std::vector<int> votes(o->place_count + 1, 0);
+    if (filtered) {
+        for (int i = 0; i < cam->n; ++i)
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t key = PlacesOracle::key_of(cam->descriptors + (size_t)i * cam->desc_stride, k);
+                if (__builtin_popcount(key) > 12) {
+                    auto it = o->tables[k].find(key);
+                    if (it != o->tables[k].end()) for (int ind : it->second) votes[ind]++;
+                }
+            }
+    } else {
+        o->match(cam->descriptors, cam->n, cam->desc_stride, votes);
+    }
+    for (int i = 0; i < o->place_count; ++i) votes_out[i] = votes[i];
 }
 
 }  // extern "C"

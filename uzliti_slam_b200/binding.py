@@ -19,6 +19,8 @@ EXPORTED_SYMBOLS = [
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
     "uz_get_timers", "uz_microbench", "uz_version",
+    "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
+    "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
 ]
 
 
@@ -31,6 +33,11 @@ class Params(C.Structure):
                 ("ransac_iterations", C.c_int32), ("do_prosac", C.c_int32),
                 ("ratio_num", C.c_int32), ("ratio_den", C.c_int32),
                 ("min_keypoints", C.c_int32), ("cross_check", C.c_int32)]
+
+
+class PlaceParams(C.Structure):
+    _fields_ = [("T", C.c_double), ("k_nearest_neighbors", C.c_int32), ("min_rows", C.c_int32),
+                ("min_key_bits", C.c_int32), ("min_gap_ns", C.c_int64)]
 
 
 class Features(C.Structure):
@@ -90,8 +97,10 @@ def load_library():
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
-                 "uz_microbench"):
+                 "uz_microbench", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
+                 "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing"):
         getattr(lib, name).restype = C.c_int
+    lib.uz_default_place_params.restype = None
     _lib = lib
     return lib
 
@@ -325,6 +334,64 @@ class EdgeEstimator:
         out = np.zeros(8, np.int64)
         self._check(self.lib.uz_debug_phases(self.ctx, int(pair_index), _p(out)))
         return out
+
+    # ---- candidate generation (PlaceRecognizer / LshSetRecognizer) ---------------------------------
+    def setPlaceConfig(self, **kw):
+        p = PlaceParams()
+        self.lib.uz_default_place_params(C.byref(p))
+        cur = getattr(self, "_place_params", None)
+        if cur is not None:
+            p = cur
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        self._check(self.lib.uz_places_set_params(self.ctx, C.byref(p)))
+        self._place_params = p
+
+    def _places_call(self, fn, handles, stamps_ns, capacity):
+        h = np.ascontiguousarray(handles, np.int32)
+        t = np.ascontiguousarray(stamps_ns, np.int64)
+        assert len(h) == len(t)
+        if capacity is None:
+            k = getattr(self, "_place_params", None)
+            capacity = len(h) * (k.k_nearest_neighbors if k is not None else 20) * 4 + 16
+        pairs = np.zeros((max(capacity, 1), 2), np.int32)
+        n = C.c_int32()
+        self._check(fn(self.ctx, _p(h), _p(t), len(h), _p(pairs), int(capacity), C.byref(n)))
+        return pairs[:min(n.value, capacity)].copy(), n.value
+
+    def searchAndAddPlaces(self, handles, stamps_ns, capacity=None):
+        """addNode + searchAndAddPlace for each keyframe in order -> (from, to) handle pairs [m,2]."""
+        return self._places_call(self.lib.uz_places_search_and_add, handles, stamps_ns, capacity)[0]
+
+    def searchPlaces(self, handles, stamps_ns, capacity=None):
+        return self._places_call(self.lib.uz_places_search, handles, stamps_ns, capacity)[0]
+
+    def addPlaces(self, handles, stamps_ns):
+        h = np.ascontiguousarray(handles, np.int32)
+        t = np.ascontiguousarray(stamps_ns, np.int64)
+        self._check(self.lib.uz_places_add(self.ctx, _p(h), _p(t), len(h)))
+
+    def removePlace(self, handle):
+        self._check(self.lib.uz_places_remove(self.ctx, int(handle)))
+
+    def clearPlaces(self):
+        self._check(self.lib.uz_places_clear(self.ctx))
+
+    def place_count(self):
+        return self.lib.uz_places_count(self.ctx)
+
+    def place_votes(self, handle, cam=0, filtered=False):
+        n = self.place_count()
+        out = np.zeros(max(n, 1), np.int32)
+        self._check(self.lib.uz_places_votes(self.ctx, int(handle), int(cam), int(bool(filtered)), _p(out), n))
+        return out[:n]
+
+    def places_last_timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.uz_places_last_timing(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(insert_ms=a.value, vote_ms=b.value, select_ms=c.value)
 
     # ---- introspection ---------------------------------------------------------------------------
     def launch_count(self):

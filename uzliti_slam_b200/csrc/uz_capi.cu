@@ -17,10 +17,12 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/uzliti_edge.h"
 #include "uz_knn2.cuh"
+#include "uz_places.cuh"
 #include "uz_samples.h"
 #include "uz_solve.cuh"
 
@@ -121,6 +123,22 @@ struct Keyframe {
 // one keyframe pair as two camera spans (store keyframes or transient uploads)
 struct PairRef { const Cam* from; int n_from; const Cam* to; int n_to; };
 
+// Host mirror + device buffers of the place recogniser (uz_places.cuh)
+struct PlaceInfo { int32_t handle; long long stamp_ns; bool live; };
+struct PlacesState {
+    uz_place_params params;
+    std::vector<PlaceInfo> places;                      // index = place index (place_count_ == places.size())
+    std::unordered_map<int32_t, int32_t> by_handle;     // live places only (place_id_map_.right)
+    std::unordered_set<uint64_t> checked;               // checked_: (from handle << 32) | to handle
+    std::vector<PlaceCam> inserted;                     // every camera ever inserted (relink on growth)
+    PlaceSlot* d_slots = nullptr; uint32_t n_slots = 0;
+    PlaceNode* d_nodes = nullptr; size_t node_cap = 0, n_nodes = 0;
+    size_t live_entries = 0;                            // upper bound of distinct keys (for the load factor)
+    long long* d_stamps = nullptr; uint8_t* d_live = nullptr; size_t place_cap = 0;
+    DevBuf d_cams, d_votes, d_out, d_out_votes;
+    int64_t last_votes_bytes = 0;
+};
+
 }  // namespace
 
 struct uz_context {
@@ -148,6 +166,8 @@ struct uz_context {
     int gather_upload = 1;           // UZ_GATHER_UPLOAD=0 forces the cudaMemcpyAsync path
     int copy_beside_compute = 0;     // set while uploads are enqueued that overlap the match kernel
     int copy_ctas = 64;              // UZ_COPY_CTAS
+    PlacesState places;
+    double places_ms[3] = {0, 0, 0};
     int host_chunks = 0;             // UZ_HOST_CHUNKS: upload/compute pipeline depth of uz_estimate_edges_host (0 = auto)
     BumpPool<false> d_chunks;
     BumpPool<true> h_chunks;
@@ -193,6 +213,9 @@ struct uz_context {
 };
 
 namespace {
+
+void places_release(uz_context* ctx);
+uz_status places_reset(uz_context* ctx);
 
 // UZ_TRACE=1: host-side stage times of the batched entry points on stderr
 struct Trace {
@@ -708,6 +731,7 @@ uz_status uz_create(int32_t device, uz_context** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     uz_default_params(&ctx->params);
+    uz_default_place_params(&ctx->places.params);
     const char* v = getenv("UZ_KNN_VARIANT");
     if (v && v[0] == '1') ctx->variant_csa = 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
@@ -738,6 +762,7 @@ void uz_destroy(uz_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    places_release(ctx);
     ctx->store_arena.release(); ctx->transient.release();
     for (auto& sl : ctx->slots) {
         sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release();
@@ -837,6 +862,7 @@ uz_status uz_store_clear(uz_context* ctx) {
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->kfs.clear(); ctx->free_handles.clear(); ctx->live = 0; ctx->store_max_n = 0;
     ctx->store_arena.reset();
+    if ((st = places_reset(ctx)) != UZ_OK) return st;      // the recogniser's nodes point into the store
     return UZ_OK;
 }
 
@@ -1309,3 +1335,5 @@ uz_status uz_microbench(uz_context* ctx, int32_t op, double* gops_out) {
 }
 
 }  // extern "C"
+
+#include "uz_capi_places.inl"
