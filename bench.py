@@ -282,6 +282,41 @@ class ClockSampler:
                     source=self.source, reasons=reasons)
 
 
+def measure_places(est, handles, kfs, my_pairs=None, cpu_keyframes=1500):
+    """SURVEY 8f-1 (the step before the path): searchAndAddPlace for the whole map in one batch on the device vs the
+    sequential oracle restatement of LshSetRecognizer on one host core (bounded to the first `cpu_keyframes`)."""
+    from oracle import binding as O
+    n = len(handles)
+    stamps = (np.arange(n, dtype=np.int64) * 10_000_000_000)
+    est.setPlaceConfig(T=2.0, k_nearest_neighbors=20)
+    best = None
+    for rep in range(3):
+        est.clearPlaces()
+        t0 = time.perf_counter()
+        pairs = est.searchAndAddPlaces(handles, stamps)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, est.places_last_timing())
+    dt, tm = best
+    cluster = 25
+    true = (pairs[:, 0] // cluster) == (pairs[:, 1] // cluster)          # handles are dense and in map order
+    entries = n * N_FEATURES * 8
+    P = O.Places(T=2.0, k=20)
+    m = min(cpu_keyframes, n)
+    t0 = time.perf_counter()
+    want = [P.search_and_add(int(handles[i]), int(stamps[i]), [kfs[i]]) for i in range(m)]
+    cpu_dt = time.perf_counter() - t0
+    want = np.concatenate([w for w in want if len(w)] + [np.zeros((0, 2), np.int64)])
+    got_head = pairs[pairs[:, 1] < handles[m - 1] + 1] if m < n else pairs
+    same = bool(np.array_equal(got_head.astype(np.int64), want))
+    return dict(what="searchAndAddPlace x %d keyframes (LSH-bucket voting, T=2, k=20), one batch" % n,
+                keyframes_per_s=round(n / dt, 1), wall_ms=round(dt * 1e3, 2), insert_ms=round(tm["insert_ms"], 3),
+                vote_ms=round(tm["vote_ms"], 3), select_ms=round(tm["select_ms"], 3), bucket_entries=entries,
+                pairs=int(len(pairs)), true_pair_frac=round(float(true.mean()), 4) if len(pairs) else None,
+                cpu_oracle=dict(keyframes=m, keyframes_per_s=round(m / cpu_dt, 1), cores=1, kind="port",
+                                same_pairs_as_gpu=same))
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -420,6 +455,10 @@ def run_gpu(args):
     e2e_val = world * pairs_per_gpu * e2e_steps / e2e_s
     assert prep["res"].tobytes() == out.tobytes(), "host path and store path disagree"
 
+    places = None
+    if rank == 0 and not args.no_places:
+        places = measure_places(est, handles, kfs, my_pairs=None)
+
     if rank == 0:
         cmp_per_launch = tm["compares"] / max(tm["match_launches"], 1)
         knn_ms = tm["match_ms"] / max(tm["match_launches"], 1)
@@ -466,7 +505,7 @@ def run_gpu(args):
             cpu_baseline=cpu,
             e2e=dict(value=round(e2e_val, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                      api="uz_estimate_edges_host (pinned host FeatureData in, host edge records out)"),
-            gpu_launches=launches, clocks=clocks, sanity=sanity)
+            gpu_launches=launches, clocks=clocks, sanity=sanity, candidate_generation=places)
         print(json.dumps(line), flush=True)
     est.close()
     if world > 1:
@@ -483,6 +522,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-places", action="store_true", help="skip the candidate-generation (8f-1) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

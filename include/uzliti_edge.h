@@ -161,6 +161,32 @@ uz_status uz_debug_counts(uz_context* ctx, int32_t pair_index, int32_t* counts_o
  * hypotheses solved, winner known, refit done, end); profiling tap, debug mode only. */
 uz_status uz_debug_phases(uz_context* ctx, int32_t pair_index, int64_t* clocks8_out);
 
+/* ---- after the path -------------------------------------------------------------- */
+/* TransformationFilter::calcValidEdges (transformation_estimation/src/transformation_filter.cpp:216-285): one
+ * estimateSVD(P, Q, T, consensus, mse, 0.3, 200, 1.0, do_prosac=false) + consensus3D per edge cluster, all clusters in
+ * one launch.  P, Q: 3 x offsets[n_problems] column-major, problem b owns columns [offsets[b], offsets[b+1]).
+ * T16_out: n_problems x 16; inlier_mask_out (optional): offsets[n_problems] bytes, the consensus3D set of the final T.
+ * Problems with < 3 points return T = I, consensus 0 (the reference would index out of range). */
+uz_status uz_estimate_svd_batch(uz_context* ctx, const double* P, const double* Q, const int32_t* offsets, int32_t n_problems,
+                                double max_error, int32_t iterations, double break_percentage, int32_t do_prosac,
+                                double* T16_out, int32_t* consensus_out, double* mse_out, uint8_t* inlier_mask_out);
+
+/* GraphSlamNode::newEdgeCallback's numeric gate (graph_slam/src/graph_slam_node.cpp:798-804): an edge is linked only if
+ * matching_score_ >= min_matching_score, |translation| <= max_edge_distance_T (m) and the rotation angle
+ * (Eigen::AngleAxisd(transform_.linear()).angle(), degrees) <= max_edge_distance_R.  The graph-state checks around it
+ * (isMerged, existsEdge, checkEdgeHeuristic) stay with the graph. */
+typedef struct {
+    double min_matching_score;     /* graph_slam/cfg/GraphSlam.cfg: min_matching_score   */
+    double max_edge_distance_T;    /* max_edge_distance_T                                */
+    double max_edge_distance_R;    /* max_edge_distance_R (degrees)                      */
+} uz_gate_params;
+void      uz_default_gate_params(uz_gate_params* g);      /* iti_slam_launch/yaml/slam.yaml:25-27: 1.5 m, 30 deg, score 20 */
+uz_status uz_gate_edges(uz_context* ctx, const uz_edge_result* results, int32_t n, const uz_gate_params* gate,
+                        uint8_t* accept_out, double* translation_norm_out, double* rotation_deg_out);
+/* Same on records that are still on the device (straight behind uz_estimate_edges_device); asynchronous. */
+uz_status uz_gate_edges_device(uz_context* ctx, const void* results_device, int32_t n, const uz_gate_params* gate,
+                               void* accept_device, void* translation_norm_device, void* rotation_deg_device);
+
 /* ---- candidate generation (the step before the path) --------------------------- */
 /* place_recognition: LshSetRecognizer (place_recognition/src/lsh_set_recognizer.cpp:46-94,96-165,188-305: 8 hash tables
  * over descriptor bytes [4k,4k+4), one vote per bucket entry) behind PlaceRecognizer's filters

@@ -169,6 +169,15 @@ def estimate_edge(cams_from, cams_to, thr=0.1, iterations=100, bp=0.6, do_prosac
                 inlier_mask=mask[:M].astype(bool), counts=counts)
 
 
+def gate_edge(T, ok, consensus, min_score=20.0, max_T=1.5, max_R=30.0):
+    """newEdgeCallback's numeric gate -> (accept, |t|, rotation in degrees)"""
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    tn, rot = C.c_double(), C.c_double()
+    a = lib().uzo_gate_edge(_p(T), int(bool(ok)), int(consensus), C.c_double(min_score), C.c_double(max_T), C.c_double(max_R),
+                            C.byref(tn), C.byref(rot))
+    return bool(a), tn.value, rot.value
+
+
 class Places:
     """Sequential CPU restatement of LshSetRecognizer behind PlaceRecognizer's filters (oracle/uz_oracle.cpp, 8f-1).
     ids are arbitrary integers (the tests use store handles), stamps are nanoseconds."""

@@ -741,3 +741,44 @@ void uzo_places_votes(void* h, const uzo_features* cam, int filtered, int32_t* v
 }
 
 }  // extern "C"
+
+
+// =================================================================================================
+// 8f-2: edge acceptance gate of GraphSlamNode::newEdgeCallback (graph_slam/src/graph_slam_node.cpp:798-804).
+// Eigen 3.2 arithmetic written out: Quaternion(Matrix3d) (Quaternion.h, Shoemake) then AngleAxis(Quaternion)
+// (AngleAxis.h: angle = 2 acos(clamp(w)), 0 if |vec|^2 < dummy_precision^2).
+// =================================================================================================
+extern "C" int uzo_gate_edge(const double* T16, int ok, int consensus, double min_score, double max_T, double max_R,
+                             double* tnorm_out, double* rot_deg_out) {
+    double m[3][3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m[r][c] = T16[4 * r + c];
+    double q[3], w;
+    double t = (m[0][0] + m[1][1]) + m[2][2];
+    if (t > 0.0) {
+        t = std::sqrt(t + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (m[2][1] - m[1][2]) * t; q[1] = (m[0][2] - m[2][0]) * t; q[2] = (m[1][0] - m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        w = (m[k][j] - m[j][k]) * t;
+        q[j] = (m[j][i] + m[i][j]) * t;
+        q[k] = (m[k][i] + m[i][k]) * t;
+    }
+    double n2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+    double angle = 0.0;
+    if (!(n2 < 1e-12 * 1e-12)) angle = 2.0 * std::acos(std::min(std::max(-1.0, w), 1.0));
+    double rot = std::fabs(angle) * 180 / M_PI;
+    double tx = T16[3], ty = T16[7], tz = T16[11];
+    double tn = std::sqrt((tx * tx + ty * ty) + tz * tz);
+    if (tnorm_out) *tnorm_out = tn;
+    if (rot_deg_out) *rot_deg_out = rot;
+    double score = ok ? (double)consensus : 0.0;           // transformation_estimator.cpp:53-55
+    return (score >= min_score && tn <= max_T && rot <= max_R) ? 1 : 0;
+}

@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
     "uz_get_timers", "uz_microbench", "uz_version",
+    "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
 ]
@@ -33,6 +34,10 @@ class Params(C.Structure):
                 ("ransac_iterations", C.c_int32), ("do_prosac", C.c_int32),
                 ("ratio_num", C.c_int32), ("ratio_den", C.c_int32),
                 ("min_keypoints", C.c_int32), ("cross_check", C.c_int32)]
+
+
+class GateParams(C.Structure):
+    _fields_ = [("min_matching_score", C.c_double), ("max_edge_distance_T", C.c_double), ("max_edge_distance_R", C.c_double)]
 
 
 class PlaceParams(C.Structure):
@@ -97,10 +102,11 @@ def load_library():
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
-                 "uz_microbench", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
+                 "uz_microbench", "uz_estimate_svd_batch", "uz_gate_edges", "uz_gate_edges_device", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
                  "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing"):
         getattr(lib, name).restype = C.c_int
     lib.uz_default_place_params.restype = None
+    lib.uz_default_gate_params.restype = None
     _lib = lib
     return lib
 
@@ -334,6 +340,37 @@ class EdgeEstimator:
         out = np.zeros(8, np.int64)
         self._check(self.lib.uz_debug_phases(self.ctx, int(pair_index), _p(out)))
         return out
+
+    # ---- after the path: cluster RANSAC (calcValidEdges) and the acceptance gate (newEdgeCallback) ----
+    def estimateSVDBatch(self, Ps, Qs, maxError=0.3, iterations=200, breakPercentage=1.0, do_prosac=False):
+        """Ps, Qs: lists of (M_i, 3) arrays -> list of dicts(T, consensus, mse, mask), one launch for all."""
+        offs = np.zeros(len(Ps) + 1, np.int32)
+        for i, P in enumerate(Ps):
+            offs[i + 1] = offs[i] + len(P)
+        tot = int(offs[-1])
+        P = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float64).reshape(-1, 3) for p in Ps] + [np.zeros((0, 3))]))
+        Q = np.ascontiguousarray(np.concatenate([np.asarray(q, np.float64).reshape(-1, 3) for q in Qs] + [np.zeros((0, 3))]))
+        n = len(Ps)
+        T = np.zeros((max(n, 1), 16), np.float64)
+        cons = np.zeros(max(n, 1), np.int32)
+        mse = np.zeros(max(n, 1), np.float64)
+        mask = np.zeros(max(tot, 1), np.uint8)
+        self._check(self.lib.uz_estimate_svd_batch(self.ctx, _p(P), _p(Q), _p(offs), n, C.c_double(maxError), int(iterations),
+                                                   C.c_double(breakPercentage), int(bool(do_prosac)), _p(T), _p(cons), _p(mse),
+                                                   _p(mask)))
+        return [dict(T=T[i].reshape(4, 4).copy(), consensus=int(cons[i]), mse=float(mse[i]),
+                     mask=mask[offs[i]:offs[i + 1]].astype(bool)) for i in range(n)]
+
+    def gateEdges(self, results, min_matching_score=20.0, max_edge_distance_T=1.5, max_edge_distance_R=30.0):
+        """newEdgeCallback's gate over RESULT_DTYPE records -> (accept bool[n], |t|[n], rotation_deg[n])"""
+        res = np.ascontiguousarray(results, RESULT_DTYPE)
+        n = len(res)
+        g = GateParams(min_matching_score, max_edge_distance_T, max_edge_distance_R)
+        acc = np.zeros(max(n, 1), np.uint8)
+        tn = np.zeros(max(n, 1), np.float64)
+        rot = np.zeros(max(n, 1), np.float64)
+        self._check(self.lib.uz_gate_edges(self.ctx, _p(res), n, C.byref(g), _p(acc), _p(tn), _p(rot)))
+        return acc[:n].astype(bool), tn[:n], rot[:n]
 
     # ---- candidate generation (PlaceRecognizer / LshSetRecognizer) ---------------------------------
     def setPlaceConfig(self, **kw):

@@ -1044,6 +1044,111 @@ uz_status uz_consensus3d(uz_context* ctx, const double* P, const double* Q, int3
     return UZ_OK;
 }
 
+// ---- after the path: cluster RANSAC of TransformationFilter::calcValidEdges, edge acceptance gate ----
+// One estimateSVD per cluster in ONE launch (transformation_filter.cpp:266-275: estimateSVD(P, Q, T, consensus, mse,
+// 0.3, 200, 1.0, false) then consensus3D(P, Q, T, 0.3) — the mask returned here IS that second call's set, both use the
+// refitted T and the same threshold).
+uz_status uz_estimate_svd_batch(uz_context* ctx, const double* P, const double* Q, const int32_t* offsets, int32_t n_problems,
+                                double max_error, int32_t iterations, double break_percentage, int32_t do_prosac,
+                                double* T16_out, int32_t* consensus_out, double* mse_out, uint8_t* inlier_mask_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_problems < 0 || (n_problems > 0 && (!offsets || !T16_out || !consensus_out || !mse_out))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    if (iterations < 1 || iterations > UZ_MAX_ITERATIONS) return fail(ctx, UZ_ERR_INVALID, "iterations out of range");
+    if (n_problems == 0) return UZ_OK;
+    int max_m = 0;
+    if (offsets[0] != 0) return fail(ctx, UZ_ERR_INVALID, "offsets[0] must be 0");
+    for (int i = 0; i < n_problems; ++i) {
+        const int m = offsets[i + 1] - offsets[i];
+        if (m < 0 || m > UZ_MAX_FEATURES) return fail(ctx, UZ_ERR_INVALID, "problem size out of range");
+        max_m = std::max(max_m, m);
+    }
+    const int total = offsets[n_problems];
+    if (total > 0 && (!P || !Q)) return fail(ctx, UZ_ERR_INVALID, "null points");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    const int cap = std::max(128, pow2ceil(std::max(max_m, 1)));
+    double* dP = (double*)ctx->transient.alloc((size_t)std::max(total, 1) * 24);
+    double* dQ = (double*)ctx->transient.alloc((size_t)std::max(total, 1) * 24);
+    int32_t* doff = (int32_t*)ctx->transient.alloc((size_t)(n_problems + 1) * 4);
+    uint8_t* dmask = (uint8_t*)ctx->transient.alloc((size_t)cap * n_problems);
+    uz_edge_result* dres = (uz_edge_result*)ctx->transient.alloc(sizeof(uz_edge_result) * (size_t)n_problems);
+    if (!dP || !dQ || !doff || !dmask || !dres) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    if (total > 0) {
+        UZ_CUDA(ctx, cudaMemcpyAsync(dP, P, (size_t)total * 24, cudaMemcpyHostToDevice, ctx->stream));
+        UZ_CUDA(ctx, cudaMemcpyAsync(dQ, Q, (size_t)total * 24, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UZ_CUDA(ctx, cudaMemcpyAsync(doff, offsets, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    UZ_CUDA(ctx, cudaMemsetAsync(dmask, 0, (size_t)cap * n_problems, ctx->stream));
+    st = ensure_samples(ctx, iterations, do_prosac, max_m);
+    if (st != UZ_OK) return st;
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.samples = (const uint16_t*)ctx->d_samples.p; sp.samples_by_m = 1;
+    sp.thr = max_error; sp.thr_sq_star = thr_sq_star(max_error); sp.break_pct = break_percentage;
+    sp.iterations = iterations; sp.ratio_num = 99; sp.ratio_den = 100; sp.cap = cap;
+    sp.direct_P = dP; sp.direct_Q = dQ; sp.direct_M = 0; sp.direct_offsets = doff;
+    sp.dbg_mask = dmask;
+    solve_kernel<kSolveThreads><<<n_problems, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(nullptr, nullptr, nullptr, sp, dres);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    std::vector<uz_edge_result> r((size_t)n_problems);
+    std::vector<uint8_t> hm(inlier_mask_out ? (size_t)cap * n_problems : 0);
+    UZ_CUDA(ctx, cudaMemcpyAsync(r.data(), dres, sizeof(uz_edge_result) * (size_t)n_problems, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inlier_mask_out) UZ_CUDA(ctx, cudaMemcpyAsync(hm.data(), dmask, hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_problems; ++i) {
+        memcpy(T16_out + 16 * (size_t)i, r[i].T, sizeof(r[i].T));
+        consensus_out[i] = r[i].consensus; mse_out[i] = r[i].mse;
+        if (inlier_mask_out) memcpy(inlier_mask_out + offsets[i], hm.data() + (size_t)i * cap, (size_t)(offsets[i + 1] - offsets[i]));
+    }
+    return UZ_OK;
+}
+
+void uz_default_gate_params(uz_gate_params* g) {
+    if (!g) return;
+    g->min_matching_score = 20.0;      // iti_slam_launch/yaml/slam.yaml:27
+    g->max_edge_distance_T = 1.5;      // slam.yaml:25
+    g->max_edge_distance_R = 30.0;     // slam.yaml:26
+}
+
+uz_status uz_gate_edges_device(uz_context* ctx, const void* results_device, int32_t n, const uz_gate_params* gate,
+                               void* accept_device, void* translation_norm_device, void* rotation_deg_device) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n < 0 || !gate || (n > 0 && (!results_device || !accept_device))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    if (n == 0) return UZ_OK;
+    GateParams g{gate->min_matching_score, gate->max_edge_distance_T, gate->max_edge_distance_R};
+    gate_edges_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uz_edge_result*)results_device, n, g, (uint8_t*)accept_device,
+                                                                 (double*)translation_norm_device, (double*)rotation_deg_device);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    return UZ_OK;
+}
+
+uz_status uz_gate_edges(uz_context* ctx, const uz_edge_result* results, int32_t n, const uz_gate_params* gate,
+                        uint8_t* accept_out, double* translation_norm_out, double* rotation_deg_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n < 0 || !gate || (n > 0 && (!results || !accept_out))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    if (n == 0) return UZ_OK;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    uz_edge_result* dres = (uz_edge_result*)ctx->transient.alloc(sizeof(uz_edge_result) * (size_t)n);
+    uint8_t* dacc = (uint8_t*)ctx->transient.alloc((size_t)n);
+    double* dt = (double*)ctx->transient.alloc((size_t)n * 8);
+    double* dr = (double*)ctx->transient.alloc((size_t)n * 8);
+    if (!dres || !dacc || !dt || !dr) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    UZ_CUDA(ctx, cudaMemcpyAsync(dres, results, sizeof(uz_edge_result) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    st = uz_gate_edges_device(ctx, dres, n, gate, dacc, dt, dr);
+    if (st != UZ_OK) return st;
+    UZ_CUDA(ctx, cudaMemcpyAsync(accept_out, dacc, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (translation_norm_out) UZ_CUDA(ctx, cudaMemcpyAsync(translation_norm_out, dt, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rotation_deg_out) UZ_CUDA(ctx, cudaMemcpyAsync(rotation_deg_out, dr, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
 // ---- the batched path ----------------------------------------------------------------------------------
 static uz_status pairs_from_handles(uz_context* ctx, const int32_t* from_handles, const int32_t* to_handles,
                                     int32_t n_pairs, std::vector<PairRef>& pairs) {

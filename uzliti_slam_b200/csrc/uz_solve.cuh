@@ -33,6 +33,7 @@ struct SolveParams {
     int32_t samples_by_m;
     // direct mode (uz_estimate_svd / uz_consensus3d): P,Q given, stages K2 skipped
     const double* direct_P; const double* direct_Q; int32_t direct_M;
+    const int32_t* direct_offsets;   // batched direct mode: problem b owns points [offsets[b], offsets[b+1]) of P,Q; null = one problem
     // parity taps (may be null)
     int32_t* dbg_matches;    // [pair][cap][3]
     uint8_t* dbg_mask;       // [pair][cap]
@@ -75,6 +76,61 @@ __device__ __noinline__ int exact_inlier(const double* T12, const double* gP, co
     const double* p = gP + 3 * (tq & 0xFFFFu);
     const double* q = gQ + 3 * (tq >> 16);
     return residual_sq(T12, p[0], p[1], p[2], q[0], q[1], q[2]) < thr_sq_star;
+}
+
+// ---- edge acceptance gate ----------------------------------------------------------------
+// GraphSlamNode::newEdgeCallback (/root/reference/graph_slam/src/graph_slam_node.cpp:798-804): an edge is linked only
+// if matching_score_ >= min_matching_score, |t| <= max_edge_distance_T and the rotation angle of transform_.linear()
+// (Eigen::AngleAxisd(R).angle(), degrees) <= max_edge_distance_R.  Eigen 3.2 goes matrix -> quaternion (Shoemake,
+// Quaternion.h quaternionbase_assign_impl<Other,3,3>) -> angle = 2 acos(clamp(w)) (AngleAxis.h), 0 when |vec|^2 is
+// below dummy_precision^2.
+struct GateParams { double min_matching_score, max_edge_distance_T, max_edge_distance_R; };
+
+__device__ __forceinline__ double rotation_angle_deg(const double* T /* row-major 4x4 */) {
+    const double m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+    double w, x, y, z;
+    double t = UZ_DADD(UZ_DADD(m00, m11), m22);
+    if (t > 0.0) {
+        t = UZ_DSQRT(UZ_DADD(t, 1.0));
+        w = UZ_DMUL(0.5, t);
+        t = UZ_DDIV(0.5, t);
+        x = UZ_DMUL(UZ_DSUB(m21, m12), t); y = UZ_DMUL(UZ_DSUB(m02, m20), t); z = UZ_DMUL(UZ_DSUB(m10, m01), t);
+    } else {
+        const double m[3][3] = {{m00, m01, m02}, {m10, m11, m12}, {m20, m21, m22}};
+        int i = 0;
+        if (m11 > m00) i = 1;
+        if (m22 > m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = UZ_DSQRT(UZ_DADD(UZ_DSUB(UZ_DSUB(m[i][i], m[j][j]), m[k][k]), 1.0));
+        double q[3];
+        q[i] = UZ_DMUL(0.5, t);
+        t = UZ_DDIV(0.5, t);
+        w = UZ_DMUL(UZ_DSUB(m[k][j], m[j][k]), t);
+        q[j] = UZ_DMUL(UZ_DADD(m[j][i], m[i][j]), t);
+        q[k] = UZ_DMUL(UZ_DADD(m[k][i], m[i][k]), t);
+        x = q[0]; y = q[1]; z = q[2];
+    }
+    const double n2 = UZ_DADD(UZ_DADD(UZ_DMUL(x, x), UZ_DMUL(y, y)), UZ_DMUL(z, z));
+    if (n2 < 1e-12 * 1e-12) return 0.0;                           // NumTraits<double>::dummy_precision()^2
+    const double wc = fmin(fmax(-1.0, w), 1.0);
+    const double angle = 2.0 * acos(wc);
+    return fabs(angle) * 180.0 / 3.14159265358979323846;
+}
+
+__global__ void __launch_bounds__(256) gate_edges_kernel(const uz_edge_result* __restrict__ res, int n, GateParams g,
+                                                         uint8_t* __restrict__ accept, double* __restrict__ tnorm_out,
+                                                         double* __restrict__ rot_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uz_edge_result* r = res + i;
+    const double tx = r->T[3], ty = r->T[7], tz = r->T[11];
+    const double tn = UZ_DSQRT(UZ_DADD(UZ_DADD(UZ_DMUL(tx, tx), UZ_DMUL(ty, ty)), UZ_DMUL(tz, tz)));
+    const double rot = rotation_angle_deg(r->T);
+    // estimateEdgeImpl false => matching_score_ = 0 (transformation_estimator.cpp:53-55); consensus IS the score (:155)
+    const double score = r->ok ? (double)r->consensus : 0.0;
+    accept[i] = (score >= g.min_matching_score && tn <= g.max_edge_distance_T && rot <= g.max_edge_distance_R) ? 1 : 0;
+    if (tnorm_out) tnorm_out[i] = tn;
+    if (rot_out) rot_out[i] = rot;
 }
 
 // block-wide maximum of a non-negative float (NaN contributions are ignored by fmaxf)
@@ -241,6 +297,10 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         M = prm.direct_M;
         gP = prm.direct_P;
         gQ = prm.direct_Q;
+        if (prm.direct_offsets) {                     // calcValidEdges-style batch: one CTA per cluster
+            const int o0 = prm.direct_offsets[pair], o1 = prm.direct_offsets[pair + 1];
+            M = o1 - o0; gP += 3 * (size_t)o0; gQ += 3 * (size_t)o0;
+        }
         for (int i = tid; i < M; i += THREADS) {
             const float x = (float)gP[3 * i], y = (float)gP[3 * i + 1], z = (float)gP[3 * i + 2];
             const float u = (float)gQ[3 * i], v = (float)gQ[3 * i + 1], w = (float)gQ[3 * i + 2];
