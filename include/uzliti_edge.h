@@ -106,6 +106,39 @@ uz_status uz_store_clear(uz_context* ctx);
 int32_t   uz_store_size(const uz_context* ctx);            /* live keyframes */
 int64_t   uz_store_bytes(const uz_context* ctx);           /* device bytes held by the store */
 
+/* ---- ingestion on the device ---------------------------------------------- */
+/* Pinhole model + depth gate of FeatureExtractionCore::extract3dFeatures
+ * (feature_extraction/src/feature_extraction_core.cpp:254-295; max_depth 0 = no limit, slam.yaml:7 uses 7 m). */
+typedef struct {
+    double  fx, fy, cx, cy;
+    double  max_depth;
+    int32_t width, height;         /* depth image size in pixels */
+} uz_camera;
+/* extract3dFeatures on the device: (u, v) clamped into the image, depth read as float; valid iff depth != 0, not NaN
+ * and <= max_depth; invalid keypoints get (0, 0, -1).  depth: height rows of float32, depth_stride_bytes apart.
+ * reverse != 0 writes feature i to slot n-1-i, the order the reference produces (it walks its input back to front). */
+uz_status uz_backproject(uz_context* ctx, const int32_t* u, const int32_t* v, int32_t n, const float* depth,
+                         int32_t depth_stride_bytes, const uz_camera* cam, int32_t reverse, double* positions_out,
+                         uint8_t* valid_out);
+/* Same, but the keyframe goes straight into the store (positions never exist on the host): descriptors n x 32 bytes
+ * (row stride desc_stride) + pixels + the depth image in, a handle out. */
+uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t desc_stride, const int32_t* u, const int32_t* v,
+                            int32_t n, const float* depth, int32_t depth_stride_bytes, const uz_camera* cam, int32_t feature_type,
+                            int32_t sensor_frame, int32_t reverse, int32_t* handle_out);
+/* FeatureData::fromMsg (graph_slam_common/src/sensor_data.cpp:124-171) applied on the device to the ROS1-serialised
+ * graph_slam_msgs/Feature[] field (graph_slam_msgs/msg/Feature.msg: int32 u, int32 v, bool is_3d, float32
+ * keypoint_strength, float32[] descriptor, geometry_msgs/Point keypoint_position; little endian, unpadded): blob =
+ * uint32 count followed by the elements, as it sits in a SensorData message or a RosbagStorage record
+ * (graph_slam_common/src/rosbag_storage.cpp:135-211).  Descriptor floats are narrowed to bytes as the reference does. */
+uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t feature_type,
+                            int32_t sensor_frame, int32_t* handle_out);
+/* The decode alone, results back on the host (uv_out optional: n x 2 int32). */
+uz_status uz_wire_decode(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t capacity, int32_t* n_out,
+                         uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out, int32_t* uv_out);
+/* Read one stored camera back (descriptors n x 32 as given, positions 3 x n, valid n); any output may be NULL. */
+uz_status uz_store_read(uz_context* ctx, int32_t handle, int32_t cam, int32_t capacity, int32_t* n_out,
+                        uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out);
+
 /* ---- stage entry points (parity + direct callers) -------------------------------------------- */
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) (feature_transformation_estimator.cpp:38,58).
  * idx/dist: nq x 2 int32, ordered by (distance, trainIdx); missing neighbours (nt < 2) are -1. */

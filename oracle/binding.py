@@ -178,6 +178,35 @@ def gate_edge(T, ok, consensus, min_score=20.0, max_T=1.5, max_R=30.0):
     return bool(a), tn.value, rot.value
 
 
+def backproject(u, v, depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, max_depth=7.0, reverse=False):
+    """extract3dFeatures -> (pos float64[n,3], valid uint8[n])"""
+    u = np.ascontiguousarray(u, np.int32)
+    v = np.ascontiguousarray(v, np.int32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    n = len(u)
+    pos = np.zeros((max(n, 1), 3), np.float64)
+    valid = np.zeros(max(n, 1), np.uint8)
+    lib().uzo_backproject.restype = None
+    lib().uzo_backproject(_p(u), _p(v), n, _p(depth), depth.shape[1], depth.shape[1], depth.shape[0], C.c_double(fx),
+                          C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_double(max_depth), int(bool(reverse)),
+                          _p(pos), _p(valid))
+    return pos[:n], valid[:n]
+
+
+def wire_decode(blob, capacity=4096, cols=32):
+    """FeatureData::fromMsg on serialised Feature[] bytes -> (desc uint8[n,cols], pos[n,3], valid[n], uv[n,2]) or None"""
+    blob = np.frombuffer(bytes(blob), np.uint8)
+    desc = np.zeros((capacity, cols), np.uint8)
+    pos = np.zeros((capacity, 3), np.float64)
+    valid = np.zeros(capacity, np.uint8)
+    uv = np.zeros((capacity, 2), np.int32)
+    c = C.c_int()
+    n = lib().uzo_wire_decode(_p(blob), C.c_size_t(len(blob)), capacity, _p(desc), C.byref(c), _p(pos), _p(valid), _p(uv))
+    if n < 0 or (n > 0 and c.value != cols):
+        return None
+    return desc[:n], pos[:n], valid[:n], uv[:n]
+
+
 class Places:
     """Sequential CPU restatement of LshSetRecognizer behind PlaceRecognizer's filters (oracle/uz_oracle.cpp, 8f-1).
     ids are arbitrary integers (the tests use store handles), stamps are nanoseconds."""

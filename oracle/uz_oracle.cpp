@@ -13,6 +13,9 @@
 //     :299-314 estimatePoseSVD     (pcl::TransformationFromCorrespondences, float32, weight==1 bug)
 //     :337-347 consensus3D         (double, strict '<')
 //   /root/reference/transformation_estimation/src/transformation_estimator.cpp:53-55 (score 0 on failure)
+// of the data formats in front of the store:
+//   /root/reference/feature_extraction/src/feature_extraction_core.cpp:254-295 (extract3dFeatures)
+//   /root/reference/graph_slam_common/src/sensor_data.cpp:124-171             (FeatureData::fromMsg)
 // and of the step before the path (candidate generation):
 //   /root/reference/place_recognition/src/lsh_set_recognizer.cpp:46-94,96-165,188-305 (LshSetRecognizer, FastLshSet/Table)
 //   /root/reference/place_recognition/src/place_recognizer.cpp:73-118,140-190        (searchAndAddPlace / searchPlace filters)
@@ -781,4 +784,71 @@ extern "C" int uzo_gate_edge(const double* T16, int ok, int consensus, double mi
     if (rot_deg_out) *rot_deg_out = rot;
     double score = ok ? (double)consensus : 0.0;           // transformation_estimator.cpp:53-55
     return (score >= min_score && tn <= max_T && rot <= max_R) ? 1 : 0;
+}
+
+
+// =================================================================================================
+// 8f-3: extract3dFeatures (feature_extraction_core.cpp:254-295), literal.  positions: 3 x n column-major.
+// =================================================================================================
+extern "C" void uzo_backproject(const int32_t* u_in, const int32_t* v_in, int n, const float* depth, int stride_floats,
+                                int width, int height, double fx, double fy, double cx, double cy, double max_depth,
+                                int reverse, double* positions, uint8_t* valid) {
+    int out = 0;
+    for (int i = n - 1; i >= 0; i--) {                       // :263 walks back to front
+        int u = (int)round((double)u_in[i]);
+        if (u < 0) u = 0; else if (u >= width) u = width - 1;
+        int v = (int)round((double)v_in[i]);
+        if (v < 0) v = 0; else if (v >= height) v = height - 1;
+        double d = ((double)depth[(size_t)v * stride_floats + u]);
+        const int o = reverse ? out : i;                     // reverse: the reference's push_back order
+        if (d != 0 && !std::isnan(d) && (max_depth == 0. || d <= max_depth)) {
+            positions[3 * o + 2] = d;
+            positions[3 * o + 0] = (u - cx) * d / fx;
+            positions[3 * o + 1] = (v - cy) * d / fy;
+            valid[o] = 1;
+        } else {
+            positions[3 * o + 2] = -1; positions[3 * o + 0] = 0; positions[3 * o + 1] = 0;
+            valid[o] = 0;
+        }
+        ++out;
+    }
+}
+
+// =================================================================================================
+// 8f-4: FeatureData::fromMsg (sensor_data.cpp:124-171) on a ROS1-serialised graph_slam_msgs/Feature[] field.
+// ROS1 wire format: little endian, fields in .msg order, no padding, variable arrays behind a uint32 length, bool = 1 byte.
+// Returns the feature count, or -1 if the blob is malformed / a descriptor length differs from the first one.
+// =================================================================================================
+extern "C" int uzo_wire_decode(const uint8_t* blob, size_t bytes, int capacity, uint8_t* desc /* n x cols */, int* cols_out,
+                               double* positions, uint8_t* valid, int32_t* uv) {
+    if (bytes < 4) return -1;
+    uint32_t n;
+    std::memcpy(&n, blob, 4);
+    size_t off = 4;
+    int cols = -1;
+    if ((int)n > capacity) return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (off + 17 > bytes) return -1;
+        int32_t u, v;
+        uint8_t is3d;
+        uint32_t len;
+        std::memcpy(&u, blob + off, 4); std::memcpy(&v, blob + off + 4, 4);
+        is3d = blob[off + 8];
+        std::memcpy(&len, blob + off + 13, 4);
+        off += 17;
+        if (cols < 0) cols = (int)len;
+        if ((int)len != cols || off + 4 * (size_t)len + 24 > bytes) return -1;
+        for (uint32_t j = 0; j < len; ++j) {
+            float val;
+            std::memcpy(&val, blob + off + 4 * j, 4);
+            desc[(size_t)i * cols + j] = (unsigned char)val;             // :140
+        }
+        off += 4 * (size_t)len;
+        std::memcpy(positions + 3 * (size_t)i, blob + off, 24);          // :159-161
+        off += 24;
+        valid[i] = is3d ? 1 : 0;                                         // :164
+        if (uv) { uv[2 * i] = u; uv[2 * i + 1] = v; }
+    }
+    if (cols_out) *cols_out = cols < 0 ? 0 : cols;
+    return (int)n;
 }

@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
     "uz_get_timers", "uz_microbench", "uz_version",
+    "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_store_read",
     "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
@@ -34,6 +35,11 @@ class Params(C.Structure):
                 ("ransac_iterations", C.c_int32), ("do_prosac", C.c_int32),
                 ("ratio_num", C.c_int32), ("ratio_den", C.c_int32),
                 ("min_keypoints", C.c_int32), ("cross_check", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("max_depth", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32)]
 
 
 class GateParams(C.Structure):
@@ -102,7 +108,8 @@ def load_library():
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
-                 "uz_microbench", "uz_estimate_svd_batch", "uz_gate_edges", "uz_gate_edges_device", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
+                 "uz_microbench", "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_store_read",
+                 "uz_estimate_svd_batch", "uz_gate_edges", "uz_gate_edges_device", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
                  "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing"):
         getattr(lib, name).restype = C.c_int
     lib.uz_default_place_params.restype = None
@@ -213,6 +220,65 @@ class EdgeEstimator:
 
     def store_bytes(self):
         return self.lib.uz_store_bytes(self.ctx)
+
+    # ---- ingestion on the device ---------------------------------------------------------------------
+    @staticmethod
+    def _camera(depth, fx, fy, cx, cy, max_depth):
+        return Camera(fx, fy, cx, cy, max_depth, depth.shape[1], depth.shape[0])
+
+    def backproject(self, u, v, depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, max_depth=7.0, reverse=False):
+        u = np.ascontiguousarray(u, np.int32)
+        v = np.ascontiguousarray(v, np.int32)
+        depth = np.asarray(depth)
+        if depth.dtype != np.float32 or depth.strides[1] != 4:
+            depth = np.ascontiguousarray(depth, np.float32)
+        n = len(u)
+        pos = np.zeros((max(n, 1), 3), np.float64)
+        valid = np.zeros(max(n, 1), np.uint8)
+        cam = self._camera(depth, fx, fy, cx, cy, max_depth)
+        self._check(self.lib.uz_backproject(self.ctx, _p(u), _p(v), n, _p(depth), depth.strides[0], C.byref(cam),
+                                            int(bool(reverse)), _p(pos), _p(valid)))
+        return pos[:n], valid[:n]
+
+    def add_keyframe_rgbd(self, desc, u, v, depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, max_depth=7.0, reverse=False,
+                          feature_type=2, sensor_frame=0):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        u = np.ascontiguousarray(u, np.int32)
+        v = np.ascontiguousarray(v, np.int32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        cam = self._camera(depth, fx, fy, cx, cy, max_depth)
+        h = C.c_int32()
+        self._check(self.lib.uz_store_add_rgbd(self.ctx, _p(desc), 32, _p(u), _p(v), len(u), _p(depth), depth.strides[0],
+                                               C.byref(cam), int(feature_type), int(sensor_frame), int(bool(reverse)),
+                                               C.byref(h)))
+        return h.value
+
+    def add_keyframe_wire(self, blob, feature_type=2, sensor_frame=0):
+        b = np.frombuffer(bytes(blob), np.uint8)
+        h = C.c_int32()
+        self._check(self.lib.uz_store_add_wire(self.ctx, _p(b), C.c_size_t(len(b)), int(feature_type), int(sensor_frame),
+                                               C.byref(h)))
+        return h.value
+
+    def wire_decode(self, blob, capacity=4096):
+        b = np.frombuffer(bytes(blob), np.uint8)
+        desc = np.zeros((capacity, 32), np.uint8)
+        pos = np.zeros((capacity, 3), np.float64)
+        valid = np.zeros(capacity, np.uint8)
+        uv = np.zeros((capacity, 2), np.int32)
+        n = C.c_int32()
+        self._check(self.lib.uz_wire_decode(self.ctx, _p(b), C.c_size_t(len(b)), capacity, C.byref(n), _p(desc), _p(pos),
+                                            _p(valid), _p(uv)))
+        return desc[:n.value], pos[:n.value], valid[:n.value], uv[:n.value]
+
+    def read_keyframe(self, handle, cam=0, capacity=4096):
+        desc = np.zeros((capacity, 32), np.uint8)
+        pos = np.zeros((capacity, 3), np.float64)
+        valid = np.zeros(capacity, np.uint8)
+        n = C.c_int32()
+        self._check(self.lib.uz_store_read(self.ctx, int(handle), int(cam), capacity, C.byref(n), _p(desc), _p(pos), _p(valid)))
+        return dict(desc=desc[:n.value].copy(), pos=pos[:n.value].copy(), valid=valid[:n.value].copy(), feature_type=2,
+                    sensor_frame=0)
 
     # ---- stages ---------------------------------------------------------------------------------
     def knnMatch(self, query, train):

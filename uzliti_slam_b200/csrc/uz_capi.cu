@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/uzliti_edge.h"
+#include "uz_ingest.cuh"
 #include "uz_knn2.cuh"
 #include "uz_places.cuh"
 #include "uz_samples.h"
@@ -1442,3 +1443,4 @@ uz_status uz_microbench(uz_context* ctx, int32_t op, double* gops_out) {
 }  // extern "C"
 
 #include "uz_capi_places.inl"
+#include "uz_capi_ingest.inl"
