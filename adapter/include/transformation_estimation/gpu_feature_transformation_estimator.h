@@ -69,6 +69,21 @@ public:
     void estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
                            std::vector<char>& ok);
 
+    // the steps after the path, batched
+    // GraphSlamNode::newEdgeCallback's numeric gate (graph_slam_node.cpp:798-804) for many edges at once
+    void acceptEdges(const std::vector<SlamEdge>& edges, double min_matching_score, double max_edge_distance_T,
+                     double max_edge_distance_R, std::vector<char>& accept);
+    // TransformationFilter::calcValidEdges' per-cluster estimateSVD + consensus3D (transformation_filter.cpp:266-275)
+    void estimateSVDBatch(const std::vector<Eigen::MatrixXd>& P, const std::vector<Eigen::MatrixXd>& Q,
+                          std::vector<Eigen::Isometry3d>& T, std::vector<int>& consensus, std::vector<double>& mse,
+                          std::vector<std::vector<char> >& consensus_sets, double maxError = 0.3, int iterations = 200,
+                          double breakPercentage = 1.0, bool do_prosac = false);
+
+    // shared with the place recogniser (adapter/include/place_recognition/gpu_lsh_set_recognizer.h)
+    uz_context* context() { return ctx_; }
+    std::mutex& gpuMutex() { return gpu_mutex_; }
+    bool residentHandle(const SlamNode& node, int32_t* handle);       // uploads the node if needed; gpuMutex() must be held
+
     // device-resident keyframe store: nodes are uploaded once and addressed by id_ afterwards
     void forgetNode(const std::string& id);
     size_t residentNodes() const { return handles_.size(); }

@@ -270,3 +270,66 @@ int GpuFeatureTransformationEstimator::consensus3D(Eigen::MatrixXd P, Eigen::Mat
     for (int i = 0; i < P.cols(); ++i) consensusSet[i] = set[i] != 0;
     return count;
 }
+
+bool GpuFeatureTransformationEstimator::residentHandle(const SlamNode& node, int32_t* handle) {
+    Resident* r = nullptr;
+    if (!ensureResident(node, &r)) return false;
+    *handle = r->handle;
+    return true;
+}
+
+void GpuFeatureTransformationEstimator::acceptEdges(const std::vector<SlamEdge>& edges, double min_matching_score,
+                                                    double max_edge_distance_T, double max_edge_distance_R, std::vector<char>& accept) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    const size_t n = edges.size();
+    accept.assign(n, 0);
+    if (n == 0) return;
+    std::vector<uz_edge_result> rec(n);
+    for (size_t i = 0; i < n; ++i) {
+        std::memset(&rec[i], 0, sizeof(rec[i]));
+        rec[i].ok = 1;                                                   // a failed estimate already carries score 0
+        rec[i].consensus = (int32_t)edges[i].matching_score_;            // matching_score_ = consensus (:155)
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) rec[i].T[4 * a + b] = edges[i].transform_(a, b);
+    }
+    uz_gate_params g;
+    g.min_matching_score = min_matching_score; g.max_edge_distance_T = max_edge_distance_T; g.max_edge_distance_R = max_edge_distance_R;
+    std::vector<uint8_t> acc(n);
+    if (uz_gate_edges(ctx_, rec.data(), (int32_t)n, &g, acc.data(), nullptr, nullptr) != UZ_OK) {
+        std::fprintf(stderr, "acceptEdges: %s\n", uz_last_error(ctx_));
+        return;
+    }
+    for (size_t i = 0; i < n; ++i) accept[i] = (char)acc[i];
+}
+
+void GpuFeatureTransformationEstimator::estimateSVDBatch(const std::vector<Eigen::MatrixXd>& P, const std::vector<Eigen::MatrixXd>& Q,
+                                                         std::vector<Eigen::Isometry3d>& T, std::vector<int>& consensus,
+                                                         std::vector<double>& mse, std::vector<std::vector<char> >& consensus_sets,
+                                                         double maxError, int iterations, double breakPercentage, bool do_prosac) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    const size_t n = P.size();
+    T.assign(n, Eigen::Isometry3d::Identity());
+    consensus.assign(n, 0); mse.assign(n, 0.); consensus_sets.assign(n, std::vector<char>());
+    if (n == 0 || Q.size() != n) return;
+    std::vector<int32_t> off(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + P[i].cols();
+    std::vector<double> p((size_t)off[n] * 3 + 3), q((size_t)off[n] * 3 + 3);
+    for (size_t i = 0; i < n; ++i) {
+        std::memcpy(p.data() + (size_t)off[i] * 3, P[i].data(), (size_t)P[i].cols() * 24);
+        std::memcpy(q.data() + (size_t)off[i] * 3, Q[i].data(), (size_t)Q[i].cols() * 24);
+    }
+    std::vector<double> T16(16 * n), m(n);
+    std::vector<int32_t> c(n);
+    std::vector<uint8_t> mask((size_t)off[n] + 1);
+    if (uz_estimate_svd_batch(ctx_, p.data(), q.data(), off.data(), (int32_t)n, maxError, iterations, breakPercentage, do_prosac ? 1 : 0,
+                              T16.data(), c.data(), m.data(), mask.data()) != UZ_OK) {
+        std::fprintf(stderr, "estimateSVDBatch: %s\n", uz_last_error(ctx_));
+        return;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) T[i](a, b) = T16[16 * i + 4 * a + b];
+        consensus[i] = c[i]; mse[i] = m[i];
+        consensus_sets[i].assign(mask.begin() + off[i], mask.begin() + off[i + 1]);
+    }
+}

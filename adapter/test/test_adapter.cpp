@@ -1,6 +1,7 @@
 // test_adapter.cpp — drives the adapter the way GraphSlamNode drives the reference estimator
 // (graph_slam/src/graph_slam_node.cpp:48 construction with a callback, :266/:284 estimateEdge per candidate,
 // :779-829 newEdgeCallback).  Needs a B200; run by tests/test_adapter.py (-m gpu).
+#include <place_recognition/gpu_lsh_set_recognizer.h>
 #include <transformation_estimation/gpu_feature_transformation_estimator.h>
 
 #include <cmath>
@@ -132,6 +133,57 @@ int main() {
     CHECK(consensus == 60 && mse < 1e-3);
     Eigen::Array<bool, 1, Eigen::Dynamic> set;
     CHECK(est.consensus3D(P, Q, T, 0.3, set) == 60 && set.count() == 60 && !set[0] && set[1]);
+
+    // 4. the steps either side of the path through the mirrored interfaces
+    //    (a) place recognition: a revisit sequence; node B[i] was observed from the same place as A[i]
+    {
+        GpuLshSetRecognizer pr(est);
+        place_recognition::PlaceRecognizerConfig pc;
+        pc.k_nearest_neighbors = 5; pc.T = 2;                                  // global_slam.yaml:31,33
+        pr.setConfig(pc);
+        for (int i = 0; i < NP; ++i) { A[i].stamps_.assign(1, ros::Time()); A[i].stamps_[0].sec = 10.0 * i; }
+        for (int i = 0; i < NP; ++i) { B[i].stamps_.assign(1, ros::Time()); B[i].stamps_[0].sec = 1000.0 + 10.0 * i; }
+        for (int i = 0; i < NP; ++i) pr.addNode(A[i]);
+        pr.waitIdle();
+        CHECK(!pr.hasRecognizedPlaces());                                       // unrelated places: nothing recognised
+        for (int i = 0; i < NP; ++i) pr.addNode(B[i]);
+        pr.waitIdle();
+        CHECK(pr.hasRecognizedPlaces());
+        auto nb = pr.recognizedPlaces();
+        CHECK((int)nb.size() == NP && !pr.hasRecognizedPlaces());
+        std::map<std::string, std::string> from_of;
+        for (auto& p : nb) from_of[p.second] = p.first;
+        for (int i = 0; i < NP; ++i) CHECK(from_of["b" + std::to_string(i)] == "a" + std::to_string(i));
+        // the recognised pairs are exactly what estimateEdge takes next (graph_slam_node.cpp:512-530)
+        auto again = pr.searchPlace(B[3]);
+        CHECK(again.empty());                                                   // checked_: already reported
+        pr.removePlace("a5");
+        pr.clear();
+    }
+    //    (b) acceptance gate and cluster RANSAC
+    {
+        std::vector<SlamEdge> es;
+        for (auto& kv : got) es.push_back(kv.second);
+        for (int i = 0; i < NP; ++i) es.push_back(SlamEdge());
+        std::vector<char> acc;
+        est.acceptEdges(es, 20., 1.5, 30., acc);
+        CHECK(acc.size() == es.size());
+        CHECK(!acc[0]);                                                          // the failed x|y edge: score 0
+        for (size_t i = es.size() - NP; i < es.size(); ++i) CHECK(!acc[i]);      // default edges: score 0
+        SlamEdge good;
+        CHECK(est.estimateEdgeDirect(A[1].sensor_data_, B[1].sensor_data_, good));
+        std::vector<SlamEdge> one(1, good);
+        est.acceptEdges(one, 20., 1.5, 30., acc);
+        CHECK(acc.size() == 1 && acc[0]);                                        // |t| <= 0.87 m, angle <= 17 deg, score >= 100
+        est.acceptEdges(one, 20., 1e-6, 30., acc);
+        CHECK(!acc[0]);
+        std::vector<Eigen::MatrixXd> Ps(3, P), Qs(3, Q);
+        std::vector<Eigen::Isometry3d> Ts; std::vector<int> cs; std::vector<double> ms; std::vector<std::vector<char> > sets;
+        est.estimateSVDBatch(Ps, Qs, Ts, cs, ms, sets);
+        CHECK(cs.size() == 3 && cs[0] == 60 && cs[2] == 60 && (int)sets[1].size() == 80 && !sets[1][0] && sets[1][1]);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) CHECK(Ts[1](r, c) == T(r, c));
+    }
 
     est.forgetNode("a0");
     CHECK(est.residentNodes() == (size_t)2 * NP + 2 - 1);

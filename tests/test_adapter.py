@@ -9,20 +9,32 @@ ADAPTER = os.path.join(ROOT, "adapter")
 
 
 def _build():
+    subprocess.check_call(["make", "-C", ADAPTER, "CXX=g++"], stdout=subprocess.DEVNULL)
     if not os.path.exists(os.path.join(ADAPTER, "test_adapter")) or not os.path.exists(os.path.join(ADAPTER, "libuz_adapter.so")):
         subprocess.check_call(["make", "-C", ADAPTER, "CXX=g++"])
 
 
 def test_adapter_builds_and_exposes_the_reference_interface(built):
     _build()
-    syms = subprocess.check_output(["nm", "-DC", os.path.join(ADAPTER, "libuz_adapter.so")], text=True)
+    syms = subprocess.check_output(["nm", "-DC", os.path.join(ADAPTER, "libuz_adapter.so")], text=True).replace("[abi:cxx11]", "")
     for name in ("TransformationEstimator::estimateEdge(SlamNode&, SlamNode&)",
                  "GpuFeatureTransformationEstimator::estimateEdgeImpl(SlamNode&, SlamNode&, SlamEdge&)",
                  "GpuFeatureTransformationEstimator::estimateEdgeDirect(",
                  "GpuFeatureTransformationEstimator::estimateSVD(",
                  "GpuFeatureTransformationEstimator::consensus3D(",
                  "GpuFeatureTransformationEstimator::setConfig(",
-                 "GpuFeatureTransformationEstimator::estimateEdgeBatch("):
+                 "GpuFeatureTransformationEstimator::estimateEdgeBatch(",
+                 "GpuFeatureTransformationEstimator::acceptEdges(",
+                 "GpuFeatureTransformationEstimator::estimateSVDBatch(",
+                 "GpuLshSetRecognizer::addNode(SlamNode const&)",
+                 "GpuLshSetRecognizer::searchAndAddPlace(SlamNode const&)",
+                 "GpuLshSetRecognizer::searchPlace(SlamNode const&)",
+                 "GpuLshSetRecognizer::addPlace(SlamNode const&)",
+                 "GpuLshSetRecognizer::removePlace(",
+                 "GpuLshSetRecognizer::recognizedPlaces()",
+                 "GpuLshSetRecognizer::hasRecognizedPlaces()",
+                 "GpuLshSetRecognizer::setConfig(",
+                 "GpuLshSetRecognizer::clear()"):
         assert name in syms, name
     # the adapter reaches the GPU only through the C-ABI
     undefined = subprocess.check_output(["nm", "-Du", os.path.join(ADAPTER, "libuz_adapter.so")], text=True)
