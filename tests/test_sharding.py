@@ -30,6 +30,14 @@ def _worker(rank, world, port, q):
     from uzliti_slam_b200.sharding import gather_records, shard_pairs
     dist.init_process_group("gloo", rank=rank, world_size=world)
     kfs, pairs, _ = S.make_map(12, n_features=120, cluster=4, pool=120, n_shared=70, k_candidates=3, cross_cluster=1, seed=2)
+    # store maintenance: only rank 0 "ingests" the map, every rank ends up with identical keyframes
+    from uzliti_slam_b200.sharding import broadcast_keyframes
+    ragged = [dict(k, desc=k["desc"][:100 + i], pos=k["pos"][:100 + i], valid=k["valid"][:100 + i], sensor_frame=i % 3) for i, k in enumerate(kfs)]
+    got = broadcast_keyframes(ragged if rank == 0 else None, src=0)
+    assert len(got) == len(ragged)
+    for a, b in zip(got, ragged):
+        assert np.array_equal(a["desc"], b["desc"]) and a["pos"].tobytes() == b["pos"].tobytes() and np.array_equal(a["valid"], b["valid"])
+        assert a["sensor_frame"] == b["sensor_frame"] and a["feature_type"] == b["feature_type"]
     mine, lo = shard_pairs(pairs, world, rank)
     rec = np.zeros(len(mine), RESULT_DTYPE)
     for i, (a, b) in enumerate(mine):       # the per-rank compute step, here through the oracle (CPU test)

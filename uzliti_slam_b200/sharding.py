@@ -48,3 +48,48 @@ def gather_records(local_records, n_pairs, group=None):
         full[lo:hi] = np.frombuffer(chunk.tobytes(), dtype=local_records.dtype)
     assert sizes[rank][1] - sizes[rank][0] == len(local_records)
     return full
+
+
+def broadcast_keyframes(keyframes, src=0, group=None):
+    """Store maintenance for a replicated store: the rank that ingests keyframes (in the reference ONE
+    process receives the sensor messages, graph_slam/src/graph_slam_node.cpp:207-301) broadcasts them packed — counts,
+    descriptor rows, positions, valid bytes as four flat tensors — and every rank rebuilds the same keyframe list to feed
+    its own `EdgeEstimator.add_keyframes`.  `keyframes` (a list of single-camera dicts) is only read on `src`."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    if rank == src:
+        meta = np.array([[len(k["desc"]), int(k.get("feature_type", 2)), int(k.get("sensor_frame", 0))] for k in keyframes],
+                        np.int64).reshape(-1, 3)
+        head = torch.tensor([len(keyframes)], dtype=torch.int64)
+    else:
+        meta, head = None, torch.zeros(1, dtype=torch.int64)
+    head = head.to(dev)
+    dist.broadcast(head, src, group=group)
+    n_kf = int(head.item())
+    t_meta = (torch.from_numpy(meta) if rank == src else torch.zeros((n_kf, 3), dtype=torch.int64)).to(dev)
+    dist.broadcast(t_meta, src, group=group)
+    meta = t_meta.cpu().numpy()
+    total = int(meta[:, 0].sum())
+    if rank == src:
+        desc = np.concatenate([np.ascontiguousarray(k["desc"], np.uint8).reshape(-1, 32) for k in keyframes] + [np.zeros((0, 32), np.uint8)])
+        pos = np.concatenate([np.ascontiguousarray(k["pos"], np.float64).reshape(-1, 3) for k in keyframes] + [np.zeros((0, 3))])
+        valid = np.concatenate([np.ascontiguousarray(k["valid"], np.uint8).reshape(-1) for k in keyframes] + [np.zeros(0, np.uint8)])
+        tens = [torch.from_numpy(desc), torch.from_numpy(pos), torch.from_numpy(valid)]
+    else:
+        tens = [torch.zeros((total, 32), dtype=torch.uint8), torch.zeros((total, 3), dtype=torch.float64),
+                torch.zeros(total, dtype=torch.uint8)]
+    out = []
+    for t in tens:
+        t = t.to(dev)
+        dist.broadcast(t, src, group=group)
+        out.append(t.cpu().numpy())
+    desc, pos, valid = out
+    kfs, o = [], 0
+    for n, ftype, frame in meta:
+        n = int(n)
+        kfs.append(dict(desc=desc[o:o + n], pos=pos[o:o + n], valid=valid[o:o + n], feature_type=int(ftype), sensor_frame=int(frame)))
+        o += n
+    return kfs
