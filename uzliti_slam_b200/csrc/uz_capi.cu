@@ -152,6 +152,7 @@ struct uz_context {
     uz_params params;
     std::string err;
     int variant_csa = 1;
+    int variant_pack16 = 1;          // UZ_KNN_VARIANT=2: CSA layout with 32-bit keys (the previous kernel), =1: textbook 8-POPC
     int sm_count = 148;
 
     Arena store_arena, transient;
@@ -459,7 +460,9 @@ uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max
 // ---- launches --------------------------------------------------------------------------------------
 template <int THREADS, int QPT>
 void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys) {
-    if (ctx->variant_csa)
+    if (ctx->variant_csa && ctx->variant_pack16)
+        knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+    else if (ctx->variant_csa)
         knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
     else
         knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
@@ -735,6 +738,7 @@ uz_status uz_create(int32_t device, uz_context** out) {
     uz_default_place_params(&ctx->places.params);
     const char* v = getenv("UZ_KNN_VARIANT");
     if (v && v[0] == '1') ctx->variant_csa = 0;
+    if (v && v[0] == '2') ctx->variant_pack16 = 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
     {

@@ -109,6 +109,58 @@ __device__ __forceinline__ void top2_update2(uint32_t& m1, uint32_t& m2, uint32_
     m2 = min(min(m2, t), hi);
 }
 
+// ---- packed 16-bit keys: two queries per register ---------------------------------------------------
+// Inside a block of 128 train rows a key needs only 9 bits of distance (0..256) and 7 bits of row:
+//   key16 = (distance << 7) | (row & 127)   (<= 32895, 0xFFFF = none)
+// so the keys of TWO queries against the same train row share one register and the running top-2 of both
+// is kept with VIMNMX.U16x2 / VIMNMX3.U16x2: 2.5 min/max per two compares instead of 2.5 per compare (the
+// min/max share the ALU pipe with the 13 LOP3 of a compare).  The weighted popcounts of both queries are
+// accumulated by one IMAD chain (weights << 7 for the low half, << 23 for the high half; no carry crosses
+// the halves).  Every 128 rows the four 16-bit winners are widened to full keys and merged into m1/m2.
+__constant__ uint32_t kPopcWeightLo[3] = {1u << 7, 2u << 7, 4u << 7};
+__constant__ uint32_t kPopcWeightHi[3] = {1u << 23, 2u << 23, 4u << 23};
+
+template <bool HI>
+__device__ __forceinline__ uint32_t csa_acc16(const uint32_t (&U)[8], const uint4& a, const uint4& b, uint32_t acc) {
+    const uint32_t x0 = U[0] ^ a.x, x1 = U[1] ^ a.y, S1 = U[2] ^ a.z;
+    const uint32_t C1 = lop3<0xD4>(x0, x1, S1);
+    const uint32_t x3 = U[3] ^ a.w, x4 = U[4] ^ b.x, S2 = U[5] ^ b.y;
+    const uint32_t C2 = lop3<0xD4>(x3, x4, S2);
+    const uint32_t S3 = U[6] ^ b.z;
+    const uint32_t C3 = lop3<0xD4>(S1, S2, S3);
+    const uint32_t x7 = U[7] ^ b.w;
+    const uint32_t S5 = lop3<0x96>(C1, C2, C3);
+    const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
+    const uint32_t w1 = HI ? kPopcWeightHi[0] : kPopcWeightLo[0];
+    const uint32_t w2 = HI ? kPopcWeightHi[1] : kPopcWeightLo[1];
+    const uint32_t w4 = HI ? kPopcWeightHi[2] : kPopcWeightLo[2];
+    uint32_t k = mad_u32(__popc(C5), w4, acc);
+    k = mad_u32(__popc(S5), w2, k);
+    k = mad_u32(__popc(x7), w1, k);
+    k = mad_u32(__popc(S3), w1, k);
+    return k;
+}
+__device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b) {
+    uint32_t d; asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+    uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ void top2_update2_u16x2(uint32_t& m1, uint32_t& m2, uint32_t ka, uint32_t kb) {
+    const uint32_t lo = min_u16x2(ka, kb), hi = max_u16x2(ka, kb);
+    const uint32_t t = max_u16x2(m1, lo);
+    m1 = min_u16x2(m1, lo);
+    m2 = min_u16x2(min_u16x2(m2, t), hi);
+}
+// widen one 16-bit winner pair (v1 < v2, both real) of the block starting at train row `base` and merge it
+__device__ __forceinline__ void merge_block16(uint32_t& m1, uint32_t& m2, uint32_t v1, uint32_t v2, uint32_t base) {
+    const uint32_t k1 = ((v1 & 0xFF80u) << 9) | (base + (v1 & 127u));
+    const uint32_t k2 = ((v2 & 0xFF80u) << 9) | (base + (v2 & 127u));
+    const uint32_t t = max(m1, k1);
+    m1 = min(m1, k1);
+    m2 = min(min(m2, t), k2);
+}
+
 // ---- mbarrier / bulk-copy helpers (PTX) --------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -134,7 +186,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // tiles[blockIdx.x] = (task index, first query row of the tile)
-template <int THREADS, int QPT, bool CSA>
+template <int THREADS, int QPT, bool CSA, bool PACK16 = false>
 __global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys) {
@@ -191,29 +243,72 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restri
         const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(smem + stage * kTrainTileRows * 32);
         const int r0 = ti * kTrainTileRows;
         const int nrows = min(nt - r0, kTrainTileRows);
-        int j = 0;
+        if (PACK16) {
+            static_assert(!PACK16 || (CSA && QPT % 2 == 0), "packed keys need the CSA layout and an even QPT");
+            for (int b0 = 0; b0 < nrows; b0 += 128) {
+                const int nb = min(nrows - b0, 128);
+                const uint4* __restrict__ brows = rows + 2 * b0;
+                uint32_t p1[QPT / 2], p2[QPT / 2];
+#pragma unroll
+                for (int kk = 0; kk < QPT / 2; ++kk) { p1[kk] = 0xFFFFFFFFu; p2[kk] = 0xFFFFFFFFu; }
+                int j = 0;
 #pragma unroll 1
-        for (; j + 4 <= nrows; j += 4) {
+                for (; j + 4 <= nb; j += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-                const uint4 a0 = rows[2 * (j + u)], b0 = rows[2 * (j + u) + 1];
-                const uint4 a1 = rows[2 * (j + u) + 2], b1 = rows[2 * (j + u) + 3];
-                const uint32_t jkey = (uint32_t)(r0 + j + u);
+                    for (int u = 0; u < 4; u += 2) {
+                        const uint4 a0 = brows[2 * (j + u)], b0v = brows[2 * (j + u) + 1];
+                        const uint4 a1 = brows[2 * (j + u) + 2], b1v = brows[2 * (j + u) + 3];
+                        const uint32_t jj = (uint32_t)(j + u) * 0x00010001u;
 #pragma unroll
-                for (int k = 0; k < QPT; ++k) {
-                    const uint32_t k0 = CSA ? csa_key(U[k], a0, b0, jkey) : plain_key(U[k], a0, b0, jkey);
-                    const uint32_t k1 = CSA ? csa_key(U[k], a1, b1, jkey + 1) : plain_key(U[k], a1, b1, jkey + 1);
-                    top2_update2(m1[k], m2[k], k0, k1);
+                        for (int kk = 0; kk < QPT / 2; ++kk) {
+                            uint32_t k0 = csa_acc16<false>(U[2 * kk], a0, b0v, jj);
+                            uint32_t k1 = csa_acc16<false>(U[2 * kk], a1, b1v, jj + 0x00010001u);
+                            k0 = csa_acc16<true>(U[2 * kk + 1], a0, b0v, k0);
+                            k1 = csa_acc16<true>(U[2 * kk + 1], a1, b1v, k1);
+                            top2_update2_u16x2(p1[kk], p2[kk], k0, k1);
+                        }
+                    }
+                }
+                if (j > 0) {
+                    const uint32_t base = (uint32_t)(r0 + b0);
+#pragma unroll
+                    for (int kk = 0; kk < QPT / 2; ++kk) {
+                        merge_block16(m1[2 * kk], m2[2 * kk], p1[kk] & 0xFFFFu, p2[kk] & 0xFFFFu, base);
+                        merge_block16(m1[2 * kk + 1], m2[2 * kk + 1], p1[kk] >> 16, p2[kk] >> 16, base);
+                    }
+                }
+                for (; j < nb; ++j) {
+                    const uint4 a = brows[2 * j], b = brows[2 * j + 1];
+                    const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+#pragma unroll
+                    for (int k = 0; k < QPT; ++k) top2_update(m1[k], m2[k], csa_key(U[k], a, b, jkey));
                 }
             }
-        }
-        for (; j < nrows; ++j) {
-            const uint4 a = rows[2 * j], b = rows[2 * j + 1];
-            const uint32_t jkey = (uint32_t)(r0 + j);
+        } else {
+            int j = 0;
+#pragma unroll 1
+            for (; j + 4 <= nrows; j += 4) {
 #pragma unroll
-            for (int k = 0; k < QPT; ++k) {
-                const uint32_t key = CSA ? csa_key(U[k], a, b, jkey) : plain_key(U[k], a, b, jkey);
-                top2_update(m1[k], m2[k], key);
+                for (int u = 0; u < 4; u += 2) {
+                    const uint4 a0 = rows[2 * (j + u)], b0 = rows[2 * (j + u) + 1];
+                    const uint4 a1 = rows[2 * (j + u) + 2], b1 = rows[2 * (j + u) + 3];
+                    const uint32_t jkey = (uint32_t)(r0 + j + u);
+#pragma unroll
+                    for (int k = 0; k < QPT; ++k) {
+                        const uint32_t k0 = CSA ? csa_key(U[k], a0, b0, jkey) : plain_key(U[k], a0, b0, jkey);
+                        const uint32_t k1 = CSA ? csa_key(U[k], a1, b1, jkey + 1) : plain_key(U[k], a1, b1, jkey + 1);
+                        top2_update2(m1[k], m2[k], k0, k1);
+                    }
+                }
+            }
+            for (; j < nrows; ++j) {
+                const uint4 a = rows[2 * j], b = rows[2 * j + 1];
+                const uint32_t jkey = (uint32_t)(r0 + j);
+#pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    const uint32_t key = CSA ? csa_key(U[k], a, b, jkey) : plain_key(U[k], a, b, jkey);
+                    top2_update(m1[k], m2[k], key);
+                }
             }
         }
         __syncthreads();
