@@ -259,6 +259,14 @@ uz_status uz_places_votes(uz_context* ctx, int32_t handle, int32_t cam, int32_t 
 /* Device time (ms) of the insert / vote / select kernels of the last uz_places_* call and its bucket-entry visits. */
 uz_status uz_places_last_timing(uz_context* ctx, double* insert_ms, double* vote_ms, double* select_ms);
 
+/* ---- execution form ------------------------------------------------------------------------------ */
+/* How the solve (K2..K5) of a large batch is scheduled.  ctas_per_sm > 0 (default 1): a persistent solve grid of that
+ * many CTAs per SM runs BESIDE the match kernel on a high-priority stream and consumes pairs as the match kernel
+ * publishes them; it never blocks the match kernel and falls back to a launch behind it if the two cannot share the
+ * device.  0: one solve CTA per pair, launched behind the match kernel.  Results are identical in both forms.  (The
+ * reference has no such knob: its estimator owns one worker thread, transformation_estimator.cpp:26.) */
+uz_status uz_set_stream_solve(uz_context* ctx, int32_t ctas_per_sm);
+
 /* ---- introspection for the bench harness ----------------------------------------------------- */
 /* Kernel launches issued by this context since creation (the bench's gpu_launches claim). */
 int64_t   uz_launch_count(const uz_context* ctx);

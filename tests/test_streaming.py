@@ -1,0 +1,112 @@
+"""The streaming form of the solve (solve_stream_kernel: a persistent grid beside the match kernel, fed through per-pair
+completion counters) must produce exactly the records of the one-CTA-per-pair form, which test_gpu_parity.py pins to the
+oracle.  UZ_STREAM_SOLVE / UZ_STREAM_SOLVE_MIN_PAIRS are read by uz_create, so each form gets its own context.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from uzliti_slam_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _estimator(**env):
+    from uzliti_slam_b200 import EdgeEstimator
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return EdgeEstimator(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _ragged_map(seed, n_keyframes=120):
+    """keyframes of different sizes (1-3 match tiles per pair), some too small to be matched (< 7 keypoints)"""
+    kfs, pairs, _ = S.make_map(n_keyframes, n_features=600, cluster=12, pool=600, n_shared=350, k_candidates=10,
+                               cross_cluster=3, seed=seed)
+    rng = np.random.default_rng(seed)
+    out = []
+    for i, kf in enumerate(kfs):
+        n = [600, 520, 300, 64, 5][i % 5] if i % 7 else 600
+        out.append({k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in kf.items()})
+    return out, pairs[rng.permutation(len(pairs))]
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+def test_streaming_equals_one_cta_per_pair(ctas):
+    kfs, pairs = _ragged_map(5)
+    plain = _estimator(UZ_STREAM_SOLVE=0)
+    stream = _estimator(UZ_STREAM_SOLVE=ctas, UZ_STREAM_SOLVE_MIN_PAIRS=1)
+    try:
+        hp = plain.add_keyframes(kfs)
+        hs = stream.add_keyframes(kfs)
+        for cross in (0, 1):
+            plain.setConfig(cross_check=cross)
+            stream.setConfig(cross_check=cross)
+            a = plain.estimateEdges(hp[pairs[:, 0]], hp[pairs[:, 1]])
+            n0 = stream.launch_count()
+            b = stream.estimateEdges(hs[pairs[:, 0]], hs[pairs[:, 1]])
+            assert stream.launch_count() - n0 == 3          # match launch + persistent solve launch + (empty) cleanup launch
+            assert a.tobytes() == b.tobytes()
+            assert (a["ok"] == 0).any() and (a["consensus"] > 50).any()
+            # twice in a row (double-buffered staging, counters re-armed), and a tiny batch
+            assert stream.estimateEdges(hs[pairs[:, 0]], hs[pairs[:, 1]]).tobytes() == a.tobytes()
+            assert stream.estimateEdges(hs[pairs[:3, 0]], hs[pairs[:3, 1]]).tobytes() == a[:3].tobytes()
+    finally:
+        plain.close()
+        stream.close()
+
+
+def test_streaming_against_oracle_with_taps(oracle):
+    kfs, pairs, _ = S.make_map(24, n_features=500, cluster=6, pool=500, n_shared=300, k_candidates=4, cross_cluster=1, seed=21)
+    est = _estimator(UZ_STREAM_SOLVE=1, UZ_STREAM_SOLVE_MIN_PAIRS=1)
+    try:
+        h = est.add_keyframes(kfs)
+        est.set_debug(True)
+        res = est.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]])
+        for i, (a, b) in enumerate(pairs):
+            o = oracle.estimate_edge([kfs[a]], [kfs[b]])
+            assert bool(res[i]["ok"]) == o["ok"] and res[i]["consensus"] == o["consensus"]
+            assert res[i]["best_iteration"] == o["best_iteration"] and res[i]["iterations_run"] == o["iterations_run"]
+            assert np.abs(res[i]["T"].reshape(4, 4) - o["T"]).max() < 1e-5
+            m, mask = est.debug_pair(i, res[i]["n_matches"])
+            assert np.array_equal(m, o["matches"])
+            if o["ok"]:
+                assert np.array_equal(mask, o["inlier_mask"])
+    finally:
+        est.close()
+
+
+def test_streaming_host_path_equals_store_path():
+    kfs, pairs, _ = S.make_map(60, n_features=500, cluster=10, pool=500, n_shared=300, k_candidates=8, cross_cluster=2, seed=4)
+    est = _estimator(UZ_STREAM_SOLVE=1, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_HOST_CHUNKS=3)
+    try:
+        h = est.add_keyframes(kfs)
+        a = est.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]])
+        b = est.estimateEdgesHost([([kfs[i]], [kfs[j]]) for i, j in pairs])
+        assert a.tobytes() == b.tobytes()
+    finally:
+        est.close()
+
+
+def test_streaming_survives_starvation():
+    """UZ_STREAM_PROBE=9 holds the match kernel back for 3 x the starvation limit: the streaming CTAs must give up, free
+    the SMs, and the cleanup launch behind the match kernel must solve every pair - same records as the plain form."""
+    kfs, pairs = _ragged_map(8, n_keyframes=60)
+    plain = _estimator(UZ_STREAM_SOLVE=0)
+    starved = _estimator(UZ_STREAM_SOLVE=1, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_STREAM_PROBE=9)
+    try:
+        hp = plain.add_keyframes(kfs)
+        hs = starved.add_keyframes(kfs)
+        a = plain.estimateEdges(hp[pairs[:, 0]], hp[pairs[:, 1]])
+        for _ in range(2):
+            assert starved.estimateEdges(hs[pairs[:, 0]], hs[pairs[:, 1]]).tobytes() == a.tobytes()
+    finally:
+        plain.close()
+        starved.close()

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_remove", "uz_store_clear",
     "uz_store_size", "uz_store_bytes", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
-    "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers",
+    "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers", "uz_set_stream_solve",
     "uz_get_timers", "uz_microbench", "uz_version",
     "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_store_read",
     "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
@@ -497,6 +497,9 @@ class EdgeEstimator:
         return dict(insert_ms=a.value, vote_ms=b.value, select_ms=c.value)
 
     # ---- introspection ---------------------------------------------------------------------------
+    def set_stream_solve(self, ctas_per_sm=1):
+        self._check(self.lib.uz_set_stream_solve(self.ctx, int(ctas_per_sm)))
+
     def launch_count(self):
         return self.lib.uz_launch_count(self.ctx)
 

@@ -147,7 +147,10 @@ struct uz_context {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t side = nullptr;     // high-priority stream the solve kernels of a chunked batch run on
-    int overlap_chunks = 1;          // UZ_OVERLAP_CHUNKS > 1: chunked 2-stream pipeline (measured: no gain on B200)
+    cudaStream_t solve_stream = nullptr;   // high-priority stream of the streaming solve grid (runs beside the match kernel)
+    int stream_probe = 0;            // UZ_STREAM_PROBE: measurement / test hooks of the streaming solve (scripts/gpu_stream_probe.py)
+    int stream_min_pairs = 0;        // UZ_STREAM_SOLVE_MIN_PAIRS: smallest batch that takes the streaming form (0 = two pairs per CTA)
+    int stream_solve_ctas = 1;       // UZ_STREAM_SOLVE: persistent solve CTAs per SM (0 = off: one solve CTA per pair behind the match kernel)
     int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
     uz_params params;
     std::string err;
@@ -182,8 +185,8 @@ struct uz_context {
     // per-batch staging, double buffered: the host prepares batch i+1 (task/tile tables in pinned memory) while
     // the GPU still works on batch i; a slot is reused once the event recorded behind its last kernel fired
     struct Slot {
-        DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys;
-        PinBuf h_tasks, h_tiles, h_pair_tasks;
+        DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_pending;
+        PinBuf h_tasks, h_tiles, h_pair_tasks, h_pending;
         cudaEvent_t done = nullptr;
         bool used = false;
     };
@@ -459,13 +462,41 @@ uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max
 
 // ---- launches --------------------------------------------------------------------------------------
 template <int THREADS, int QPT>
-void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys) {
+void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
+                 unsigned int* d_progress) {
     if (ctx->variant_csa && ctx->variant_pack16)
-        knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+        knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else if (ctx->variant_csa)
-        knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+        knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else
-        knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys);
+        knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+}
+
+// Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
+// an SM is only reconfigured when it is empty, so a kernel that asks for another split waits until the resident
+// kernel's CTAs have drained - which serialises the two (and starves a consumer that polls its producer).
+template <typename K>
+cudaError_t max_shared_carveout(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+template <int THREADS, int QPT>
+cudaError_t knn2_carveout() {
+    cudaError_t e = max_shared_carveout(knn2_kernel<THREADS, QPT, true, true>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_kernel<THREADS, QPT, true, false>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_kernel<THREADS, QPT, false, false>);
+    return e;
+}
+cudaError_t set_carveouts() {
+    cudaError_t e = knn2_carveout<256, 4>();
+    if (e == cudaSuccess) e = knn2_carveout<128, 4>();
+    if (e == cudaSuccess) e = knn2_carveout<64, 2>();
+    if (e == cudaSuccess) e = knn2_carveout<256, 2>();
+    if (e == cudaSuccess) e = knn2_carveout<128, 2>();
+    if (e == cudaSuccess) e = max_shared_carveout(solve_kernel<kSolveThreads>);
+    if (e == cudaSuccess) e = max_shared_carveout(solve_stream_kernel<kSolveThreads>);
+    if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
+    return e;
 }
 
 struct KnnConfig { int threads, qpt; };
@@ -539,7 +570,11 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
 
     int best_cfg = 0;
     double best_cost = 1e300;
-    for (int c = 0; c < 3; ++c) {
+    // candidates: two queries per thread (40-56 registers: 6 resident CTAs per SM, measured 8 % faster than the
+    // four-query shapes, which stay reachable through UZ_KNN_CFG), largest tile first
+    static const int kCandidates[3] = {3, 4, 2};
+    for (int ci = 0; ci < 3; ++ci) {
+        const int c = kCandidates[ci];
         const int tile = kKnnConfigs[c].threads * kKnnConfigs[c].qpt;
         double padded = 0; size_t tiles = 0;
         for (size_t t = 0; t < n_tasks; ++t) {
@@ -577,24 +612,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
-    // 3. launch geometry: one launch pair per chunk of pairs; the solve of chunk c runs on the side stream and
-    // overlaps the knn2 of chunk c+1 (INT pipes vs FP32/FP64 pipes of the same SMs)
+    // 3. launches.  Large batches: ONE match launch plus the persistent streaming solve beside it (uz_solve.cuh);
+    // small batches, the parity taps and UZ_STREAM_SOLVE=0: match launch, then one solve CTA per pair behind it.
     const bool with_solve = d_results != nullptr;
-    int n_chunks = 1;
-    if (with_solve && ctx->overlap_chunks > 1 && n_pairs >= 64 * ctx->sm_count) n_chunks = std::min(ctx->overlap_chunks, n_pairs / (16 * ctx->sm_count));
-    n_chunks = std::max(n_chunks, 1);
-    std::vector<int> chunk_pair(n_chunks + 1), chunk_tile(n_chunks + 1);
-    for (int c = 0; c <= n_chunks; ++c) chunk_pair[c] = (int)((int64_t)n_pairs * c / n_chunks);
-    {
-        int c = 0;
-        chunk_tile[0] = 0;
-        for (size_t k = 0; k < n_tiles; ++k) {
-            const int pr = tasks[tiles[k].x].pair;
-            while (c + 1 <= n_chunks && pr >= chunk_pair[c + 1]) chunk_tile[++c] = (int)k;
-        }
-        while (c < n_chunks) chunk_tile[++c] = (int)n_tiles;
-    }
-
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
     int cap = 0;
@@ -620,53 +640,90 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             ctx->dbg_cap = cap; ctx->dbg_pairs = n_pairs; ctx->dbg_iters = prm.ransac_iterations;
         }
     }
-    const bool two_streams = with_solve && n_chunks > 1;
-    cudaStream_t sB = two_streams ? ctx->side : ctx->stream;
+    // the streaming solve needs its 96-register CTAs to fit beside the match CTAs: one pair's on-chip state must
+    // leave room for them (cap <= 1024: 44 KB), and the batch must be large enough to be worth a persistent grid
+    const int stream_ctas = ctx->stream_solve_ctas * ctx->sm_count;
+    const bool streaming = with_solve && ctx->solve_stream != nullptr && ctx->stream_solve_ctas > 0 && cap <= 1024 &&
+                           n_pairs >= (ctx->stream_min_pairs > 0 ? ctx->stream_min_pairs : 2 * stream_ctas) && n_tiles > 0;
     if (ctx->timers) ctx->compares += compares;
 
-    for (int c = 0; c < n_chunks; ++c) {
-        uz_context::Timed tm;
-        tm.e[0] = tm.e[1] = tm.e[2] = tm.e[3] = nullptr; tm.has_solve = false;
-        const int t0 = chunk_tile[c], nt_c = chunk_tile[c + 1] - chunk_tile[c];
-        const int p0 = chunk_pair[c], np_c = chunk_pair[c + 1] - chunk_pair[c];
-        if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
-        if (nt_c > 0) {
-            const int2* d_t = (const int2*)sl.d_tiles.p + t0;
-            switch (best_cfg) {
-                case 0: launch_knn2<256, 4>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
-                case 1: launch_knn2<128, 4>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
-                case 2: launch_knn2<64, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
-                case 3: launch_knn2<256, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
-                default: launch_knn2<128, 2>(ctx, (const MatchTask*)sl.d_tasks.p, d_t, nt_c, (uint2*)sl.d_keys.p); break;
-            }
-            ctx->launches++;
-            UZ_CUDA(ctx, cudaGetLastError());
-            if (ctx->timers) ctx->match_launches++;
+    int* d_pending = nullptr;
+    int* d_deferred = nullptr;
+    StreamCtl* d_ctl = nullptr;
+    if (streaming) {
+        UZ_CUDA(ctx, sl.h_pending.ensure((size_t)n_pairs * sizeof(int)));
+        UZ_CUDA(ctx, sl.d_pending.ensure((size_t)n_pairs * 2 * sizeof(int) + 256));
+        int* pend = (int*)sl.h_pending.p;
+        memset(pend, 0, (size_t)n_pairs * sizeof(int));
+        for (size_t k = 0; k < n_tiles; ++k) pend[tasks[tiles[k].x].pair]++;
+        d_ctl = (StreamCtl*)sl.d_pending.p;                       // control block first, counters 256 B behind it
+        d_pending = (int*)((uint8_t*)sl.d_pending.p + 256);
+        d_deferred = d_pending + n_pairs;
+        UZ_CUDA(ctx, cudaMemsetAsync(d_ctl, 0, sizeof(StreamCtl), ctx->stream));
+        UZ_CUDA(ctx, cudaMemcpyAsync(d_pending, pend, (size_t)n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    uz_context::Timed tm;
+    tm.e[0] = tm.e[1] = tm.e[2] = tm.e[3] = nullptr; tm.has_solve = false;
+    if (ctx->timers) { tm.e[0] = ctx->get_event(); tm.e[1] = ctx->get_event(); cudaEventRecord(tm.e[0], ctx->stream); }
+    cudaEvent_t ev_tables = nullptr;
+    if (streaming) {            // the side grid may start once the tables, counters and everything before them are in place
+        ev_tables = ctx->get_event();
+        UZ_CUDA(ctx, cudaEventRecord(ev_tables, ctx->stream));
+        if (ctx->stream_probe == 9) delay_kernel<<<1, 1, 0, ctx->stream>>>(3 * kStallNs);     // test hook: starve the streaming grid
+    }
+    if (n_tiles > 0) {
+        const MatchTask* d_tk = (const MatchTask*)sl.d_tasks.p;
+        const int2* d_t = (const int2*)sl.d_tiles.p;
+        uint2* d_k = (uint2*)sl.d_keys.p;
+        const int nt = (int)n_tiles;
+        unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
+        switch (best_cfg) {
+            case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            default: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
         }
-        if (ctx->timers) cudaEventRecord(tm.e[1], ctx->stream);
-        if (with_solve && np_c > 0) {
-            if (two_streams) {
-                cudaEvent_t ev = ctx->get_event();
-                UZ_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
-                UZ_CUDA(ctx, cudaStreamWaitEvent(sB, ev, 0));
-                ctx->event_pool.push_back(ev);        // safe to recycle: the wait has captured it
-            }
-            if (ctx->timers) { tm.e[2] = ctx->get_event(); tm.e[3] = ctx->get_event(); tm.has_solve = true; cudaEventRecord(tm.e[2], sB); }
-            sp.pair_base = p0;
-            solve_kernel<kSolveThreads><<<np_c, kSolveThreads, solve_smem_bytes(cap), sB>>>(
+        ctx->launches++;
+        UZ_CUDA(ctx, cudaGetLastError());
+        if (ctx->timers) ctx->match_launches++;
+    }
+    if (ctx->timers) cudaEventRecord(tm.e[1], ctx->stream);
+    if (with_solve) {
+        cudaStream_t sB = streaming ? ctx->solve_stream : ctx->stream;
+        if (streaming) {
+            UZ_CUDA(ctx, cudaStreamWaitEvent(sB, ev_tables, 0));
+            ctx->event_pool.push_back(ev_tables);         // safe to recycle: the wait has captured it
+        }
+        if (ctx->timers) { tm.e[2] = ctx->get_event(); tm.e[3] = ctx->get_event(); tm.has_solve = true; cudaEventRecord(tm.e[2], sB); }
+        sp.pair_base = 0;
+        sp.dbg_skip = streaming ? ctx->stream_probe : 0;
+        if (streaming)
+            solve_stream_kernel<kSolveThreads><<<stream_ctas, kSolveThreads, solve_smem_bytes(cap), sB>>>(
+                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
+                n_pairs, d_pending, d_ctl, d_deferred, 0);
+        else
+            solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), sB>>>(
                 (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results);
+        ctx->launches++;
+        UZ_CUDA(ctx, cudaGetLastError());
+        if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
+        if (streaming) {        // rejoin: everything the caller enqueues next on its stream sees the results
+            cudaEvent_t ev = ctx->get_event();
+            UZ_CUDA(ctx, cudaEventRecord(ev, sB));
+            UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+            ctx->event_pool.push_back(ev);
+            // cleanup form, stream-ordered behind the match kernel: pairs the streaming grid deferred or never drew
+            // (only if it starved - normally every CTA of this launch exits on its first look)
+            solve_stream_kernel<kSolveThreads><<<4 * ctx->sm_count, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
+                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
+                n_pairs, d_pending, d_ctl, d_deferred, 1);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
-            if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
         }
-        if (ctx->timers) ctx->pending.push_back(tm);
     }
-    if (two_streams) {           // rejoin: everything the caller enqueues next on its stream sees the results
-        cudaEvent_t ev = ctx->get_event();
-        UZ_CUDA(ctx, cudaEventRecord(ev, sB));
-        UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
-        ctx->event_pool.push_back(ev);
-    }
+    if (ctx->timers) ctx->pending.push_back(tm);
     UZ_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
     sl.used = true;
     return UZ_OK;
@@ -676,6 +733,7 @@ uz_status resolve_timers(uz_context* ctx) {
     if (ctx->pending.empty()) return UZ_OK;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->side) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->side));
+    if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
     for (auto& t : ctx->pending) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, t.e[0], t.e[1]);
@@ -745,8 +803,13 @@ uz_status uz_create(int32_t device, uz_context** out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(e)); }
-        const char* oc = getenv("UZ_OVERLAP_CHUNKS");
-        if (oc && atoi(oc) >= 1) ctx->overlap_chunks = atoi(oc);
+        if ((e = cudaStreamCreateWithPriority(&ctx->solve_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(e)); }
+        const char* mp = getenv("UZ_STREAM_SOLVE_MIN_PAIRS");
+        if (mp && atoi(mp) > 0) ctx->stream_min_pairs = atoi(mp);
+        const char* sq = getenv("UZ_STREAM_PROBE");
+        if (sq) ctx->stream_probe = atoi(sq);
+        const char* ss = getenv("UZ_STREAM_SOLVE");
+        if (ss && atoi(ss) >= 0 && atoi(ss) <= 4) ctx->stream_solve_ctas = atoi(ss);
         const char* fc = getenv("UZ_KNN_CFG");
         if (fc) ctx->force_cfg = atoi(fc);
         const char* gu = getenv("UZ_GATHER_UPLOAD");
@@ -758,6 +821,10 @@ uz_status uz_create(int32_t device, uz_context** out) {
     }
     e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)solve_smem_bytes(UZ_MAX_FEATURES));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(solve_stream_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(1024));
+    if (e == cudaSuccess) e = set_carveouts();
     if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
     *out = ctx;
     return UZ_OK;
@@ -770,8 +837,8 @@ void uz_destroy(uz_context* ctx) {
     places_release(ctx);
     ctx->store_arena.release(); ctx->transient.release();
     for (auto& sl : ctx->slots) {
-        sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release();
-        sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release();
+        sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release(); sl.d_pending.release();
+        sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release(); sl.h_pending.release();
         if (sl.done) cudaEventDestroy(sl.done);
     }
     ctx->d_samples.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release(); ctx->h_results.release();
@@ -779,6 +846,7 @@ void uz_destroy(uz_context* ctx) {
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->solve_stream) { cudaStreamSynchronize(ctx->solve_stream); cudaStreamDestroy(ctx->solve_stream); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1388,6 +1456,13 @@ uz_status uz_debug_phases(uz_context* ctx, int32_t pair_index, int64_t* clocks8_
 }
 
 // ---- introspection -------------------------------------------------------------------------------------
+uz_status uz_set_stream_solve(uz_context* ctx, int32_t ctas_per_sm) {
+    if (!ctx) return UZ_ERR_INVALID;
+    if (ctas_per_sm < 0 || ctas_per_sm > 4) return fail(ctx, UZ_ERR_INVALID, "ctas_per_sm must be 0..4");
+    ctx->stream_solve_ctas = ctas_per_sm;
+    return UZ_OK;
+}
+
 int64_t uz_launch_count(const uz_context* ctx) { return ctx ? ctx->launches : 0; }
 
 uz_status uz_enable_timers(uz_context* ctx, int32_t enable) {

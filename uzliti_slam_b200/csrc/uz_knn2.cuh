@@ -31,6 +31,7 @@ constexpr int kTrainTileRows = 512;                 // 16 KB per stage
 constexpr int kStages = 2;
 constexpr int kKnnSmemBytes = kStages * kTrainTileRows * 32 + 64;
 
+
 struct MatchTask {
     const uint32_t* q_desc;   // "to" camera descriptors (OpenCV query), layout per UZ variant, 32 B rows
     const uint32_t* t_desc;   // "from" camera descriptors (OpenCV train)
@@ -186,10 +187,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // tiles[blockIdx.x] = (task index, first query row of the tile)
+#ifndef UZ_KNN_MINB
+#define UZ_KNN_MINB 6        // resident CTAs per SM the <256,2> shape is compiled for (40 registers, no spills)
+#endif
 template <int THREADS, int QPT, bool CSA, bool PACK16 = false>
-__global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restrict__ tasks,
+__global__ void __launch_bounds__(THREADS, (QPT == 2 && THREADS == 256) ? UZ_KNN_MINB : 1) knn2_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
-                                                       uint2* __restrict__ keys) {
+                                                       uint2* __restrict__ keys,
+                                                       int* __restrict__ pair_pending,
+                                                       unsigned int* __restrict__ progress) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kTrainTileRows * 32);
 
@@ -318,6 +324,17 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const MatchTask* __restri
     for (int k = 0; k < QPT; ++k) {
         const int q = tile.y + k * THREADS + tid;
         if (q < nq) keys[tk->key_off + q] = make_uint2(m1[k], m2[k]);
+    }
+    // Streaming hand-over to the solve kernel that runs beside this one (uz_solve.cuh, solve_stream_kernel):
+    // pair_pending[pair] counts the tiles of the pair that have not published their keys yet.  bar.sync orders
+    // every thread's key stores before thread 0's fence + atomic (release); the consumer polls with ld.acquire.
+    if (pair_pending != nullptr) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicSub(pair_pending + tk->pair, 1);
+            atomicAdd(progress, 1u);          // liveness signal for the consumer's starvation test
+        }
     }
 }
 

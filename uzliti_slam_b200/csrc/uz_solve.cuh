@@ -40,9 +40,19 @@ struct SolveParams {
     int32_t* dbg_counts;     // [pair][iterations] consensus count of every evaluated hypothesis, -1 = not run
     long long* dbg_phase;    // [pair][8] clock64() at the phase boundaries of the CTA (profiling tap)
     int32_t pair_base;       // index of this launch's first pair inside the batch (chunked launches)
+    int32_t dbg_skip;        // UZ_STREAM_PROBE=1 (measurement only): the streaming grid draws pairs but does not solve them
 };
 
 constexpr int kSolveThreads = 128;
+#ifndef UZ_SOLVE_H
+#define UZ_SOLVE_H 2
+#endif
+#ifndef UZ_STREAM_H
+#define UZ_STREAM_H 2
+#endif
+#ifndef UZ_SOLVE_MINB
+#define UZ_SOLVE_MINB 5
+#endif
 
 __host__ __device__ constexpr size_t solve_smem_bytes(int cap) {
     return (size_t)cap * 24 /*float32 copies of P,Q (also: unsorted keys, later the residual norms)*/ +
@@ -65,10 +75,30 @@ __device__ __forceinline__ void write_identity(double* T16) {
 // hence | sqrt(s_f) - ||d|| | <= m := K (4.5 L1(p) + 1.5 L1(q) + 3.5 L1(t)),  K = 1.2e-7 > sqrt(3) u (1 + slack);
 // the kernel uses ONE margin per hypothesis chunk (max over the pair's points + max over the chunk's
 // translations), so the loop compares against two CTA-uniform thresholds.
-// A point is a certain inlier if sqrt(s_f) < thr(1-1e-6) - m and a certain outlier if sqrt(s_f) > thr(1+1e-6) + m;
-// everything else (about 1e-6 of the evaluations, and any NaN) is re-evaluated exactly in double.  The
-// result is therefore bit-identical to the double-only evaluation at ~1/3 of its pipe time.
+// A point is a certain inlier if sqrt(s_f) < thr(1-1e-6) - m and a certain outlier if sqrt(s_f) > thr(1+1e-6) + m.
+// Per hypothesis the loop counts the certain inliers and the not-certainly-outside points; when the two counts differ
+// (a borderline evaluation: about 1e-6 of them) the hypothesis is recounted exactly in double.  A NaN is outside in
+// both views, exactly as in the double evaluation.  The result is therefore bit-identical to the double-only
+// evaluation at a fraction of its pipe time.
 constexpr float kScreenK = 1.2e-7f;
+
+// K4 runs on packed float32 pairs (FFMA2 / FADD2 / FMUL2, sm_100): a lane scores TWO points per instruction.  The
+// float32 copies are therefore stored pair-interleaved: logical point i lives at pidx(i), so that the 8-byte word at
+// [64 b + 2 l] holds points 64 b + l and 64 b + 32 + l - one conflict-free LDS.64 per lane and coordinate.  The arrays
+// are padded to a multiple of 64 with a point that is outside for every finite transform (p = 0, q = 1e18).
+__device__ __forceinline__ int pidx(int i) { return (i & ~63) | ((i & 31) << 1) | ((i >> 5) & 1); }
+constexpr float kPadQ = 1.0e18f;
+
+// Counting without the ALU pipe (which the match kernel running beside this one saturates): for a power of two BIG,
+//   fma.rn.sat(s, -BIG, c * BIG)  ==  1.0f if s < c, else 0.0f     (c * BIG exact; NaN and -inf saturate to 0)
+// as long as one ulp of c times BIG is >= 1 and c * BIG is finite - solve_pair checks that and otherwise sends every
+// hypothesis through the exact path.
+constexpr float kSatBig = 1.2676506e30f;      // 2^100
+__device__ __forceinline__ float sat_less(float s, float c_big) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(s), "f"(-kSatBig), "f"(c_big));
+    return r;
+}
 
 // Rare path of the pre-screen, deliberately not inlined: it must not drag the double-precision transforms
 // into registers inside the float loop.
@@ -150,18 +180,23 @@ __device__ __forceinline__ float block_max(float v, float* s_red /* [THREADS/32]
 // Ratio test (:65-71) of query row q, plus the opt-in cross-check (uz_params.cross_check; the reference has none):
 // the survivor (q, t = best train of q) is kept only if q is also the best query of t in the reversed matching,
 // ties by lowest index - i.e. (q, t) is what cv::BFMatcher(NORM_HAMMING, crossCheck=true).match() returns for q.
+// Keys are always loaded with ld.global.cg (L2 only): in streaming mode they were written, moments ago, by the match
+// kernel running beside this one, so neither the non-coherent path nor a stale L1 sector may serve them.
+__device__ __forceinline__ uint2 load_key(const uint2* p) { return __ldcg(p); }
+
 __device__ __forceinline__ bool match_survives(const uint2 m, int q, int ratio_num, int ratio_den,
-                                               const uint2* __restrict__ keys, uint32_t rev_key_off) {
+                                               const uint2* keys, uint32_t rev_key_off) {
     bool pass = (m.y != kNoKey) && ((int)(m.x >> 16) * ratio_den < (int)(m.y >> 16) * ratio_num);
-    if (pass && rev_key_off != kNoRev) pass = (int)(keys[rev_key_off + (m.x & 0xFFFFu)].x & 0xFFFFu) == q;
+    if (pass && rev_key_off != kNoRev) pass = (int)(load_key(keys + rev_key_off + (m.x & 0xFFFFu)).x & 0xFFFFu) == q;
     return pass;
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __restrict__ tasks,
-                                                        const int2* __restrict__ pair_tasks,
-                                                        const uint2* __restrict__ keys, SolveParams prm,
-                                                        uz_edge_result* __restrict__ results) {
+// Everything after matching for ONE pair (or one direct problem); called by all THREADS threads of a CTA.  Every
+// early return below is CTA-uniform.
+template <int THREADS, int H /* hypotheses scored per pass over the points (each lane: 2 points x H hypotheses) */>
+__device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, const int2* __restrict__ pair_tasks,
+                                           const uint2* keys, const SolveParams& prm,
+                                           uz_edge_result* __restrict__ results, const int pair) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int cap = prm.cap;
     // On-chip state of the pair.  Only float32 copies of the matched 3-D points live here (the scoring loop
@@ -187,8 +222,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int pair = prm.pair_base + blockIdx.x;       // batch-wide index; pair_tasks/results are indexed by it
-    uz_edge_result* res = results + pair;
+    uz_edge_result* res = results + pair;              // batch-wide index; pair_tasks/results are indexed by it
 #define UZ_PHASE(k) do { if (prm.dbg_phase && tid == 0) prm.dbg_phase[(size_t)pair * 8 + (k)] = clock64(); } while (0)
     UZ_PHASE(0);
     int M = 0;
@@ -208,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
                 for (int base = 0; base < tk->nq; base += THREADS) {
                     const int q = base + tid;
                     bool pass = false;
-                    if (q < tk->nq) pass = match_survives(k[q], q, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
+                    if (q < tk->nq) pass = match_survives(load_key(k + q), q, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
                     cnt += __syncthreads_count(pass);
                 }
                 if (cnt > best_score) { best_score = cnt; best = t; }   // :81 strict '>' keeps the first
@@ -223,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
             return;
         }
         const MatchTask* tk = tasks + pt.x + best;
-        const uint2* __restrict__ k = keys + tk->key_off;
+        const uint2* k = keys + tk->key_off;
         const int nq = tk->nq;
         cam_from = tk->cam_from; cam_to = tk->cam_to;
         const uint8_t* __restrict__ vq = tk->q_valid;
@@ -237,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         if (tid == 0) { s_nvalid = 0; s_nratio = 0; }
         __syncthreads();
         for (int i = tid; i < nq; i += THREADS) {
-            const uint2 m = k[i];
+            const uint2 m = load_key(k + i);
             const bool pass = match_survives(m, i, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
             uint16_t d = 0xFFFFu;
             if (pass) {
@@ -282,10 +316,11 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         for (int i = tid; i < M; i += THREADS) {
             const uint32_t key = skeys[i];
             const int q = key & 0xFFFFu;
-            const int t = k[q].x & 0xFFFFu;
+            const int t = load_key(k + q).x & 0xFFFFu;
             const float x = (float)gP[3 * q], y = (float)gP[3 * q + 1], z = (float)gP[3 * q + 2];
             const float u = (float)gQ[3 * t], v = (float)gQ[3 * t + 1], w = (float)gQ[3 * t + 2];
-            pxf[i] = x; pyf[i] = y; pzf[i] = z; qxf[i] = u; qyf[i] = v; qzf[i] = w;
+            const int pi = pidx(i);
+            pxf[pi] = x; pyf[pi] = y; pzf[pi] = z; qxf[pi] = u; qyf[pi] = v; qzf[pi] = w;
             kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
             tq[i] = ((uint32_t)t << 16) | (uint32_t)q;
             if (prm.dbg_matches) {
@@ -304,14 +339,20 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         for (int i = tid; i < M; i += THREADS) {
             const float x = (float)gP[3 * i], y = (float)gP[3 * i + 1], z = (float)gP[3 * i + 2];
             const float u = (float)gQ[3 * i], v = (float)gQ[3 * i + 1], w = (float)gQ[3 * i + 2];
-            pxf[i] = x; pyf[i] = y; pzf[i] = z; qxf[i] = u; qyf[i] = v; qzf[i] = w;
+            const int pi = pidx(i);
+            pxf[pi] = x; pyf[pi] = y; pzf[pi] = z; qxf[pi] = u; qyf[pi] = v; qzf[pi] = w;
             kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
             tq[i] = ((uint32_t)i << 16) | (uint32_t)i;
         }
     }
+    for (int i = M + tid; i < ((M + 63) & ~63); i += THREADS) {      // padding of the last 64-point block
+        const int pi = pidx(i);
+        pxf[pi] = 0.f; pyf[pi] = 0.f; pzf[pi] = 0.f; qxf[pi] = kPadQ; qyf[pi] = kPadQ; qzf[pi] = kPadQ;
+    }
     if (tid == 0) { s_best = -1; s_maxc = 0; s_break = 0; s_run = 0; }
     const float kp_max = block_max<THREADS>(kp_local, s_red, tid);     // (also the barrier after the gather)
     UZ_PHASE(3);
+    if (prm.dbg_skip == 2) return;
 
     if (M < 3) {                 // :118/:158 not enough depth-valid matches
         if (tid == 0) {
@@ -328,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     const uint16_t* __restrict__ samp = prm.samples + (prm.samples_by_m ? (size_t)M * I * 3 : 0);
     const float thr_dn = __double2float_rd(prm.thr * (1.0 - 1e-6));
     const float thr_up = __double2float_ru(prm.thr * (1.0 + 1e-6));
-    constexpr int H = 4;         // hypotheses scored per pass over the points
+    const int M64 = (M + 63) & ~63;
     for (int h0 = 0; h0 < I; h0 += THREADS) {
         const int nh = min(THREADS, I - h0);
         float kt_local = 0.f;
@@ -337,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
             pose_reset(acc);
 #pragma unroll 1
             for (int j = 0; j < 3; ++j) {
-                const int s = samp[(size_t)(h0 + tid) * 3 + j];
+                const int s = pidx(samp[(size_t)(h0 + tid) * 3 + j]);
                 pose_add(acc, pxf[s], pyf[s], pzf[s], qxf[s], qyf[s], qzf[s]);       // == (float) of the doubles (:303-304)
             }
             pose_finish(acc, Th + tid * 12);
@@ -347,48 +388,53 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         const float m_scr = kScreenK * (kp_max + block_max<THREADS>(kt_local, s_red, tid));     // (barrier inside)
         const float lo = thr_dn - m_scr, hi = thr_up + m_scr;
         const float lo2 = lo > 0.f ? lo * lo : -1.f;      // sf < lo2  =>  certainly inside  (never if lo <= 0)
-        const float hi2 = hi * hi;                        // sf > hi2  =>  certainly outside
+        const float hi2 = nextafterf(hi * hi, INFINITY);  // sf >= hi2 =>  certainly outside
+        // the saturating-FMA counters need lo2 * 2^100 exact and finite with ulp(lo2) * 2^100 >= 1; outside that range
+        // of thresholds (below ~1e-11 m or above ~1 km), or with a non-finite margin, every hypothesis is recounted exactly
+        const bool screen_ok = lo2 > 1.4e-23f && hi2 < 1.0e6f;
+        const float lo2_big = lo2 * kSatBig, hi2_big = hi2 * kSatBig;
         if (h0 == 0) UZ_PHASE(4);
+        if (prm.dbg_skip == 4) return;
         for (int hb = warp * H; hb < nh; hb += NW * H) {
-            float T[H][12];
-            int cnt[H];
+            float2 T[H][12];
+            float2 in_c[H], in_b[H];      // per lane and point slot: certain inliers / not certainly outside
 #pragma unroll
             for (int a = 0; a < H; ++a) {
                 const int h = min(hb + a, nh - 1);          // tail: duplicates, their counts are discarded
 #pragma unroll
-                for (int e = 0; e < 12; ++e) T[a][e] = (float)Th[h * 12 + e];   // exact: T holds float32 values
-                cnt[a] = 0;
+                for (int e = 0; e < 12; ++e) { const float t = -(float)Th[h * 12 + e]; T[a][e] = make_float2(t, t); }   // -T (exact: float32 values), so that d = q - T p needs no negation of q
+                in_c[a] = make_float2(0.f, 0.f); in_b[a] = make_float2(0.f, 0.f);
             }
-            for (int base = 0; base < M; base += 32) {       // whole warp stays converged: branch-free common path
-                const bool live = base + lane < M;
-                const int i = live ? base + lane : M - 1;
-                const float x = pxf[i], y = pyf[i], z = pzf[i];
-                const float u = qxf[i], v = qyf[i], w = qzf[i];
-                unsigned need = 0;
+            for (int base = 0; base < M64; base += 64) {      // branch-free: 64 points x H hypotheses per warp step
+                const int o = base + 2 * lane;
+                const float2 x = *reinterpret_cast<const float2*>(pxf + o), y = *reinterpret_cast<const float2*>(pyf + o);
+                const float2 z = *reinterpret_cast<const float2*>(pzf + o), u = *reinterpret_cast<const float2*>(qxf + o);
+                const float2 v = *reinterpret_cast<const float2*>(qyf + o), w = *reinterpret_cast<const float2*>(qzf + o);
 #pragma unroll
                 for (int a = 0; a < H; ++a) {
-                    const float dx = fmaf(T[a][0], x, fmaf(T[a][1], y, fmaf(T[a][2], z, T[a][3]))) - u;
-                    const float dy = fmaf(T[a][4], x, fmaf(T[a][5], y, fmaf(T[a][6], z, T[a][7]))) - v;
-                    const float dz = fmaf(T[a][8], x, fmaf(T[a][9], y, fmaf(T[a][10], z, T[a][11]))) - w;
-                    const float sf = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    const bool inl = sf < lo2;                 // certainly inside
-                    const bool und = !(inl || sf > hi2);       // neither certain (borderline or NaN)
-                    cnt[a] += (int)(inl && live);
-                    need |= (unsigned)(und && live) << a;
-                }
-                if (__any_sync(0xffffffffu, need != 0)) {     // ~1e-6 of the evaluations: exact double, as the reference
-#pragma unroll
-                    for (int a = 0; a < H; ++a)
-                        if ((need >> a) & 1u)
-                            cnt[a] += exact_inlier(Th + min(hb + a, nh - 1) * 12, gP, gQ, tq[i], prm.thr_sq_star);
+                    const float2 dx = __fadd2_rn(__ffma2_rn(T[a][0], x, __ffma2_rn(T[a][1], y, __ffma2_rn(T[a][2], z, T[a][3]))), u);
+                    const float2 dy = __fadd2_rn(__ffma2_rn(T[a][4], x, __ffma2_rn(T[a][5], y, __ffma2_rn(T[a][6], z, T[a][7]))), v);
+                    const float2 dz = __fadd2_rn(__ffma2_rn(T[a][8], x, __ffma2_rn(T[a][9], y, __ffma2_rn(T[a][10], z, T[a][11]))), w);
+                    const float2 sf = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+                    in_c[a] = __fadd2_rn(in_c[a], make_float2(sat_less(sf.x, lo2_big), sat_less(sf.y, lo2_big)));
+                    in_b[a] = __fadd2_rn(in_b[a], make_float2(sat_less(sf.x, hi2_big), sat_less(sf.y, hi2_big)));
                 }
             }
 #pragma unroll
             for (int a = 0; a < H; ++a) {
-                int c = cnt[a];
+                // both counts in one register (each <= 4096 over the warp): certain | (not certainly outside) << 16
+                int c = (int)(in_c[a].x + in_c[a].y) | ((int)(in_b[a].x + in_b[a].y) << 16);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                if (lane == 0 && hb + a < nh) counts[hb + a] = c;
+                int cnt = c & 0xFFFF;
+                if (!screen_ok || cnt != (c >> 16)) {        // a borderline evaluation somewhere: recount exactly, as the reference
+                    cnt = 0;
+                    const double* Texact = Th + min(hb + a, nh - 1) * 12;
+                    for (int i = lane; i < M; i += 32) cnt += exact_inlier(Texact, gP, gQ, tq[i], prm.thr_sq_star);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                }
+                if (lane == 0 && hb + a < nh) counts[hb + a] = cnt;
             }
         }
         __syncthreads();
@@ -411,6 +457,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     }
 
     const int maxc = s_maxc;
+    if (prm.dbg_skip == 3) return;
     if (maxc < 3) {              // :291-294 no hypothesis reached 3 inliers: T = I, consensus 0, still "true"
         if (tid == 0) {
             res->ok = 1; res->cam_from = cam_from; res->cam_to = cam_to;
@@ -459,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
         for (int c0 = 0; c0 < n_in; c0 += CH) {
             const int nch = min(CH, n_in - c0);
             for (int k = tid; k < nch; k += THREADS) {
-                const int i = ilist[c0 + k];
+                const int i = pidx(ilist[c0 + k]);
                 fb[0 * CH + k] = pxf[i]; fb[1 * CH + k] = pyf[i]; fb[2 * CH + k] = pzf[i];
                 fb[3 * CH + k] = qxf[i]; fb[4 * CH + k] = qyf[i]; fb[5 * CH + k] = qzf[i];
                 const float alpha = UZ_FDIV(1.0f, (float)(c0 + k + 1));     // accumulated weight == n exactly
@@ -530,6 +577,107 @@ __global__ void __launch_bounds__(THREADS, 4) solve_kernel(const MatchTask* __re
     }
     UZ_PHASE(7);
 #undef UZ_PHASE
+}
+
+// One CTA per pair: the launch form of small batches, of the direct entry points (uz_estimate_svd, cluster RANSAC) and of
+// everything that runs under a tool that serialises kernels.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, UZ_SOLVE_MINB) solve_kernel(const MatchTask* __restrict__ tasks,
+                                                        const int2* __restrict__ pair_tasks,
+                                                        const uint2* keys, SolveParams prm,
+                                                        uz_edge_result* __restrict__ results) {
+    solve_pair<THREADS, UZ_SOLVE_H>(tasks, pair_tasks, keys, prm, results, prm.pair_base + (int)blockIdx.x);
+}
+
+// Streaming form: a small persistent grid (a CTA or two per SM, 96 registers so that it fits beside five match CTAs)
+// that runs BESIDE the match kernel of the same batch on a high-priority stream.  CTAs draw pairs in batch order from
+// a ticket counter and wait until the match kernel has published every tile of the pair (pair_pending[pair] == 0,
+// written by knn2_kernel with fence + atomic, read here with ld.acquire).  The latency-bound phases of the solve
+// (sort, sequential refit, scans) then fill issue slots the POPC-bound match warps leave idle instead of costing
+// their own 3 ms behind the match kernel.
+//
+// Forward progress does not depend on the two kernels being co-resident: a CTA whose pair makes it wait while the match
+// kernel shows no progress at all for kStallNs (ctl->progress counts finished match tiles) puts the pair on the
+// deferred list, raises ctl->gave_up and exits, and so does every other CTA at its next look; that frees the SMs.
+// A second launch of the same kernel in CLEANUP form, stream-ordered behind the match kernel, then solves the deferred
+// pairs and whatever the ticket counter had not handed out (normally nothing: it exits at once).  Under a tool that
+// serialises kernels (ncu, compute-sanitizer) the match kernel simply runs first and nobody waits.
+struct StreamCtl {
+    unsigned int ticket;       // next pair in batch order
+    unsigned int progress;     // match tiles finished so far (knn2_kernel)
+    unsigned int gave_up;      // a streaming CTA starved: everyone defers and leaves
+    unsigned int n_deferred;   // entries of the deferred list
+    unsigned int ticket2;      // next deferred entry (cleanup form)
+};
+constexpr unsigned long long kStallNs = 20ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Test hook (UZ_STREAM_PROBE=9): holds the match kernel back for a while so that the streaming grid really starves and
+// the give-up + cleanup path above is exercised (tests/test_streaming.py).
+__global__ void delay_kernel(unsigned long long ns) {
+    const unsigned long long t0 = global_timer_ns();
+    while (global_timer_ns() - t0 < ns) __nanosleep(1000);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 5) solve_stream_kernel(const MatchTask* __restrict__ tasks,
+                                                               const int2* __restrict__ pair_tasks,
+                                                               const uint2* keys, SolveParams prm,
+                                                               uz_edge_result* __restrict__ results, int n_pairs,
+                                                               const int* pair_pending, StreamCtl* ctl,
+                                                               int* deferred, int cleanup) {
+    __shared__ int s_next;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int p = -1;
+            if (cleanup) {
+                const unsigned int k = atomicAdd(&ctl->ticket2, 1u);
+                if (k < ld_relaxed_u32(&ctl->n_deferred)) p = deferred[k];
+            }
+            if (p < 0 && (cleanup || ld_relaxed_u32(&ctl->gave_up) == 0)) {
+                const unsigned int t = atomicAdd(&ctl->ticket, 1u);
+                if (t < (unsigned int)n_pairs) p = (int)t;
+            }
+            if (p >= 0 && !cleanup && ld_acquire_s32(pair_pending + p) > 0) {
+                unsigned int seen = ld_relaxed_u32(&ctl->progress), spins = 0;
+                unsigned long long t_seen = global_timer_ns();
+                while (ld_acquire_s32(pair_pending + p) > 0) {
+                    __nanosleep(spins < 32 ? 200 : 1000);
+                    if ((++spins & 31u) != 0) continue;
+                    const unsigned int now = ld_relaxed_u32(&ctl->progress);
+                    const unsigned long long t_now = global_timer_ns();
+                    if (now != seen) { seen = now; t_seen = t_now; continue; }
+                    if (t_now - t_seen > kStallNs || ld_relaxed_u32(&ctl->gave_up) != 0) {
+                        atomicExch(&ctl->gave_up, 1u);
+                        deferred[atomicAdd(&ctl->n_deferred, 1u)] = p;
+                        p = -1;
+                        break;
+                    }
+                }
+            }
+            s_next = p;
+        }
+        __syncthreads();
+        const int pair = s_next;
+        if (pair < 0) return;
+        if (prm.dbg_skip != 1) solve_pair<THREADS, UZ_STREAM_H>(tasks, pair_tasks, keys, prm, results, prm.pair_base + pair);
+        __syncthreads();             // the pair's shared-memory state (and s_next) is reused by the next one
+    }
 }
 
 }  // namespace uz
