@@ -503,10 +503,16 @@ struct KnnConfig { int threads, qpt; };
 const KnnConfig kKnnConfigs[5] = {{256, 4}, {128, 4}, {64, 2}, {256, 2}, {128, 2}};
 
 // Runs K1 (+ optionally K2..K5) for a list of pairs whose cameras are already on the device.
-uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_results) {
+// join = false (chunked callers): the caller's stream is NOT made to wait for a streaming solve, so that the next chunk's
+// match kernel starts while this chunk's last pairs are still being solved; *result_stream is then the stream behind
+// which the records are complete.
+uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_results, bool join = true,
+                    cudaStream_t* result_stream = nullptr) {
     const uz_params prm = ctx->params;     // snapshot (setConfig may race with a batch in the reference)
     const int n_pairs = (int)pairs.size();
+    if (result_stream) *result_stream = ctx->stream;
     if (n_pairs == 0) return UZ_OK;
+    cudaStream_t results_on = ctx->stream;
     ctx->cur_slot ^= 1;
     uz_context::Slot& sl = ctx->slots[ctx->cur_slot];
     if (!sl.done) UZ_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
@@ -709,23 +715,32 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());
         if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
-        if (streaming) {        // rejoin: everything the caller enqueues next on its stream sees the results
-            cudaEvent_t ev = ctx->get_event();
-            UZ_CUDA(ctx, cudaEventRecord(ev, sB));
-            UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
-            ctx->event_pool.push_back(ev);
-            // cleanup form, stream-ordered behind the match kernel: pairs the streaming grid deferred or never drew
-            // (only if it starved - normally every CTA of this launch exits on its first look)
-            solve_stream_kernel<kSolveThreads><<<4 * ctx->sm_count, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(
+        if (streaming) {
+            // cleanup form, ordered behind the match kernel by an event: pairs the streaming grid deferred or never
+            // drew (only if it starved - normally every CTA of this launch exits on its first look)
+            cudaEvent_t ev_match = ctx->get_event();
+            UZ_CUDA(ctx, cudaEventRecord(ev_match, ctx->stream));
+            UZ_CUDA(ctx, cudaStreamWaitEvent(sB, ev_match, 0));
+            ctx->event_pool.push_back(ev_match);
+            solve_stream_kernel<kSolveThreads><<<4 * ctx->sm_count, kSolveThreads, solve_smem_bytes(cap), sB>>>(
                 (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
                 n_pairs, d_pending, d_ctl, d_deferred, 1);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
+            if (join) {         // rejoin: everything the caller enqueues next on its stream sees the results
+                cudaEvent_t ev = ctx->get_event();
+                UZ_CUDA(ctx, cudaEventRecord(ev, sB));
+                UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+                ctx->event_pool.push_back(ev);
+            } else {
+                results_on = sB;
+            }
         }
     }
     if (ctx->timers) ctx->pending.push_back(tm);
-    UZ_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+    UZ_CUDA(ctx, cudaEventRecord(sl.done, results_on));     // the slot's tables and keys are free once the solve is through
     sl.used = true;
+    if (result_stream) *result_stream = results_on;
     return UZ_OK;
 }
 
@@ -1280,12 +1295,22 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     }
     if ((tf && !from_cams) || (tt && !to_cams)) return fail(ctx, UZ_ERR_INVALID, "null camera array");
 
-    // The batch is cut into chunks of pairs.  Chunk c's cameras are uploaded on the high-priority side stream while
-    // chunk c-1 is matched and solved on the main stream, so only the first chunk's H2D time is exposed.
+    // The batch is cut into chunks of pairs and every chunk goes through the whole host pipeline on its own -
+    // intern its cameras, enqueue their upload on the high-priority side stream, enqueue match + solve on the main
+    // stream behind the upload's event, queue its records' way home - so the GPU starts after the host has looked at
+    // the FIRST chunk only, uploads of later chunks run beside the matching of earlier ones, and records are copied
+    // out to the caller while later chunks still compute.  The first chunks are small (1/16 of the batch): what stays
+    // exposed is their upload.
     int n_chunks = ctx->host_chunks;
-    if (n_chunks <= 0) n_chunks = n_pairs >= 8192 ? 4 : (n_pairs >= 2048 ? 2 : 1);
+    if (n_chunks <= 0) n_chunks = n_pairs >= 8192 ? 9 : (n_pairs >= 2048 ? 4 : 1);
     n_chunks = std::max(1, std::min(n_chunks, n_pairs));
     if (ctx->debug) n_chunks = 1;        // the parity taps describe ONE launch pair
+    std::vector<size_t> chunk_pair_end((size_t)n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        // auto: two sixteenths, then eighths; forced chunk counts: equal parts
+        const double frac = (ctx->host_chunks <= 0 && n_chunks == 9) ? (c < 2 ? (c + 1) / 16.0 : (c - 0.0) / 8.0) : (c + 1.0) / n_chunks;
+        chunk_pair_end[c] = c + 1 == n_chunks ? (size_t)n_pairs : std::min<size_t>((size_t)n_pairs, (size_t)(frac * n_pairs + 0.5));
+    }
 
     // unique cameras (a keyframe that appears in many pairs - one query vs many candidates - is uploaded once),
     // numbered in order of first use so that every chunk uploads exactly the cameras nobody before it needed
@@ -1304,10 +1329,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         }
     };
     std::unordered_map<CamKey, uint32_t, CamKeyHash> seen;
-    seen.reserve((tf + tt) * 2);
+    seen.reserve(std::min<size_t>(tf + tt, (size_t)1 << 20) * 2);
     std::vector<const uz_features*> uniq;
-    std::vector<uint32_t> from_u(tf), to_u(tt);
-    std::vector<size_t> chunk_uniq_end((size_t)n_chunks), chunk_pair_end((size_t)n_chunks);
+    std::vector<Cam> up;                       // device views of the unique cameras, in order of first use
     auto intern = [&](const uz_features* f) -> uint32_t {
         const CamKey k{f->descriptors, f->positions, f->valid_3d, f->n, f->desc_stride, f->feature_type, f->sensor_frame};
         auto it = seen.find(k);
@@ -1317,95 +1341,101 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         uniq.push_back(f);
         return id;
     };
-    {
-        size_t cf = 0, ct = 0;
-        int c = 0;
-        for (int i = 0; i < n_pairs; ++i) {
-            for (int k = 0; k < n_from[i]; ++k, ++cf) from_u[cf] = intern(from_cams + cf);
-            for (int k = 0; k < n_to[i]; ++k, ++ct) to_u[ct] = intern(to_cams + ct);
-            if (i + 1 == (int)((int64_t)n_pairs * (c + 1) / n_chunks)) {
-                chunk_uniq_end[c] = uniq.size(); chunk_pair_end[c] = (size_t)i + 1;
-                ++c;
-            }
-        }
-    }
-    tr.lap("dedupe");
 
-    // enqueue every chunk's upload (+ CSA pass) on the side stream, one event behind each
     cudaStream_t main_stream = ctx->stream;
     const bool piped = n_chunks > 1 && ctx->side != nullptr;
-    std::vector<Cam> up(uniq.size());
-    std::vector<cudaEvent_t> ready((size_t)n_chunks, nullptr);
     if (piped) {            // the side stream must not run ahead of work the caller queued on the main stream
         cudaEvent_t ev = ctx->get_event();
         UZ_CUDA(ctx, cudaEventRecord(ev, main_stream));
         UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ev, 0));
         ctx->event_pool.push_back(ev);
-        ctx->stream = ctx->side;
     }
-    for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
-        const size_t u0 = c ? chunk_uniq_end[c - 1] : 0, u1 = chunk_uniq_end[c];
-        std::vector<const uz_features*> part(uniq.begin() + u0, uniq.begin() + u1);
-        std::vector<Cam> got;
-        ctx->copy_beside_compute = piped && c > 0;       // chunk 0 has the chip to itself
-        st = upload_cams(ctx, ctx->transient, part, got);
-        ctx->copy_beside_compute = 0;
-        if (st != UZ_OK) break;
-        std::copy(got.begin(), got.end(), up.begin() + u0);
-        if (piped) {
-            ready[c] = ctx->get_event();
-            if (cudaEventRecord(ready[c], ctx->stream) != cudaSuccess) { st = fail(ctx, UZ_ERR_CUDA, "cudaEventRecord failed"); break; }
-        }
-    }
-    ctx->stream = main_stream;
-    if (st != UZ_OK) { for (auto e : ready) if (e) ctx->event_pool.push_back(e); return st; }
-    tr.lap("upload_cams (enqueue)");
-
-    std::vector<Cam> fcams(tf), tcams(tt);
-    for (size_t i = 0; i < tf; ++i) fcams[i] = up[from_u[i]];
-    for (size_t i = 0; i < tt; ++i) tcams[i] = up[to_u[i]];
-    std::vector<PairRef> pairs((size_t)n_pairs);
-    {
-        size_t cf = 0, ct = 0;
-        for (int i = 0; i < n_pairs; ++i) {
-            pairs[i] = PairRef{fcams.data() + cf, n_from[i], tcams.data() + ct, n_to[i]};
-            cf += (size_t)n_from[i]; ct += (size_t)n_to[i];
-        }
-    }
-    tr.lap("pair refs");
     UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
     UZ_CUDA(ctx, ctx->h_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
     uz_edge_result* h_res = (uz_edge_result*)ctx->h_results.p;
     std::vector<cudaEvent_t> home((size_t)n_chunks, nullptr);
-    for (int c = 0; c < n_chunks; ++c) {
-        const size_t p0 = c ? chunk_pair_end[c - 1] : 0, p1 = chunk_pair_end[c];
-        if (piped) {
-            cudaStreamWaitEvent(ctx->stream, ready[c], 0);
-            ctx->event_pool.push_back(ready[c]);
-            ready[c] = nullptr;
+    std::vector<char> copied((size_t)n_chunks, 0);
+    std::vector<uint32_t> from_u, to_u;
+    std::vector<Cam> fcams, tcams;
+    std::vector<PairRef> part;
+    auto chunk_begin = [&](int c) { return c ? chunk_pair_end[c - 1] : (size_t)0; };
+    // records of finished chunks go out to the caller while the GPU works on later ones
+    auto drain = [&](int upto, bool wait) {
+        for (int d = 0; d < upto && st == UZ_OK; ++d) {
+            if (copied[d] || !home[d]) continue;
+            if (!wait && cudaEventQuery(home[d]) != cudaSuccess) { cudaGetLastError(); break; }
+            if (wait && cudaEventSynchronize(home[d]) != cudaSuccess) { st = fail(ctx, UZ_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+            memcpy(results + chunk_begin(d), h_res + chunk_begin(d), (chunk_pair_end[d] - chunk_begin(d)) * sizeof(uz_edge_result));
+            copied[d] = 1;
         }
-        if (p1 > p0 && st == UZ_OK) {
-            std::vector<PairRef> part(pairs.begin() + p0, pairs.begin() + p1);
-            st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0);
-            // records come home chunk by chunk behind their solve kernel, into pinned memory (a pageable
-            // destination would make the copy synchronous and stall the enqueue of the next chunk)
-            if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
-                                               cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-                st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
-            if (st == UZ_OK) { home[c] = ctx->get_event(); cudaEventRecord(home[c], ctx->stream); }
+    };
+    size_t cf = 0, ct = 0;
+    for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
+        const size_t p0 = chunk_begin(c), p1 = chunk_pair_end[c];
+        if (p1 <= p0) continue;
+        // (1) intern the chunk's cameras
+        const size_t u0 = uniq.size(), cf0 = cf, ct0 = ct;
+        from_u.clear(); to_u.clear();
+        for (size_t i = p0; i < p1; ++i) {
+            for (int k = 0; k < n_from[i]; ++k, ++cf) from_u.push_back(intern(from_cams + cf));
+            for (int k = 0; k < n_to[i]; ++k, ++ct) to_u.push_back(intern(to_cams + ct));
         }
+        // (2) upload (+ CSA pass) of the cameras nobody before this chunk needed, on the side stream
+        cudaEvent_t ready = nullptr;
+        if (uniq.size() > u0) {
+            std::vector<const uz_features*> fresh(uniq.begin() + u0, uniq.end());
+            std::vector<Cam> got;
+            if (piped) ctx->stream = ctx->side;
+            ctx->copy_beside_compute = piped && c > 0;       // chunk 0 has the chip to itself
+            st = upload_cams(ctx, ctx->transient, fresh, got);
+            ctx->copy_beside_compute = 0;
+            if (st == UZ_OK && piped) {
+                ready = ctx->get_event();
+                if (cudaEventRecord(ready, ctx->stream) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "cudaEventRecord failed");
+            }
+            ctx->stream = main_stream;
+            if (st != UZ_OK) { if (ready) ctx->event_pool.push_back(ready); break; }
+            up.insert(up.end(), got.begin(), got.end());
+        }
+        // (3) match + solve behind the upload, records home behind the solve
+        fcams.resize(cf - cf0); tcams.resize(ct - ct0);
+        for (size_t i = 0; i < fcams.size(); ++i) fcams[i] = up[from_u[i]];
+        for (size_t i = 0; i < tcams.size(); ++i) tcams[i] = up[to_u[i]];
+        part.resize(p1 - p0);
+        {
+            size_t a = 0, b2 = 0;
+            for (size_t i = p0; i < p1; ++i) {
+                part[i - p0] = PairRef{fcams.data() + a, n_from[i], tcams.data() + b2, n_to[i]};
+                a += (size_t)n_from[i]; b2 += (size_t)n_to[i];
+            }
+        }
+        if (ready) {
+            cudaStreamWaitEvent(ctx->stream, ready, 0);
+            ctx->event_pool.push_back(ready);
+        }
+        cudaStream_t rs = ctx->stream;
+        st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0, /*join=*/false, &rs);
+        // into pinned memory: a pageable destination would make the copy synchronous and stall the next chunk's enqueue
+        if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
+                                           cudaMemcpyDeviceToHost, rs) != cudaSuccess)
+            st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
+        if (st == UZ_OK) { home[c] = ctx->get_event(); cudaEventRecord(home[c], rs); }
+        if (c == 0) tr.lap("first chunk enqueued");
+        drain(c, false);
     }
-    tr.lap("run_pairs (enqueue)");
-    for (int c = 0; c < n_chunks; ++c) {
-        if (!home[c]) continue;
-        const size_t p0 = c ? chunk_pair_end[c - 1] : 0, p1 = chunk_pair_end[c];
-        if (st == UZ_OK && cudaEventSynchronize(home[c]) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "cudaEventSynchronize failed");
-        if (st == UZ_OK) memcpy(results + p0, h_res + p0, (p1 - p0) * sizeof(uz_edge_result));
-        ctx->event_pool.push_back(home[c]);
+    tr.lap("all chunks enqueued");
+    drain(n_chunks, true);
+    for (auto e : home) if (e) ctx->event_pool.push_back(e);
+    if (st != UZ_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->side) cudaStreamSynchronize(ctx->side);
+        if (ctx->solve_stream) cudaStreamSynchronize(ctx->solve_stream);
+        cudaGetLastError();
+        return st;
     }
-    if (st != UZ_OK) { cudaStreamSynchronize(ctx->stream); cudaGetLastError(); return st; }
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    tr.lap("wait GPU + D2H");
+    if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
+    tr.lap("wait GPU + records out");
     return UZ_OK;
 }
 
