@@ -318,6 +318,89 @@ def measure_places(est, handles, kfs, my_pairs=None, cpu_keyframes=1500):
                                 same_pairs_as_gpu=same))
 
 
+def measure_other_configs(est, handles, kfs):
+    """The other BASELINE.json configs, each as one short measurement beside the headline (rank 0, not part of the timed
+    region; parity for these shapes is in tests/): C1 single pair latency, C3 one query vs 1000 candidates, C5 rigs of
+    4 x 2000 features with 1000 hypotheses.  CPU figures are the single-thread oracle port on the same inputs."""
+    from oracle import binding as O
+    from uzliti_slam_b200 import synthetic as S
+    out = {}
+
+    # C1: one pair, 500 ORB-256 features each, through the store (handles) and from host buffers
+    f, t, _ = S.make_pair(500, seed=1)
+    h = est.add_keyframes([f, t])
+    lat = []
+    for _ in range(60):
+        t0 = time.perf_counter()
+        r = est.estimateEdges(h[:1], h[1:2])
+        lat.append(time.perf_counter() - t0)
+    lat_host = []
+    for _ in range(60):
+        t0 = time.perf_counter()
+        est.estimateEdgesHost([([f], [t])])
+        lat_host.append(time.perf_counter() - t0)
+    cpu = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        o = O.estimate_edge([f], [t])
+        cpu.append(time.perf_counter() - t0)
+    out["C1_single_pair_500"] = dict(latency_us_store=round(float(np.median(lat[10:])) * 1e6, 1),
+                                     latency_us_host_buffers=round(float(np.median(lat_host[10:])) * 1e6, 1),
+                                     cpu_port_1thread_us=round(float(np.median(cpu)) * 1e6, 1),
+                                     same_consensus_as_cpu=bool(int(r[0]["consensus"]) == int(o["consensus"])))
+    for x in h:
+        est.remove_keyframe(int(x))
+
+    # C3: one query keyframe against 1000 candidates of the resident map (N = 1000)
+    q = np.full(1000, handles[0], dtype=handles.dtype)
+    cand = handles[1:1001]
+    est.estimateEdges(cand, q)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        est.estimateEdges(cand, q)
+    dt = (time.perf_counter() - t0) / reps
+    out["C3_one_query_vs_1000"] = dict(ms_per_query=round(dt * 1e3, 3), edges_per_s=round(1000 / dt, 1),
+                                       note="1e9 descriptor compares + 1000 RANSACs per query keyframe, records back on the host")
+
+    # C5: rig keyframes (4 cameras x 2000 features), 4 same-frame matchings of 2000 x 2000 per pair, 1000 hypotheses
+    rigs_f, rigs_t = [], []
+    for p in range(8):
+        cf, ct = [], []
+        for cam in range(4):
+            a, b, _ = S.make_pair(2000, seed=900 + 10 * p + cam, rho=0.2 + 0.1 * ((cam + p) % 4), sensor_frame=cam)
+            cf.append(a); ct.append(b)
+        rigs_f.append(cf); rigs_t.append(ct)
+    hf = est.add_keyframes(rigs_f)
+    ht = est.add_keyframes(rigs_t)
+    n5 = 592
+    pf, pt = np.resize(hf, n5), np.resize(ht, n5)
+    est.setConfig(ransac_iterations=1000)
+    try:
+        est.estimateEdges(pf, pt)
+        est.enable_timers(True)
+        est.reset_timers()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r5 = est.estimateEdges(pf, pt)
+        dt = (time.perf_counter() - t0) / 3
+        tm = est.get_timers()
+        est.enable_timers(False)
+        t0 = time.perf_counter()
+        o5 = O.estimate_edge(rigs_f[0], rigs_t[0], iterations=1000)
+        cpu5 = time.perf_counter() - t0
+    finally:
+        est.setConfig(ransac_iterations=100)
+    out["C5_rig_4x2000_1000hyp"] = dict(pairs=n5, edges_per_s=round(n5 / dt, 1),
+                                        knn2_gcmp_per_s=round(tm["compares"] / (tm["match_ms"] * 1e-3) * 1e-9, 1),
+                                        knn2_ms=round(tm["match_ms"] / 3, 3), solve_ms=round(tm["solve_ms"] / 3, 3),
+                                        cpu_port_1thread_edges_per_s=round(1.0 / cpu5, 2),
+                                        same_consensus_as_cpu=bool(int(r5[0]["consensus"]) == int(o5["consensus"])))
+    for x in list(hf) + list(ht):
+        est.remove_keyframe(int(x))
+    return out
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -476,6 +559,10 @@ def run_gpu(args):
     if rank == 0 and not args.no_places:
         places = measure_places(est, handles, kfs, my_pairs=None)
 
+    others = None
+    if rank == 0 and not args.no_extras:
+        others = measure_other_configs(est, handles, kfs)
+
     if rank == 0:
         cmp_per_launch = tm["compares"] / max(tm["match_launches"], 1)
         knn_ms = tm["match_ms"] / max(tm["match_launches"], 1)
@@ -531,7 +618,7 @@ def run_gpu(args):
             cpu_baseline=cpu,
             e2e=dict(value=round(e2e_val, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                      api="uz_estimate_edges_host (pinned host FeatureData in, host edge records out)"),
-            gpu_launches=launches, clocks=clocks, sanity=sanity, candidate_generation=places)
+            gpu_launches=launches, clocks=clocks, sanity=sanity, candidate_generation=places, other_configs=others)
         print(json.dumps(line), flush=True)
     est.close()
     if world > 1:
@@ -549,6 +636,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-places", action="store_true", help="skip the candidate-generation (8f-1) measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short C1/C3/C5 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

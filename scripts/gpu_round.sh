@@ -11,13 +11,16 @@ cat gpurun_out/bench_$TAG.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_ref_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 3 -c 1 -f -o gpurun_out/knn2_full_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 3 -c 1 -f -o gpurun_out/solve_full_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
+# streaming form (persistent grid; under ncu it is serialised behind the match kernel) and the one-CTA-per-pair form
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_stream_kernel -s 6 -c 1 -f -o gpurun_out/solve_stream_full_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -c 1 -f -o gpurun_out/solve_full_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 for k in places_insert_kernel places_vote_kernel places_select_kernel; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/${k}_full_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 done
 ls -la gpurun_out
