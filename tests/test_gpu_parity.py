@@ -200,6 +200,29 @@ def test_edge_host_path(est, oracle, n, seed, kw):
     est.set_debug(False)
 
 
+def test_edge_maximum_size(est, oracle):
+    """UZ_MAX_FEATURES = 4096 keypoints per camera: the largest pair the on-chip solve holds (cap 4096, one CTA per SM),
+    with and without depth gaps; one more keypoint is refused with an error, not truncated."""
+    for seed, kw in ((70, dict(rho=0.9, invalid_frac=0.0)), (71, dict(rho=0.6))):
+        f, t, _ = S.make_pair(4096, seed=seed, **kw)
+        est.set_debug(True)
+        r = est.estimateEdgeDirect([f], [t])
+        o = oracle.estimate_edge([f], [t])
+        _check_edge(r, o, f"max size seed={seed}")
+        assert r["n_matches"] > 2000
+        m, mask = est.debug_pair(0, r["n_matches"])
+        assert np.array_equal(m, o["matches"])
+        assert np.array_equal(mask, o["inlier_mask"])
+        assert np.array_equal(est.debug_counts(0), o["counts"])
+        est.set_debug(False)
+    f, t, _ = S.make_pair(4097, seed=72)
+    with pytest.raises(Exception, match="feature count out of range"):
+        est.estimateEdgeDirect([f], [t])
+    # the context is still usable after the refusal
+    f, t, _ = S.make_pair(100, seed=73, rho=0.8)
+    _check_edge(est.estimateEdgeDirect([f], [t]), oracle.estimate_edge([f], [t]), "after refusal")
+
+
 def test_edge_recovers_ground_truth(est):
     f, t, Tgt = S.make_pair(1000, seed=21)
     r = est.estimateEdgeDirect([f], [t])

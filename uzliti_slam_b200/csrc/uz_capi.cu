@@ -465,11 +465,11 @@ template <int THREADS, int QPT>
 void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
                  unsigned int* d_progress) {
     if (ctx->variant_csa && ctx->variant_pack16)
-        knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+        knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else if (ctx->variant_csa)
-        knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+        knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else
-        knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, kKnnSmemBytes, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+        knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
 }
 
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
@@ -492,6 +492,7 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = knn2_carveout<64, 2>();
     if (e == cudaSuccess) e = knn2_carveout<256, 2>();
     if (e == cudaSuccess) e = knn2_carveout<128, 2>();
+    if (e == cudaSuccess) e = knn2_carveout<32, 2>();
     if (e == cudaSuccess) e = max_shared_carveout(solve_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(solve_stream_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
@@ -499,8 +500,9 @@ cudaError_t set_carveouts() {
     return e;
 }
 
-struct KnnConfig { int threads, qpt; };
-const KnnConfig kKnnConfigs[5] = {{256, 4}, {128, 4}, {64, 2}, {256, 2}, {128, 2}};
+// relative throughput of a shape at full occupancy (measured on C4-sized work; the one-warp CTA is capped at 32 warps per SM)
+struct KnnConfig { int threads, qpt; double speed; };
+const KnnConfig kKnnConfigs[6] = {{256, 4, 0.92}, {128, 4, 0.92}, {64, 2, 0.985}, {256, 2, 1.0}, {128, 2, 1.0}, {32, 2, 0.95}};
 
 // Runs K1 (+ optionally K2..K5) for a list of pairs whose cameras are already on the device.
 // join = false (chunked callers): the caller's stream is NOT made to wait for a streaming solve, so that the next chunk's
@@ -578,8 +580,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     double best_cost = 1e300;
     // candidates: two queries per thread (40-56 registers: 6 resident CTAs per SM, measured 8 % faster than the
     // four-query shapes, which stay reachable through UZ_KNN_CFG), largest tile first
-    static const int kCandidates[3] = {3, 4, 2};
-    for (int ci = 0; ci < 3; ++ci) {
+    static const int kCandidates[4] = {3, 4, 2, 5};
+    for (int ci = 0; ci < 4; ++ci) {
         const int c = kCandidates[ci];
         const int tile = kKnnConfigs[c].threads * kKnnConfigs[c].qpt;
         double padded = 0; size_t tiles = 0;
@@ -587,12 +589,12 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             const size_t nt = ((size_t)tasks[t].nq + tile - 1) / tile;
             tiles += nt; padded += (double)nt * tile * tasks[t].nt;
         }
-        // a launch that cannot fill the chip twice pays for its idle SMs
-        const double fill = std::min(1.0, (double)tiles * kKnnConfigs[c].threads / (2.0 * ctx->sm_count * 512));
-        const double cost = padded / std::max(fill, 1e-3);
+        // a launch that cannot fill the chip (48 resident warps per SM) pays for its idle warp slots
+        const double fill = std::min(1.0, (double)tiles * kKnnConfigs[c].threads / ((double)ctx->sm_count * 1536));
+        const double cost = padded / (kKnnConfigs[c].speed * std::max(fill, 1e-3));
         if (cost < best_cost * 0.999) { best_cost = cost; best_cfg = c; }
     }
-    if (ctx->force_cfg >= 0 && ctx->force_cfg < 5) best_cfg = ctx->force_cfg;
+    if (ctx->force_cfg >= 0 && ctx->force_cfg < 6) best_cfg = ctx->force_cfg;
     const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
     size_t n_tiles = 0;
     for (size_t t = 0; t < n_tasks; ++t) n_tiles += ((size_t)tasks[t].nq + tile_rows - 1) / tile_rows;
@@ -689,7 +691,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
             case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
             case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            default: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
         }
         ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());

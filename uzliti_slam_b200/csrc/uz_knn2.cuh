@@ -27,9 +27,17 @@
 namespace uz {
 
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
-constexpr int kTrainTileRows = 512;                 // 16 KB per stage
 constexpr int kStages = 2;
-constexpr int kKnnSmemBytes = kStages * kTrainTileRows * 32 + 64;
+// Shape of one CTA: THREADS x QPT query rows, train rows staged in kStages tiles of knn_train_rows() rows.  The
+// two-queries-per-thread shapes scale their staging with the CTA (128 B of shared memory per thread) and are compiled
+// for 40 registers, so that every one of them keeps 48 warps resident per SM (32 for the one-warp CTA: 32 CTAs per SM is
+// the hardware limit); small CTAs exist so that ragged query counts waste little (a 400-row camera costs 448 rows in
+// one-warp CTAs, 512 in anything larger).
+__host__ __device__ constexpr int knn_train_rows(int threads, int qpt) { return qpt == 2 ? (threads >= 64 ? 2 * threads : 128) : 512; }
+__host__ __device__ constexpr int knn_smem_bytes(int threads, int qpt) { return kStages * knn_train_rows(threads, qpt) * 32 + 64; }
+__host__ __device__ constexpr int knn_min_ctas(int threads, int qpt) {
+    return qpt == 2 ? (threads == 256 ? 6 : threads == 128 ? 12 : threads == 64 ? 24 : 32) : 1;
+}
 
 
 struct MatchTask {
@@ -187,15 +195,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // tiles[blockIdx.x] = (task index, first query row of the tile)
-#ifndef UZ_KNN_MINB
-#define UZ_KNN_MINB 6        // resident CTAs per SM the <256,2> shape is compiled for (40 registers, no spills)
-#endif
 template <int THREADS, int QPT, bool CSA, bool PACK16 = false>
-__global__ void __launch_bounds__(THREADS, (QPT == 2 && THREADS == 256) ? UZ_KNN_MINB : 1) knn2_kernel(const MatchTask* __restrict__ tasks,
+__global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys,
                                                        int* __restrict__ pair_pending,
                                                        unsigned int* __restrict__ progress) {
+    constexpr int kTrainTileRows = knn_train_rows(THREADS, QPT);
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kTrainTileRows * 32);
 
