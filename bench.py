@@ -608,6 +608,12 @@ def run_gpu(args):
                           alone=dict(knn2_ms_per_launch=round(alone["knn2_ms"], 3), solve_ms_per_launch=round(alone["solve_ms"], 3),
                                      achieved=round(gcmp_alone, 2), frac=round(gcmp_alone / peak, 4)),
                           stream_solve_ctas_per_sm=STREAM_SOLVE,
+                          solve=dict(kernel="solve_kernel (one CTA per pair, alone)", bound="latency/issue, not HBM (reported as the north star asks)",
+                                     algorithmic_bytes_per_pair=int(N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec),
+                                     achieved_gbs=round(pairs_per_gpu * (N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
+                                                        / (alone["solve_ms"] * 1e-3) * 1e-9, 2),
+                                     frac_of_hbm=round(pairs_per_gpu * (N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
+                                                       / (alone["solve_ms"] * 1e-3) * 1e-9 / hbm_peak, 5)),
                           pipe_peaks_gops={k: round(v, 1) for k, v in peaks.items()},
                           textbook_peak_8popc=round(peaks["popc"] / 8.0, 2), frac_of_textbook=round(gcmp / (peaks["popc"] / 8.0), 4),
                           knn2_ms_per_launch=round(knn_ms, 3), solve_ms_per_launch=round(solve_ms, 3),

@@ -649,7 +649,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         }
     }
     // the streaming solve needs its 96-register CTAs to fit beside the match CTAs: one pair's on-chip state must
-    // leave room for them (cap <= 1024: 44 KB), and the batch must be large enough to be worth a persistent grid
+    // leave room for them (cap <= 1024: 44 KB; at cap 2048 the gain measured on C5 rigs was 1 %), and the batch must be large enough to be worth a persistent grid
     const int stream_ctas = ctx->stream_solve_ctas * ctx->sm_count;
     const bool streaming = with_solve && ctx->solve_stream != nullptr && ctx->stream_solve_ctas > 0 && cap <= 1024 &&
                            n_pairs >= (ctx->stream_min_pairs > 0 ? ctx->stream_min_pairs : 2 * stream_ctas) && n_tiles > 0;
