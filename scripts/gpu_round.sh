@@ -12,6 +12,10 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 cat gpurun_out/bench_ref_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench_$TAG.log 2>&1
+# the same list with the solve BEHIND the match kernel (UZ_STREAM_SOLVE=0): under ncu kernels are serialised, so only this
+# form's per-kernel shares are comparable with a live step
+UZ_STREAM_SOLVE=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches_serial_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-places > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 3 -c 1 -f -o gpurun_out/knn2_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 # streaming form (persistent grid; under ncu it is serialised behind the match kernel) and the one-CTA-per-pair form
