@@ -6,9 +6,10 @@
 // OpenCV's order by (distance, trainIdx); 0xFFFFFFFF marks a missing neighbour (nt < 2).
 //
 // Mapping: one CTA per (matching, query tile).  Every thread keeps QPT query descriptors in registers
-// (8 x u32 each); train descriptors stream through shared memory in 2-stage tiles filled by 1-D TMA
-// bulk copies (cp.async.bulk + mbarrier) and are read with warp-broadcast 128-bit loads, so one
-// LDS.128 pair feeds 32 x QPT compares.
+// (8 x u32 each; QPT = 2 in the shapes the host picks, 40 registers, 48 resident warps per SM); train
+// descriptors stream through shared memory in 2-stage tiles filled by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier) and are read with warp-broadcast 128-bit loads, so one LDS.128 pair feeds
+// 32 x QPT compares.
 //
 // Arithmetic.  A 256-bit compare is 8 XOR + 8 POPC in the textbook form; POPC issues at a quarter of
 // the LOP3 rate, so the kernel trades POPCs for LOP3s with a carry-save adder tree.  Descriptors are
@@ -19,7 +20,8 @@
 //   C1=maj(x0,x1,x2)  C2=maj(x3,x4,x5)  C3=maj(S1,S2,x6)       (x2,x5,x6 are implied: lut 0xD4)
 //   S5=C1^C2^C3       C5=maj(C1,C2,C3)
 //   distance = popc(S3) + popc(x7) + 2 popc(S5) + 4 popc(C5)
-// = 13 LOP3 + 4 POPC + 4 IMAD (weights and the <<16 folded into the key build) + 3 VIMNMX (top-2).
+// = 13 LOP3 + 4 POPC + 4 IMAD (weights and the key shift folded into the key build); the top-2 update costs
+// 2.5 VIMNMX per compare on 32-bit keys and 1.25 on the packed 16-bit keys below (PACK16, the default).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
