@@ -118,6 +118,7 @@ static void feature_view(const FeatureData& f, int frame_tag, std::vector<uint8_
     out->valid_3d = valid_bytes.data();
     out->n = n;
     out->desc_stride = (int)f.features_.step;
+    out->desc_bytes = f.features_.cols;          // 32 (ORB, BRIEF) or 64 (BRISK, FREAK)
     out->feature_type = f.feature_type_;
     out->sensor_frame = frame_tag;
 }

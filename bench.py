@@ -398,6 +398,33 @@ def measure_other_configs(est, handles, kfs):
                                         same_consensus_as_cpu=bool(int(r5[0]["consensus"]) == int(o5["consensus"])))
     for x in list(hf) + list(ht):
         est.remove_keyframe(int(x))
+
+    # BRISK / FREAK rows (64 bytes; cv::BRISK is FeatureExtractionCore's default, feature_extraction_core.cpp:46-49): the same
+    # loop-closure batch shape on a small map of 512-bit descriptors, through knn2_wide_kernel (8 POPC per compare)
+    kw, pw, _ = S.make_map(400, n_features=1000, k_candidates=20, seed=77, desc_bytes=64)
+    hw = est.add_keyframes(kw)
+    est.estimateEdges(hw[pw[:, 0]], hw[pw[:, 1]])
+    est.enable_timers(True)
+    est.reset_timers()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rw = est.estimateEdges(hw[pw[:, 0]], hw[pw[:, 1]])
+    dt = (time.perf_counter() - t0) / 3
+    tm = est.get_timers()
+    est.enable_timers(False)
+    t0 = time.perf_counter()
+    ow = O.estimate_edge([kw[pw[0, 0]]], [kw[pw[0, 1]]])
+    cpuw = time.perf_counter() - t0
+    gcmp = tm["compares"] / (tm["match_ms"] * 1e-3) * 1e-9
+    popc = est.microbench(0)
+    out["BRISK512_loop_closure"] = dict(pairs=int(len(pw)), edges_per_s=round(len(pw) / dt, 1),
+                                        knn2_wide_gcmp512_per_s=round(gcmp, 1), knn2_wide_ms=round(tm["match_ms"] / 3, 3),
+                                        frac_of_popc_ceiling=round(gcmp * 8 / popc, 4),
+                                        popc_per_compare=8, lop3_per_compare=26,
+                                        cpu_port_1thread_edges_per_s=round(1.0 / cpuw, 2),
+                                        same_consensus_as_cpu=bool(int(rw[0]["consensus"]) == int(ow["consensus"])))
+    for x in hw:
+        est.remove_keyframe(int(x))
     return out
 
 

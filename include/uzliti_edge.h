@@ -25,6 +25,7 @@ extern "C" {
 #endif
 
 #define UZ_DESC_BYTES 32          /* ORB/BRIEF-256: feature_extraction/external/aorb/aorb.h:54 (kBytes = 32) */
+#define UZ_MAX_DESC_BYTES 64      /* BRISK/FREAK-512: cv::BRISK / cv::FREAK rows, feature_extraction_core.cpp:69-77 */
 #define UZ_MAX_FEATURES 4096      /* per camera (solve kernel keeps a pair on-chip); reference front-end caps at 400 (cfg/FeatureExtraction.cfg:11) */
 #define UZ_MAX_ITERATIONS 4096    /* cfg/FeatureLinkEstimation.cfg:11 allows 1..1000 */
 
@@ -33,7 +34,7 @@ typedef enum {
     UZ_ERR_INVALID = -1,      /* bad argument (null pointer, size out of range, unknown keyframe handle) */
     UZ_ERR_CUDA = -2,         /* CUDA runtime error or no usable device; see uz_last_error() */
     UZ_ERR_NOMEM = -3,
-    UZ_ERR_UNSUPPORTED = -4   /* e.g. descriptor width != 32 bytes, non-binary feature type */
+    UZ_ERR_UNSUPPORTED = -4   /* e.g. descriptor width other than 32 or 64 bytes */
 } uz_status;
 
 /* graph_slam_msgs/msg/Features.msg:1-6 */
@@ -60,11 +61,14 @@ typedef struct {
 
 /* One FeatureData (graph_slam_common/include/graph_slam_common/sensor_data.h:49-70) as borrowed POD. */
 typedef struct {
-    const uint8_t* descriptors;    /* features_: n rows x 32 bytes, row stride desc_stride (cv::Mat CV_8U) */
+    const uint8_t* descriptors;    /* features_: n rows x desc_bytes, row stride desc_stride (cv::Mat CV_8U) */
     const double*  positions;      /* feature_positions_: 3 x n column-major doubles (Eigen::MatrixXd)      */
     const uint8_t* valid_3d;       /* valid_3d_: n bytes, non-zero = has depth                               */
     int32_t n;
-    int32_t desc_stride;           /* bytes between descriptor rows (>= 32)                                  */
+    int32_t desc_stride;           /* bytes between descriptor rows (>= desc_bytes; features_.step)          */
+    int32_t desc_bytes;            /* features_.cols: 32 (ORB, BRIEF) or 64 (BRISK, FREAK); 0 means 32.  Cameras of
+                                      different widths are never compared (cv::BFMatcher would throw): such a camera
+                                      pair is skipped like one with different feature_type_                   */
     int32_t feature_type;          /* feature_type_                                                          */
     int32_t sensor_frame;          /* sensor_frame_ interned by the caller (equal strings <=> equal tags)    */
 } uz_features;
@@ -120,9 +124,10 @@ typedef struct {
 uz_status uz_backproject(uz_context* ctx, const int32_t* u, const int32_t* v, int32_t n, const float* depth,
                          int32_t depth_stride_bytes, const uz_camera* cam, int32_t reverse, double* positions_out,
                          uint8_t* valid_out);
-/* Same, but the keyframe goes straight into the store (positions never exist on the host): descriptors n x 32 bytes
- * (row stride desc_stride) + pixels + the depth image in, a handle out. */
-uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t desc_stride, const int32_t* u, const int32_t* v,
+/* Same, but the keyframe goes straight into the store (positions never exist on the host): descriptors n x desc_bytes
+ * (32 or 64; row stride desc_stride) + pixels + the depth image in, a handle out. */
+uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t desc_stride, int32_t desc_bytes,
+                            const int32_t* u, const int32_t* v,
                             int32_t n, const float* depth, int32_t depth_stride_bytes, const uz_camera* cam, int32_t feature_type,
                             int32_t sensor_frame, int32_t reverse, int32_t* handle_out);
 /* FeatureData::fromMsg (graph_slam_common/src/sensor_data.cpp:124-171) applied on the device to the ROS1-serialised
@@ -132,17 +137,22 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
  * (graph_slam_common/src/rosbag_storage.cpp:135-211).  Descriptor floats are narrowed to bytes as the reference does. */
 uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t feature_type,
                             int32_t sensor_frame, int32_t* handle_out);
-/* The decode alone, results back on the host (uv_out optional: n x 2 int32). */
+/* The decode alone, results back on the host (uv_out optional: n x 2 int32).  The descriptor width is what the
+ * elements carry (32 or 64, all equal): descriptors_out needs capacity x UZ_MAX_DESC_BYTES bytes and receives n packed
+ * rows of *desc_bytes_out bytes. */
 uz_status uz_wire_decode(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t capacity, int32_t* n_out,
-                         uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out, int32_t* uv_out);
-/* Read one stored camera back (descriptors n x 32 as given, positions 3 x n, valid n); any output may be NULL. */
+                         int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out,
+                         int32_t* uv_out);
+/* Read one stored camera back (descriptors n x *desc_bytes_out as given, positions 3 x n, valid n); any output may be
+ * NULL; descriptors_out needs capacity x UZ_MAX_DESC_BYTES bytes. */
 uz_status uz_store_read(uz_context* ctx, int32_t handle, int32_t cam, int32_t capacity, int32_t* n_out,
-                        uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out);
+                        int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out);
 
 /* ---- stage entry points (parity + direct callers) -------------------------------------------- */
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) (feature_transformation_estimator.cpp:38,58).
- * idx/dist: nq x 2 int32, ordered by (distance, trainIdx); missing neighbours (nt < 2) are -1. */
-uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32_t q_stride,
+ * desc_bytes: 32 or 64 (both matrices).  idx/dist: nq x 2 int32, ordered by (distance, trainIdx); missing
+ * neighbours (nt < 2) are -1. */
+uz_status uz_match_knn2(uz_context* ctx, int32_t desc_bytes, const uint8_t* query, int32_t nq, int32_t q_stride,
                         const uint8_t* train, int32_t nt, int32_t t_stride,
                         int32_t* idx_out, int32_t* dist_out);
 

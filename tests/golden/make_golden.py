@@ -36,7 +36,10 @@ def main():
     out = {}
     cases = [("random300", dict(n_from=300, seed=501)), ("ties256", dict(n_from=256, seed=502, tie_stress=True)),
              ("ragged", dict(n_from=190, n_to=333, seed=503)), ("highinlier", dict(n_from=200, seed=504, rho=0.9)),
-             ("nodepth", dict(n_from=150, seed=505, invalid_frac=0.95))]
+             ("nodepth", dict(n_from=150, seed=505, invalid_frac=0.95)),
+             # BRISK / FREAK rows (64 bytes, feature_extraction_core.cpp:69-77)
+             ("wide300", dict(n_from=300, seed=506, desc_bytes=64)),
+             ("wide_ties", dict(n_from=200, n_to=257, seed=507, desc_bytes=64, tie_stress=True))]
     for name, kw in cases:
         f, t, Tgt = S.make_pair(**kw)
         ci, cd = cv2_knn(t["desc"], f["desc"])

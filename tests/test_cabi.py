@@ -31,13 +31,15 @@ def test_header_is_plain_c_and_struct_layout_matches_binding(built, tmp_path):
     from uzliti_slam_b200 import binding
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uzliti_edge.h"\n'
-                    'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(uz_edge_result), offsetof(uz_edge_result, mse),'
-                    ' offsetof(uz_edge_result, T), sizeof(uz_params), sizeof(uz_features), offsetof(uz_features, n));return 0;}\n')
+                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uz_edge_result), offsetof(uz_edge_result, mse),'
+                    ' offsetof(uz_edge_result, T), sizeof(uz_params), sizeof(uz_features), offsetof(uz_features, n),'
+                    ' offsetof(uz_features, desc_bytes), offsetof(uz_features, sensor_frame));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(binding.EdgeResult), binding.EdgeResult.mse.offset, binding.EdgeResult.T.offset,
-                     C.sizeof(binding.Params), C.sizeof(binding.Features), binding.Features.n.offset]
+                     C.sizeof(binding.Params), C.sizeof(binding.Features), binding.Features.n.offset,
+                     binding.Features.desc_bytes.offset, binding.Features.sensor_frame.offset]
     assert sizes[0] == 176 == binding.RESULT_DTYPE.itemsize
 
 

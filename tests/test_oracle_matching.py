@@ -45,6 +45,23 @@ def test_oracle_tie_rule_is_lowest_train_index(oracle, keep):
     assert np.array_equal(oi, ci) and np.array_equal(od, cd)
 
 
+@pytest.mark.parametrize("nq,nt,keep", [(500, 500, 64), (1000, 700, 64), (129, 65, 64), (300, 400, 33), (400, 300, 2),
+                                        (3, 2, 64), (1, 1, 64)])
+def test_oracle_knn2_matches_cv2_on_512_bit_rows(oracle, nq, nt, keep):
+    """BRISK / FREAK rows are 64 bytes (feature_extraction_core.cpp:69-77); same matcher, same tie rule, distances to 512."""
+    rng = np.random.default_rng(nq + 17 * nt + keep)
+    q = rng.integers(0, 256, (nq, 64), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 64), dtype=np.uint8)
+    q[:, keep:] = 0
+    t[:, keep:] = 0
+    if nt > 1:
+        t[-1] = 255 - q[0]                            # one exact complement: distance 512 when keep == 64
+    oi, od = oracle.knn2(q, t)
+    ci, cd = _cv2_knn(q, t)
+    assert np.array_equal(oi, ci) and np.array_equal(od, cd)
+    assert od.max() <= 512
+
+
 def test_oracle_synthetic_pair_matches_cv2(oracle):
     f, t, _ = S.make_pair(1000, seed=5)
     oi, od = oracle.knn2(t["desc"], f["desc"])
@@ -54,7 +71,7 @@ def test_oracle_synthetic_pair_matches_cv2(oracle):
 
 def test_ratio_predicate_equals_integer_form(oracle):
     """d0 < 0.99*d1 in float/double (reference :67) == 100*d0 < 99*d1 for every reachable distance pair."""
-    for d1 in range(0, 257):
+    for d1 in range(0, 513):                             # 512: BRISK / FREAK rows
         for d0 in range(0, d1 + 1):
             assert oracle.ratio_pass(d0, d1) == (100 * d0 < 99 * d1), (d0, d1)
 
@@ -70,12 +87,13 @@ def _cv2_cross(q, t):
 
 
 @pytest.mark.parametrize("nq,nt,keep", [(500, 500, 32), (300, 700, 32), (700, 300, 32), (400, 600, 2), (600, 400, 1),
-                                        (5, 1, 32), (1, 5, 32)])
+                                        (5, 1, 32), (1, 5, 32), (300, 500, 64), (500, 300, 3)])
 def test_oracle_cross_check_matches_cv2(oracle, nq, nt, keep):
     """The opt-in cross-check (uz_params.cross_check) is OpenCV's crossCheck matcher, tie rules included."""
     rng = np.random.default_rng(7 * nq + nt + keep)
-    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
-    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    nb = 64 if keep in (64, 3) else 32
+    q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, nb), dtype=np.uint8)
     q[:, keep:] = 0
     t[:, keep:] = 0
     oi, od = oracle.cross_match(q, t)

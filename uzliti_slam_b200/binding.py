@@ -53,8 +53,8 @@ class PlaceParams(C.Structure):
 
 class Features(C.Structure):
     _fields_ = [("descriptors", C.c_void_p), ("positions", C.c_void_p), ("valid_3d", C.c_void_p),
-                ("n", C.c_int32), ("desc_stride", C.c_int32), ("feature_type", C.c_int32),
-                ("sensor_frame", C.c_int32)]
+                ("n", C.c_int32), ("desc_stride", C.c_int32), ("desc_bytes", C.c_int32),
+                ("feature_type", C.c_int32), ("sensor_frame", C.c_int32)]
 
 
 class EdgeResult(C.Structure):
@@ -137,8 +137,9 @@ def features_array(cams, keep):
             v = np.ascontiguousarray(v, np.uint8)
         keep += [d, p, v]
         n = d.shape[0]
-        stride = d.strides[0] if n > 1 else 32
-        arr[i] = Features(d.ctypes.data, p.ctypes.data, v.ctypes.data, n, stride,
+        nb = d.shape[1] if d.ndim == 2 else 32            # features_.cols: 32 (ORB, BRIEF) or 64 (BRISK, FREAK)
+        stride = d.strides[0] if n > 1 else nb
+        arr[i] = Features(d.ctypes.data, p.ctypes.data, v.ctypes.data, n, stride, nb,
                           int(c.get("feature_type", 2)), int(c.get("sensor_frame", 0)))
     return arr
 
@@ -248,7 +249,8 @@ class EdgeEstimator:
         depth = np.ascontiguousarray(depth, np.float32)
         cam = self._camera(depth, fx, fy, cx, cy, max_depth)
         h = C.c_int32()
-        self._check(self.lib.uz_store_add_rgbd(self.ctx, _p(desc), 32, _p(u), _p(v), len(u), _p(depth), depth.strides[0],
+        nb = desc.shape[1] if desc.ndim == 2 else 32
+        self._check(self.lib.uz_store_add_rgbd(self.ctx, _p(desc), nb, nb, _p(u), _p(v), len(u), _p(depth), depth.strides[0],
                                                C.byref(cam), int(feature_type), int(sensor_frame), int(bool(reverse)),
                                                C.byref(h)))
         return h.value
@@ -262,23 +264,26 @@ class EdgeEstimator:
 
     def wire_decode(self, blob, capacity=4096):
         b = np.frombuffer(bytes(blob), np.uint8)
-        desc = np.zeros((capacity, 32), np.uint8)
+        desc = np.zeros(capacity * 64, np.uint8)
         pos = np.zeros((capacity, 3), np.float64)
         valid = np.zeros(capacity, np.uint8)
         uv = np.zeros((capacity, 2), np.int32)
-        n = C.c_int32()
-        self._check(self.lib.uz_wire_decode(self.ctx, _p(b), C.c_size_t(len(b)), capacity, C.byref(n), _p(desc), _p(pos),
-                                            _p(valid), _p(uv)))
-        return desc[:n.value], pos[:n.value], valid[:n.value], uv[:n.value]
+        n, nb = C.c_int32(), C.c_int32()
+        self._check(self.lib.uz_wire_decode(self.ctx, _p(b), C.c_size_t(len(b)), capacity, C.byref(n), C.byref(nb), _p(desc),
+                                            _p(pos), _p(valid), _p(uv)))
+        nb = nb.value or 32
+        return desc[:n.value * nb].reshape(n.value, nb), pos[:n.value], valid[:n.value], uv[:n.value]
 
     def read_keyframe(self, handle, cam=0, capacity=4096):
-        desc = np.zeros((capacity, 32), np.uint8)
+        desc = np.zeros(capacity * 64, np.uint8)
         pos = np.zeros((capacity, 3), np.float64)
         valid = np.zeros(capacity, np.uint8)
-        n = C.c_int32()
-        self._check(self.lib.uz_store_read(self.ctx, int(handle), int(cam), capacity, C.byref(n), _p(desc), _p(pos), _p(valid)))
-        return dict(desc=desc[:n.value].copy(), pos=pos[:n.value].copy(), valid=valid[:n.value].copy(), feature_type=2,
-                    sensor_frame=0)
+        n, nb = C.c_int32(), C.c_int32()
+        self._check(self.lib.uz_store_read(self.ctx, int(handle), int(cam), capacity, C.byref(n), C.byref(nb), _p(desc), _p(pos),
+                                           _p(valid)))
+        nb = nb.value or 32
+        return dict(desc=desc[:n.value * nb].reshape(n.value, nb).copy(), pos=pos[:n.value].copy(),
+                    valid=valid[:n.value].copy(), feature_type=2, sensor_frame=0)
 
     # ---- stages ---------------------------------------------------------------------------------
     def knnMatch(self, query, train):
@@ -290,11 +295,12 @@ class EdgeEstimator:
         if train.dtype != np.uint8 or (train.ndim == 2 and train.strides[1] != 1):
             train = np.ascontiguousarray(train, np.uint8)
         nq, nt = query.shape[0], train.shape[0]
+        nb = query.shape[1] if query.ndim == 2 else train.shape[1]
         idx = np.full((nq, 2), -7, np.int32)
         dist = np.full((nq, 2), -7, np.int32)
-        qs = query.strides[0] if nq > 1 else 32
-        ts = train.strides[0] if nt > 1 else 32
-        self._check(self.lib.uz_match_knn2(self.ctx, _p(query), nq, qs, _p(train), nt, ts, _p(idx), _p(dist)))
+        qs = query.strides[0] if nq > 1 else nb
+        ts = train.strides[0] if nt > 1 else nb
+        self._check(self.lib.uz_match_knn2(self.ctx, nb, _p(query), nq, qs, _p(train), nt, ts, _p(idx), _p(dist)))
         return idx, dist
 
     def estimateSVD(self, P, Q, maxError, iterations, breakPercentage, do_prosac=True, samples=None):

@@ -109,11 +109,12 @@ struct Arena {
 };
 
 struct Cam {
-    uint32_t* raw = nullptr;   // n x 8 words, bytes as given
-    uint32_t* csa = nullptr;   // n x 8 words, CSA layout (uz_knn2.cuh)
+    uint32_t* raw = nullptr;   // n x dbytes/4 words, bytes as given
+    uint32_t* csa = nullptr;   // same rows, every 256-bit half in CSA layout (uz_knn2.cuh)
     double* pos = nullptr;     // 3 x n column-major
     uint8_t* valid = nullptr;  // n
     int32_t n = 0, feature_type = 0, sensor_frame = 0;
+    int32_t dbytes = UZ_DESC_BYTES;   // descriptor width: 32 or 64
 };
 
 struct Keyframe {
@@ -152,6 +153,8 @@ struct uz_context {
     int stream_min_pairs = 0;        // UZ_STREAM_SOLVE_MIN_PAIRS: smallest batch that takes the streaming form (0 = two pairs per CTA)
     int stream_solve_ctas = 1;       // UZ_STREAM_SOLVE: persistent solve CTAs per SM (0 = off: one solve CTA per pair behind the match kernel)
     int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
+    int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
+    std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     uz_params params;
     std::string err;
     int variant_csa = 1;
@@ -253,6 +256,12 @@ uz_status fail(uz_context* ctx, uz_status st, const std::string& msg) {
     } while (0)
 
 int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// features_.cols as the ABI carries it: 0 = 32; anything but 32 / 64 is unsupported (0)
+int desc_width(int desc_bytes) {
+    if (desc_bytes == 0) return UZ_DESC_BYTES;
+    return (desc_bytes == UZ_DESC_BYTES || desc_bytes == UZ_MAX_DESC_BYTES) ? desc_bytes : 0;
+}
 
 bool is_binary_type(int t) { return t >= UZ_FEATURE_BRIEF && t <= UZ_FEATURE_FREAK; }   // :54-57
 
@@ -386,7 +395,9 @@ uz_status flush_runs(uz_context* ctx, const std::vector<Run>& runs) {
 uz_status validate_features(uz_context* ctx, const uz_features* f) {
     if (f->n < 0 || f->n > UZ_MAX_FEATURES) return fail(ctx, UZ_ERR_INVALID, "feature count out of range (0..UZ_MAX_FEATURES)");
     if (f->n > 0 && (!f->descriptors || !f->positions || !f->valid_3d)) return fail(ctx, UZ_ERR_INVALID, "null feature buffer");
-    if (f->n > 0 && f->desc_stride < UZ_DESC_BYTES) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor stride < 32 bytes (only 256-bit binary descriptors)");
+    const int db = desc_width(f->desc_bytes);
+    if (db == 0) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor width must be 32 or 64 bytes (256- or 512-bit binary descriptors)");
+    if (f->n > 0 && f->desc_stride < db) return fail(ctx, UZ_ERR_INVALID, "descriptor stride < descriptor width");
     return UZ_OK;
 }
 
@@ -402,8 +413,9 @@ uz_status upload_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_
         uz_status st = validate_features(ctx, f);
         if (st != UZ_OK) return st;
         out[i].n = f->n; out[i].feature_type = f->feature_type; out[i].sensor_frame = f->sensor_frame;
+        out[i].dbytes = desc_width(f->desc_bytes);
         if (f->n == 0) continue;
-        if (f->desc_stride == UZ_DESC_BYTES) dspans.push_back(Span{f->descriptors, (size_t)f->n * 32, &d_raw[i]});
+        if (f->desc_stride == out[i].dbytes) dspans.push_back(Span{f->descriptors, (size_t)f->n * out[i].dbytes, &d_raw[i]});
         else strided.push_back(i);
         pspans.push_back(Span{(const uint8_t*)f->positions, (size_t)f->n * 24, &d_pos[i]});
         vspans.push_back(Span{f->valid_3d, (size_t)f->n, &d_val[i]});
@@ -416,25 +428,27 @@ uz_status upload_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_
     if ((st = plan_spans(ctx, arena, pspans, runs)) != UZ_OK) return st;
     if ((st = plan_spans(ctx, arena, vspans, runs)) != UZ_OK) return st;
     if ((st = flush_runs(ctx, runs)) != UZ_OK) return st;
-    // CSA layout of the packed block: one launch, the CSA block mirrors the raw block row for row
+    // CSA layout of the packed block: one launch, the CSA block mirrors the raw block 256-bit half by half (a 64-byte
+    // row is two halves, each with its own transform; runs are 32 B aligned inside the block)
     if (raw_bytes) {
         uint8_t* csa = (uint8_t*)arena.alloc(raw_bytes);
         if (!csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
         const size_t rows = raw_bytes / 32;
         pack_descriptors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(
-            raw_block, (int)rows, 32, (uint32_t*)raw_block, (uint32_t*)csa);
+            raw_block, (int)rows, 32, (uint32_t*)raw_block, (uint32_t*)csa, 1);
         ctx->launches++;
         for (size_t i = 0; i < feats.size(); ++i)
             if (d_raw[i]) { out[i].raw = (uint32_t*)d_raw[i]; out[i].csa = (uint32_t*)(csa + (d_raw[i] - raw_block)); }
     }
     for (size_t i : strided) {   // padded cv::Mat rows: pitch copy into packed rows, then their own CSA pass
         const uz_features* f = feats[i];
-        d_raw[i] = (uint8_t*)arena.alloc((size_t)f->n * 32);
-        uint8_t* csa = (uint8_t*)arena.alloc((size_t)f->n * 32);
+        const int db = out[i].dbytes, halves = f->n * (db / 32);
+        d_raw[i] = (uint8_t*)arena.alloc((size_t)f->n * db);
+        uint8_t* csa = (uint8_t*)arena.alloc((size_t)f->n * db);
         if (!d_raw[i] || !csa) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
-        UZ_CUDA(ctx, cudaMemcpy2DAsync(d_raw[i], 32, f->descriptors, f->desc_stride, 32, f->n,
+        UZ_CUDA(ctx, cudaMemcpy2DAsync(d_raw[i], db, f->descriptors, f->desc_stride, db, f->n,
                                        cudaMemcpyHostToDevice, ctx->stream));
-        pack_descriptors_kernel<<<(f->n + 255) / 256, 256, 0, ctx->stream>>>(d_raw[i], f->n, 32, (uint32_t*)d_raw[i], (uint32_t*)csa);
+        pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>(d_raw[i], halves, 32, (uint32_t*)d_raw[i], (uint32_t*)csa, 1);
         ctx->launches++;
         out[i].raw = (uint32_t*)d_raw[i]; out[i].csa = (uint32_t*)csa;
     }
@@ -472,6 +486,12 @@ void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles,
         knn2_kernel<THREADS, QPT, false><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
 }
 
+template <int THREADS>
+void launch_knn2_wide(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
+                      unsigned int* d_progress) {
+    knn2_wide_kernel<THREADS><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+}
+
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
 // an SM is only reconfigured when it is empty, so a kernel that asks for another split waits until the resident
 // kernel's CTAs have drained - which serialises the two (and starves a consumer that polls its producer).
@@ -493,6 +513,8 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = knn2_carveout<256, 2>();
     if (e == cudaSuccess) e = knn2_carveout<128, 2>();
     if (e == cudaSuccess) e = knn2_carveout<32, 2>();
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<256>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<64>);
     if (e == cudaSuccess) e = max_shared_carveout(solve_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(solve_stream_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
@@ -532,6 +554,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     size_t n_tasks = 0, key_rows = 0;
     int max_nq = 0;
     int64_t compares = 0;
+    std::vector<uint8_t>& task_wide = ctx->task_wide;      // host-side: 1 = 64-byte rows (knn2_wide_kernel)
+    task_wide.assign(std::max<size_t>(max_tasks, 1) * (cross ? 2 : 1), 0);
+    size_t n_wide = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const int first = (int)n_tasks;
         const Cam* fc = pairs[i].from;
@@ -541,11 +566,13 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
                 const Cam& F = fc[a];
                 const Cam& T = tc[b];
                 if (F.n >= prm.min_keypoints && T.n >= prm.min_keypoints && F.feature_type == T.feature_type &&
-                    F.sensor_frame == T.sensor_frame) {
+                    F.sensor_frame == T.sensor_frame && F.dbytes == T.dbytes) {
+                    if (F.dbytes != UZ_DESC_BYTES) { task_wide[n_tasks] = 1; ++n_wide; }
                     MatchTask& tk = tasks[n_tasks++];
                     const bool bin = is_binary_type(F.feature_type);   // unknown type: empty matches (:60-62)
-                    tk.q_desc = ctx->variant_csa ? T.csa : T.raw;
-                    tk.t_desc = ctx->variant_csa ? F.csa : F.raw;
+                    const bool use_csa = ctx->variant_csa || F.dbytes != UZ_DESC_BYTES;     // the wide kernel has the CSA form only
+                    tk.q_desc = use_csa ? T.csa : T.raw;
+                    tk.t_desc = use_csa ? F.csa : F.raw;
                     tk.nq = bin ? T.n : 0; tk.nt = F.n;
                     tk.key_off = (uint32_t)key_rows; tk.pair = i;
                     tk.q_pos = T.pos; tk.q_valid = T.valid; tk.t_pos = F.pos; tk.t_valid = F.valid;
@@ -567,6 +594,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             r = f;
             r.q_desc = f.t_desc; r.t_desc = f.q_desc; r.nq = f.nt; r.nt = f.nq;
             r.key_off = (uint32_t)key_rows; r.rev_key_off = kNoRev;
+            task_wide[n_tasks] = task_wide[t];
             f.rev_key_off = r.key_off;
             key_rows += (size_t)r.nq;
             compares += (int64_t)r.nq * r.nt;
@@ -576,37 +604,65 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     }
     if (key_rows >= ((size_t)1 << 32)) return fail(ctx, UZ_ERR_INVALID, "batch too large: split it (key scratch > 2^32 rows)");
 
-    int best_cfg = 0;
-    double best_cost = 1e300;
-    // candidates: two queries per thread (40-56 registers: 6 resident CTAs per SM, measured 8 % faster than the
-    // four-query shapes, which stay reachable through UZ_KNN_CFG), largest tile first
-    static const int kCandidates[4] = {3, 4, 2, 5};
-    for (int ci = 0; ci < 4; ++ci) {
-        const int c = kCandidates[ci];
-        const int tile = kKnnConfigs[c].threads * kKnnConfigs[c].qpt;
-        double padded = 0; size_t tiles = 0;
-        for (size_t t = 0; t < n_tasks; ++t) {
-            const size_t nt = ((size_t)tasks[t].nq + tile - 1) / tile;
-            tiles += nt; padded += (double)nt * tile * tasks[t].nt;
+    // tile shape per descriptor width.  256-bit rows: two queries per thread (40-56 registers: 6 resident CTAs per SM,
+    // measured 8 % faster than the four-query shapes, which stay reachable through UZ_KNN_CFG), largest tile first.
+    // 512-bit rows: the 256 x 2 and 64 x 2 shapes of knn2_wide_kernel.
+    auto pick = [&](const int* cand, int n_cand, const int* threads, const int* qpt, const double* speed, int warps_per_sm,
+                    bool wide) {
+        int best = cand[0];
+        double best_cost = 1e300;
+        for (int ci = 0; ci < n_cand; ++ci) {
+            const int c = cand[ci];
+            const int tile = threads[c] * qpt[c];
+            double padded = 0; size_t tiles = 0;
+            for (size_t t = 0; t < n_tasks; ++t) {
+                if ((task_wide[t] != 0) != wide) continue;
+                const size_t nt = ((size_t)tasks[t].nq + tile - 1) / tile;
+                tiles += nt; padded += (double)nt * tile * tasks[t].nt;
+            }
+            // a launch that cannot fill the chip pays for its idle warp slots
+            const double fill = std::min(1.0, (double)tiles * threads[c] / ((double)ctx->sm_count * 32 * warps_per_sm));
+            const double cost = padded / (speed[c] * std::max(fill, 1e-3));
+            if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
         }
-        // a launch that cannot fill the chip (48 resident warps per SM) pays for its idle warp slots
-        const double fill = std::min(1.0, (double)tiles * kKnnConfigs[c].threads / ((double)ctx->sm_count * 1536));
-        const double cost = padded / (kKnnConfigs[c].speed * std::max(fill, 1e-3));
-        if (cost < best_cost * 0.999) { best_cost = cost; best_cfg = c; }
+        return best;
+    };
+    int best_cfg = 3, wide_cfg = 0;
+    {
+        static const int kCandidates[4] = {3, 4, 2, 5};
+        int th[6], qp[6]; double sp[6];
+        for (int c = 0; c < 6; ++c) { th[c] = kKnnConfigs[c].threads; qp[c] = kKnnConfigs[c].qpt; sp[c] = kKnnConfigs[c].speed; }
+        if (n_wide < n_tasks) best_cfg = pick(kCandidates, 4, th, qp, sp, 48, false);
+        if (ctx->force_cfg >= 0 && ctx->force_cfg < 6) best_cfg = ctx->force_cfg;
+        static const int kWideCand[2] = {0, 1};
+        static const int wth[2] = {256, 64}, wqp[2] = {2, 2};
+        static const double wsp[2] = {1.0, 0.97};
+        if (n_wide) wide_cfg = pick(kWideCand, 2, wth, wqp, wsp, 32, true);
+        if (ctx->force_wide_cfg >= 0 && ctx->force_wide_cfg < 2) wide_cfg = ctx->force_wide_cfg;
     }
-    if (ctx->force_cfg >= 0 && ctx->force_cfg < 6) best_cfg = ctx->force_cfg;
     const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
-    size_t n_tiles = 0;
-    for (size_t t = 0; t < n_tasks; ++t) n_tiles += ((size_t)tasks[t].nq + tile_rows - 1) / tile_rows;
+    const int wide_tile_rows = wide_cfg == 0 ? 512 : 128;
+    auto rows_of = [&](size_t t) { return task_wide[t] ? wide_tile_rows : tile_rows; };
+    size_t n_tiles = 0, n_tiles_wide = 0;
+    for (size_t t = 0; t < n_tasks; ++t) {
+        const size_t k = ((size_t)tasks[t].nq + rows_of(t) - 1) / rows_of(t);
+        n_tiles += k;
+        if (task_wide[t]) n_tiles_wide += k;
+    }
+    const size_t n_tiles_narrow = n_tiles - n_tiles_wide;
     UZ_CUDA(ctx, sl.h_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
     int2* tiles = (int2*)sl.h_tiles.p;
     {
-        size_t k = 0;
-        for (size_t t = 0; t < n_fwd; ++t) {         // forward tiles, then the reversed tiles of the same matching
-            for (int q0 = 0; q0 < tasks[t].nq; q0 += tile_rows) tiles[k++] = make_int2((int)t, q0);
+        // 256-bit tiles first, 512-bit tiles behind them (one launch each); inside a list: forward tiles, then the
+        // reversed tiles of the same matching
+        size_t kn = 0, kw = n_tiles_narrow;
+        for (size_t t = 0; t < n_fwd; ++t) {
+            size_t& k = task_wide[t] ? kw : kn;
+            const int tr = rows_of(t);
+            for (int q0 = 0; q0 < tasks[t].nq; q0 += tr) tiles[k++] = make_int2((int)t, q0);
             if (tasks[t].rev_key_off != kNoRev) {
                 const int r = (int)tasks[t].pad_;
-                for (int q0 = 0; q0 < tasks[r].nq; q0 += tile_rows) tiles[k++] = make_int2(r, q0);
+                for (int q0 = 0; q0 < tasks[r].nq; q0 += tr) tiles[k++] = make_int2(r, q0);
             }
         }
     }
@@ -684,9 +740,16 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         const MatchTask* d_tk = (const MatchTask*)sl.d_tasks.p;
         const int2* d_t = (const int2*)sl.d_tiles.p;
         uint2* d_k = (uint2*)sl.d_keys.p;
-        const int nt = (int)n_tiles;
+        const int nt = (int)n_tiles_narrow;
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
-        switch (best_cfg) {
+        if (n_tiles_wide > 0) {
+            if (wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog);
+            else launch_knn2_wide<64>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog);
+            ctx->launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
+            if (ctx->timers) ctx->match_launches++;
+        }
+        if (nt > 0) switch (best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
             case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
             case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
@@ -694,9 +757,11 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
             default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
         }
-        ctx->launches++;
-        UZ_CUDA(ctx, cudaGetLastError());
-        if (ctx->timers) ctx->match_launches++;
+        if (nt > 0) {
+            ctx->launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
+            if (ctx->timers) ctx->match_launches++;
+        }
     }
     if (ctx->timers) cudaEventRecord(tm.e[1], ctx->stream);
     if (with_solve) {
@@ -830,6 +895,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (ss && atoi(ss) >= 0 && atoi(ss) <= 4) ctx->stream_solve_ctas = atoi(ss);
         const char* fc = getenv("UZ_KNN_CFG");
         if (fc) ctx->force_cfg = atoi(fc);
+        const char* fw = getenv("UZ_KNN_WIDE_CFG");
+        if (fw) ctx->force_wide_cfg = atoi(fw);
         const char* gu = getenv("UZ_GATHER_UPLOAD");
         if (gu) ctx->gather_upload = atoi(gu);
         const char* cc = getenv("UZ_COPY_CTAS");
@@ -967,28 +1034,31 @@ int64_t uz_store_bytes(const uz_context* ctx) {
 }
 
 // ---- stage entry points ----------------------------------------------------------------------------
-uz_status uz_match_knn2(uz_context* ctx, const uint8_t* query, int32_t nq, int32_t q_stride,
+uz_status uz_match_knn2(uz_context* ctx, int32_t desc_bytes, const uint8_t* query, int32_t nq, int32_t q_stride,
                         const uint8_t* train, int32_t nt, int32_t t_stride, int32_t* idx_out, int32_t* dist_out) {
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
     if (nq < 0 || nt < 0 || nq > 65535 || nt > 65535) return fail(ctx, UZ_ERR_INVALID, "nq/nt out of range (0..65535)");
     if (nq == 0) return UZ_OK;
     if (!query || !idx_out || !dist_out || (nt > 0 && !train)) return fail(ctx, UZ_ERR_INVALID, "null buffer");
-    if (q_stride < 32 || (nt > 0 && t_stride < 32)) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor stride < 32 bytes");
+    const int db = desc_width(desc_bytes);
+    if (db == 0) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor width must be 32 or 64 bytes");
+    if (q_stride < db || (nt > 0 && t_stride < db)) return fail(ctx, UZ_ERR_INVALID, "descriptor stride < descriptor width");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     // two position-less cameras
     Keyframe kq, kt;
     kq.cams.resize(1); kt.cams.resize(1);
     auto up = [&](const uint8_t* h, int n, int stride, Cam& c) -> uz_status {
-        c.n = n; c.feature_type = UZ_FEATURE_ORB;
+        c.n = n; c.feature_type = UZ_FEATURE_ORB; c.dbytes = db;
         if (n == 0) return UZ_OK;
-        c.raw = (uint32_t*)ctx->transient.alloc((size_t)n * 32);
-        c.csa = (uint32_t*)ctx->transient.alloc((size_t)n * 32);
+        const int halves = n * (db / 32);
+        c.raw = (uint32_t*)ctx->transient.alloc((size_t)n * db);
+        c.csa = (uint32_t*)ctx->transient.alloc((size_t)n * db);
         uint8_t* stage = (uint8_t*)ctx->transient.alloc((size_t)n * stride);
         if (!c.raw || !c.csa || !stage) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
-        UZ_CUDA(ctx, cudaMemcpyAsync(stage, h, (size_t)(n - 1) * stride + 32, cudaMemcpyHostToDevice, ctx->stream));
-        pack_descriptors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(stage, n, stride, c.raw, c.csa);
+        UZ_CUDA(ctx, cudaMemcpyAsync(stage, h, (size_t)(n - 1) * stride + db, cudaMemcpyHostToDevice, ctx->stream));
+        pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>(stage, halves, stride, c.raw, c.csa, db / 32);
         ctx->launches++;
         return UZ_OK;
     };
@@ -1321,9 +1391,10 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // unique cameras (a keyframe that appears in many pairs - one query vs many candidates - is uploaded once),
     // numbered in order of first use so that every chunk uploads exactly the cameras nobody before it needed
     struct CamKey {
-        const void* d; const void* p; const void* v; int32_t n, stride, type, frame;
+        const void* d; const void* p; const void* v; int32_t n, stride, bytes, type, frame;
         bool operator==(const CamKey& o) const {
-            return d == o.d && p == o.p && v == o.v && n == o.n && stride == o.stride && type == o.type && frame == o.frame;
+            return d == o.d && p == o.p && v == o.v && n == o.n && stride == o.stride && bytes == o.bytes && type == o.type &&
+                   frame == o.frame;
         }
     };
     struct CamKeyHash {
@@ -1339,7 +1410,7 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     std::vector<const uz_features*> uniq;
     std::vector<Cam> up;                       // device views of the unique cameras, in order of first use
     auto intern = [&](const uz_features* f) -> uint32_t {
-        const CamKey k{f->descriptors, f->positions, f->valid_3d, f->n, f->desc_stride, f->feature_type, f->sensor_frame};
+        const CamKey k{f->descriptors, f->positions, f->valid_3d, f->n, f->desc_stride, f->desc_bytes, f->feature_type, f->sensor_frame};
         auto it = seen.find(k);
         if (it != seen.end()) return it->second;
         const uint32_t id = (uint32_t)uniq.size();

@@ -28,12 +28,12 @@ int32_t register_keyframe(uz_context* ctx, const Cam& c) {
     return h;
 }
 
-uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int feature_type, int sensor_frame, Cam& c) {
+uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int dbytes, int feature_type, int sensor_frame, Cam& c) {
     c = Cam();
-    c.n = n; c.feature_type = feature_type; c.sensor_frame = sensor_frame;
+    c.n = n; c.feature_type = feature_type; c.sensor_frame = sensor_frame; c.dbytes = dbytes;
     if (n == 0) return UZ_OK;
-    c.raw = (uint32_t*)arena.alloc((size_t)n * 32);
-    c.csa = (uint32_t*)arena.alloc((size_t)n * 32);
+    c.raw = (uint32_t*)arena.alloc((size_t)n * dbytes);
+    c.csa = (uint32_t*)arena.alloc((size_t)n * dbytes);
     c.pos = (double*)arena.alloc((size_t)n * 24);
     c.valid = (uint8_t*)arena.alloc((size_t)n);
     if (!c.raw || !c.csa || !c.pos || !c.valid) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
@@ -73,21 +73,24 @@ uz_status uz_backproject(uz_context* ctx, const int32_t* u, const int32_t* v, in
     return UZ_OK;
 }
 
-uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t desc_stride, const int32_t* u, const int32_t* v,
-                            int32_t n, const float* depth, int32_t depth_stride_bytes, const uz_camera* cam, int32_t feature_type,
+uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t desc_stride, int32_t desc_bytes,
+                            const int32_t* u, const int32_t* v, int32_t n, const float* depth, int32_t depth_stride_bytes, const uz_camera* cam, int32_t feature_type,
                             int32_t sensor_frame, int32_t reverse, int32_t* handle_out) {
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
     if (!handle_out || n < 0 || n > UZ_MAX_FEATURES || (n > 0 && (!descriptors || !u || !v))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
-    if (n > 0 && desc_stride < UZ_DESC_BYTES) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor stride < 32 bytes (only 256-bit binary descriptors)");
+    const int db = desc_width(desc_bytes);
+    if (db == 0) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor width must be 32 or 64 bytes");
+    if (n > 0 && desc_stride < db) return fail(ctx, UZ_ERR_INVALID, "descriptor stride < descriptor width");
     if ((st = check_camera(ctx, cam, depth, depth_stride_bytes)) != UZ_OK) return st;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     Cam c;
-    if ((st = alloc_cam(ctx, ctx->store_arena, n, feature_type, sensor_frame, c)) != UZ_OK) return st;
+    if ((st = alloc_cam(ctx, ctx->store_arena, n, db, feature_type, sensor_frame, c)) != UZ_OK) return st;
     if (n > 0) {
+        const int halves = n * (db / 32);
         const size_t img = (size_t)depth_stride_bytes * cam->height;
-        const size_t dbytes = (size_t)(n - 1) * desc_stride + 32;
+        const size_t dbytes = (size_t)(n - 1) * desc_stride + db;
         int32_t* du = (int32_t*)ctx->transient.alloc((size_t)n * 4);
         int32_t* dv = (int32_t*)ctx->transient.alloc((size_t)n * 4);
         float* dd = (float*)ctx->transient.alloc(img);
@@ -99,11 +102,11 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
         UZ_CUDA(ctx, cudaMemcpyAsync(ddesc, descriptors, dbytes, cudaMemcpyHostToDevice, ctx->stream));
         backproject_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(du, dv, n, dd, depth_stride_bytes / 4, to_model(cam), reverse ? 1 : 0, c.pos, c.valid);
         if (reverse) {
-            reverse_rows32_kernel<<<(n * 8 + 255) / 256, 256, 0, ctx->stream>>>(ddesc, n, desc_stride, c.raw);
-            pack_descriptors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, n, 32, c.raw, c.csa);
+            reverse_rows_kernel<<<(n * (db / 4) + 255) / 256, 256, 0, ctx->stream>>>(ddesc, n, desc_stride, db / 4, c.raw);
+            pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, halves, 32, c.raw, c.csa, 1);
             ctx->launches++;
         } else {
-            pack_descriptors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ddesc, n, desc_stride, c.raw, c.csa);
+            pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>(ddesc, halves, desc_stride, c.raw, c.csa, db / 32);
         }
         ctx->launches += 2;
         UZ_CUDA(ctx, cudaGetLastError());
@@ -114,7 +117,8 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
 }
 
 // blob: the serialised graph_slam_msgs/Feature[] field (uint32 count, then the elements)
-static uz_status wire_prepare(uz_context* ctx, const uint8_t* blob, size_t blob_bytes, int32_t* n_out) {
+static uz_status wire_prepare(uz_context* ctx, const uint8_t* blob, size_t blob_bytes, int32_t* n_out, int32_t* cols_out) {
+    *cols_out = UZ_DESC_BYTES;
     if (!blob || blob_bytes < 4) return fail(ctx, UZ_ERR_INVALID, "feature blob too short");
     uint32_t n;
     memcpy(&n, blob, 4);
@@ -123,27 +127,30 @@ static uz_status wire_prepare(uz_context* ctx, const uint8_t* blob, size_t blob_
         if (blob_bytes < 4 + 17) return fail(ctx, UZ_ERR_INVALID, "feature blob truncated");
         uint32_t len;
         memcpy(&len, blob + 4 + 13, 4);
-        if (len != 32) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor length != 32 (only 256-bit binary descriptors)");
-        if (blob_bytes < 4 + (size_t)n * kWireElemBytes32) return fail(ctx, UZ_ERR_INVALID, "feature blob truncated");
+        if (len != UZ_DESC_BYTES && len != UZ_MAX_DESC_BYTES) return fail(ctx, UZ_ERR_UNSUPPORTED, "descriptor length must be 32 or 64 (256- or 512-bit binary descriptors)");
+        if (blob_bytes < 4 + (size_t)n * wire_elem_bytes((int)len)) return fail(ctx, UZ_ERR_INVALID, "feature blob truncated");
+        *cols_out = (int32_t)len;
     }
     *n_out = (int32_t)n;
     return UZ_OK;
 }
 
 uz_status uz_wire_decode(uz_context* ctx, const uint8_t* blob, size_t blob_bytes, int32_t capacity, int32_t* n_out,
-                         uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out, int32_t* uv_out) {
+                         int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out,
+                         int32_t* uv_out) {
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
-    int32_t n = 0;
-    if ((st = wire_prepare(ctx, blob, blob_bytes, &n)) != UZ_OK) return st;
+    int32_t n = 0, cols = UZ_DESC_BYTES;
+    if ((st = wire_prepare(ctx, blob, blob_bytes, &n, &cols)) != UZ_OK) return st;
     if (n_out) *n_out = n;
+    if (desc_bytes_out) *desc_bytes_out = cols;
     if (n == 0) return UZ_OK;
     if (n > capacity || !descriptors_out || !positions_out || !valid_out) return fail(ctx, UZ_ERR_INVALID, "output capacity too small / null output");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
-    const size_t body = (size_t)n * kWireElemBytes32;
+    const size_t body = (size_t)n * wire_elem_bytes(cols);
     uint8_t* db = (uint8_t*)ctx->transient.alloc(body);
-    uint8_t* dd = (uint8_t*)ctx->transient.alloc((size_t)n * 32);
+    uint8_t* dd = (uint8_t*)ctx->transient.alloc((size_t)n * cols);
     double* dp = (double*)ctx->transient.alloc((size_t)n * 24);
     uint8_t* dv = (uint8_t*)ctx->transient.alloc((size_t)n);
     int32_t* duv = (int32_t*)ctx->transient.alloc((size_t)n * 8);
@@ -151,17 +158,17 @@ uz_status uz_wire_decode(uz_context* ctx, const uint8_t* blob, size_t blob_bytes
     if (!db || !dd || !dp || !dv || !duv || !dstat) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
     UZ_CUDA(ctx, cudaMemcpyAsync(db, blob + 4, body, cudaMemcpyHostToDevice, ctx->stream));
     UZ_CUDA(ctx, cudaMemsetAsync(dstat, 0, 4, ctx->stream));
-    wire_decode_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(db, n, dd, dp, dv, duv, dstat);
+    wire_decode_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(db, n, cols, dd, dp, dv, duv, dstat);
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     int stat = 0;
     UZ_CUDA(ctx, cudaMemcpyAsync(&stat, dstat, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    UZ_CUDA(ctx, cudaMemcpyAsync(descriptors_out, dd, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaMemcpyAsync(descriptors_out, dd, (size_t)n * cols, cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(positions_out, dp, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(valid_out, dv, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (uv_out) UZ_CUDA(ctx, cudaMemcpyAsync(uv_out, duv, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (stat) return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length is not 32");
+    if (stat) return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length differs from the first element's");
     return UZ_OK;
 }
 
@@ -170,27 +177,28 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* blob, size_t blob_by
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
     if (!handle_out) return UZ_ERR_INVALID;
-    int32_t n = 0;
-    if ((st = wire_prepare(ctx, blob, blob_bytes, &n)) != UZ_OK) return st;
+    int32_t n = 0, cols = UZ_DESC_BYTES;
+    if ((st = wire_prepare(ctx, blob, blob_bytes, &n, &cols)) != UZ_OK) return st;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     Cam c;
-    if ((st = alloc_cam(ctx, ctx->store_arena, n, feature_type, sensor_frame, c)) != UZ_OK) return st;
+    if ((st = alloc_cam(ctx, ctx->store_arena, n, cols, feature_type, sensor_frame, c)) != UZ_OK) return st;
     if (n > 0) {
-        const size_t body = (size_t)n * kWireElemBytes32;
+        const int halves = n * (cols / 32);
+        const size_t body = (size_t)n * wire_elem_bytes(cols);
         uint8_t* db = (uint8_t*)ctx->transient.alloc(body);
         int* dstat = (int*)ctx->transient.alloc(4);
         if (!db || !dstat) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
         UZ_CUDA(ctx, cudaMemcpyAsync(db, blob + 4, body, cudaMemcpyHostToDevice, ctx->stream));
         UZ_CUDA(ctx, cudaMemsetAsync(dstat, 0, 4, ctx->stream));
-        wire_decode_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(db, n, (uint8_t*)c.raw, c.pos, c.valid, nullptr, dstat);
-        pack_descriptors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, n, 32, c.raw, c.csa);
+        wire_decode_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(db, n, cols, (uint8_t*)c.raw, c.pos, c.valid, nullptr, dstat);
+        pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, halves, 32, c.raw, c.csa, 1);
         ctx->launches += 2;
         UZ_CUDA(ctx, cudaGetLastError());
         int stat = 0;
         UZ_CUDA(ctx, cudaMemcpyAsync(&stat, dstat, 4, cudaMemcpyDeviceToHost, ctx->stream));
         UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (stat) return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length is not 32");
+        if (stat) return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length differs from the first element's");
     }
     *handle_out = register_keyframe(ctx, c);
     return UZ_OK;
@@ -198,16 +206,17 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* blob, size_t blob_by
 
 // read a stored camera back (parity tap for the ingestion paths; also what a toMsg adapter would serialise)
 uz_status uz_store_read(uz_context* ctx, int32_t handle, int32_t cam, int32_t capacity, int32_t* n_out,
-                        uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out) {
+                        int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out) {
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
     if (handle < 0 || handle >= (int32_t)ctx->kfs.size() || !ctx->kfs[handle].live) return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle");
     if (cam < 0 || cam >= (int32_t)ctx->kfs[handle].cams.size()) return fail(ctx, UZ_ERR_INVALID, "camera index out of range");
     const Cam& c = ctx->kfs[handle].cams[cam];
     if (n_out) *n_out = c.n;
+    if (desc_bytes_out) *desc_bytes_out = c.dbytes;
     if (c.n == 0) return UZ_OK;
     if (c.n > capacity) return fail(ctx, UZ_ERR_INVALID, "output capacity too small");
-    if (descriptors_out) UZ_CUDA(ctx, cudaMemcpyAsync(descriptors_out, c.raw, (size_t)c.n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (descriptors_out) UZ_CUDA(ctx, cudaMemcpyAsync(descriptors_out, c.raw, (size_t)c.n * c.dbytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (positions_out) UZ_CUDA(ctx, cudaMemcpyAsync(positions_out, c.pos, (size_t)c.n * 24, cudaMemcpyDeviceToHost, ctx->stream));
     if (valid_out) UZ_CUDA(ctx, cudaMemcpyAsync(valid_out, c.valid, (size_t)c.n, cudaMemcpyDeviceToHost, ctx->stream));
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

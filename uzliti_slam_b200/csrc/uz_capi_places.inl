@@ -139,6 +139,7 @@ uz_status places_run(uz_context* ctx, PlaceMode mode, const int32_t* handles, co
             PlaceCam pc;
             memset(&pc, 0, sizeof(pc));
             pc.raw = c.raw; pc.n = c.n; pc.place = place; pc.stamp_ns = (long long)stamps_ns[i];
+            pc.wide_shift = c.dbytes == UZ_DESC_BYTES ? 0 : 1;
             const bool big = c.n > prm.min_rows;          // lsh_set_recognizer.cpp:66 / :108
             if (mode != kSearchOnly && big) {
                 pc.node_base = (uint32_t)(ps.n_nodes + new_nodes);
@@ -331,6 +332,7 @@ uz_status uz_places_votes(uz_context* ctx, int32_t handle, int32_t cam, int32_t 
     PlaceCam pc;
     memset(&pc, 0, sizeof(pc));
     pc.raw = c.raw; pc.n = c.n; pc.place = -1; pc.query_filtered = filtered ? 1 : 0; pc.place_limit = n_places; pc.row = 0;
+    pc.wide_shift = c.dbytes == UZ_DESC_BYTES ? 0 : 1;
     UZ_CUDA(ctx, ps.d_cams.ensure(sizeof(PlaceCam)));
     UZ_CUDA(ctx, ps.d_votes.ensure((size_t)n_places * 4));
     UZ_CUDA(ctx, cudaMemcpyAsync(ps.d_cams.p, &pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));

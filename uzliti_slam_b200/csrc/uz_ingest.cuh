@@ -8,7 +8,8 @@
 //   wire_decode_kernel      FeatureData::fromMsg (/root/reference/graph_slam_common/src/sensor_data.cpp:124-171) applied to
 //                           the ROS1-serialised graph_slam_msgs/Feature[] (graph_slam_msgs/msg/Feature.msg:1-13): per
 //                           element  int32 u, int32 v, uint8 is_3d, float32 keypoint_strength, uint32 len, len x float32
-//                           descriptor, float64 x, y, z  — little endian, unpadded, so a 32-column element is 169 bytes.
+//                           descriptor, float64 x, y, z  — little endian, unpadded, so a 32-column element is 169 bytes
+//                           and a 64-column one (BRISK, FREAK) 297.
 //                           Descriptor values are narrowed float -> unsigned char exactly as the x86 build does
 //                           ((unsigned char)val == low byte of cvttss2si).
 #pragma once
@@ -43,10 +44,11 @@ __global__ void __launch_bounds__(256) backproject_kernel(const int32_t* __restr
 }
 
 // rows of a descriptor matrix in reverse order (companion of backproject's reverse mode)
-__global__ void __launch_bounds__(256) reverse_rows32_kernel(const uint8_t* __restrict__ src, int n, int stride, uint32_t* __restrict__ dst) {
+__global__ void __launch_bounds__(256) reverse_rows_kernel(const uint8_t* __restrict__ src, int n, int stride, int row_words,
+                                                           uint32_t* __restrict__ dst) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;        // one thread per 4 bytes
-    if (e >= n * 8) return;
-    const int i = e >> 3, w = e & 7;
+    if (e >= n * row_words) return;
+    const int i = e / row_words, w = e - i * row_words;
     const uint8_t* p = src + (size_t)(n - 1 - i) * stride + 4 * w;
     dst[e] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
@@ -64,22 +66,25 @@ __device__ __forceinline__ uint8_t narrow_x86(float val) {
     return (uint8_t)(__float2int_rz(val) & 0xFF);
 }
 
-constexpr int kWireElemBytes32 = 4 + 4 + 1 + 4 + 4 + 32 * 4 + 24;      // 169
+__host__ __device__ constexpr int wire_elem_bytes(int cols) { return 4 + 4 + 1 + 4 + 4 + cols * 4 + 24; }      // 169 / 297
+static_assert(wire_elem_bytes(32) == 169 && wire_elem_bytes(64) == 297, "Feature.msg element size");
 
-// blob points at the first element (behind the uint32 element count).  One warp per feature.
-// status[0] is set to 1 if an element's descriptor length is not 32.
-__global__ void __launch_bounds__(256) wire_decode_kernel(const uint8_t* __restrict__ blob, int n, uint8_t* __restrict__ desc,
+// blob points at the first element (behind the uint32 element count).  One warp per feature, cols = 32 or 64 columns
+// (the first element's length, read by the host).  status[0] is set to 1 if an element's descriptor length differs.
+__global__ void __launch_bounds__(256) wire_decode_kernel(const uint8_t* __restrict__ blob, int n, int cols, uint8_t* __restrict__ desc,
                                                           double* __restrict__ pos, uint8_t* __restrict__ valid,
                                                           int32_t* __restrict__ uv, int* __restrict__ status) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= n) return;
-    const uint8_t* e = blob + (size_t)f * kWireElemBytes32;
+    const uint8_t* e = blob + (size_t)f * wire_elem_bytes(cols);
     const uint32_t len = load_u32_unaligned(e + 13);
-    if (len != 32u) { if (lane == 0) atomicExch(status, 1); return; }
-    const float val = __uint_as_float(load_u32_unaligned(e + 17 + 4 * lane));
-    desc[(size_t)f * 32 + lane] = narrow_x86(val);
-    if (lane < 3) pos[3 * (size_t)f + lane] = load_f64_unaligned(e + 17 + 128 + 8 * lane);
+    if (len != (uint32_t)cols) { if (lane == 0) atomicExch(status, 1); return; }
+    for (int j = lane; j < cols; j += 32) {
+        const float val = __uint_as_float(load_u32_unaligned(e + 17 + 4 * j));
+        desc[(size_t)f * cols + j] = narrow_x86(val);
+    }
+    if (lane < 3) pos[3 * (size_t)f + lane] = load_f64_unaligned(e + 17 + 4 * cols + 8 * lane);
     if (lane == 3) valid[f] = e[8] ? 1 : 0;
     if (uv && lane == 4) { uv[2 * f] = (int32_t)load_u32_unaligned(e); uv[2 * f + 1] = (int32_t)load_u32_unaligned(e + 4); }
 }

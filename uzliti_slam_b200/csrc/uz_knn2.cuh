@@ -346,12 +346,179 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
     }
 }
 
-// raw descriptor rows (any byte stride) -> packed 8-word rows, raw and CSA layout
+// ---- 512-bit rows (BRISK / FREAK: 64-byte descriptors, feature_transformation_estimator.cpp:56-57) ----------
+// A wide row is stored as two independent CSA-layout halves (csa_pack applied to words 0..7 and 8..15), so a compare
+// is two 256-bit CSA trees feeding ONE weighted-popcount chain: 26 LOP3 + 8 POPC + 8 IMAD per 512-bit compare, the
+// same POPC-per-bit cost as the 256-bit kernel.  Distances reach 512, so the packed 16-bit keys carry 10 bits of
+// distance and 6 bits of row:  key16 = (distance << 6) | (row & 63)  (<= 32831), merged into the 32-bit keys every
+// 64 train rows.  Shape: THREADS x 2 queries per CTA (32 query words per thread, 64 registers, 32 resident warps per
+// SM), THREADS train rows per stage.
+__constant__ uint32_t kPopcWeightLo6[3] = {1u << 6, 2u << 6, 4u << 6};
+__constant__ uint32_t kPopcWeightHi6[3] = {1u << 22, 2u << 22, 4u << 22};
+
+__host__ __device__ constexpr int knn_wide_train_rows(int threads) { return threads; }
+__host__ __device__ constexpr int knn_wide_smem_bytes(int threads) { return kStages * knn_wide_train_rows(threads) * 64 + 64; }
+__host__ __device__ constexpr int knn_wide_min_ctas(int threads) { return threads == 256 ? 4 : threads == 128 ? 8 : 16; }
+
+// one 256-bit half: U points at the 8 query words of that half (registers after unrolling)
+template <bool HI>
+__device__ __forceinline__ uint32_t csa_acc16w(const uint32_t* U, const uint4& a, const uint4& b, uint32_t acc) {
+    const uint32_t x0 = U[0] ^ a.x, x1 = U[1] ^ a.y, S1 = U[2] ^ a.z;
+    const uint32_t C1 = lop3<0xD4>(x0, x1, S1);
+    const uint32_t x3 = U[3] ^ a.w, x4 = U[4] ^ b.x, S2 = U[5] ^ b.y;
+    const uint32_t C2 = lop3<0xD4>(x3, x4, S2);
+    const uint32_t S3 = U[6] ^ b.z;
+    const uint32_t C3 = lop3<0xD4>(S1, S2, S3);
+    const uint32_t x7 = U[7] ^ b.w;
+    const uint32_t S5 = lop3<0x96>(C1, C2, C3);
+    const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
+    const uint32_t w1 = HI ? kPopcWeightHi6[0] : kPopcWeightLo6[0];
+    const uint32_t w2 = HI ? kPopcWeightHi6[1] : kPopcWeightLo6[1];
+    const uint32_t w4 = HI ? kPopcWeightHi6[2] : kPopcWeightLo6[2];
+    uint32_t k = mad_u32(__popc(C5), w4, acc);
+    k = mad_u32(__popc(S5), w2, k);
+    k = mad_u32(__popc(x7), w1, k);
+    k = mad_u32(__popc(S3), w1, k);
+    return k;
+}
+// full 32-bit key of one wide compare (tail rows)
+__device__ __forceinline__ uint32_t csa_key_wide(const uint32_t* U, const uint4& a, const uint4& b, const uint4& c,
+                                                 const uint4& d, uint32_t jkey) {
+    uint32_t Ulo[8], Uhi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { Ulo[i] = U[i]; Uhi[i] = U[8 + i]; }
+    return csa_key(Uhi, c, d, csa_key(Ulo, a, b, jkey));
+}
+__device__ __forceinline__ void merge_block16w(uint32_t& m1, uint32_t& m2, uint32_t v1, uint32_t v2, uint32_t base) {
+    const uint32_t k1 = ((v1 & 0xFFC0u) << 10) | (base + (v1 & 63u));
+    const uint32_t k2 = ((v2 & 0xFFC0u) << 10) | (base + (v2 & 63u));
+    const uint32_t t = max(m1, k1);
+    m1 = min(m1, k1);
+    m2 = min(min(m2, t), k2);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide_kernel(const MatchTask* __restrict__ tasks,
+                                                       const int2* __restrict__ tiles,
+                                                       uint2* __restrict__ keys,
+                                                       int* __restrict__ pair_pending,
+                                                       unsigned int* __restrict__ progress) {
+    constexpr int kRows = knn_wide_train_rows(THREADS);
+    static_assert(kRows % 64 == 0, "train tiles are cut into 64-row key blocks");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kRows * 64);
+
+    const int2 tile = tiles[blockIdx.x];
+    const MatchTask* tk = tasks + tile.x;
+    const uint32_t* __restrict__ qd = tk->q_desc;
+    const uint32_t* __restrict__ td = tk->t_desc;
+    const int nq = tk->nq, nt = tk->nt;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int ntiles = (nt + kRows - 1) / kRows;
+    if (tid == 0 && ntiles > 0) {
+        const uint32_t bytes = (uint32_t)min(nt, kRows) * 64u;
+        mbar_expect_tx(&bars[0], bytes);
+        bulk_g2s(smem, td, bytes, &bars[0]);
+    }
+
+    uint32_t U[2][16];
+    uint32_t m1[2], m2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = tile.y + k * THREADS + tid;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint4 a = make_uint4(0, 0, 0, 0);
+            if (q < nq) a = __ldg(reinterpret_cast<const uint4*>(qd + (size_t)q * 16) + h);
+            U[k][4 * h] = a.x; U[k][4 * h + 1] = a.y; U[k][4 * h + 2] = a.z; U[k][4 * h + 3] = a.w;
+        }
+        m1[k] = kNoKey; m2[k] = kNoKey;
+    }
+
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int stage = ti & 1;
+        if (tid == 0 && ti + 1 < ntiles) {
+            const int r0n = (ti + 1) * kRows;
+            const uint32_t bytes = (uint32_t)min(nt - r0n, kRows) * 64u;
+            mbar_expect_tx(&bars[stage ^ 1], bytes);
+            bulk_g2s(smem + (stage ^ 1) * kRows * 64, td + (size_t)r0n * 16, bytes, &bars[stage ^ 1]);
+        }
+        mbar_wait(&bars[stage], (ti >> 1) & 1);
+        const uint4* __restrict__ rows = reinterpret_cast<const uint4*>(smem + stage * kRows * 64);
+        const int r0 = ti * kRows;
+        const int nrows = min(nt - r0, kRows);
+        for (int b0 = 0; b0 < nrows; b0 += 64) {
+            const int nb = min(nrows - b0, 64);
+            const uint4* __restrict__ brows = rows + 4 * b0;
+            uint32_t p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
+            int j = 0;
+#pragma unroll 1
+            for (; j + 2 <= nb; j += 2) {
+                const uint32_t jj = (uint32_t)j * 0x00010001u;
+                uint32_t k0, k1;
+                {
+                    const uint4 a0 = brows[4 * j], b0v = brows[4 * j + 1];
+                    const uint4 a1 = brows[4 * j + 4], b1v = brows[4 * j + 5];
+                    k0 = csa_acc16w<false>(U[0], a0, b0v, jj);
+                    k1 = csa_acc16w<false>(U[0], a1, b1v, jj + 0x00010001u);
+                    k0 = csa_acc16w<true>(U[1], a0, b0v, k0);
+                    k1 = csa_acc16w<true>(U[1], a1, b1v, k1);
+                }
+                {
+                    const uint4 c0 = brows[4 * j + 2], d0 = brows[4 * j + 3];
+                    const uint4 c1 = brows[4 * j + 6], d1 = brows[4 * j + 7];
+                    k0 = csa_acc16w<false>(U[0] + 8, c0, d0, k0);
+                    k1 = csa_acc16w<false>(U[0] + 8, c1, d1, k1);
+                    k0 = csa_acc16w<true>(U[1] + 8, c0, d0, k0);
+                    k1 = csa_acc16w<true>(U[1] + 8, c1, d1, k1);
+                }
+                top2_update2_u16x2(p1, p2, k0, k1);
+            }
+            if (j > 0) {
+                const uint32_t base = (uint32_t)(r0 + b0);
+                merge_block16w(m1[0], m2[0], p1 & 0xFFFFu, p2 & 0xFFFFu, base);
+                merge_block16w(m1[1], m2[1], p1 >> 16, p2 >> 16, base);
+            }
+            for (; j < nb; ++j) {
+                const uint4 a = brows[4 * j], b = brows[4 * j + 1], c = brows[4 * j + 2], d = brows[4 * j + 3];
+                const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) top2_update(m1[k], m2[k], csa_key_wide(U[k], a, b, c, d, jkey));
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = tile.y + k * THREADS + tid;
+        if (q < nq) keys[tk->key_off + q] = make_uint2(m1[k], m2[k]);
+    }
+    if (pair_pending != nullptr) {          // streaming hand-over, as in knn2_kernel
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicSub(pair_pending + tk->pair, 1);
+            atomicAdd(progress, 1u);
+        }
+    }
+}
+
+// raw descriptor rows (any byte stride) -> packed rows, raw and CSA layout.  A row is `halves` 256-bit halves
+// (1: ORB/BRIEF, 2: BRISK/FREAK); one thread per half, n counts halves, every half gets its own CSA transform.
 __global__ void pack_descriptors_kernel(const uint8_t* __restrict__ src, int n, int stride,
-                                        uint32_t* __restrict__ raw, uint32_t* __restrict__ csa) {
+                                        uint32_t* __restrict__ raw, uint32_t* __restrict__ csa, int halves) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t* p = src + (size_t)i * stride;
+    const uint8_t* p = halves == 1 ? src + (size_t)i * stride : src + (size_t)(i >> 1) * stride + (i & 1) * 32;
     uint32_t w[8], o[8];
     if ((((uintptr_t)p) & 15) == 0) {
         const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);

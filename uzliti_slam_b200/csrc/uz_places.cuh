@@ -27,7 +27,8 @@ struct PlaceNode { uint32_t place; uint32_t next; };                            
 
 // one FEATURE sensor of one keyframe taking part in a launch
 struct PlaceCam {
-    const uint32_t* raw;      // n x 8 words, descriptor bytes as given (store "raw" layout)
+    const uint32_t* raw;      // n rows of 8 << wide_shift words, descriptor bytes as given (store "raw" layout); the
+                              // tables key on bytes [0, 32) of a row whatever its width (lsh_set_recognizer.cpp:243)
     int32_t n;
     int32_t place;            // place index of the owning keyframe
     uint32_t node_base;       // first node of this camera in the node array (insert launches)
@@ -35,7 +36,7 @@ struct PlaceCam {
     int32_t query_filtered;   // 1: matchAndAdd (popcount filter on the query keys); 0: FastLshSet::match
     int32_t place_limit;      // count only nodes with place < place_limit
     int32_t row;              // votes row of this camera in the launch
-    int32_t pad;
+    int32_t wide_shift;       // 0: 32-byte rows, 1: 64-byte rows
     long long stamp_ns;       // time stamp of the querying keyframe (pr_time_map_[id])
 };
 
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) places_insert_kernel(const PlaceCam* __re
     const PlaceCam cam = cams[blockIdx.y];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cam.n * 8; e += gridDim.x * blockDim.x) {
         const int k = e & 7;
-        const uint32_t key = cam.raw[e];                       // word k of row e/8 == bytes [4k, 4k+4) little endian
+        const uint32_t key = cam.raw[((e >> 3) << (3 + cam.wide_shift)) + k];     // word k of row e/8 == bytes [4k, 4k+4) little endian
         const uint32_t node = cam.node_base + (uint32_t)e;
         if (cam.insert_filtered && __popc(key) <= min_key_bits) { nodes[node] = PlaceNode{0xFFFFFFFFu, 0u}; continue; }
         const unsigned long long tag = place_tag(k, key);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) places_vote_kernel(const PlaceCam* __rest
     uint32_t* __restrict__ row = votes + (size_t)cam.row * n_places;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cam.n * 8; e += gridDim.x * blockDim.x) {
         const int k = e & 7;
-        const uint32_t key = cam.raw[e];
+        const uint32_t key = cam.raw[((e >> 3) << (3 + cam.wide_shift)) + k];
         if (cam.query_filtered && __popc(key) <= min_key_bits) continue;
         const unsigned long long tag = place_tag(k, key);
         uint32_t s = place_hash(tag) & slot_mask;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256) places_relink_kernel(const PlaceCam* __re
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cam.n * 8; e += gridDim.x * blockDim.x) {
         const uint32_t node = cam.node_base + (uint32_t)e;
         if (nodes[node].place == 0xFFFFFFFFu) continue;                  // filtered out at insertion
-        const unsigned long long tag = place_tag(e & 7, cam.raw[e]);
+        const unsigned long long tag = place_tag(e & 7, cam.raw[((e >> 3) << (3 + cam.wide_shift)) + (e & 7)]);
         uint32_t s = place_hash(tag) & slot_mask;
         while (true) {
             const unsigned long long cur = atomicCAS(&slots[s].tag, 0ull, tag);

@@ -44,6 +44,10 @@ struct SolveParams {
 };
 
 constexpr int kSolveThreads = 128;
+constexpr int kHistPerLane = 17;                   // counting sort by distance: 0..512 (64-byte descriptors) in 32 x 17 bins
+constexpr int kHistBins = 32 * kHistPerLane;
+static_assert(kHistBins > 8 * UZ_MAX_DESC_BYTES, "one bin per possible Hamming distance");
+static_assert(kHistBins * 4 <= kSolveThreads * 12 * 8, "the histogram lives in the hypothesis buffer");
 #ifndef UZ_SOLVE_H
 #define UZ_SOLVE_H 2
 #endif
@@ -265,9 +269,9 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         // ratio test (:65-71) + valid_3d filter (:103-112) + the sort of :114 as a STABLE COUNTING SORT by
         // distance: matches are produced in query order, so equal distances keep ascending queryIdx, which
         // is exactly the (distance, queryIdx) order.  Pass 1 (all warps): per-query distance + histogram.
-        int* hist = reinterpret_cast<int*>(Th);                 // [288] bins; Th is not used before K3
+        int* hist = reinterpret_cast<int*>(Th);                 // [kHistBins] bins (distances 0..512); Th is not used before K3
         uint16_t* dq = reinterpret_cast<uint16_t*>(pf);         // [cap] distance of query i, 0xFFFF = dropped
-        for (int bidx = tid; bidx < 288; bidx += THREADS) hist[bidx] = 0;
+        for (int bidx = tid; bidx < kHistBins; bidx += THREADS) hist[bidx] = 0;
         if (tid == 0) { s_nvalid = 0; s_nratio = 0; }
         __syncthreads();
         for (int i = tid; i < nq; i += THREADS) {
@@ -284,16 +288,16 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         n_ratio = s_nratio;
         UZ_PHASE(1);
         if (warp == 0) {
-            // exclusive prefix over the 257 bins: 9 consecutive bins per lane
-            int loc[9], sum = 0;
+            // exclusive prefix over the 513 bins: kHistPerLane consecutive bins per lane
+            int loc[kHistPerLane], sum = 0;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { loc[j] = hist[lane * 9 + j]; sum += loc[j]; }
+            for (int j = 0; j < kHistPerLane; ++j) { loc[j] = hist[lane * kHistPerLane + j]; sum += loc[j]; }
             int inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             int run = inc - sum;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { hist[lane * 9 + j] = run; run += loc[j]; }
+            for (int j = 0; j < kHistPerLane; ++j) { hist[lane * kHistPerLane + j] = run; run += loc[j]; }
             if (lane == 31) s_nvalid = inc;
             __syncwarp();
             // pass 2 (one warp, query order): slot = bin offset + rank among equal distances seen so far

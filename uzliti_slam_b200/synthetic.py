@@ -4,9 +4,10 @@ Camera 640x480, fx=fy=525, cx=319.5, cy=239.5 (the constants of the reference's 
 graph_slam_common/src/transformation/feature_transformation_estimator.cpp:37); depth uniform in
 [0.5, 7] m (feature_max_depth, iti_slam_launch/yaml/slam.yaml:7); missing depth is z=-1, x=y=0,
 valid=False (feature_extraction/src/feature_extraction_core.cpp:286-289); descriptors are 32-byte
-ORB-256 rows (feature_extraction/external/aorb/aorb.h:54).
+ORB-256 rows (feature_extraction/external/aorb/aorb.h:54) or, with desc_bytes=64, BRISK/FREAK-512 rows
+(feature_extraction_core.cpp:69-77).
 
-A keyframe is a dict: desc uint8[N,32], pos float64[N,3] (memory layout == Eigen 3xN column-major),
+A keyframe is a dict: desc uint8[N,desc_bytes], pos float64[N,3] (memory layout == Eigen 3xN column-major),
 valid uint8[N], feature_type (2 = ORB), sensor_frame (interned tag).
 """
 import numpy as np
@@ -15,6 +16,7 @@ FX = FY = 525.0
 CX, CY = 319.5, 239.5
 W, H = 640, 480
 ORB = 2
+BRISK = 3
 
 
 def _rand_rotation(rng, max_angle_rad):
@@ -63,7 +65,7 @@ def _flip(rng, desc, k=4):
     return desc ^ m
 
 
-def _finish(rng, desc, pos, invalid_frac, tie_stress, sensor_frame, shuffle=True):
+def _finish(rng, desc, pos, invalid_frac, tie_stress, sensor_frame, shuffle=True, feature_type=ORB):
     n = len(desc)
     valid = np.ones(n, np.uint8)
     if invalid_frac > 0 and n > 0:
@@ -76,11 +78,11 @@ def _finish(rng, desc, pos, invalid_frac, tie_stress, sensor_frame, shuffle=True
         desc[:, 4:] = 0
     perm = rng.permutation(n) if shuffle else np.arange(n)
     return dict(desc=np.ascontiguousarray(desc[perm]), pos=np.ascontiguousarray(pos[perm]),
-                valid=np.ascontiguousarray(valid[perm]), feature_type=ORB, sensor_frame=sensor_frame), perm
+                valid=np.ascontiguousarray(valid[perm]), feature_type=feature_type, sensor_frame=sensor_frame), perm
 
 
 def make_pair(n_from, n_to=None, seed=0, rho=0.5, invalid_frac=0.15, gross_outlier_frac=0.10,
-              tie_stress=False, noise=True, max_angle_deg=30.0, max_trans=1.5, sensor_frame=0):
+              tie_stress=False, noise=True, max_angle_deg=30.0, max_trans=1.5, sensor_frame=0, desc_bytes=32):
     """One (from, to) keyframe pair.  Returns (kf_from, kf_to, T_gt) with T_gt * p_to = x_from,
     i.e. the transform the reference stores in edge.transform_ (estimateSVD(Pd /*to*/, Xd /*from*/))."""
     n_to = n_from if n_to is None else n_to
@@ -89,22 +91,23 @@ def make_pair(n_from, n_to=None, seed=0, rho=0.5, invalid_frac=0.15, gross_outli
     T_gt = _rand_pose(rng, max_angle_deg, max_trans)
     Tinv = np.linalg.inv(T_gt)
     Xs = _landmarks(rng, ns)                                   # shared, in from-frame
-    Ds = rng.integers(0, 256, (ns, 32), dtype=np.uint8)
+    ftype = ORB if desc_bytes == 32 else BRISK
+    Ds = rng.integers(0, 256, (ns, desc_bytes), dtype=np.uint8)
     Xf = np.concatenate([Xs, _landmarks(rng, n_from - ns)])
-    Df = np.concatenate([_flip(rng, Ds), rng.integers(0, 256, (n_from - ns, 32), dtype=np.uint8)])
+    Df = np.concatenate([_flip(rng, Ds), rng.integers(0, 256, (n_from - ns, desc_bytes), dtype=np.uint8)])
     Ps = Xs @ Tinv[:3, :3].T + Tinv[:3, 3]
     if gross_outlier_frac > 0 and ns > 0:
         g = rng.random(ns) < gross_outlier_frac
         Ps[g] = _landmarks(rng, int(g.sum()))
     Pt = np.concatenate([Ps, _landmarks(rng, n_to - ns)])
-    Dt = np.concatenate([_flip(rng, Ds), rng.integers(0, 256, (n_to - ns, 32), dtype=np.uint8)])
-    kf_from, _ = _finish(rng, Df, _observe(rng, Xf, noise), invalid_frac, tie_stress, sensor_frame)
-    kf_to, _ = _finish(rng, Dt, _observe(rng, Pt, noise), invalid_frac, tie_stress, sensor_frame)
+    Dt = np.concatenate([_flip(rng, Ds), rng.integers(0, 256, (n_to - ns, desc_bytes), dtype=np.uint8)])
+    kf_from, _ = _finish(rng, Df, _observe(rng, Xf, noise), invalid_frac, tie_stress, sensor_frame, feature_type=ftype)
+    kf_to, _ = _finish(rng, Dt, _observe(rng, Pt, noise), invalid_frac, tie_stress, sensor_frame, feature_type=ftype)
     return kf_from, kf_to, T_gt
 
 
 def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, k_candidates=20,
-             cross_cluster=4, seed=0, invalid_frac=0.15, out=None):
+             cross_cluster=4, seed=0, invalid_frac=0.15, out=None, desc_bytes=32):
     """A keyframe map with loop-closure candidates (configs C3/C4 of BASELINE.json).
 
     Keyframes come in clusters that share a pool of landmarks: each keyframe observes n_shared pool
@@ -113,7 +116,7 @@ def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, 
     partners: k_candidates - cross_cluster from its own cluster (true loop closures) and
     cross_cluster from random other clusters (place-recognition false positives).
 
-    `out` = (desc uint8[n,N,32], pos float64[n,N,3], valid uint8[n,N]) optionally receives the keyframes
+    `out` = (desc uint8[n,N,desc_bytes], pos float64[n,N,3], valid uint8[n,N]) optionally receives the keyframes
     as slices of three big arrays (e.g. pinned host memory), so the whole map is contiguous per field.
 
     Returns (keyframes list, pairs int32[n_pairs,2] (from,to), poses float64[n,4,4] (cluster->keyframe)).
@@ -124,15 +127,15 @@ def make_map(n_keyframes, n_features=1000, cluster=25, pool=1000, n_shared=600, 
     for c0 in range(0, n_keyframes, cluster):
         nk = min(cluster, n_keyframes - c0)
         Xp = _landmarks(rng, pool)
-        Dp = rng.integers(0, 256, (pool, 32), dtype=np.uint8)
+        Dp = rng.integers(0, 256, (pool, desc_bytes), dtype=np.uint8)
         for _ in range(nk):
             G = _rand_pose(rng, 15.0, 0.75)
             sel = rng.permutation(pool)[:n_shared]
             Xs = Xp[sel] @ G[:3, :3].T + G[:3, 3]
             X = np.concatenate([Xs, _landmarks(rng, n_features - n_shared)])
             D = np.concatenate([_flip(rng, Dp[sel]),
-                                rng.integers(0, 256, (n_features - n_shared, 32), dtype=np.uint8)])
-            kf, _ = _finish(rng, D, _observe(rng, X), invalid_frac, False, 0)
+                                rng.integers(0, 256, (n_features - n_shared, desc_bytes), dtype=np.uint8)])
+            kf, _ = _finish(rng, D, _observe(rng, X), invalid_frac, False, 0, feature_type=ORB if desc_bytes == 32 else BRISK)
             if out is not None:
                 k = len(kfs)
                 out[0][k] = kf["desc"]; out[1][k] = kf["pos"]; out[2][k] = kf["valid"]
