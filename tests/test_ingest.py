@@ -129,8 +129,12 @@ def test_gpu_wire_decode_and_ingest(est, oracle):
     # malformed input is refused, not decoded
     with pytest.raises(Exception):
         est.add_keyframe_wire(blobs[0][:-10])
-    b64 = encode_features(np.zeros((3, 64), np.float32), [0] * 3, [0] * 3, [1] * 3, [0] * 3, np.zeros((3, 3)))
+    b48 = encode_features(np.zeros((3, 48), np.float32), [0] * 3, [0] * 3, [1] * 3, [0] * 3, np.zeros((3, 3)))
+    with pytest.raises(Exception):                      # neither 32 nor 64 columns
+        est.add_keyframe_wire(b48)
+    mixed = encode_features(np.zeros((2, 64), np.float32), [0] * 2, [0] * 2, [1] * 2, [0] * 2, np.zeros((2, 3)))
+    mixed = struct.pack("<I", 3) + mixed[4:] + b48[4:4 + 17 + 48 * 4 + 24] + b"\0" * 64      # third element has another length
     with pytest.raises(Exception):
-        est.add_keyframe_wire(b64)
+        est.add_keyframe_wire(mixed)
     assert est.read_keyframe(est.add_keyframe_wire(struct.pack("<I", 0)))["desc"].shape == (0, 32)
     est.clear()
