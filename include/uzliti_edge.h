@@ -56,7 +56,7 @@ typedef struct {
     int32_t min_keypoints;         /* :47 (7)                                                    */
     int32_t cross_check;           /* opt-in (reference: none, 0): keep a ratio survivor (q,t) only if q is also the
                                       nearest query row of t, lowest index on ties == cv::BFMatcher(crossCheck=true);
-                                      runs every matching a second time, reversed                  */
+                                      the match kernel tracks the per-train-row minima in the same pass (+10-15 %)  */
 } uz_params;
 
 /* One FeatureData (graph_slam_common/include/graph_slam_common/sensor_data.h:49-70) as borrowed POD. */

@@ -310,7 +310,8 @@ def test_edge_params(est, oracle, params):
 @pytest.mark.parametrize("n,seed,kw", [(500, 70, {}), (1000, 71, dict(tie_stress=True)), (300, 72, dict(rho=0.9)),
                                        (1500, 73, dict(gross_outlier_frac=0.4))])
 def test_edge_cross_check(est, oracle, n, seed, kw):
-    """opt-in mutual filter (uz_params.cross_check): the reversed matching runs through the same kernel"""
+    """opt-in mutual filter (uz_params.cross_check): column minima tracked by the match kernel (tests/test_shapes.py compares the
+    fused form with the reversed matching)"""
     f, t, _ = S.make_pair(n, seed=seed, **kw)
     try:
         est.setConfig(cross_check=1)

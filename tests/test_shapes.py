@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+from uzliti_slam_b200 import synthetic as S
+
 pytestmark = pytest.mark.gpu
 
 SIZES = [(1000, 1000), (400, 300), (65, 129), (1, 5), (513, 4096), (130, 127), (64, 2)]
@@ -36,3 +38,48 @@ def test_every_cta_shape_matches_the_oracle(oracle, cfg):
             assert np.array_equal(dist, od), (cfg, nq, nt)
     finally:
         est.close()
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5])
+def test_cross_check_fused_and_reversed_forms_agree_with_the_oracle(oracle, cfg):
+    """uz_params.cross_check in both forms: column minima tracked by the forward match kernel (default) and a second,
+    reversed matching (UZ_XCHECK_FUSED=0), for every two-queries-per-thread CTA shape, on ragged tiles (clamped duplicate
+    queries in the last tile), tie-heavy rows (lowest query index must win a column), a rig and both descriptor widths."""
+    from uzliti_slam_b200 import EdgeEstimator
+    ests = []
+    for fused in (1, 0):
+        os.environ["UZ_KNN_CFG"] = str(cfg)
+        os.environ["UZ_KNN_WIDE_CFG"] = "0" if cfg in (3, 4) else "1"
+        os.environ["UZ_XCHECK_FUSED"] = str(fused)
+        os.environ["UZ_STREAM_SOLVE"] = "0"
+        try:
+            e = EdgeEstimator(0)
+            e.setConfig(cross_check=1)
+            ests.append(e)
+        finally:
+            for k in ("UZ_KNN_CFG", "UZ_KNN_WIDE_CFG", "UZ_XCHECK_FUSED", "UZ_STREAM_SOLVE"):
+                os.environ.pop(k, None)
+    try:
+        cases = []
+        for nb in (32, 64):
+            for kw in (dict(n_from=1000, seed=1), dict(n_from=700, n_to=333, seed=2), dict(n_from=129, n_to=577, seed=3),
+                       dict(n_from=300, seed=4, tie_stress=True), dict(n_from=65, n_to=31, seed=5, tie_stress=True),
+                       dict(n_from=513, n_to=1025, seed=6)):
+                f, t, _ = S.make_pair(desc_bytes=nb, **kw)
+                cases.append(([f], [t]))
+        fa, ta, _ = S.make_pair(400, 300, seed=7, sensor_frame=0, tie_stress=True)
+        fb, tb, _ = S.make_pair(350, 450, seed=8, sensor_frame=1)
+        cases.append(([fa, fb], [ta, tb]))
+        got = [e.estimateEdgesHost(cases) for e in ests]
+        assert got[0].tobytes() == got[1].tobytes()
+        dropped = 0
+        for r, (cf, ct) in zip(got[0], cases):
+            o = oracle.estimate_edge(cf, ct, cross_check=True)
+            assert r["n_ratio_matches"] == o["n_ratio_matches"] and r["n_matches"] == o["n_matches"]
+            assert r["consensus"] == o["consensus"] and r["cam_from"] == o["cam_from"]
+            assert np.abs(r["T"].reshape(4, 4) - o["T"]).max() < 1e-5
+            dropped += oracle.estimate_edge(cf, ct)["n_ratio_matches"] - o["n_ratio_matches"]
+        assert dropped > 500
+    finally:
+        for e in ests:
+            e.close()

@@ -153,6 +153,7 @@ struct uz_context {
     int stream_min_pairs = 0;        // UZ_STREAM_SOLVE_MIN_PAIRS: smallest batch that takes the streaming form (0 = two pairs per CTA)
     int stream_solve_ctas = 1;       // UZ_STREAM_SOLVE: persistent solve CTAs per SM (0 = off: one solve CTA per pair behind the match kernel)
     int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
+    int xcheck_fused = 1;            // UZ_XCHECK_FUSED=0: cross-check by a second, reversed matching (the measured alternative)
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     uz_params params;
@@ -477,8 +478,11 @@ uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max
 // ---- launches --------------------------------------------------------------------------------------
 template <int THREADS, int QPT>
 void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
-                 unsigned int* d_progress) {
-    if (ctx->variant_csa && ctx->variant_pack16)
+                 unsigned int* d_progress, bool xchk) {
+    if (xchk) {
+        if constexpr (QPT == 2)      // fused cross-check: column minima in the same pass (+ 4 B of shared memory per staged train row)
+            knn2_kernel<THREADS, QPT, true, true, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT) + knn_train_rows(THREADS, QPT) * 4, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+    } else if (ctx->variant_csa && ctx->variant_pack16)
         knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else if (ctx->variant_csa)
         knn2_kernel<THREADS, QPT, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
@@ -488,8 +492,11 @@ void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles,
 
 template <int THREADS>
 void launch_knn2_wide(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
-                      unsigned int* d_progress) {
-    knn2_wide_kernel<THREADS><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+                      unsigned int* d_progress, bool xchk) {
+    if (xchk)
+        knn2_wide_kernel<THREADS, true><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS) + knn_wide_train_rows(THREADS) * 4, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+    else
+        knn2_wide_kernel<THREADS><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
 }
 
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
@@ -504,6 +511,7 @@ cudaError_t knn2_carveout() {
     cudaError_t e = max_shared_carveout(knn2_kernel<THREADS, QPT, true, true>);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_kernel<THREADS, QPT, true, false>);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_kernel<THREADS, QPT, false, false>);
+    if constexpr (QPT == 2) { if (e == cudaSuccess) e = max_shared_carveout(knn2_kernel<THREADS, QPT, true, true, true>); }
     return e;
 }
 cudaError_t set_carveouts() {
@@ -515,6 +523,8 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = knn2_carveout<32, 2>();
     if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<256>);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<64>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<256, true>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_wide_kernel<64, true>);
     if (e == cudaSuccess) e = max_shared_carveout(solve_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(solve_stream_kernel<kSolveThreads>);
     if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
@@ -586,7 +596,20 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         pair_tasks[i] = make_int2(first, (int)n_tasks - first);
     }
     const size_t n_fwd = n_tasks;
-    if (cross) {
+    // Cross-check.  Fused form (default): the forward match kernel also keeps, per train row, the minimum over the
+    // queries (uz_knn2.cuh, col_update16); the matching's column keys live behind the row keys in the same scratch.
+    // Reversed form (UZ_XCHECK_FUSED=0, and the kernel variants without the packed-key shapes): every matching runs
+    // a second time with query and train swapped.
+    const bool fused = cross && ctx->xcheck_fused && ctx->variant_csa && ctx->variant_pack16 &&
+                       !(ctx->force_cfg >= 0 && ctx->force_cfg < 2);
+    const size_t col_begin = key_rows;
+    if (fused) {
+        for (size_t t = 0; t < n_fwd; ++t) {
+            if (tasks[t].nq == 0) continue;
+            tasks[t].rev_key_off = (uint32_t)key_rows;
+            key_rows += (size_t)tasks[t].nt;
+        }
+    } else if (cross) {
         for (size_t t = 0; t < n_fwd; ++t) {
             MatchTask& f = tasks[t];
             if (f.nq == 0) continue;                 // non-binary type: no matches to check
@@ -660,7 +683,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             size_t& k = task_wide[t] ? kw : kn;
             const int tr = rows_of(t);
             for (int q0 = 0; q0 < tasks[t].nq; q0 += tr) tiles[k++] = make_int2((int)t, q0);
-            if (tasks[t].rev_key_off != kNoRev) {
+            if (!fused && tasks[t].rev_key_off != kNoRev) {
                 const int r = (int)tasks[t].pad_;
                 for (int q0 = 0; q0 < tasks[r].nq; q0 += tr) tiles[k++] = make_int2(r, q0);
             }
@@ -672,6 +695,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     UZ_CUDA(ctx, sl.d_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
     UZ_CUDA(ctx, sl.d_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
     UZ_CUDA(ctx, sl.d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
+    if (fused && key_rows > col_begin)       // column keys start at "none"; the match kernel lowers them with atomicMin
+        UZ_CUDA(ctx, cudaMemsetAsync((uint2*)sl.d_keys.p + col_begin, 0xFF, (key_rows - col_begin) * sizeof(uint2), ctx->stream));
     if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
     if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -743,19 +768,19 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         const int nt = (int)n_tiles_narrow;
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
         if (n_tiles_wide > 0) {
-            if (wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog);
-            else launch_knn2_wide<64>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog);
+            if (wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog, fused);
+            else launch_knn2_wide<64>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog, fused);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) ctx->match_launches++;
         }
         if (nt > 0) switch (best_cfg) {
-            case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
-            default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog); break;
+            case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
         }
         if (nt > 0) {
             ctx->launches++;
@@ -895,6 +920,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (ss && atoi(ss) >= 0 && atoi(ss) <= 4) ctx->stream_solve_ctas = atoi(ss);
         const char* fc = getenv("UZ_KNN_CFG");
         if (fc) ctx->force_cfg = atoi(fc);
+        const char* xf = getenv("UZ_XCHECK_FUSED");
+        if (xf) ctx->xcheck_fused = atoi(xf) != 0;
         const char* fw = getenv("UZ_KNN_WIDE_CFG");
         if (fw) ctx->force_wide_cfg = atoi(fw);
         const char* gu = getenv("UZ_GATHER_UPLOAD");

@@ -172,6 +172,50 @@ __device__ __forceinline__ void merge_block16(uint32_t& m1, uint32_t& m2, uint32
     m2 = min(min(m2, t), k2);
 }
 
+// ---- fused cross-check (uz_params.cross_check): column minima beside the row top-2 -----------------------
+// cv::BFMatcher(crossCheck = true) keeps (q, t) only if q is also the nearest query row of t (lowest index on ties).
+// The distances that decide this are the ones the forward matching computes anyway, so the match kernel tracks, per
+// train row, the minimum over its query tile instead of running the whole matching a second time, reversed:
+//   per thread  v = min over its two queries of  (key16 << 16) | local query index      (1 IMAD + 1 LOP3 + 1 VIMNMX)
+//   per warp    REDUX.MIN over the 32 lanes, one shared-memory ATOMS.MIN per warp and train row
+//   per tile    one global atomicMin per train row on keys[rev_key_off + t].x = (distance << 16) | queryIdx
+// The key16 of both queries carries the same train row, so the order of v is (distance, query index).  Threads
+// beyond the last query of a ragged tile recompute the last valid query (same candidates, no effect on a minimum).
+__constant__ uint32_t kShift16 = 65536u;
+// v is warp-uniform (the REDUX result): lane 0 alone issues the shared-memory reduction.  The address arrives as a
+// per-thread shared-window offset (col_base: base + 4 * lane, used by lane 0 only): with an address it can prove warp-uniform, ptxas
+// wraps every such reduction in its own warp aggregation - a leader election and a second REDUX per call.
+__device__ __forceinline__ uint32_t col_base(const uint32_t* s_col) {
+    uint32_t a;             // base + 4 * lane: the right address in lane 0, the only lane that ever uses it
+    asm volatile("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(threadIdx.x & 31u), "r"((uint32_t)__cvta_generic_to_shared(s_col)));
+    return a;
+}
+__device__ __forceinline__ void col_publish(uint32_t v, uint32_t s_col_row) {
+    if ((threadIdx.x & 31) == 0) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(s_col_row), "r"(v) : "memory");
+}
+template <int DSHIFT /* distance position inside key16: 7 (256-bit rows) or 6 (512-bit rows) */>
+__device__ __forceinline__ void col_update16(uint32_t k, uint32_t c0, uint32_t c1, uint32_t s_col_row) {
+    const uint32_t x = mad_u32(k, kShift16, c0);                 // query 0: (key16 << 16) + index       (FMA pipe)
+    const uint32_t y = lop3<0xEA>(k, 0xFFFF0000u, c1);           // query 1: (k & 0xFFFF0000) | index
+    col_publish(__reduce_min_sync(0xffffffffu, min(x, y)), s_col_row);
+}
+// the same from two full 32-bit keys (tail rows): only the distance and the index matter for the flush
+template <int DSHIFT>
+__device__ __forceinline__ void col_update32(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t s_col_row) {
+    const uint32_t x = ((key0 >> 16) << (16 + DSHIFT)) | c0;
+    const uint32_t y = ((key1 >> 16) << (16 + DSHIFT)) | c1;
+    col_publish(__reduce_min_sync(0xffffffffu, min(x, y)), s_col_row);
+}
+// end of a train tile: publish the tile's column minima and re-arm the shared array
+template <int THREADS, int DSHIFT>
+__device__ __forceinline__ void col_flush(uint32_t* s_col, int nrows, uint2* col_keys, int r0, int q_base) {
+    for (int r = threadIdx.x; r < nrows; r += THREADS) {
+        const uint32_t v = s_col[r];
+        s_col[r] = 0xFFFFFFFFu;
+        if (v != 0xFFFFFFFFu) atomicMin(&col_keys[r0 + r].x, ((v >> (16 + DSHIFT)) << 16) | (uint32_t)(q_base + (int)(v & 0xFFFFu)));
+    }
+}
+
 // ---- mbarrier / bulk-copy helpers (PTX) --------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -197,15 +241,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // tiles[blockIdx.x] = (task index, first query row of the tile)
-template <int THREADS, int QPT, bool CSA, bool PACK16 = false>
+template <int THREADS, int QPT, bool CSA, bool PACK16 = false, bool XCHK = false>
 __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys,
                                                        int* __restrict__ pair_pending,
                                                        unsigned int* __restrict__ progress) {
     constexpr int kTrainTileRows = knn_train_rows(THREADS, QPT);
+    static_assert(!XCHK || (PACK16 && QPT == 2), "the fused cross-check lives in the packed-key, two-queries-per-thread shapes");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kTrainTileRows * 32);
+    uint32_t* s_col = reinterpret_cast<uint32_t*>(smem + kStages * kTrainTileRows * 32 + 64);     // XCHK: [kTrainTileRows]
+    const uint32_t s_col_a = XCHK ? col_base(s_col) : 0u;
 
     const int2 tile = tiles[blockIdx.x];
     const MatchTask* tk = tasks + tile.x;
@@ -219,6 +266,7 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (XCHK) for (int r = tid; r < kTrainTileRows; r += THREADS) s_col[r] = 0xFFFFFFFFu;
     __syncthreads();
 
     const int ntiles = (nt + kTrainTileRows - 1) / kTrainTileRows;
@@ -231,9 +279,11 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
     // query rows of this thread: q0 + k*THREADS + tid (coalesced 32 B per thread)
     uint32_t U[QPT][8];
     uint32_t m1[QPT], m2[QPT];
+    uint32_t cq[2] = {0u, 0u};          // XCHK: local index (inside the tile) of the query each slot really holds
 #pragma unroll
     for (int k = 0; k < QPT; ++k) {
-        const int q = tile.y + k * THREADS + tid;
+        int q = tile.y + k * THREADS + tid;
+        if (XCHK) { q = min(q, nq - 1); cq[k & 1] = (uint32_t)(q - tile.y); }      // ragged tile: recompute the last query
         uint4 a = make_uint4(0, 0, 0, 0), b = a;
         if (q < nq) {
             const uint4* p = reinterpret_cast<const uint4*>(qd + (size_t)q * 8);
@@ -280,6 +330,10 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
                             k0 = csa_acc16<true>(U[2 * kk + 1], a0, b0v, k0);
                             k1 = csa_acc16<true>(U[2 * kk + 1], a1, b1v, k1);
                             top2_update2_u16x2(p1[kk], p2[kk], k0, k1);
+                            if (XCHK) {
+                                col_update16<7>(k0, cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j + u));
+                                col_update16<7>(k1, cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j + u + 1));
+                            }
                         }
                     }
                 }
@@ -294,8 +348,10 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
                 for (; j < nb; ++j) {
                     const uint4 a = brows[2 * j], b = brows[2 * j + 1];
                     const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+                    uint32_t kq[QPT];
 #pragma unroll
-                    for (int k = 0; k < QPT; ++k) top2_update(m1[k], m2[k], csa_key(U[k], a, b, jkey));
+                    for (int k = 0; k < QPT; ++k) { kq[k] = csa_key(U[k], a, b, jkey); top2_update(m1[k], m2[k], kq[k]); }
+                    if (XCHK) col_update32<7>(kq[0], kq[QPT - 1], cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j));
                 }
             }
         } else {
@@ -326,6 +382,10 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
             }
         }
         __syncthreads();
+        if (XCHK) {
+            col_flush<THREADS, 7>(s_col, nrows, keys + tk->rev_key_off, r0, tile.y);
+            __syncthreads();
+        }
     }
 
 #pragma unroll
@@ -397,7 +457,7 @@ __device__ __forceinline__ void merge_block16w(uint32_t& m1, uint32_t& m2, uint3
     m2 = min(min(m2, t), k2);
 }
 
-template <int THREADS>
+template <int THREADS, bool XCHK = false>
 __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys,
@@ -407,6 +467,8 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
     static_assert(kRows % 64 == 0, "train tiles are cut into 64-row key blocks");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kRows * 64);
+    uint32_t* s_col = reinterpret_cast<uint32_t*>(smem + kStages * kRows * 64 + 64);       // XCHK: [kRows]
+    const uint32_t s_col_a = XCHK ? col_base(s_col) : 0u;
 
     const int2 tile = tiles[blockIdx.x];
     const MatchTask* tk = tasks + tile.x;
@@ -420,6 +482,7 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (XCHK) for (int r = tid; r < kRows; r += THREADS) s_col[r] = 0xFFFFFFFFu;
     __syncthreads();
 
     const int ntiles = (nt + kRows - 1) / kRows;
@@ -431,9 +494,11 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
 
     uint32_t U[2][16];
     uint32_t m1[2], m2[2];
+    uint32_t cq[2] = {0u, 0u};          // XCHK: local index of the query each slot really holds (see col_update16)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const int q = tile.y + k * THREADS + tid;
+        int q = tile.y + k * THREADS + tid;
+        if (XCHK) { q = min(q, nq - 1); cq[k] = (uint32_t)(q - tile.y); }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             uint4 a = make_uint4(0, 0, 0, 0);
@@ -481,6 +546,10 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
                     k1 = csa_acc16w<true>(U[1] + 8, c1, d1, k1);
                 }
                 top2_update2_u16x2(p1, p2, k0, k1);
+                if (XCHK) {
+                    col_update16<6>(k0, cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j));
+                    col_update16<6>(k1, cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j + 1));
+                }
             }
             if (j > 0) {
                 const uint32_t base = (uint32_t)(r0 + b0);
@@ -490,11 +559,17 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
             for (; j < nb; ++j) {
                 const uint4 a = brows[4 * j], b = brows[4 * j + 1], c = brows[4 * j + 2], d = brows[4 * j + 3];
                 const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+                uint32_t kq[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) top2_update(m1[k], m2[k], csa_key_wide(U[k], a, b, c, d, jkey));
+                for (int k = 0; k < 2; ++k) { kq[k] = csa_key_wide(U[k], a, b, c, d, jkey); top2_update(m1[k], m2[k], kq[k]); }
+                if (XCHK) col_update32<6>(kq[0], kq[1], cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j));
             }
         }
         __syncthreads();
+        if (XCHK) {
+            col_flush<THREADS, 6>(s_col, nrows, keys + tk->rev_key_off, r0, tile.y);
+            __syncthreads();
+        }
     }
 
 #pragma unroll
