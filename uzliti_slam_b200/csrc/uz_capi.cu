@@ -148,6 +148,9 @@ struct uz_context {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t side = nullptr;     // high-priority stream the solve kernels of a chunked batch run on
+    cudaStream_t alt = nullptr;      // second compute stream: odd chunks of a chunked host batch run here, so that the
+                                     // next chunk's match CTAs fill the SMs while the previous chunk's last wave drains
+    int alt_chunks = 1;              // UZ_ALT_CHUNKS=0: every chunk on the context stream (kernel boundaries serialise)
     cudaStream_t solve_stream = nullptr;   // high-priority stream of the streaming solve grid (runs beside the match kernel)
     int stream_probe = 0;            // UZ_STREAM_PROBE: measurement / test hooks of the streaming solve (scripts/gpu_stream_probe.py)
     int stream_min_pairs = 0;        // UZ_STREAM_SOLVE_MIN_PAIRS: smallest batch that takes the streaming form (0 = two pairs per CTA)
@@ -841,6 +844,7 @@ uz_status resolve_timers(uz_context* ctx) {
     if (ctx->pending.empty()) return UZ_OK;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->side) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->side));
+    if (ctx->alt) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->alt));
     if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
     for (auto& t : ctx->pending) {
         float a = 0, b = 0;
@@ -911,6 +915,9 @@ uz_status uz_create(int32_t device, uz_context** out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(e)); }
+        if ((e = cudaStreamCreateWithFlags(&ctx->alt, cudaStreamNonBlocking)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+        const char* ac = getenv("UZ_ALT_CHUNKS");
+        if (ac) ctx->alt_chunks = atoi(ac) != 0;
         if ((e = cudaStreamCreateWithPriority(&ctx->solve_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) { uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(e)); }
         const char* mp = getenv("UZ_STREAM_SOLVE_MIN_PAIRS");
         if (mp && atoi(mp) > 0) ctx->stream_min_pairs = atoi(mp);
@@ -958,6 +965,7 @@ void uz_destroy(uz_context* ctx) {
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->alt) { cudaStreamSynchronize(ctx->alt); cudaStreamDestroy(ctx->alt); }
     if (ctx->solve_stream) { cudaStreamSynchronize(ctx->solve_stream); cudaStreamDestroy(ctx->solve_stream); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1452,8 +1460,10 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         cudaEvent_t ev = ctx->get_event();
         UZ_CUDA(ctx, cudaEventRecord(ev, main_stream));
         UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ev, 0));
+        if (ctx->alt) UZ_CUDA(ctx, cudaStreamWaitEvent(ctx->alt, ev, 0));
         ctx->event_pool.push_back(ev);
     }
+    const bool alternate = piped && ctx->alt != nullptr && ctx->alt_chunks;
     UZ_CUDA(ctx, ctx->d_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
     UZ_CUDA(ctx, ctx->h_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
     uz_edge_result* h_res = (uz_edge_result*)ctx->h_results.p;
@@ -1474,6 +1484,7 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         }
     };
     size_t cf = 0, ct = 0;
+    cudaEvent_t last_ready = nullptr;
     for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
         const size_t p0 = chunk_begin(c), p1 = chunk_pair_end[c];
         if (p1 <= p0) continue;
@@ -1513,12 +1524,19 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
                 a += (size_t)n_from[i]; b2 += (size_t)n_to[i];
             }
         }
+        // odd chunks compute on the second stream: two match kernels of one stream run strictly one after the other, and
+        // every such boundary leaves the SMs partly idle while the last CTAs of the earlier kernel finish
+        if (alternate && (c & 1)) ctx->stream = ctx->alt;
+        // the upload stream is in order, so the newest upload event covers every camera uploaded so far; a chunk on the
+        // other compute stream needs it even when it brought no camera of its own
         if (ready) {
-            cudaStreamWaitEvent(ctx->stream, ready, 0);
-            ctx->event_pool.push_back(ready);
+            if (last_ready) ctx->event_pool.push_back(last_ready);
+            last_ready = ready;
         }
+        if (last_ready && (ready || alternate)) cudaStreamWaitEvent(ctx->stream, last_ready, 0);
         cudaStream_t rs = ctx->stream;
         st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0, /*join=*/false, &rs);
+        ctx->stream = main_stream;
         // into pinned memory: a pageable destination would make the copy synchronous and stall the next chunk's enqueue
         if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
                                            cudaMemcpyDeviceToHost, rs) != cudaSuccess)
@@ -1530,14 +1548,17 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     tr.lap("all chunks enqueued");
     drain(n_chunks, true);
     for (auto e : home) if (e) ctx->event_pool.push_back(e);
+    if (last_ready) ctx->event_pool.push_back(last_ready);
     if (st != UZ_OK) {
         cudaStreamSynchronize(ctx->stream);
         if (ctx->side) cudaStreamSynchronize(ctx->side);
+        if (ctx->alt) cudaStreamSynchronize(ctx->alt);
         if (ctx->solve_stream) cudaStreamSynchronize(ctx->solve_stream);
         cudaGetLastError();
         return st;
     }
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->alt) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->alt));
     if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
     tr.lap("wait GPU + records out");
     return UZ_OK;
