@@ -363,6 +363,23 @@ def measure_other_configs(est, handles, kfs):
     out["C3_one_query_vs_1000"] = dict(ms_per_query=round(dt * 1e3, 3), edges_per_s=round(1000 / dt, 1),
                                        note="1e9 descriptor compares + 1000 RANSACs per query keyframe, records back on the host")
 
+    # the same C3 batch with the opt-in cross-check (uz_params.cross_check; north star: "ratio test and cross-check"):
+    # column minima tracked inside the match kernel
+    est.enable_timers(True)
+    ms = {}
+    for cross in (0, 1):
+        est.setConfig(cross_check=cross)
+        est.estimateEdges(cand, q)
+        est.reset_timers()
+        for _ in range(reps):
+            est.estimateEdges(cand, q)
+        ms[cross] = est.get_timers()["match_ms"] / reps
+    est.setConfig(cross_check=0)
+    est.enable_timers(False)
+    out["C3_cross_check"] = dict(match_ms_plain=round(ms[0], 3), match_ms_cross_check=round(ms[1], 3),
+                                 cost_factor=round(ms[1] / ms[0], 3),
+                                 note="fused form: per-train-row minima in the same pass (a second, reversed matching costs 2.0 x)")
+
     # C5: rig keyframes (4 cameras x 2000 features), 4 same-frame matchings of 2000 x 2000 per pair, 1000 hypotheses
     rigs_f, rigs_t = [], []
     for p in range(8):

@@ -1407,17 +1407,19 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // intern its cameras, enqueue their upload on the high-priority side stream, enqueue match + solve on the main
     // stream behind the upload's event, queue its records' way home - so the GPU starts after the host has looked at
     // the FIRST chunk only, uploads of later chunks run beside the matching of earlier ones, and records are copied
-    // out to the caller while later chunks still compute.  The first chunks are small (1/16 of the batch): what stays
-    // exposed is their upload.
-    // Chunk ends as fractions of the batch.  Default for large batches: two sixteenths, then eighths - the exposed first
-    // chunk is small, every later upload hides behind the matching of the chunk before it, and the chunks stay large
-    // enough for the streaming solve.  Measured alternatives on C4 (874 k edges/s): a smaller first chunk (1/32, 1/16,
-    // eighths) 866 k, a geometric 1/32 .. 1/2 split 865 k, 4 equal parts 850 k.  UZ_HOST_CHUNKS = k > 0 forces k equal parts.
+    // out to the caller while later chunks still compute.  What stays exposed is the first chunk's upload.
+    // Chunk ends as fractions of the batch: equal chunks of about 768 pairs, between 4 and 40 of them.  Consecutive chunks
+    // compute on two alternating streams (below), so a chunk boundary costs next to nothing and small chunks win: the
+    // exposed first upload shrinks and records go home earlier, until the chunks get too small for the persistent solve
+    // grid.  Measured on C4 (25 000 pairs, store-resident 937 k edges/s): 8 chunks 894 k, 16: 916 k, 32: 926 k, 48: 930 k,
+    // 64: 903 k, 80: 839 k; on one stream the same 9-chunk split that gave 869 k gives 909 k on two.
+    // UZ_HOST_CHUNKS = k > 0 forces k equal parts.
     std::vector<double> fracs;
-    if (ctx->debug || n_pairs < 2048) fracs = {1.0};          // the parity taps describe ONE launch pair
-    else if (ctx->host_chunks > 0) for (int c = 1; c <= ctx->host_chunks; ++c) fracs.push_back((double)c / ctx->host_chunks);
-    else if (n_pairs >= 8192) fracs = {1 / 16.0, 2 / 16.0, 2 / 8.0, 3 / 8.0, 4 / 8.0, 5 / 8.0, 6 / 8.0, 7 / 8.0, 1.0};
-    else fracs = {1 / 4.0, 2 / 4.0, 3 / 4.0, 1.0};
+    int want_chunks = 1;
+    if (ctx->debug || n_pairs < 2048) want_chunks = 1;          // the parity taps describe ONE launch pair
+    else if (ctx->host_chunks > 0) want_chunks = ctx->host_chunks;
+    else want_chunks = std::min(40, std::max(4, n_pairs / 768));
+    for (int c = 1; c <= want_chunks; ++c) fracs.push_back((double)c / want_chunks);
     const int n_chunks = (int)fracs.size();
     std::vector<size_t> chunk_pair_end((size_t)n_chunks);
     for (int c = 0; c < n_chunks; ++c)
