@@ -83,3 +83,35 @@ def test_cross_check_fused_and_reversed_forms_agree_with_the_oracle(oracle, cfg)
     finally:
         for e in ests:
             e.close()
+
+
+@pytest.mark.parametrize("nb", [32, 64])
+def test_random_shapes_fuzz(est, oracle, nb):
+    """seeded random (nq, nt) around the tile / key-block / stage boundaries, with and without the fused cross-check:
+    neighbours through uz_match_knn2, ratio survivors and match counts through the whole path"""
+    rng = np.random.default_rng(1234 + nb)
+    edges = [1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 767, 1023, 1024, 1025]
+    try:
+        for it in range(36):
+            nq = int(rng.choice(edges)) if it % 3 else int(rng.integers(1, 1400))
+            nt = int(rng.choice(edges)) if it % 2 else int(rng.integers(1, 1400))
+            keep = int(rng.choice([1, 2, nb]))
+            q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+            t = rng.integers(0, 256, (nt, nb), dtype=np.uint8)
+            q[:, keep:] = 0
+            t[:, keep:] = 0
+            idx, dist = est.knnMatch(q, t)
+            oi, od = oracle.knn2(q, t)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nb, nq, nt, keep)
+            if nq >= 7 and nt >= 7:
+                cam = lambda d: dict(desc=d, pos=rng.normal(size=(len(d), 3)) + [0, 0, 3], valid=np.ones(len(d), np.uint8),
+                                     feature_type=2, sensor_frame=0)
+                cf, ct = cam(t), cam(q)
+                for cross in (0, 1):
+                    est.setConfig(cross_check=cross)
+                    r = est.estimateEdgeDirect([cf], [ct])
+                    o = oracle.estimate_edge([cf], [ct], cross_check=bool(cross))
+                    assert r["n_ratio_matches"] == o["n_ratio_matches"] and r["n_matches"] == o["n_matches"], (nb, nq, nt, keep, cross)
+                    assert r["consensus"] == o["consensus"] and bool(r["ok"]) == o["ok"], (nb, nq, nt, keep, cross)
+    finally:
+        est.setConfig(cross_check=0)
