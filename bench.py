@@ -43,6 +43,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries loaded later may write to file descriptor 1 on their own (NCCL prints
+# its version banner there when NCCL_DEBUG is set in the environment), so the process keeps a private duplicate of the
+# real stdout for the result line and points descriptor 1 at stderr for everybody else.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def build_map(n_keyframes, out=None):
     from uzliti_slam_b200 import synthetic as S
     t0 = time.time()
@@ -170,7 +190,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port", sample=sample_desc),
                 e2e=dict(value=round(val, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -669,7 +689,7 @@ def run_gpu(args):
             e2e=dict(value=round(e2e_val, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
                      api="uz_estimate_edges_host (pinned host FeatureData in, host edge records out)"),
             gpu_launches=launches, clocks=clocks, sanity=sanity, candidate_generation=places, other_configs=others)
-        print(json.dumps(line), flush=True)
+        emit(line)
     est.close()
     if world > 1:
         dist.destroy_process_group()
@@ -688,6 +708,7 @@ def main():
     ap.add_argument("--no-places", action="store_true", help="skip the candidate-generation (8f-1) measurement")
     ap.add_argument("--no-extras", action="store_true", help="skip the short C1/C3/C5 measurements")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
