@@ -413,6 +413,9 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
 // distance and 6 bits of row:  key16 = (distance << 6) | (row & 63)  (<= 32831), merged into the 32-bit keys every
 // 64 train rows.  Shape: THREADS x 2 queries per CTA (32 query words per thread, 64 registers, 32 resident warps per
 // SM), THREADS train rows per stage.
+#ifndef UZ_WIDE_MERGE
+#define UZ_WIDE_MERGE 0        // measured alternative, see csa_acc16w_merged: 15.56 ms against 15.10 ms for the plain halves
+#endif
 __constant__ uint32_t kPopcWeightLo6[3] = {1u << 6, 2u << 6, 4u << 6};
 __constant__ uint32_t kPopcWeightHi6[3] = {1u << 22, 2u << 22, 4u << 22};
 
@@ -440,6 +443,50 @@ __device__ __forceinline__ uint32_t csa_acc16w(const uint32_t* U, const uint4& a
     k = mad_u32(__popc(x7), w1, k);
     k = mad_u32(__popc(S3), w1, k);
     return k;
+}
+// One whole 512-bit compare with the two halves' weight-1 planes merged by one more full adder (UZ_WIDE_MERGE):
+// (S3a, x7a, S3b) -> sum (weight 1) + carry (weight 2), so 7 POPC + 28 LOP3 instead of 8 + 26.  The XU pipe (POPC) is
+// this kernel's binding unit at 94 % busy and the ALU pipe has slack on paper, but the trade LOSES on B200: 514 against
+// 530 G cmp512/s (same instruction count, the two pipes share dispatch bandwidth).  Kept as the measured alternative.
+template <bool HI>
+__device__ __forceinline__ uint32_t csa_acc16w_merged(const uint32_t* U, const uint4& a, const uint4& b, const uint4& c,
+                                                      const uint4& d, uint32_t acc) {
+    const uint32_t w1 = HI ? kPopcWeightHi6[0] : kPopcWeightLo6[0];
+    const uint32_t w2 = HI ? kPopcWeightHi6[1] : kPopcWeightLo6[1];
+    const uint32_t w4 = HI ? kPopcWeightHi6[2] : kPopcWeightLo6[2];
+    uint32_t S3a, x7a;
+    {
+        const uint32_t x0 = U[0] ^ a.x, x1 = U[1] ^ a.y, S1 = U[2] ^ a.z;
+        const uint32_t C1 = lop3<0xD4>(x0, x1, S1);
+        const uint32_t x3 = U[3] ^ a.w, x4 = U[4] ^ b.x, S2 = U[5] ^ b.y;
+        const uint32_t C2 = lop3<0xD4>(x3, x4, S2);
+        S3a = U[6] ^ b.z;
+        const uint32_t C3 = lop3<0xD4>(S1, S2, S3a);
+        x7a = U[7] ^ b.w;
+        const uint32_t S5 = lop3<0x96>(C1, C2, C3);
+        const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
+        acc = mad_u32(__popc(C5), w4, acc);
+        acc = mad_u32(__popc(S5), w2, acc);
+    }
+    {
+        const uint32_t x0 = U[8] ^ c.x, x1 = U[9] ^ c.y, S1 = U[10] ^ c.z;
+        const uint32_t C1 = lop3<0xD4>(x0, x1, S1);
+        const uint32_t x3 = U[11] ^ c.w, x4 = U[12] ^ d.x, S2 = U[13] ^ d.y;
+        const uint32_t C2 = lop3<0xD4>(x3, x4, S2);
+        const uint32_t S3b = U[14] ^ d.z;
+        const uint32_t C3 = lop3<0xD4>(S1, S2, S3b);
+        const uint32_t x7b = U[15] ^ d.w;
+        const uint32_t S5 = lop3<0x96>(C1, C2, C3);
+        const uint32_t C5 = lop3<0xE8>(C1, C2, C3);
+        const uint32_t s1 = lop3<0x96>(S3a, x7a, S3b);       // weight 1
+        const uint32_t c1 = lop3<0xE8>(S3a, x7a, S3b);       // weight 2
+        acc = mad_u32(__popc(C5), w4, acc);
+        acc = mad_u32(__popc(S5), w2, acc);
+        acc = mad_u32(__popc(c1), w2, acc);
+        acc = mad_u32(__popc(s1), w1, acc);
+        acc = mad_u32(__popc(x7b), w1, acc);
+    }
+    return acc;
 }
 // full 32-bit key of one wide compare (tail rows)
 __device__ __forceinline__ uint32_t csa_key_wide(const uint32_t* U, const uint4& a, const uint4& b, const uint4& c,
@@ -529,6 +576,18 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
             for (; j + 2 <= nb; j += 2) {
                 const uint32_t jj = (uint32_t)j * 0x00010001u;
                 uint32_t k0, k1;
+#if UZ_WIDE_MERGE
+                {
+                    const uint4 a0 = brows[4 * j], b0v = brows[4 * j + 1], c0 = brows[4 * j + 2], d0 = brows[4 * j + 3];
+                    k0 = csa_acc16w_merged<false>(U[0], a0, b0v, c0, d0, jj);
+                    k0 = csa_acc16w_merged<true>(U[1], a0, b0v, c0, d0, k0);
+                }
+                {
+                    const uint4 a1 = brows[4 * j + 4], b1v = brows[4 * j + 5], c1 = brows[4 * j + 6], d1 = brows[4 * j + 7];
+                    k1 = csa_acc16w_merged<false>(U[0], a1, b1v, c1, d1, jj + 0x00010001u);
+                    k1 = csa_acc16w_merged<true>(U[1], a1, b1v, c1, d1, k1);
+                }
+#else
                 {
                     const uint4 a0 = brows[4 * j], b0v = brows[4 * j + 1];
                     const uint4 a1 = brows[4 * j + 4], b1v = brows[4 * j + 5];
@@ -545,6 +604,7 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
                     k0 = csa_acc16w<true>(U[1] + 8, c0, d0, k0);
                     k1 = csa_acc16w<true>(U[1] + 8, c1, d1, k1);
                 }
+#endif
                 top2_update2_u16x2(p1, p2, k0, k1);
                 if (XCHK) {
                     col_update16<6>(k0, cq[0], cq[1], s_col_a + 4u * (uint32_t)(b0 + j));
