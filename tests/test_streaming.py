@@ -110,3 +110,26 @@ def test_streaming_survives_starvation():
     finally:
         plain.close()
         starved.close()
+
+
+@pytest.mark.parametrize("chunks,alt,stream", [(2, 1, 1), (5, 1, 1), (7, 0, 1), (5, 1, 0), (16, 1, 1)])
+def test_chunked_host_pipeline_equals_store_path(chunks, alt, stream):
+    """uz_estimate_edges_host cuts a batch into chunks that upload, match and solve on their own, consecutive chunks on two
+    alternating compute streams (UZ_ALT_CHUNKS=0: one stream).  A later chunk reuses cameras an earlier chunk uploaded
+    (every keyframe appears in many pairs, pairs shuffled), ragged sizes, both descriptor widths, pageable host memory."""
+    kn, pn = _ragged_map(11, n_keyframes=60)
+    kw, pw, _ = S.make_map(30, n_features=400, cluster=10, pool=400, n_shared=250, k_candidates=6, cross_cluster=2, seed=12,
+                           desc_bytes=64)
+    kfs = kn + kw
+    pairs = np.concatenate([pn, pw + len(kn)])
+    pairs = pairs[np.random.default_rng(3).permutation(len(pairs))]
+    est = _estimator(UZ_STREAM_SOLVE=stream, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_HOST_CHUNKS=chunks, UZ_ALT_CHUNKS=alt)
+    try:
+        h = est.add_keyframes(kfs)
+        a = est.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]])
+        for _ in range(2):
+            b = est.estimateEdgesHost([([kfs[i]], [kfs[j]]) for i, j in pairs])
+            assert a.tobytes() == b.tobytes()
+        assert (a["consensus"] > 50).sum() > 100 and (a["ok"] == 0).any()
+    finally:
+        est.close()

@@ -1416,8 +1416,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // UZ_HOST_CHUNKS = k > 0 forces k equal parts.
     std::vector<double> fracs;
     int want_chunks = 1;
-    if (ctx->debug || n_pairs < 2048) want_chunks = 1;          // the parity taps describe ONE launch pair
-    else if (ctx->host_chunks > 0) want_chunks = ctx->host_chunks;
+    if (ctx->debug) want_chunks = 1;                            // the parity taps describe ONE launch pair
+    else if (ctx->host_chunks > 0) want_chunks = std::min(ctx->host_chunks, n_pairs);
+    else if (n_pairs < 2048) want_chunks = 1;
     else want_chunks = std::min(40, std::max(4, n_pairs / 768));
     for (int c = 1; c <= want_chunks; ++c) fracs.push_back((double)c / want_chunks);
     const int n_chunks = (int)fracs.size();
