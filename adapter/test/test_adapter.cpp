@@ -30,21 +30,21 @@ static Pose small_pose(double ang, double tr) {
 
 // n landmarks shared by both nodes (+ n fresh each); node B observes them through pose G: p_b = G * x
 static void make_pair_nodes(int n, const Pose& G, SlamNode& a, SlamNode& b, const std::string& ida, const std::string& idb,
-                            const std::string& frame) {
+                            const std::string& frame, int cols = 32, int ftype = graph_slam_msgs::Features::ORB) {
     FeatureDataPtr fa(new FeatureData()), fb(new FeatureData());
     for (FeatureDataPtr f : {fa, fb}) {
-        f->feature_type_ = graph_slam_msgs::Features::ORB;
+        f->feature_type_ = ftype;
         f->sensor_frame_ = frame;
-        f->features_.create(2 * n, 32, CV_8U);
+        f->features_.create(2 * n, cols, CV_8U);
         f->feature_positions_.resize(3, 2 * n);
         f->valid_3d_.assign(2 * n, true);
     }
     for (int i = 0; i < 2 * n; ++i) {
         double z = 0.5 + 6.5 * uni(), x = (uni() * 640 - 319.5) * z / 525., y = (uni() * 480 - 239.5) * z / 525.;
-        for (int k = 0; k < 32; ++k) fa->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
+        for (int k = 0; k < cols; ++k) fa->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
         fa->feature_positions_(0, i) = x; fa->feature_positions_(1, i) = y; fa->feature_positions_(2, i) = z;
         if (i < n) {           // shared landmark: same descriptor with a few flipped bits, transformed position
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < cols; ++k) {
                 unsigned char m = (unsigned char)(rnd() & rnd() & rnd() & rnd());
                 fb->features_.at<unsigned char>(i, k) = fa->features_.at<unsigned char>(i, k) ^ m;
             }
@@ -52,7 +52,7 @@ static void make_pair_nodes(int n, const Pose& G, SlamNode& a, SlamNode& b, cons
             fb->feature_positions_(1, i) = G.R[3] * x + G.R[4] * y + G.R[5] * z + G.t[1] + (uni() - .5) * 0.004;
             fb->feature_positions_(2, i) = G.R[6] * x + G.R[7] * y + G.R[8] * z + G.t[2] + (uni() - .5) * 0.004;
         } else {
-            for (int k = 0; k < 32; ++k) fb->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
+            for (int k = 0; k < cols; ++k) fb->features_.at<unsigned char>(i, k) = (unsigned char)rnd();
             double z2 = 0.5 + 6.5 * uni();
             fb->feature_positions_(0, i) = (uni() * 640 - 319.5) * z2 / 525.;
             fb->feature_positions_(1, i) = (uni() * 480 - 239.5) * z2 / 525.;
@@ -103,6 +103,34 @@ int main() {
         CHECK(d.matching_score_ == e.matching_score_);
         for (int r = 0; r < 4; ++r)
             for (int c = 0; c < 4; ++c) CHECK(d.transform_(r, c) == e.transform_(r, c));
+    }
+
+    // 1b. BRISK keyframes (64-byte rows; cv::BRISK is FeatureExtractionCore's default, feature_extraction_core.cpp:46-49)
+    //     through the same queue, and one BRISK-vs-ORB pair: never compared (cv::BFMatcher would throw), score 0
+    {
+        got.clear();
+        std::vector<SlamNode> WA(6), WB(6);
+        for (int i = 0; i < 6; ++i) {
+            make_pair_nodes(200, G[i], WA[i], WB[i], "wa" + std::to_string(i), "wb" + std::to_string(i), "/camera_rgb_optical_frame",
+                            64, graph_slam_msgs::Features::BRISK);
+            est.estimateEdge(WA[i], WB[i]);
+        }
+        boost::dynamic_pointer_cast<FeatureData>(A[0].sensor_data_[0])->feature_type_ = graph_slam_msgs::Features::BRISK;
+        SlamNode A0 = A[0];
+        A0.id_ = "a0_as_brisk";
+        est.estimateEdge(WA[0], A0);
+        est.waitIdle();
+        boost::dynamic_pointer_cast<FeatureData>(A[0].sensor_data_[0])->feature_type_ = graph_slam_msgs::Features::ORB;
+        CHECK((int)got.size() == 7);
+        for (int i = 0; i < 6; ++i) {
+            const SlamEdge& e = got["wa" + std::to_string(i) + "|wb" + std::to_string(i)];
+            CHECK(e.matching_score_ >= 80);
+            double err = 0;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) err = std::fmax(err, std::fabs(e.transform_(r, c) - G[i].R[3 * c + r]));
+            CHECK(err < 2e-3);
+        }
+        CHECK(got["wa0|a0_as_brisk"].matching_score_ == 0.);
     }
 
     // 2. failure convention: different sensor frames -> no comparable pair -> score 0, callback still fires
@@ -186,7 +214,7 @@ int main() {
     }
 
     est.forgetNode("a0");
-    CHECK(est.residentNodes() == (size_t)2 * NP + 2 - 1);
+    CHECK(est.residentNodes() == (size_t)2 * NP + 13 + 2 - 1);          // + the 13 nodes of section 1b
     std::printf("ADAPTER OK: %d queued pairs, callbacks delivered, direct/batch identical\n", NP);
     return 0;
 }
