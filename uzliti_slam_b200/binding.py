@@ -7,7 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_SO = os.path.join(_HERE, "libuzliti_edge.so")
+_SO = os.environ.get("UZ_LIB_PATH") or os.path.join(_HERE, "libuzliti_edge.so")      # UZ_LIB_PATH: A/B measurements of two builds
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

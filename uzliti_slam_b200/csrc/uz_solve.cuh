@@ -402,11 +402,19 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         for (int hb = warp * H; hb < nh; hb += NW * H) {
             float2 T[H][12];
             float2 in_c[H], in_b[H];      // per lane and point slot: certain inliers / not certainly outside
+            // -T (exact: the doubles hold float32 values), so that d = q - T p needs no negation of q.  The double -> float
+            // conversions run on the XU pipe, which the match kernel beside this one saturates: lane l converts ONE of the
+            // 12 H elements and the warp shares them by shuffle (1 conversion per pass instead of 12 H).
+            static_assert(12 * H <= 32, "one transform element per lane");
+            float t_lane;
+            {
+                const int a_l = min(lane / 12, H - 1), e_l = lane % 12;
+                t_lane = -(float)Th[min(hb + a_l, nh - 1) * 12 + e_l];          // tail: duplicates, their counts are discarded
+            }
 #pragma unroll
             for (int a = 0; a < H; ++a) {
-                const int h = min(hb + a, nh - 1);          // tail: duplicates, their counts are discarded
 #pragma unroll
-                for (int e = 0; e < 12; ++e) { const float t = -(float)Th[h * 12 + e]; T[a][e] = make_float2(t, t); }   // -T (exact: float32 values), so that d = q - T p needs no negation of q
+                for (int e = 0; e < 12; ++e) { const float t = __shfl_sync(0xffffffffu, t_lane, a * 12 + e); T[a][e] = make_float2(t, t); }
                 in_c[a] = make_float2(0.f, 0.f); in_b[a] = make_float2(0.f, 0.f);
             }
             for (int base = 0; base < M64; base += 64) {      // branch-free: 64 points x H hypotheses per warp step
@@ -426,8 +434,12 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
             }
 #pragma unroll
             for (int a = 0; a < H; ++a) {
-                // both counts in one register (each <= 4096 over the warp): certain | (not certainly outside) << 16
-                int c = (int)(in_c[a].x + in_c[a].y) | ((int)(in_b[a].x + in_b[a].y) << 16);
+                // both counts in one register (each <= 4096 over the warp): certain | (not certainly outside) << 16.
+                // float -> int without the XU pipe: the counts are small integers, so the low mantissa bits of
+                // (count + 2^23) ARE the count
+                const int cc = __float_as_int(__fadd_rn(__fadd_rn(in_c[a].x, in_c[a].y), 8388608.0f)) & 0x7FFFFF;
+                const int cb = __float_as_int(__fadd_rn(__fadd_rn(in_b[a].x, in_b[a].y), 8388608.0f)) & 0x7FFFFF;
+                int c = cc | (cb << 16);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
                 int cnt = c & 0xFFFF;
