@@ -48,7 +48,7 @@
 
 namespace uz {
 
-UZ_HD float f_abs(float x) { return x < 0.f ? -x : (x == 0.f ? 0.f : x); }   // |x|, -0 -> +0
+UZ_HD float f_abs(float x) { return fabsf(x); }                                // |x|, -0 -> +0 (an operand modifier on the device)
 UZ_HD float f_max(float a, float b) { return a < b ? b : a; }                  // std::max
 
 // Running state of pcl::TransformationFromCorrespondences (all float32).
