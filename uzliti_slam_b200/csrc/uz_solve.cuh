@@ -104,6 +104,17 @@ __device__ __forceinline__ float sat_less(float s, float c_big) {
     return r;
 }
 
+#ifdef UZ_K4_SCALAR      // measured alternative: the same arithmetic as scalar FFMA / FADD / FMUL (twice the instructions):
+                         // solve alone 2.88 -> 3.07 ms, streaming step 26.20 -> 26.44 ms
+__device__ __forceinline__ float2 k4_fma(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 k4_add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 k4_mul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+__device__ __forceinline__ float2 k4_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 k4_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 k4_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#endif
+
 // Rare path of the pre-screen, deliberately not inlined: it must not drag the double-precision transforms
 // into registers inside the float loop.
 __device__ __noinline__ int exact_inlier(const double* T12, const double* gP, const double* gQ, uint32_t tq, double thr_sq_star) {
@@ -424,12 +435,12 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
                 const float2 v = *reinterpret_cast<const float2*>(qyf + o), w = *reinterpret_cast<const float2*>(qzf + o);
 #pragma unroll
                 for (int a = 0; a < H; ++a) {
-                    const float2 dx = __fadd2_rn(__ffma2_rn(T[a][0], x, __ffma2_rn(T[a][1], y, __ffma2_rn(T[a][2], z, T[a][3]))), u);
-                    const float2 dy = __fadd2_rn(__ffma2_rn(T[a][4], x, __ffma2_rn(T[a][5], y, __ffma2_rn(T[a][6], z, T[a][7]))), v);
-                    const float2 dz = __fadd2_rn(__ffma2_rn(T[a][8], x, __ffma2_rn(T[a][9], y, __ffma2_rn(T[a][10], z, T[a][11]))), w);
-                    const float2 sf = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-                    in_c[a] = __fadd2_rn(in_c[a], make_float2(sat_less(sf.x, lo2_big), sat_less(sf.y, lo2_big)));
-                    in_b[a] = __fadd2_rn(in_b[a], make_float2(sat_less(sf.x, hi2_big), sat_less(sf.y, hi2_big)));
+                    const float2 dx = k4_add(k4_fma(T[a][0], x, k4_fma(T[a][1], y, k4_fma(T[a][2], z, T[a][3]))), u);
+                    const float2 dy = k4_add(k4_fma(T[a][4], x, k4_fma(T[a][5], y, k4_fma(T[a][6], z, T[a][7]))), v);
+                    const float2 dz = k4_add(k4_fma(T[a][8], x, k4_fma(T[a][9], y, k4_fma(T[a][10], z, T[a][11]))), w);
+                    const float2 sf = k4_fma(dx, dx, k4_fma(dy, dy, k4_mul(dz, dz)));
+                    in_c[a] = k4_add(in_c[a], make_float2(sat_less(sf.x, lo2_big), sat_less(sf.y, lo2_big)));
+                    in_b[a] = k4_add(in_b[a], make_float2(sat_less(sf.x, hi2_big), sat_less(sf.y, hi2_big)));
                 }
             }
 #pragma unroll
