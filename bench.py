@@ -371,6 +371,18 @@ def measure_other_configs(est, handles, kfs):
     for x in h:
         est.remove_keyframe(int(x))
 
+    # the online case: one new keyframe against its visual-odometry predecessor + 20 loop-closure candidates (N = 1000),
+    # a launch far too small to fill the chip unless the train rows are cut into segments as well
+    qo = np.full(21, handles[30], dtype=handles.dtype)
+    co = handles[5:26]
+    lat_o = []
+    for _ in range(60):
+        t0 = time.perf_counter()
+        est.estimateEdges(co, qo)
+        lat_o.append(time.perf_counter() - t0)
+    out["online_21_pairs"] = dict(latency_us=round(float(np.median(lat_o[10:])) * 1e6, 1),
+                                  note="1 keyframe vs 21 stored keyframes (2.1e7 compares + 21 RANSACs), records on the host")
+
     # C3: one query keyframe against 1000 candidates of the resident map (N = 1000)
     q = np.full(1000, handles[0], dtype=handles.dtype)
     cand = handles[1:1001]

@@ -159,6 +159,8 @@ struct uz_context {
     int xcheck_fused = 1;            // UZ_XCHECK_FUSED=0: cross-check by a second, reversed matching (the measured alternative)
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
+    std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments
+    int segment_small = 1;           // UZ_SEGMENT=0: never cut small launches along the train rows
     uz_params params;
     std::string err;
     int variant_csa = 1;
@@ -481,10 +483,15 @@ uz_status ensure_samples(uz_context* ctx, int iterations, int do_prosac, int max
 // ---- launches --------------------------------------------------------------------------------------
 template <int THREADS, int QPT>
 void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
-                 unsigned int* d_progress, bool xchk) {
-    if (xchk) {
-        if constexpr (QPT == 2)      // fused cross-check: column minima in the same pass (+ 4 B of shared memory per staged train row)
-            knn2_kernel<THREADS, QPT, true, true, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT) + knn_train_rows(THREADS, QPT) * 4, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+                 unsigned int* d_progress, bool xchk, bool seg) {
+    if (xchk || seg) {
+        if constexpr (QPT == 2) {    // fused cross-check: column minima in the same pass (+ 4 B of shared memory per staged train row);
+                                     // seg: tiles are int4 and name a segment of the train rows (small launches)
+            const size_t sm = knn_smem_bytes(THREADS, QPT) + (xchk ? knn_train_rows(THREADS, QPT) * 4 : 0);
+            if (xchk && seg) knn2_kernel<THREADS, QPT, true, true, true, true><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+            else if (xchk) knn2_kernel<THREADS, QPT, true, true, true, false><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+            else knn2_kernel<THREADS, QPT, true, true, false, true><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+        }
     } else if (ctx->variant_csa && ctx->variant_pack16)
         knn2_kernel<THREADS, QPT, true, true><<<n_tiles, THREADS, knn_smem_bytes(THREADS, QPT), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else if (ctx->variant_csa)
@@ -495,11 +502,12 @@ void launch_knn2(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles,
 
 template <int THREADS>
 void launch_knn2_wide(uz_context* ctx, const MatchTask* d_tasks, const int2* d_tiles, int n_tiles, uint2* d_keys, int* d_pending,
-                      unsigned int* d_progress, bool xchk) {
-    if (xchk)
-        knn2_wide_kernel<THREADS, true><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS) + knn_wide_train_rows(THREADS) * 4, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
-    else
-        knn2_wide_kernel<THREADS><<<n_tiles, THREADS, knn_wide_smem_bytes(THREADS), ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+                      unsigned int* d_progress, bool xchk, bool seg) {
+    const size_t sm = knn_wide_smem_bytes(THREADS) + (xchk ? knn_wide_train_rows(THREADS) * 4 : 0);
+    if (xchk && seg) knn2_wide_kernel<THREADS, true, true><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+    else if (xchk) knn2_wide_kernel<THREADS, true, false><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+    else if (seg) knn2_wide_kernel<THREADS, false, true><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+    else knn2_wide_kernel<THREADS><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
 }
 
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
@@ -605,31 +613,22 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     // a second time with query and train swapped.
     const bool fused = cross && ctx->xcheck_fused && ctx->variant_csa && ctx->variant_pack16 &&
                        !(ctx->force_cfg >= 0 && ctx->force_cfg < 2);
-    const size_t col_begin = key_rows;
-    if (fused) {
-        for (size_t t = 0; t < n_fwd; ++t) {
-            if (tasks[t].nq == 0) continue;
-            tasks[t].rev_key_off = (uint32_t)key_rows;
-            key_rows += (size_t)tasks[t].nt;
-        }
-    } else if (cross) {
+    if (!fused && cross) {
         for (size_t t = 0; t < n_fwd; ++t) {
             MatchTask& f = tasks[t];
             if (f.nq == 0) continue;                 // non-binary type: no matches to check
             MatchTask& r = tasks[n_tasks];
             r = f;
             r.q_desc = f.t_desc; r.t_desc = f.q_desc; r.nq = f.nt; r.nt = f.nq;
-            r.key_off = (uint32_t)key_rows; r.rev_key_off = kNoRev;
+            r.rev_key_off = kNoRev;
             task_wide[n_tasks] = task_wide[t];
-            f.rev_key_off = r.key_off;
-            key_rows += (size_t)r.nq;
+            f.rev_key_off = 0;                       // "has a reversed task"; the offset is assigned below
+
             compares += (int64_t)r.nq * r.nt;
             f.pad_ = (uint32_t)n_tasks;              // index of the reversed task (host-side only)
             ++n_tasks;
         }
     }
-    if (key_rows >= ((size_t)1 << 32)) return fail(ctx, UZ_ERR_INVALID, "batch too large: split it (key scratch > 2^32 rows)");
-
     // tile shape per descriptor width.  256-bit rows: two queries per thread (40-56 registers: 6 resident CTAs per SM,
     // measured 8 % faster than the four-query shapes, which stay reachable through UZ_KNN_CFG), largest tile first.
     // 512-bit rows: the 256 x 2 and 64 x 2 shapes of knn2_wide_kernel.
@@ -667,51 +666,113 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         if (ctx->force_wide_cfg >= 0 && ctx->force_wide_cfg < 2) wide_cfg = ctx->force_wide_cfg;
     }
     const int tile_rows = kKnnConfigs[best_cfg].threads * kKnnConfigs[best_cfg].qpt;
-    const int wide_tile_rows = wide_cfg == 0 ? 512 : 128;
+    const int wide_threads = wide_cfg == 0 ? 256 : 64;
+    const int wide_tile_rows = 2 * wide_threads;
     auto rows_of = [&](size_t t) { return task_wide[t] ? wide_tile_rows : tile_rows; };
-    size_t n_tiles = 0, n_tiles_wide = 0;
+    auto qtiles_of = [&](size_t t) { return ((size_t)tasks[t].nq + rows_of(t) - 1) / rows_of(t); };
+
+    // Small launches are cut along the train rows as well (SEG kernels): a handful of pairs - the online case, one new
+    // keyframe against its candidates - would otherwise run on a handful of CTAs that each walk every train row.  Every
+    // (query tile, train segment) CTA writes partial neighbours, merge_segments_kernel folds them.  Not for launches
+    // that fill the chip anyway, and not beside the streaming solve (it consumes keys tile by tile).
+    const bool with_solve = d_results != nullptr;
+    const int cap = with_solve ? std::max(128, pow2ceil(std::max(max_nq, 1))) : 0;
+    const int stream_ctas = ctx->stream_solve_ctas * ctx->sm_count;
+    const bool may_stream = with_solve && ctx->solve_stream != nullptr && ctx->stream_solve_ctas > 0 && cap <= 1024 &&
+                            n_pairs >= (ctx->stream_min_pairs > 0 ? ctx->stream_min_pairs : 2 * stream_ctas);
+    int seg_target = 1;
+    if (ctx->segment_small && !may_stream && ctx->variant_csa && ctx->variant_pack16 &&
+        kKnnConfigs[best_cfg].qpt == 2) {
+        double warps = 0;
+        for (size_t t = 0; t < n_tasks; ++t)
+            warps += (double)qtiles_of(t) * (task_wide[t] ? wide_threads : kKnnConfigs[best_cfg].threads) / 32.0;
+        const double capacity = (double)ctx->sm_count * 32.0;
+        if (warps > 0 && warps * 2 <= capacity) seg_target = (int)std::min(16.0, std::floor(capacity / warps));
+    }
+    const bool seg = seg_target > 1;
+    // segment of a task: a multiple of 64 train rows (the key blocks of both kernels), at least 64
+    auto seg_rows_of = [&](size_t t) {
+        if (!seg) return std::max(tasks[t].nt, 1);
+        const int want = (tasks[t].nt + seg_target - 1) / seg_target;
+        return std::max(64, (want + 63) & ~63);
+    };
+    auto nseg_of = [&](size_t t) { return seg ? std::max(1, (tasks[t].nt + seg_rows_of(t) - 1) / seg_rows_of(t)) : 1; };
+
+    // key scratch: per task nq rows per segment (segment 0 holds the final neighbours), then the column keys of the
+    // fused cross-check
+    key_rows = 0;
     for (size_t t = 0; t < n_tasks; ++t) {
-        const size_t k = ((size_t)tasks[t].nq + rows_of(t) - 1) / rows_of(t);
+        tasks[t].key_off = (uint32_t)std::min<size_t>(key_rows, 0xFFFFFFFFu);
+        key_rows += (size_t)tasks[t].nq * (size_t)nseg_of(t);
+    }
+    const size_t col_begin = key_rows;
+    for (size_t t = 0; t < n_fwd; ++t) {
+        if (tasks[t].nq == 0) continue;
+        if (fused) {
+            tasks[t].rev_key_off = (uint32_t)std::min<size_t>(key_rows, 0xFFFFFFFFu);
+            key_rows += (size_t)tasks[t].nt;
+        } else if (cross) {
+            tasks[t].rev_key_off = tasks[tasks[t].pad_].key_off;
+        }
+    }
+    if (key_rows >= ((size_t)1 << 32)) return fail(ctx, UZ_ERR_INVALID, "batch too large: split it (key scratch > 2^32 rows)");
+
+    size_t n_tiles = 0, n_tiles_wide = 0;
+    std::vector<int4>& merges = ctx->merge_table;         // (key_off, nq, segments, 0) of every task cut into segments
+    merges.clear();
+    for (size_t t = 0; t < n_tasks; ++t) {
+        const size_t k = qtiles_of(t) * (size_t)nseg_of(t);
         n_tiles += k;
         if (task_wide[t]) n_tiles_wide += k;
+        if (nseg_of(t) > 1 && tasks[t].nq > 0) merges.push_back(make_int4((int)tasks[t].key_off, tasks[t].nq, nseg_of(t), 0));
     }
     const size_t n_tiles_narrow = n_tiles - n_tiles_wide;
-    UZ_CUDA(ctx, sl.h_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    const size_t tile_bytes = seg ? sizeof(int4) : sizeof(int2);
+    UZ_CUDA(ctx, sl.h_tiles.ensure(std::max<size_t>(n_tiles, 1) * tile_bytes + merges.size() * sizeof(int4)));
     int2* tiles = (int2*)sl.h_tiles.p;
+    int4* tiles4 = (int4*)sl.h_tiles.p;
     {
         // 256-bit tiles first, 512-bit tiles behind them (one launch each); inside a list: forward tiles, then the
         // reversed tiles of the same matching
         size_t kn = 0, kw = n_tiles_narrow;
+        auto emit_tiles = [&](size_t t, size_t& k) {
+            const int tr = rows_of(t);
+            if (!seg) {
+                for (int q0 = 0; q0 < tasks[t].nq; q0 += tr) tiles[k++] = make_int2((int)t, q0);
+                return;
+            }
+            const int sr = seg_rows_of(t), ns = nseg_of(t);
+            for (int q0 = 0; q0 < tasks[t].nq; q0 += tr)
+                for (int sg = 0; sg < ns; ++sg) {
+                    const int tb = sg * sr, rows = std::max(0, std::min(tasks[t].nt - tb, sr));
+                    tiles4[k++] = make_int4((int)t, q0, tb, (sg << 16) | rows);
+                }
+        };
         for (size_t t = 0; t < n_fwd; ++t) {
             size_t& k = task_wide[t] ? kw : kn;
-            const int tr = rows_of(t);
-            for (int q0 = 0; q0 < tasks[t].nq; q0 += tr) tiles[k++] = make_int2((int)t, q0);
-            if (!fused && tasks[t].rev_key_off != kNoRev) {
-                const int r = (int)tasks[t].pad_;
-                for (int q0 = 0; q0 < tasks[r].nq; q0 += tr) tiles[k++] = make_int2(r, q0);
-            }
+            emit_tiles(t, k);
+            if (!fused && cross && tasks[t].nq > 0) emit_tiles((size_t)tasks[t].pad_, k);
         }
     }
+    int4* h_merges = (int4*)((uint8_t*)sl.h_tiles.p + std::max<size_t>(n_tiles, 1) * tile_bytes);
+    if (!merges.empty()) memcpy(h_merges, merges.data(), merges.size() * sizeof(int4));
 
     // 2. device buffers
     UZ_CUDA(ctx, sl.d_tasks.ensure(std::max<size_t>(n_tasks, 1) * sizeof(MatchTask)));
-    UZ_CUDA(ctx, sl.d_tiles.ensure(std::max<size_t>(n_tiles, 1) * sizeof(int2)));
+    UZ_CUDA(ctx, sl.d_tiles.ensure(std::max<size_t>(n_tiles, 1) * tile_bytes + merges.size() * sizeof(int4)));
     UZ_CUDA(ctx, sl.d_pair_tasks.ensure((size_t)n_pairs * sizeof(int2)));
     UZ_CUDA(ctx, sl.d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
     if (fused && key_rows > col_begin)       // column keys start at "none"; the match kernel lowers them with atomicMin
         UZ_CUDA(ctx, cudaMemsetAsync((uint2*)sl.d_keys.p + col_begin, 0xFF, (key_rows - col_begin) * sizeof(uint2), ctx->stream));
     if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
-    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * tile_bytes + merges.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
     UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
 
     // 3. launches.  Large batches: ONE match launch plus the persistent streaming solve beside it (uz_solve.cuh);
     // small batches, the parity taps and UZ_STREAM_SOLVE=0: match launch, then one solve CTA per pair behind it.
-    const bool with_solve = d_results != nullptr;
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
-    int cap = 0;
     if (with_solve) {
-        cap = std::max(128, pow2ceil(std::max(max_nq, 1)));
         uz_status st = ensure_samples(ctx, prm.ransac_iterations, prm.do_prosac, max_nq);
         if (st != UZ_OK) return st;
         sp.thr = prm.ransac_threshold; sp.thr_sq_star = thr_sq_star(prm.ransac_threshold);
@@ -734,9 +795,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     }
     // the streaming solve needs its 96-register CTAs to fit beside the match CTAs: one pair's on-chip state must
     // leave room for them (cap <= 1024: 44 KB; at cap 2048 the gain measured on C5 rigs was 1 %), and the batch must be large enough to be worth a persistent grid
-    const int stream_ctas = ctx->stream_solve_ctas * ctx->sm_count;
-    const bool streaming = with_solve && ctx->solve_stream != nullptr && ctx->stream_solve_ctas > 0 && cap <= 1024 &&
-                           n_pairs >= (ctx->stream_min_pairs > 0 ? ctx->stream_min_pairs : 2 * stream_ctas) && n_tiles > 0;
+    const bool streaming = may_stream && n_tiles > 0;
     if (ctx->timers) ctx->compares += compares;
 
     int* d_pending = nullptr;
@@ -767,28 +826,35 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     if (n_tiles > 0) {
         const MatchTask* d_tk = (const MatchTask*)sl.d_tasks.p;
         const int2* d_t = (const int2*)sl.d_tiles.p;
+        const int2* d_tw = (const int2*)((const uint8_t*)sl.d_tiles.p + n_tiles_narrow * tile_bytes);
         uint2* d_k = (uint2*)sl.d_keys.p;
         const int nt = (int)n_tiles_narrow;
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
         if (n_tiles_wide > 0) {
-            if (wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog, fused);
-            else launch_knn2_wide<64>(ctx, d_tk, d_t + n_tiles_narrow, (int)n_tiles_wide, d_k, d_pending, d_prog, fused);
+            if (wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_tw, (int)n_tiles_wide, d_k, d_pending, d_prog, fused, seg);
+            else launch_knn2_wide<64>(ctx, d_tk, d_tw, (int)n_tiles_wide, d_k, d_pending, d_prog, fused, seg);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) ctx->match_launches++;
         }
         if (nt > 0) switch (best_cfg) {
-            case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
-            case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
-            case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
-            case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
-            case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
-            default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused); break;
+            case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
+            case 1: launch_knn2<128, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
+            case 2: launch_knn2<64, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
+            case 3: launch_knn2<256, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
+            case 4: launch_knn2<128, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
+            default: launch_knn2<32, 2>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, seg); break;
         }
         if (nt > 0) {
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) ctx->match_launches++;
+        }
+        if (!merges.empty()) {
+            const int4* d_m = (const int4*)((const uint8_t*)sl.d_tiles.p + std::max<size_t>(n_tiles, 1) * tile_bytes);
+            merge_segments_kernel<<<dim3((unsigned)((max_nq + 255) / 256), (unsigned)merges.size(), 1), 256, 0, ctx->stream>>>(d_m, d_k);
+            ctx->launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
         }
     }
     if (ctx->timers) cudaEventRecord(tm.e[1], ctx->stream);
@@ -929,6 +995,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (fc) ctx->force_cfg = atoi(fc);
         const char* xf = getenv("UZ_XCHECK_FUSED");
         if (xf) ctx->xcheck_fused = atoi(xf) != 0;
+        const char* sg = getenv("UZ_SEGMENT");
+        if (sg) ctx->segment_small = atoi(sg) != 0;
         const char* fw = getenv("UZ_KNN_WIDE_CFG");
         if (fw) ctx->force_wide_cfg = atoi(fw);
         const char* gu = getenv("UZ_GATHER_UPLOAD");

@@ -241,7 +241,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // tiles[blockIdx.x] = (task index, first query row of the tile)
-template <int THREADS, int QPT, bool CSA, bool PACK16 = false, bool XCHK = false>
+// SEG (small launches): a tile also names a SEGMENT of the train rows, tiles[] holds int4 (task, first query row, first train
+// row, (segment index << 16) | train rows of the segment), and the CTA writes its partial neighbours to
+// keys[key_off + segment * nq + q]; merge_segments_kernel folds the segments into segment 0.  A batch of a few pairs then
+// spreads over the whole chip instead of a handful of CTAs that each walk every train row.
+template <int THREADS, int QPT, bool CSA, bool PACK16 = false, bool XCHK = false, bool SEG = false>
 __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys,
@@ -254,11 +258,15 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
     uint32_t* s_col = reinterpret_cast<uint32_t*>(smem + kStages * kTrainTileRows * 32 + 64);     // XCHK: [kTrainTileRows]
     const uint32_t s_col_a = XCHK ? col_base(s_col) : 0u;
 
-    const int2 tile = tiles[blockIdx.x];
+    static_assert(!SEG || (PACK16 && QPT == 2), "segmented launches use the packed-key, two-queries-per-thread shapes");
+    int4 tile4 = make_int4(0, 0, 0, 0);
+    if (SEG) tile4 = reinterpret_cast<const int4*>(tiles)[blockIdx.x];
+    const int2 tile = SEG ? make_int2(tile4.x, tile4.y) : tiles[blockIdx.x];
     const MatchTask* tk = tasks + tile.x;
+    const int t0 = SEG ? tile4.z : 0;                                   // first train row of this CTA's segment
     const uint32_t* __restrict__ qd = tk->q_desc;
-    const uint32_t* __restrict__ td = tk->t_desc;
-    const int nq = tk->nq, nt = tk->nt;
+    const uint32_t* __restrict__ td = tk->t_desc + (size_t)t0 * 8;
+    const int nq = tk->nq, nt = SEG ? (tile4.w & 0xFFFF) : tk->nt;      // train rows this CTA walks
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
                     }
                 }
                 if (j > 0) {
-                    const uint32_t base = (uint32_t)(r0 + b0);
+                    const uint32_t base = (uint32_t)(t0 + r0 + b0);
 #pragma unroll
                     for (int kk = 0; kk < QPT / 2; ++kk) {
                         merge_block16(m1[2 * kk], m2[2 * kk], p1[kk] & 0xFFFFu, p2[kk] & 0xFFFFu, base);
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
                 }
                 for (; j < nb; ++j) {
                     const uint4 a = brows[2 * j], b = brows[2 * j + 1];
-                    const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+                    const uint32_t jkey = (uint32_t)(t0 + r0 + b0 + j);
                     uint32_t kq[QPT];
 #pragma unroll
                     for (int k = 0; k < QPT; ++k) { kq[k] = csa_key(U[k], a, b, jkey); top2_update(m1[k], m2[k], kq[k]); }
@@ -383,15 +391,16 @@ __global__ void __launch_bounds__(THREADS, knn_min_ctas(THREADS, QPT)) knn2_kern
         }
         __syncthreads();
         if (XCHK) {
-            col_flush<THREADS, 7>(s_col, nrows, keys + tk->rev_key_off, r0, tile.y);
+            col_flush<THREADS, 7>(s_col, nrows, keys + tk->rev_key_off, t0 + r0, tile.y);
             __syncthreads();
         }
     }
 
+    const uint32_t out_off = tk->key_off + (SEG ? (uint32_t)(tile4.w >> 16) * (uint32_t)nq : 0u);
 #pragma unroll
     for (int k = 0; k < QPT; ++k) {
         const int q = tile.y + k * THREADS + tid;
-        if (q < nq) keys[tk->key_off + q] = make_uint2(m1[k], m2[k]);
+        if (q < nq) keys[out_off + q] = make_uint2(m1[k], m2[k]);
     }
     // Streaming hand-over to the solve kernel that runs beside this one (uz_solve.cuh, solve_stream_kernel):
     // pair_pending[pair] counts the tiles of the pair that have not published their keys yet.  bar.sync orders
@@ -504,7 +513,7 @@ __device__ __forceinline__ void merge_block16w(uint32_t& m1, uint32_t& m2, uint3
     m2 = min(min(m2, t), k2);
 }
 
-template <int THREADS, bool XCHK = false>
+template <int THREADS, bool XCHK = false, bool SEG = false>
 __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide_kernel(const MatchTask* __restrict__ tasks,
                                                        const int2* __restrict__ tiles,
                                                        uint2* __restrict__ keys,
@@ -517,11 +526,14 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
     uint32_t* s_col = reinterpret_cast<uint32_t*>(smem + kStages * kRows * 64 + 64);       // XCHK: [kRows]
     const uint32_t s_col_a = XCHK ? col_base(s_col) : 0u;
 
-    const int2 tile = tiles[blockIdx.x];
+    int4 tile4 = make_int4(0, 0, 0, 0);
+    if (SEG) tile4 = reinterpret_cast<const int4*>(tiles)[blockIdx.x];             // see knn2_kernel
+    const int2 tile = SEG ? make_int2(tile4.x, tile4.y) : tiles[blockIdx.x];
     const MatchTask* tk = tasks + tile.x;
+    const int t0 = SEG ? tile4.z : 0;
     const uint32_t* __restrict__ qd = tk->q_desc;
-    const uint32_t* __restrict__ td = tk->t_desc;
-    const int nq = tk->nq, nt = tk->nt;
+    const uint32_t* __restrict__ td = tk->t_desc + (size_t)t0 * 16;
+    const int nq = tk->nq, nt = SEG ? (tile4.w & 0xFFFF) : tk->nt;
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -612,13 +624,13 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
                 }
             }
             if (j > 0) {
-                const uint32_t base = (uint32_t)(r0 + b0);
+                const uint32_t base = (uint32_t)(t0 + r0 + b0);
                 merge_block16w(m1[0], m2[0], p1 & 0xFFFFu, p2 & 0xFFFFu, base);
                 merge_block16w(m1[1], m2[1], p1 >> 16, p2 >> 16, base);
             }
             for (; j < nb; ++j) {
                 const uint4 a = brows[4 * j], b = brows[4 * j + 1], c = brows[4 * j + 2], d = brows[4 * j + 3];
-                const uint32_t jkey = (uint32_t)(r0 + b0 + j);
+                const uint32_t jkey = (uint32_t)(t0 + r0 + b0 + j);
                 uint32_t kq[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) { kq[k] = csa_key_wide(U[k], a, b, c, d, jkey); top2_update(m1[k], m2[k], kq[k]); }
@@ -627,15 +639,16 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
         }
         __syncthreads();
         if (XCHK) {
-            col_flush<THREADS, 6>(s_col, nrows, keys + tk->rev_key_off, r0, tile.y);
+            col_flush<THREADS, 6>(s_col, nrows, keys + tk->rev_key_off, t0 + r0, tile.y);
             __syncthreads();
         }
     }
 
+    const uint32_t out_off = tk->key_off + (SEG ? (uint32_t)(tile4.w >> 16) * (uint32_t)nq : 0u);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int q = tile.y + k * THREADS + tid;
-        if (q < nq) keys[tk->key_off + q] = make_uint2(m1[k], m2[k]);
+        if (q < nq) keys[out_off + q] = make_uint2(m1[k], m2[k]);
     }
     if (pair_pending != nullptr) {          // streaming hand-over, as in knn2_kernel
         __syncthreads();
@@ -644,6 +657,22 @@ __global__ void __launch_bounds__(THREADS, knn_wide_min_ctas(THREADS)) knn2_wide
             atomicSub(pair_pending + tk->pair, 1);
             atomicAdd(progress, 1u);
         }
+    }
+}
+
+// Segmented launches: fold the partial neighbours of segments 1..S-1 into segment 0 (top-2 of sorted pairs; a missing
+// neighbour is the largest key).  table[blockIdx.y] = (key_off, nq, S, 0).
+__global__ void __launch_bounds__(256) merge_segments_kernel(const int4* __restrict__ table, uint2* __restrict__ keys) {
+    const int4 e = table[blockIdx.y];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < e.y; q += gridDim.x * blockDim.x) {
+        uint2 m = keys[(size_t)e.x + q];
+        for (int s = 1; s < e.z; ++s) {
+            const uint2 b = keys[(size_t)e.x + (size_t)s * e.y + q];
+            const uint32_t hi = max(m.x, b.x);
+            m.x = min(m.x, b.x);
+            m.y = min(hi, min(m.y, b.y));
+        }
+        keys[(size_t)e.x + q] = m;
     }
 }
 
