@@ -133,3 +133,30 @@ def test_chunked_host_pipeline_equals_store_path(chunks, alt, stream):
         assert (a["consensus"] > 50).sum() > 100 and (a["ok"] == 0).any()
     finally:
         est.close()
+
+
+def test_small_launch_forms_agree(oracle):
+    """Launches that cannot fill the chip take two extra forms - train rows cut into segments (SEG match kernels + merge) and
+    a 512-thread solve CTA: records must equal the plain forms (UZ_SEGMENT=0, UZ_SOLVE_WIDE=0) and the oracle."""
+    kfs, pairs = _ragged_map(13, n_keyframes=36)
+    kw, pw, _ = S.make_map(12, n_features=700, cluster=6, pool=700, n_shared=400, k_candidates=3, cross_cluster=1, seed=14,
+                           desc_bytes=64)
+    kfs = kfs + kw
+    pairs = np.concatenate([pairs[:40], pw + 36])
+    fast = _estimator(UZ_STREAM_SOLVE=0)
+    plain = _estimator(UZ_STREAM_SOLVE=0, UZ_SEGMENT=0, UZ_SOLVE_WIDE=0)
+    try:
+        hf, hp = fast.add_keyframes(kfs), plain.add_keyframes(kfs)
+        for cross in (0, 1):
+            fast.setConfig(cross_check=cross)
+            plain.setConfig(cross_check=cross)
+            for n in (1, 7, len(pairs)):
+                a = fast.estimateEdges(hf[pairs[:n, 0]], hf[pairs[:n, 1]])
+                b = plain.estimateEdges(hp[pairs[:n, 0]], hp[pairs[:n, 1]])
+                assert a.tobytes() == b.tobytes(), (cross, n)
+            for i in (0, 5, len(pairs) - 1):
+                o = oracle.estimate_edge([kfs[pairs[i, 0]]], [kfs[pairs[i, 1]]], cross_check=bool(cross))
+                assert a[i]["consensus"] == o["consensus"] and a[i]["n_matches"] == o["n_matches"]
+    finally:
+        fast.close()
+        plain.close()

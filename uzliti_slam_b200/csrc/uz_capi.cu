@@ -160,6 +160,7 @@ struct uz_context {
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments
+    int solve_wide = 1;              // UZ_SOLVE_WIDE=0: never use the 512-thread solve CTA for small launches
     int segment_small = 1;           // UZ_SEGMENT=0: never cut small launches along the train rows
     uz_params params;
     std::string err;
@@ -508,6 +509,16 @@ void launch_knn2_wide(uz_context* ctx, const MatchTask* d_tasks, const int2* d_t
     else if (xchk) knn2_wide_kernel<THREADS, true, false><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else if (seg) knn2_wide_kernel<THREADS, false, true><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
     else knn2_wide_kernel<THREADS><<<n_tiles, THREADS, sm, ctx->stream>>>(d_tasks, d_tiles, d_keys, d_pending, d_progress);
+}
+
+// One solve CTA per pair (or per direct problem).  Launches of at most one pair per SM take the wide CTA: the chip is
+// otherwise idle, so only the latency of that one CTA counts (UZ_SOLVE_WIDE=0: always the 128-thread CTA).
+void launch_solve(uz_context* ctx, int n_ctas, int cap, cudaStream_t st, const MatchTask* d_tasks, const int2* d_pair_tasks,
+                  const uint2* d_keys, const SolveParams& sp, uz_edge_result* d_results) {
+    if (ctx->solve_wide && n_ctas <= ctx->sm_count)
+        solve_kernel<kSolveThreadsWide><<<n_ctas, kSolveThreadsWide, solve_smem_bytes(cap, kSolveThreadsWide), st>>>(d_tasks, d_pair_tasks, d_keys, sp, d_results);
+    else
+        solve_kernel<kSolveThreads><<<n_ctas, kSolveThreads, solve_smem_bytes(cap), st>>>(d_tasks, d_pair_tasks, d_keys, sp, d_results);
 }
 
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:
@@ -872,8 +883,8 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
                 (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
                 n_pairs, d_pending, d_ctl, d_deferred, 0);
         else
-            solve_kernel<kSolveThreads><<<n_pairs, kSolveThreads, solve_smem_bytes(cap), sB>>>(
-                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results);
+            launch_solve(ctx, n_pairs, cap, sB, (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p,
+                         (const uint2*)sl.d_keys.p, sp, d_results);
         ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());
         if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
@@ -995,6 +1006,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (fc) ctx->force_cfg = atoi(fc);
         const char* xf = getenv("UZ_XCHECK_FUSED");
         if (xf) ctx->xcheck_fused = atoi(xf) != 0;
+        const char* sw = getenv("UZ_SOLVE_WIDE");
+        if (sw) ctx->solve_wide = atoi(sw) != 0;
         const char* sg = getenv("UZ_SEGMENT");
         if (sg) ctx->segment_small = atoi(sg) != 0;
         const char* fw = getenv("UZ_KNN_WIDE_CFG");
@@ -1008,6 +1021,9 @@ uz_status uz_create(int32_t device, uz_context** out) {
     }
     e = cudaFuncSetAttribute(solve_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)solve_smem_bytes(UZ_MAX_FEATURES));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(solve_kernel<kSolveThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(UZ_MAX_FEATURES, kSolveThreadsWide));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(solve_stream_kernel<kSolveThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)solve_smem_bytes(1024));
@@ -1242,7 +1258,7 @@ uz_status uz_estimate_svd(uz_context* ctx, const double* P, const double* Q, int
     sp.iterations = iterations; sp.ratio_num = 99; sp.ratio_den = 100; sp.cap = cap;
     sp.direct_P = dP; sp.direct_Q = dQ; sp.direct_M = M;
     sp.dbg_mask = dmask;
-    solve_kernel<kSolveThreads><<<1, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(nullptr, nullptr, nullptr, sp, dres);
+    launch_solve(ctx, 1, cap, ctx->stream, nullptr, nullptr, nullptr, sp, dres);
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     uz_edge_result r;
@@ -1353,7 +1369,7 @@ uz_status uz_estimate_svd_batch(uz_context* ctx, const double* P, const double* 
     sp.iterations = iterations; sp.ratio_num = 99; sp.ratio_den = 100; sp.cap = cap;
     sp.direct_P = dP; sp.direct_Q = dQ; sp.direct_M = 0; sp.direct_offsets = doff;
     sp.dbg_mask = dmask;
-    solve_kernel<kSolveThreads><<<n_problems, kSolveThreads, solve_smem_bytes(cap), ctx->stream>>>(nullptr, nullptr, nullptr, sp, dres);
+    launch_solve(ctx, n_problems, cap, ctx->stream, nullptr, nullptr, nullptr, sp, dres);
     ctx->launches++;
     UZ_CUDA(ctx, cudaGetLastError());
     std::vector<uz_edge_result> r((size_t)n_problems);

@@ -58,14 +58,18 @@ static_assert(kHistBins * 4 <= kSolveThreads * 12 * 8, "the histogram lives in t
 #define UZ_SOLVE_MINB 5
 #endif
 
-__host__ __device__ constexpr size_t solve_smem_bytes(int cap) {
+// A wide CTA (kSolveThreadsWide) serves launches of at most one pair per SM - the online case - where the chip is
+// otherwise idle and only the latency of the one CTA per pair counts: 16 warps score hypotheses instead of 4.
+constexpr int kSolveThreadsWide = 512;
+__host__ __device__ constexpr size_t solve_smem_bytes(int cap, int threads = kSolveThreads) {
     return (size_t)cap * 24 /*float32 copies of P,Q (also: unsorted keys, later the residual norms)*/ +
            (size_t)cap * 4 /*sorted keys, then packed (trainIdx<<16)|queryIdx*/ + (size_t)cap * 2 /*ordered inlier list*/ +
-           (size_t)kSolveThreads * 12 * 8 /*hypothesis transforms*/ + (size_t)kSolveThreads * 4 /*counts*/ +
+           (size_t)threads * 12 * 8 /*hypothesis transforms*/ + (size_t)threads * 4 /*counts*/ +
            256 /*Tbest, Tfin*/;
 }
 
 static_assert(solve_smem_bytes(UZ_MAX_FEATURES) + 64 <= 232448, "solve kernel exceeds the 227 KB per-CTA shared memory of sm_100");
+static_assert(solve_smem_bytes(UZ_MAX_FEATURES, kSolveThreadsWide) + 256 <= 232448, "wide solve CTA exceeds the 227 KB per-CTA shared memory");
 
 __device__ __forceinline__ void write_identity(double* T16) {
 #pragma unroll
@@ -609,7 +613,7 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
 // One CTA per pair: the launch form of small batches, of the direct entry points (uz_estimate_svd, cluster RANSAC) and of
 // everything that runs under a tool that serialises kernels.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, UZ_SOLVE_MINB) solve_kernel(const MatchTask* __restrict__ tasks,
+__global__ void __launch_bounds__(THREADS, THREADS == kSolveThreads ? UZ_SOLVE_MINB : 1) solve_kernel(const MatchTask* __restrict__ tasks,
                                                         const int2* __restrict__ pair_tasks,
                                                         const uint2* keys, SolveParams prm,
                                                         uz_edge_result* __restrict__ results) {
