@@ -195,8 +195,8 @@ struct uz_context {
     // per-batch staging, double buffered: the host prepares batch i+1 (task/tile tables in pinned memory) while
     // the GPU still works on batch i; a slot is reused once the event recorded behind its last kernel fired
     struct Slot {
-        DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_pending;
-        PinBuf h_tasks, h_tiles, h_pair_tasks, h_pending;
+        DevBuf d_tasks, d_tiles, d_pair_tasks, d_keys, d_pending, d_tables;
+        PinBuf h_tasks, h_tiles, h_pair_tasks, h_pending, h_tables;
         cudaEvent_t done = nullptr;
         bool used = false;
     };
@@ -775,9 +775,30 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     UZ_CUDA(ctx, sl.d_keys.ensure(std::max<size_t>(key_rows, 1) * sizeof(uint2)));
     if (fused && key_rows > col_begin)       // column keys start at "none"; the match kernel lowers them with atomicMin
         UZ_CUDA(ctx, cudaMemsetAsync((uint2*)sl.d_keys.p + col_begin, 0xFF, (key_rows - col_begin) * sizeof(uint2), ctx->stream));
-    if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
-    if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * tile_bytes + merges.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-    UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    // small launches: the three tables travel as ONE copy (a copy command costs more than its few KB)
+    const size_t b_tasks = (n_tasks * sizeof(MatchTask) + 255) & ~(size_t)255;
+    const size_t b_tiles = (n_tiles * tile_bytes + merges.size() * sizeof(int4) + 255) & ~(size_t)255;
+    const size_t b_pairs = ((size_t)n_pairs * sizeof(int2) + 255) & ~(size_t)255;
+    const bool one_copy = b_tasks + b_tiles + b_pairs <= ((size_t)64 << 10);
+    const MatchTask* t_tasks = (const MatchTask*)sl.d_tasks.p;
+    const uint8_t* t_tiles = (const uint8_t*)sl.d_tiles.p;
+    const int2* t_pair_tasks = (const int2*)sl.d_pair_tasks.p;
+    if (one_copy) {
+        UZ_CUDA(ctx, sl.h_tables.ensure(b_tasks + b_tiles + b_pairs));
+        UZ_CUDA(ctx, sl.d_tables.ensure(b_tasks + b_tiles + b_pairs));
+        uint8_t* hb = (uint8_t*)sl.h_tables.p;
+        memcpy(hb, tasks, n_tasks * sizeof(MatchTask));
+        memcpy(hb + b_tasks, tiles, n_tiles * tile_bytes + merges.size() * sizeof(int4));
+        memcpy(hb + b_tasks + b_tiles, pair_tasks, (size_t)n_pairs * sizeof(int2));
+        UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tables.p, hb, b_tasks + b_tiles + b_pairs, cudaMemcpyHostToDevice, ctx->stream));
+        t_tasks = (const MatchTask*)sl.d_tables.p;
+        t_tiles = (const uint8_t*)sl.d_tables.p + b_tasks;
+        t_pair_tasks = (const int2*)((const uint8_t*)sl.d_tables.p + b_tasks + b_tiles);
+    } else {
+        if (n_tasks) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tasks.p, tasks, n_tasks * sizeof(MatchTask), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_tiles) UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, tiles, n_tiles * tile_bytes + merges.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    }
 
     // 3. launches.  Large batches: ONE match launch plus the persistent streaming solve beside it (uz_solve.cuh);
     // small batches, the parity taps and UZ_STREAM_SOLVE=0: match launch, then one solve CTA per pair behind it.
@@ -835,9 +856,9 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         if (ctx->stream_probe == 9) delay_kernel<<<1, 1, 0, ctx->stream>>>(3 * kStallNs);     // test hook: starve the streaming grid
     }
     if (n_tiles > 0) {
-        const MatchTask* d_tk = (const MatchTask*)sl.d_tasks.p;
-        const int2* d_t = (const int2*)sl.d_tiles.p;
-        const int2* d_tw = (const int2*)((const uint8_t*)sl.d_tiles.p + n_tiles_narrow * tile_bytes);
+        const MatchTask* d_tk = t_tasks;
+        const int2* d_t = (const int2*)t_tiles;
+        const int2* d_tw = (const int2*)(t_tiles + n_tiles_narrow * tile_bytes);
         uint2* d_k = (uint2*)sl.d_keys.p;
         const int nt = (int)n_tiles_narrow;
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
@@ -862,7 +883,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             if (ctx->timers) ctx->match_launches++;
         }
         if (!merges.empty()) {
-            const int4* d_m = (const int4*)((const uint8_t*)sl.d_tiles.p + std::max<size_t>(n_tiles, 1) * tile_bytes);
+            const int4* d_m = (const int4*)(t_tiles + std::max<size_t>(n_tiles, 1) * tile_bytes);
             merge_segments_kernel<<<dim3((unsigned)((max_nq + 255) / 256), (unsigned)merges.size(), 1), 256, 0, ctx->stream>>>(d_m, d_k);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
@@ -880,11 +901,10 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         sp.dbg_skip = streaming ? ctx->stream_probe : 0;
         if (streaming)
             solve_stream_kernel<kSolveThreads><<<stream_ctas, kSolveThreads, solve_smem_bytes(cap), sB>>>(
-                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
+                t_tasks, t_pair_tasks, (const uint2*)sl.d_keys.p, sp, d_results,
                 n_pairs, d_pending, d_ctl, d_deferred, 0);
         else
-            launch_solve(ctx, n_pairs, cap, sB, (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p,
-                         (const uint2*)sl.d_keys.p, sp, d_results);
+            launch_solve(ctx, n_pairs, cap, sB, t_tasks, t_pair_tasks, (const uint2*)sl.d_keys.p, sp, d_results);
         ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());
         if (ctx->timers) { cudaEventRecord(tm.e[3], sB); ctx->solve_launches++; }
@@ -896,7 +916,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             UZ_CUDA(ctx, cudaStreamWaitEvent(sB, ev_match, 0));
             ctx->event_pool.push_back(ev_match);
             solve_stream_kernel<kSolveThreads><<<4 * ctx->sm_count, kSolveThreads, solve_smem_bytes(cap), sB>>>(
-                (const MatchTask*)sl.d_tasks.p, (const int2*)sl.d_pair_tasks.p, (const uint2*)sl.d_keys.p, sp, d_results,
+                t_tasks, t_pair_tasks, (const uint2*)sl.d_keys.p, sp, d_results,
                 n_pairs, d_pending, d_ctl, d_deferred, 1);
             ctx->launches++;
             UZ_CUDA(ctx, cudaGetLastError());
@@ -1040,8 +1060,8 @@ void uz_destroy(uz_context* ctx) {
     places_release(ctx);
     ctx->store_arena.release(); ctx->transient.release();
     for (auto& sl : ctx->slots) {
-        sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release(); sl.d_pending.release();
-        sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release(); sl.h_pending.release();
+        sl.d_tasks.release(); sl.d_tiles.release(); sl.d_pair_tasks.release(); sl.d_keys.release(); sl.d_pending.release(); sl.d_tables.release();
+        sl.h_tasks.release(); sl.h_tiles.release(); sl.h_pair_tasks.release(); sl.h_pending.release(); sl.h_tables.release();
         if (sl.done) cudaEventDestroy(sl.done);
     }
     ctx->d_samples.release(); ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release(); ctx->h_results.release();
