@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
 tail -3 gpurun_out/pytest_$TAG.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; tail -1 gpurun_out/smoke_$TAG.log
 timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
 cat gpurun_out/bench_$TAG.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
@@ -23,6 +24,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:solv
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -c 1 -f -o gpurun_out/solve_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_wide_kernel -s 2 -c 1 -f -o gpurun_out/knn2_wide_full_$TAG \
+    python scripts/gpu_wide_probe.py 200 > /dev/null 2>&1
 for k in places_insert_kernel places_vote_kernel places_select_kernel; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/${k}_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
