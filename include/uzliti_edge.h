@@ -143,6 +143,12 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* features_blob, size_
 uz_status uz_wire_decode(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t capacity, int32_t* n_out,
                          int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out,
                          int32_t* uv_out);
+/* FeatureData::toMsg (graph_slam_common/src/sensor_data.cpp:77-122) for one stored camera: the serialised
+ * graph_slam_msgs/Feature[] field (uint32 count + elements) as uz_store_add_wire / uz_wire_decode read it - what a
+ * SensorData message or a RosbagStorage record carries.  uv (optional, n x 2 int32) supplies feature_positions_2d_, which
+ * the store does not keep (zeros if NULL); keypoint_strength is -1 as in the reference.  *bytes_out = bytes written. */
+uz_status uz_wire_encode(uz_context* ctx, int32_t handle, int32_t cam, const int32_t* uv, uint8_t* blob_out, size_t capacity,
+                         size_t* bytes_out);
 /* Read one stored camera back (descriptors n x *desc_bytes_out as given, positions 3 x n, valid n); any output may be
  * NULL; descriptors_out needs capacity x UZ_MAX_DESC_BYTES bytes. */
 uz_status uz_store_read(uz_context* ctx, int32_t handle, int32_t cam, int32_t capacity, int32_t* n_out,

@@ -207,6 +207,23 @@ def wire_decode(blob, capacity=4096, cols=32):
     return desc[:n], pos[:n], valid[:n], uv[:n]
 
 
+def wire_encode(cam, uv=None):
+    """FeatureData::toMsg -> bytes of the serialised Feature[] field"""
+    d = np.ascontiguousarray(cam["desc"], np.uint8)
+    p = np.ascontiguousarray(cam["pos"], np.float64)
+    v = np.ascontiguousarray(cam["valid"], np.uint8)
+    n, cols = d.shape
+    out = np.zeros(4 + n * (41 + 4 * cols), np.uint8)
+    uvp = None
+    if uv is not None:
+        uv = np.ascontiguousarray(uv, np.int32)
+        uvp = _p(uv)
+    lib().uzo_wire_encode.restype = C.c_long
+    got = lib().uzo_wire_encode(_p(d), n, cols, cols, _p(p), _p(v), uvp, _p(out), C.c_size_t(len(out)))
+    assert got == len(out)
+    return out.tobytes()
+
+
 class Places:
     """Sequential CPU restatement of LshSetRecognizer behind PlaceRecognizer's filters (oracle/uz_oracle.cpp, 8f-1).
     ids are arbitrary integers (the tests use store handles), stamps are nanoseconds."""

@@ -815,6 +815,39 @@ extern "C" void uzo_backproject(const int32_t* u_in, const int32_t* v_in, int n,
 }
 
 // =================================================================================================
+// 8f-4, the other direction: FeatureData::toMsg (sensor_data.cpp:77-122) as the ROS1-serialised graph_slam_msgs/Feature[]
+// field.  u, v come from feature_positions_2d_ (the caller's n x 2 int32, zeros if absent), keypoint_strength is -1 (:92),
+// every descriptor byte becomes a float32 (:101), keypoint_position the three doubles (:113-115), is_3d = valid_3d_ (:116).
+// Returns the byte count, or -1 if the buffer is too small.
+// =================================================================================================
+extern "C" long uzo_wire_encode(const uint8_t* desc, int n, int cols, int desc_stride, const double* positions,
+                                const uint8_t* valid, const int32_t* uv, uint8_t* blob, size_t capacity) {
+    const size_t need = 4 + (size_t)n * (17 + 4 * (size_t)cols + 24);
+    if (need > capacity) return -1;
+    uint32_t cnt = (uint32_t)n;
+    std::memcpy(blob, &cnt, 4);
+    size_t off = 4;
+    for (int i = 0; i < n; ++i) {
+        int32_t u = uv ? uv[2 * i] : 0, v = uv ? uv[2 * i + 1] : 0;
+        float strength = -1.0f;
+        uint32_t len = (uint32_t)cols;
+        std::memcpy(blob + off, &u, 4); std::memcpy(blob + off + 4, &v, 4);
+        blob[off + 8] = valid[i] ? 1 : 0;
+        std::memcpy(blob + off + 9, &strength, 4);
+        std::memcpy(blob + off + 13, &len, 4);
+        off += 17;
+        for (int j = 0; j < cols; ++j) {
+            float val = desc[(size_t)i * desc_stride + j];               // :101  val = features_.at<unsigned char>(i,j)
+            std::memcpy(blob + off + 4 * j, &val, 4);
+        }
+        off += 4 * (size_t)cols;
+        std::memcpy(blob + off, positions + 3 * (size_t)i, 24);
+        off += 24;
+    }
+    return (long)off;
+}
+
+// =================================================================================================
 // 8f-4: FeatureData::fromMsg (sensor_data.cpp:124-171) on a ROS1-serialised graph_slam_msgs/Feature[] field.
 // ROS1 wire format: little endian, fields in .msg order, no padding, variable arrays behind a uint32 length, bool = 1 byte.
 // Returns the feature count, or -1 if the blob is malformed / a descriptor length differs from the first one.

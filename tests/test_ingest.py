@@ -138,3 +138,40 @@ def test_gpu_wire_decode_and_ingest(est, oracle):
         est.add_keyframe_wire(mixed)
     assert est.read_keyframe(est.add_keyframe_wire(struct.pack("<I", 0)))["desc"].shape == (0, 32)
     est.clear()
+
+
+@pytest.mark.parametrize("nb", [32, 64])
+def test_oracle_wire_encode_is_the_inverse_of_decode(oracle, nb):
+    """FeatureData::toMsg (sensor_data.cpp:77-122): u/v from feature_positions_2d_, keypoint_strength -1, one float32 per
+    descriptor byte - against the field-by-field struct packing above, and decode(encode(x)) == x"""
+    f, _, _ = S.make_pair(70, seed=3, desc_bytes=nb)
+    rng = np.random.default_rng(4)
+    uv = np.stack([rng.integers(0, 640, 70), rng.integers(0, 480, 70)], 1).astype(np.int32)
+    blob = oracle.wire_encode(f, uv)
+    assert blob == encode_features(f["desc"].astype(np.float32), uv[:, 0], uv[:, 1], f["valid"], np.full(70, -1.0), f["pos"])
+    desc, pos, valid, uv2 = oracle.wire_decode(blob, cols=nb)
+    assert np.array_equal(desc, f["desc"]) and np.array_equal(pos, f["pos"]) and np.array_equal(valid, f["valid"])
+    assert np.array_equal(uv2, uv)
+    assert oracle.wire_encode(f)[:4 + 8] == struct.pack("<Iii", 70, 0, 0)                   # no 2-D positions: zeros
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nb", [32, 64])
+def test_gpu_wire_encode(est, oracle, nb):
+    f, t, _ = S.make_pair(500, seed=8, desc_bytes=nb)
+    rng = np.random.default_rng(9)
+    uv = np.stack([rng.integers(0, 640, 500), rng.integers(0, 480, 500)], 1).astype(np.int32)
+    est.clear()
+    h = est.add_keyframe([f])
+    assert est.wire_encode(h, uv=uv) == oracle.wire_encode(f, uv)
+    assert est.wire_encode(h) == oracle.wire_encode(f)
+    # store -> message -> store: the reloaded keyframe is the same keyframe (what a RosbagStorage resume does)
+    h2 = est.add_keyframe_wire(est.wire_encode(h, uv=uv), feature_type=f["feature_type"])
+    back = est.read_keyframe(h2)
+    assert np.array_equal(back["desc"], f["desc"]) and np.array_equal(back["pos"], f["pos"]) and np.array_equal(back["valid"], f["valid"])
+    ht = est.add_keyframe([t])
+    r = est.estimateEdges([h, h2], [ht, ht])
+    assert r[0].tobytes() == r[1].tobytes() and r[0]["consensus"] == oracle.estimate_edge([f], [t])["consensus"]
+    empty = est.add_keyframe([dict(desc=np.zeros((0, nb), np.uint8), pos=np.zeros((0, 3)), valid=np.zeros(0, np.uint8))])
+    assert est.wire_encode(empty) == struct.pack("<I", 0)
+    est.clear()

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers", "uz_set_stream_solve",
     "uz_get_timers", "uz_microbench", "uz_version",
-    "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_store_read",
+    "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
     "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
@@ -108,7 +108,7 @@ def load_library():
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
-                 "uz_microbench", "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_store_read",
+                 "uz_microbench", "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
                  "uz_estimate_svd_batch", "uz_gate_edges", "uz_gate_edges_device", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
                  "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing"):
         getattr(lib, name).restype = C.c_int
@@ -273,6 +273,17 @@ class EdgeEstimator:
                                             _p(pos), _p(valid), _p(uv)))
         nb = nb.value or 32
         return desc[:n.value * nb].reshape(n.value, nb), pos[:n.value], valid[:n.value], uv[:n.value]
+
+    def wire_encode(self, handle, cam=0, uv=None, capacity=4096):
+        """FeatureData::toMsg for one stored camera -> bytes of the serialised Feature[] field"""
+        out = np.zeros(4 + capacity * (41 + 4 * 64), np.uint8)
+        uvp = None
+        if uv is not None:
+            uv = np.ascontiguousarray(uv, np.int32)
+            uvp = _p(uv)
+        nbytes = C.c_size_t()
+        self._check(self.lib.uz_wire_encode(self.ctx, int(handle), int(cam), uvp, _p(out), C.c_size_t(len(out)), C.byref(nbytes)))
+        return out[:nbytes.value].tobytes()
 
     def read_keyframe(self, handle, cam=0, capacity=4096):
         desc = np.zeros(capacity * 64, np.uint8)

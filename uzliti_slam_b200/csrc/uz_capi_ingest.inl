@@ -204,6 +204,34 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* blob, size_t blob_by
     return UZ_OK;
 }
 
+uz_status uz_wire_encode(uz_context* ctx, int32_t handle, int32_t cam, const int32_t* uv, uint8_t* blob_out, size_t capacity,
+                         size_t* bytes_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (handle < 0 || handle >= (int32_t)ctx->kfs.size() || !ctx->kfs[handle].live) return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle");
+    if (cam < 0 || cam >= (int32_t)ctx->kfs[handle].cams.size()) return fail(ctx, UZ_ERR_INVALID, "camera index out of range");
+    if (!blob_out || !bytes_out) return fail(ctx, UZ_ERR_INVALID, "null output");
+    const Cam& c = ctx->kfs[handle].cams[cam];
+    const size_t need = 4 + (size_t)c.n * wire_elem_bytes(c.dbytes);
+    if (need > capacity) return fail(ctx, UZ_ERR_INVALID, "output capacity too small");
+    const uint32_t cnt = (uint32_t)c.n;
+    memcpy(blob_out, &cnt, 4);
+    *bytes_out = need;
+    if (c.n == 0) return UZ_OK;
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    uint8_t* db = (uint8_t*)ctx->transient.alloc(need - 4);
+    int32_t* duv = uv ? (int32_t*)ctx->transient.alloc((size_t)c.n * 8) : nullptr;
+    if (!db || (uv && !duv)) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    if (uv) UZ_CUDA(ctx, cudaMemcpyAsync(duv, uv, (size_t)c.n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    wire_encode_kernel<<<(c.n * 32 + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, c.n, c.dbytes, c.pos, c.valid, duv, db);
+    ctx->launches++;
+    UZ_CUDA(ctx, cudaGetLastError());
+    UZ_CUDA(ctx, cudaMemcpyAsync(blob_out + 4, db, need - 4, cudaMemcpyDeviceToHost, ctx->stream));
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
 // read a stored camera back (parity tap for the ingestion paths; also what a toMsg adapter would serialise)
 uz_status uz_store_read(uz_context* ctx, int32_t handle, int32_t cam, int32_t capacity, int32_t* n_out,
                         int32_t* desc_bytes_out, uint8_t* descriptors_out, double* positions_out, uint8_t* valid_out) {

@@ -89,4 +89,31 @@ __global__ void __launch_bounds__(256) wire_decode_kernel(const uint8_t* __restr
     if (uv && lane == 4) { uv[2 * f] = (int32_t)load_u32_unaligned(e); uv[2 * f + 1] = (int32_t)load_u32_unaligned(e + 4); }
 }
 
+// FeatureData::toMsg (sensor_data.cpp:77-122): the inverse of wire_decode_kernel, one warp per feature.  blob points at the
+// first element; uv (n x 2, may be null) supplies feature_positions_2d_, keypoint_strength is -1.
+__device__ __forceinline__ void store_u32_unaligned(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+__global__ void __launch_bounds__(256) wire_encode_kernel(const uint8_t* __restrict__ desc, int n, int cols, const double* __restrict__ pos,
+                                                          const uint8_t* __restrict__ valid, const int32_t* __restrict__ uv,
+                                                          uint8_t* __restrict__ blob) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= n) return;
+    uint8_t* e = blob + (size_t)f * wire_elem_bytes(cols);
+    if (lane == 0) {
+        store_u32_unaligned(e, uv ? (uint32_t)uv[2 * f] : 0u);
+        store_u32_unaligned(e + 4, uv ? (uint32_t)uv[2 * f + 1] : 0u);
+        e[8] = valid[f] ? 1 : 0;
+        store_u32_unaligned(e + 9, __float_as_uint(-1.0f));
+        store_u32_unaligned(e + 13, (uint32_t)cols);
+    }
+    for (int j = lane; j < cols; j += 32) store_u32_unaligned(e + 17 + 4 * j, __float_as_uint((float)desc[(size_t)f * cols + j]));
+    if (lane < 3) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(pos[3 * (size_t)f + lane]);
+        store_u32_unaligned(e + 17 + 4 * cols + 8 * lane, (uint32_t)b);
+        store_u32_unaligned(e + 17 + 4 * cols + 8 * lane + 4, (uint32_t)(b >> 32));
+    }
+}
+
 }  // namespace uz
