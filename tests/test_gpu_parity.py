@@ -380,3 +380,34 @@ def test_full_size_properties(est, oracle):
         o = oracle.estimate_edge([kfs[pairs[i, 0]]], [kfs[pairs[i, 1]]])
         _check_edge(res[i], o, f"pair {i}")
     est.clear()
+
+
+def test_estimate_svd_fuzz_with_awkward_inputs(est, oracle):
+    """seeded fuzz of estimateSVD on raw point sets: random sizes / thresholds / iteration counts, huge and tiny
+    coordinates, exact duplicates, points at the threshold, and non-finite coordinates (a NaN or an infinity is outside for
+    every hypothesis in the reference's double evaluation; a sample that touches one yields a non-finite transform that
+    simply never wins) - inlier sets, consensus and the winner must equal the oracle's, finite transforms bit for bit"""
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        M = int(rng.choice([3, 4, 5, 17, 63, 64, 65, 130, 400, 1100]))
+        iters = int(rng.choice([1, 7, 50, 100, 129, 300]))
+        thr = float(rng.choice([1e-3, 0.05, 0.1, 0.3, 5.0]))
+        bp = float(rng.choice([0.3, 0.6, 1.0]))
+        prosac = bool(rng.integers(0, 2))
+        scale = float(rng.choice([1.0, 1.0, 1e-3, 1e3]))
+        P, Q, _ = _point_problem(rng, M, float(rng.uniform(0.2, 0.95)), noise=0.01 * scale)
+        P *= scale; Q *= scale
+        kind = it % 5
+        if kind == 1 and M > 8:                                   # duplicates of one correspondence
+            P[M // 2:M // 2 + 4] = P[0]; Q[M // 2:M // 2 + 4] = Q[0]
+        if kind == 2 and M > 8:                                   # non-finite coordinates
+            P[3, 1] = np.nan; Q[5, 2] = np.inf; P[M - 1] = -np.inf
+        if kind == 3:                                             # far from the origin: the float32 pre-screen's margin grows
+            P += 5e4; Q += 5e4
+        g = est.estimateSVD(P, Q, thr * scale, iters, bp, prosac)
+        o = oracle.estimate_svd(P, Q, thr * scale, iters, bp, prosac)
+        tag = (it, M, iters, thr, bp, prosac, scale, kind)
+        assert g["consensus"] == o["consensus"] and np.array_equal(g["mask"], o["mask"]), tag
+        assert g["best_iteration"] == o["best_iteration"] and g["iterations_run"] == o["iterations_run"], tag
+        assert np.array_equal(g["T"], o["T"], equal_nan=True), tag
+        assert (np.isnan(g["mse"]) and np.isnan(o["mse"])) or g["mse"] == o["mse"], tag
