@@ -411,3 +411,35 @@ def test_estimate_svd_fuzz_with_awkward_inputs(est, oracle):
         assert g["best_iteration"] == o["best_iteration"] and g["iterations_run"] == o["iterations_run"], tag
         assert np.array_equal(g["T"], o["T"], equal_nan=True), tag
         assert (np.isnan(g["mse"]) and np.isnan(o["mse"])) or g["mse"] == o["mse"], tag
+
+
+def test_edge_fuzz_with_awkward_keyframes(est, oracle):
+    """whole path on keyframes a front-end can actually produce: few or no depth-valid keypoints, NaN / inf positions behind
+    a set valid flag, identical descriptors everywhere (every distance 0: the ratio test drops every match), one camera far
+    larger than the other - records must equal the oracle's"""
+    rng = np.random.default_rng(77)
+    cases = []
+    for it in range(24):
+        nf, nt = int(rng.choice([7, 8, 40, 300, 1000])), int(rng.choice([7, 9, 64, 333, 900]))
+        f, t, _ = S.make_pair(nf, nt, seed=4000 + it, invalid_frac=float(rng.choice([0.0, 0.15, 0.9, 1.0])))
+        kind = it % 6
+        if kind == 1:
+            f["pos"][::3] = np.nan                                    # NaN behind valid flags
+        if kind == 2:
+            t["pos"][1::4, 0] = np.inf
+        if kind == 3:
+            f["desc"][:] = 7; t["desc"][:] = 7                        # all distances 0
+        if kind == 4:
+            t["desc"][:] = t["desc"][0]                               # every query row identical
+        if kind == 5:
+            f["valid"][:] = 1; t["valid"][:] = 1; f["pos"][:] = f["pos"][0]      # all from-points identical
+        cases.append(([f], [t]))
+    got = est.estimateEdgesHost(cases)
+    for i, (r, (cf, ct)) in enumerate(zip(got, cases)):
+        o = oracle.estimate_edge(cf, ct)
+        tag = (i, len(cf[0]["desc"]), len(ct[0]["desc"]))
+        assert bool(r["ok"]) == o["ok"] and r["n_ratio_matches"] == o["n_ratio_matches"] and r["n_matches"] == o["n_matches"], tag
+        assert r["consensus"] == o["consensus"] and r["best_iteration"] == o["best_iteration"], tag
+        assert r["iterations_run"] == o["iterations_run"], tag
+        assert np.array_equal(r["T"].reshape(4, 4), o["T"], equal_nan=True), tag
+        assert (np.isnan(r["mse"]) and np.isnan(o["mse"])) or r["mse"] == o["mse"], tag
