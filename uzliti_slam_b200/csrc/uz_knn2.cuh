@@ -678,8 +678,10 @@ __global__ void __launch_bounds__(256) merge_segments_kernel(const int4* __restr
 
 // raw descriptor rows (any byte stride) -> packed rows, raw and CSA layout.  A row is `halves` 256-bit halves
 // (1: ORB/BRIEF, 2: BRISK/FREAK); one thread per half, n counts halves, every half gets its own CSA transform.
-__global__ void pack_descriptors_kernel(const uint8_t* __restrict__ src, int n, int stride,
-                                        uint32_t* __restrict__ raw, uint32_t* __restrict__ csa, int halves) {
+// src and raw may be the SAME buffer (rows already packed: every thread reads its half before it writes it back), so
+// neither carries __restrict__.
+__global__ void pack_descriptors_kernel(const uint8_t* src, int n, int stride,
+                                        uint32_t* raw, uint32_t* __restrict__ csa, int halves) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t* p = halves == 1 ? src + (size_t)i * stride : src + (size_t)(i >> 1) * stride + (i & 1) * 32;
