@@ -275,6 +275,43 @@ uz_status uz_places_votes(uz_context* ctx, int32_t handle, int32_t cam, int32_t 
 /* Device time (ms) of the insert / vote / select kernels of the last uz_places_* call and its bucket-entry visits. */
 uz_status uz_places_last_timing(uz_context* ctx, double* insert_ms, double* vote_ms, double* select_ms);
 
+/* ---- several GPUs of one box (SURVEY.md 8b(1) "device list", 8e) -------------------------------------------- */
+/* The reference owns one worker thread per estimator (transformation_estimator.cpp:26) and handles one pair per tick; pairs
+ * are independent, so a group owns one context per device in ONE process (one host worker thread each):
+ *   - the keyframe store is replicated: uz_group_store_add* uploads once over PCIe to devices[0]; every other device pulls the
+ *     keyframe from that device's HBM over NVLink (peer memory) and derives its layouts locally; handles are identical
+ *     on all devices;
+ *   - uz_group_estimate_edges* cuts the pair list into contiguous shards (rank r of n takes [lo, hi) with
+ *     lo = r * (N / n) + min(r, N % n)) and every device's solve kernel writes its 176-byte records straight into ONE result
+ *     buffer at the pair's batch-wide index, through a host-mapped pointer (results on the host) or a peer-mapped pointer
+ *     (results in devices[0]'s memory): the gather is fused into the solve, no collective runs.
+ * Results are byte-identical to uz_estimate_edges on one device.  Devices need peer access to devices[0]. */
+typedef struct uz_group uz_group;
+uz_status uz_group_create(const int32_t* devices, int32_t n_devices, uz_group** out);
+void      uz_group_destroy(uz_group* g);
+const char* uz_group_last_error(const uz_group* g);           /* never NULL; NULL group: why the last create failed */
+int32_t   uz_group_size(const uz_group* g);
+/* Context of one device of the group (borrowed): stage entry points, parity taps and place recognition run on rank 0. */
+uz_context* uz_group_context(uz_group* g, int32_t rank);
+uz_status uz_group_set_params(uz_group* g, const uz_params* p);
+uz_status uz_group_store_add(uz_group* g, const uz_features* cams, int32_t n_cams, int32_t* handle_out);
+uz_status uz_group_store_add_bulk(uz_group* g, const uz_features* cams, const int32_t* cams_per_keyframe,
+                                  int32_t n_keyframes, int32_t* handles_out);
+uz_status uz_group_store_remove(uz_group* g, int32_t handle);
+uz_status uz_group_store_clear(uz_group* g);
+int32_t   uz_group_store_size(const uz_group* g);
+/* estimateEdge x n_pairs over all devices; results: n_pairs records in HOST memory, pair order.  Blocks until done. */
+uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
+                                  int32_t n_pairs, uz_edge_result* results);
+/* Same, records land in devices[0]'s memory (n_pairs records), e.g. for uz_gate_edges_device.  Blocks until done. */
+uz_status uz_group_estimate_edges_device(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
+                                         int32_t n_pairs, void* results_on_first_device);
+/* 0 (default): records written by the solve kernels through the mapped pointer.  1: records stay local and travel with
+ * one cudaMemcpyAsync per device (the measured alternative; host results only). */
+uz_status uz_group_set_gather(uz_group* g, int32_t mode);
+/* Device time (ms, CUDA events per device) of the last uz_group_estimate_edges* call, one value per device. */
+uz_status uz_group_last_timing(const uz_group* g, double* ms_per_device, int32_t capacity);
+
 /* ---- execution form ------------------------------------------------------------------------------ */
 /* How the solve (K2..K5) of a large batch is scheduled.  ctas_per_sm > 0 (default 1): a persistent solve grid of that
  * many CTAs per SM runs BESIDE the match kernel on a high-priority stream and consumes pairs as the match kernel

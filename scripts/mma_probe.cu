@@ -119,7 +119,7 @@ static int check(MmaDesc dsc, const char* name) {
     size_t key_rows = 0;
     for (auto& s : shapes) {
         Cam q = make_cam(s[0], rng, s[2]), t = make_cam(s[1], rng, s[2]);
-        MmaTask tk; tk.q_e8 = q.e8; tk.t_e8 = t.e8; tk.nq = s[0]; tk.nt = s[1]; tk.key_off = (uint32_t)key_rows; tk.pair = (int)tasks.size();
+        MmaTask tk; memset(&tk, 0, sizeof(tk)); tk.q_desc = (const uint32_t*)q.e8; tk.t_desc = (const uint32_t*)t.e8; tk.nq = s[0]; tk.nt = s[1]; tk.key_off = (uint32_t)key_rows; tk.pair = (int)tasks.size();
         key_rows += (size_t)s[0];
         tasks.push_back(tk);
         want.emplace_back();
@@ -167,7 +167,7 @@ int main(int argc, char** argv) {
     size_t key_rows = 0;
     for (int p = 0; p < P; ++p) {
         const int f = (p / 20) % pool, t = (int)(rng() % pool);        // 20 candidates per from-keyframe, as in C4
-        MmaTask a; a.q_e8 = cams[t].e8; a.t_e8 = cams[f].e8; a.nq = N; a.nt = N; a.key_off = (uint32_t)key_rows; a.pair = p;
+        MmaTask a; memset(&a, 0, sizeof(a)); a.q_desc = (const uint32_t*)cams[t].e8; a.t_desc = (const uint32_t*)cams[f].e8; a.nq = N; a.nt = N; a.key_off = (uint32_t)key_rows; a.pair = p;
         MatchTask b; memset(&b, 0, sizeof(b));
         b.q_desc = cams[t].csa; b.t_desc = cams[f].csa; b.nq = N; b.nt = N; b.key_off = (uint32_t)key_rows; b.pair = p; b.rev_key_off = kNoRev;
         key_rows += N;

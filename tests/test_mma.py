@@ -1,0 +1,100 @@
+"""The tensor-core match kernel (knn2_mma_kernel, uz_knn2_mma.cuh: Hamming distance as an exact int8 contraction) is the
+default for 256-bit rows.  It must return exactly what cv::BFMatcher / the oracle / the integer-pipe kernel return: same
+neighbours, same tie rule (lowest train index), on ragged query tiles, ragged train tiles, tiny and maximum sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from uzliti_slam_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1000, 1000), (400, 300), (65, 129), (1, 5), (513, 4096), (130, 127), (64, 2), (256, 256), (257, 255), (4096, 4096),
+         (7, 1), (129, 257), (1000, 31), (9, 700)]
+
+
+def _est(mma):
+    from uzliti_slam_b200 import EdgeEstimator
+    os.environ["UZ_MATCH_MMA"] = str(mma)
+    try:
+        return EdgeEstimator(0)
+    finally:
+        os.environ.pop("UZ_MATCH_MMA", None)
+
+
+def test_mma_neighbours_equal_oracle_and_popc_kernel(oracle):
+    em, ep = _est(1), _est(0)
+    try:
+        for nq, nt in SIZES:
+            for mode in range(3):
+                rng = np.random.default_rng(77 * nq + nt + mode)
+                q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+                t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+                if mode == 1:                      # tie-heavy: distances collapse onto a few values
+                    q[:, 2:] = 0; t[:, 2:] = 0
+                if mode == 2 and nt > 4:           # exact duplicates across key blocks, stages and column halves
+                    t[nt - 1] = q[0]; t[nt // 2] = q[0]; t[1] = q[nq // 2]; t[min(130, nt - 1)] = q[nq // 2]
+                idx, dist = em.knnMatch(q, t)
+                oi, od = oracle.knn2(q, t)
+                assert np.array_equal(idx, oi), (nq, nt, mode)
+                assert np.array_equal(dist, od), (nq, nt, mode)
+                pi, pd = ep.knnMatch(q, t)
+                assert np.array_equal(idx, pi) and np.array_equal(dist, pd)
+        assert em.get_timers is not None
+    finally:
+        em.close(); ep.close()
+
+
+def test_mma_all_zero_and_all_one_descriptors(oracle):
+    """distance 0 and distance 256 are the ends of the key range (dot = +256 / -256)"""
+    em = _est(1)
+    try:
+        q = np.zeros((300, 32), np.uint8)
+        t = np.zeros((520, 32), np.uint8)
+        t[::2] = 255
+        q[10] = 255
+        idx, dist = em.knnMatch(q, t)
+        oi, od = oracle.knn2(q, t)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+        assert dist.min() == 0 and od[0, 0] == 0
+        t[:] = 255
+        q[:] = 0
+        idx, dist = em.knnMatch(q, t)
+        assert (dist == 256).all() and (idx[:, 0] == 0).all() and (idx[:, 1] == 1).all()
+    finally:
+        em.close()
+
+
+def test_whole_path_records_identical_on_both_match_kernels(oracle):
+    """store path, host path, rigs and the cross-check (reversed matching on the tensor cores, fused column minima on the
+    integer pipes): byte-identical edge records"""
+    em, ep = _est(1), _est(0)
+    try:
+        kfs, pairs, _ = S.make_map(60, n_features=700, cluster=6, pool=700, n_shared=400, k_candidates=6, cross_cluster=2, seed=21)
+        for cross in (0, 1):
+            recs = []
+            for e in (em, ep):
+                e.setConfig(cross_check=cross)
+                e.clear()
+                h = e.add_keyframes(kfs)
+                recs.append(e.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]]))
+            assert recs[0].tobytes() == recs[1].tobytes()
+            assert (recs[0]["ok"] == 1).any()
+            host = em.estimateEdgesHost([([kfs[a]], [kfs[b]]) for a, b in pairs[:40]])
+            assert host.tobytes() == recs[0][:40].tobytes()
+            for r, (a, b) in list(zip(recs[0], pairs))[:12]:
+                o = oracle.estimate_edge([kfs[a]], [kfs[b]], cross_check=bool(cross))
+                assert r["n_ratio_matches"] == o["n_ratio_matches"] and r["n_matches"] == o["n_matches"]
+                assert r["consensus"] == o["consensus"]
+        em.setConfig(cross_check=0); ep.setConfig(cross_check=0)
+        # a rig with mixed widths: 256-bit cameras go to the tensor cores, 512-bit ones to knn2_wide_kernel, in one batch
+        fa, ta, _ = S.make_pair(400, 300, seed=7, sensor_frame=0)
+        fb, tb, _ = S.make_pair(350, 450, seed=8, sensor_frame=1, desc_bytes=64)
+        a = em.estimateEdgesHost([([fa, fb], [ta, tb]), ([fa], [ta]), ([fb], [tb])])
+        b = ep.estimateEdgesHost([([fa, fb], [ta, tb]), ([fa], [ta]), ([fb], [tb])])
+        assert a.tobytes() == b.tobytes()
+        o = oracle.estimate_edge([fa, fb], [ta, tb])
+        assert a[0]["consensus"] == o["consensus"] and a[0]["cam_from"] == o["cam_from"]
+    finally:
+        em.close(); ep.close()

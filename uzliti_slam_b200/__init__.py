@@ -6,4 +6,4 @@ tests and the bench harness use — it adds no compute and has NO CPU fallback: 
 missing or no B200 is visible, calls raise.
 """
 from .binding import (EdgeEstimator, UzError, Params, EdgeResult, Features, lib_path, load_library,  # noqa: F401
-                      build_library, EXPORTED_SYMBOLS)
+                      build_library, EXPORTED_SYMBOLS, GroupEstimator)

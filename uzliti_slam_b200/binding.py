@@ -23,6 +23,9 @@ EXPORTED_SYMBOLS = [
     "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
+    "uz_group_create", "uz_group_destroy", "uz_group_last_error", "uz_group_size", "uz_group_context", "uz_group_set_params",
+    "uz_group_store_add", "uz_group_store_add_bulk", "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size",
+    "uz_group_estimate_edges", "uz_group_estimate_edges_device", "uz_group_set_gather", "uz_group_last_timing",
 ]
 
 
@@ -114,6 +117,13 @@ def load_library():
         getattr(lib, name).restype = C.c_int
     lib.uz_default_place_params.restype = None
     lib.uz_default_gate_params.restype = None
+    lib.uz_group_last_error.restype = C.c_char_p
+    lib.uz_group_destroy.restype = None
+    lib.uz_group_context.restype = C.c_void_p
+    for name in ("uz_group_create", "uz_group_size", "uz_group_set_params", "uz_group_store_add", "uz_group_store_add_bulk",
+                 "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size", "uz_group_estimate_edges",
+                 "uz_group_estimate_edges_device", "uz_group_set_gather", "uz_group_last_timing"):
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 
@@ -537,3 +547,95 @@ class EdgeEstimator:
         g = C.c_double()
         self._check(self.lib.uz_microbench(self.ctx, int(op), C.byref(g)))
         return g.value
+
+
+class GroupEstimator:
+    """One uz_group: the same path on several GPUs of one box in ONE process (replicated store, sharded pair list,
+    records written by the solve kernels straight into one result buffer).  Results are byte-identical to EdgeEstimator."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self.grp = C.c_void_p()
+        st = self.lib.uz_group_create(arr, len(self.devices), C.byref(self.grp))
+        if st != 0:
+            raise UzError(f"uz_group_create({self.devices}) failed with status {st}: "
+                          f"{self.lib.uz_group_last_error(None).decode()} (there is no CPU fallback)")
+
+    def close(self):
+        if self.grp:
+            self.lib.uz_group_destroy(self.grp)
+            self.grp = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise UzError(f"status {st}: {self.lib.uz_group_last_error(self.grp).decode()}")
+
+    def size(self):
+        return self.lib.uz_group_size(self.grp)
+
+    def context(self, rank=0):
+        """EdgeEstimator view of one device's context (borrowed: do not close it)."""
+        e = EdgeEstimator.__new__(EdgeEstimator)
+        e.lib = self.lib
+        e.ctx = C.c_void_p(self.lib.uz_group_context(self.grp, int(rank)))
+        e.device = self.devices[rank]
+        e.close = lambda: None
+        return e
+
+    def setConfig(self, **kw):
+        p = Params()
+        self.lib.uz_get_params(C.c_void_p(self.lib.uz_group_context(self.grp, 0)), C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        self._check(self.lib.uz_group_set_params(self.grp, C.byref(p)))
+
+    def set_gather(self, mode):
+        self._check(self.lib.uz_group_set_gather(self.grp, int(mode)))
+
+    def add_keyframes(self, keyframes):
+        keep, flat, counts = [], [], []
+        for kf in keyframes:
+            cams = kf if isinstance(kf, (list, tuple)) else [kf]
+            flat += list(cams)
+            counts.append(len(cams))
+        arr = features_array(flat, keep)
+        counts = np.array(counts, np.int32)
+        handles = np.empty(len(keyframes), np.int32)
+        self._check(self.lib.uz_group_store_add_bulk(self.grp, arr, _p(counts), len(keyframes), _p(handles)))
+        return handles
+
+    def remove_keyframe(self, handle):
+        self._check(self.lib.uz_group_store_remove(self.grp, int(handle)))
+
+    def clear(self):
+        self._check(self.lib.uz_group_store_clear(self.grp))
+
+    def store_size(self):
+        return self.lib.uz_group_store_size(self.grp)
+
+    def estimateEdges(self, from_handles, to_handles, out=None):
+        f = np.ascontiguousarray(from_handles, np.int32)
+        t = np.ascontiguousarray(to_handles, np.int32)
+        res = out if out is not None else np.zeros(len(f), RESULT_DTYPE)
+        self._check(self.lib.uz_group_estimate_edges(self.grp, _p(f), _p(t), len(f), _p(res)))
+        return res
+
+    def estimateEdgesDevice(self, from_handles, to_handles, results_device_ptr):
+        f = np.ascontiguousarray(from_handles, np.int32)
+        t = np.ascontiguousarray(to_handles, np.int32)
+        self._check(self.lib.uz_group_estimate_edges_device(self.grp, _p(f), _p(t), len(f), C.c_void_p(results_device_ptr)))
+
+    def last_timing(self):
+        out = np.zeros(len(self.devices), np.float64)
+        self._check(self.lib.uz_group_last_timing(self.grp, _p(out), len(out)))
+        return out

@@ -15,28 +15,28 @@ uz_status check_camera(uz_context* ctx, const uz_camera* c, const float* depth, 
     return UZ_OK;
 }
 
-// registers one single-camera keyframe whose buffers are already on the device (arena memory)
-int32_t register_keyframe(uz_context* ctx, const Cam& c) {
-    int32_t h;
-    if (!ctx->free_handles.empty()) { h = ctx->free_handles.back(); ctx->free_handles.pop_back(); }
-    else { h = (int32_t)ctx->kfs.size(); ctx->kfs.emplace_back(); }
-    Keyframe& kf = ctx->kfs[h];
-    kf.cams.assign(1, c);
-    kf.live = true;
-    ctx->store_max_n = std::max(ctx->store_max_n, c.n);
-    ctx->live++;
+// registers one single-camera keyframe whose buffers are already on the device (one range of the store arena)
+int32_t register_keyframe(uz_context* ctx, const Cam& c, const BlockRef& block) {
+    int32_t h = -1;
+    std::vector<Cam> up(1, c);
+    std::vector<BlockRef> blocks(1, block);
+    const int32_t one = 1;
+    register_keyframes(ctx, up, blocks, &one, 1, &h);
     return h;
 }
 
-uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int dbytes, int feature_type, int sensor_frame, Cam& c) {
+// one camera's layouts in one range of the arena (the same layout uz_store_add uses)
+uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int dbytes, int feature_type, int sensor_frame, Cam& c, BlockRef& block) {
     c = Cam();
     c.n = n; c.feature_type = feature_type; c.sensor_frame = sensor_frame; c.dbytes = dbytes;
+    const CamLayout L = cam_layout(0, n, dbytes);
+    uint8_t* base = (uint8_t*)arena.alloc(std::max<size_t>(L.end, 1));
+    if (!base) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    block = BlockRef{base, std::max<size_t>(L.end, 1)};
     if (n == 0) return UZ_OK;
-    c.raw = (uint32_t*)arena.alloc((size_t)n * dbytes);
-    c.csa = (uint32_t*)arena.alloc((size_t)n * dbytes);
-    c.pos = (double*)arena.alloc((size_t)n * 24);
-    c.valid = (uint8_t*)arena.alloc((size_t)n);
-    if (!c.raw || !c.csa || !c.pos || !c.valid) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+    c.raw = (uint32_t*)(base + L.raw); c.pos = (double*)(base + L.pos); c.valid = base + L.valid;
+    c.csa = (uint32_t*)(base + L.csa);
+    c.e8 = dbytes == UZ_DESC_BYTES ? base + L.e8 : nullptr;
     return UZ_OK;
 }
 
@@ -86,7 +86,9 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     Cam c;
-    if ((st = alloc_cam(ctx, ctx->store_arena, n, db, feature_type, sensor_frame, c)) != UZ_OK) return st;
+    BlockRef block;
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
+    if ((st = alloc_cam(ctx, ctx->store_arena, n, db, feature_type, sensor_frame, c, block)) != UZ_OK) return st;
     if (n > 0) {
         const int halves = n * (db / 32);
         const size_t img = (size_t)depth_stride_bytes * cam->height;
@@ -95,7 +97,7 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
         int32_t* dv = (int32_t*)ctx->transient.alloc((size_t)n * 4);
         float* dd = (float*)ctx->transient.alloc(img);
         uint8_t* ddesc = (uint8_t*)ctx->transient.alloc(dbytes);
-        if (!du || !dv || !dd || !ddesc) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        if (!du || !dv || !dd || !ddesc) { ctx->store_arena.free(block.p, block.bytes); return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed"); }
         UZ_CUDA(ctx, cudaMemcpyAsync(du, u, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
         UZ_CUDA(ctx, cudaMemcpyAsync(dv, v, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
         UZ_CUDA(ctx, cudaMemcpyAsync(dd, depth, img, cudaMemcpyHostToDevice, ctx->stream));
@@ -110,9 +112,10 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
         }
         ctx->launches += 2;
         UZ_CUDA(ctx, cudaGetLastError());
+        if ((st = derive_layouts(ctx, &c, 1)) != UZ_OK) return st;      // (the CSA pass above is repeated there; E8 is what it adds)
         UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));        // host buffers are borrowed only for the call
     }
-    *handle_out = register_keyframe(ctx, c);
+    *handle_out = register_keyframe(ctx, c, block);
     return UZ_OK;
 }
 
@@ -182,25 +185,26 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* blob, size_t blob_by
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
     Cam c;
-    if ((st = alloc_cam(ctx, ctx->store_arena, n, cols, feature_type, sensor_frame, c)) != UZ_OK) return st;
+    BlockRef block;
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
+    if ((st = alloc_cam(ctx, ctx->store_arena, n, cols, feature_type, sensor_frame, c, block)) != UZ_OK) return st;
     if (n > 0) {
-        const int halves = n * (cols / 32);
         const size_t body = (size_t)n * wire_elem_bytes(cols);
         uint8_t* db = (uint8_t*)ctx->transient.alloc(body);
         int* dstat = (int*)ctx->transient.alloc(4);
-        if (!db || !dstat) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        if (!db || !dstat) { ctx->store_arena.free(block.p, block.bytes); return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed"); }
         UZ_CUDA(ctx, cudaMemcpyAsync(db, blob + 4, body, cudaMemcpyHostToDevice, ctx->stream));
         UZ_CUDA(ctx, cudaMemsetAsync(dstat, 0, 4, ctx->stream));
         wire_decode_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(db, n, cols, (uint8_t*)c.raw, c.pos, c.valid, nullptr, dstat);
-        pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t*)c.raw, halves, 32, c.raw, c.csa, 1);
-        ctx->launches += 2;
+        ctx->launches++;
         UZ_CUDA(ctx, cudaGetLastError());
+        if ((st = derive_layouts(ctx, &c, 1)) != UZ_OK) return st;
         int stat = 0;
         UZ_CUDA(ctx, cudaMemcpyAsync(&stat, dstat, 4, cudaMemcpyDeviceToHost, ctx->stream));
         UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (stat) return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length differs from the first element's");
+        if (stat) { ctx->store_arena.free(block.p, block.bytes); return fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length differs from the first element's"); }
     }
-    *handle_out = register_keyframe(ctx, c);
+    *handle_out = register_keyframe(ctx, c, block);
     return UZ_OK;
 }
 

@@ -100,6 +100,26 @@ uz_status places_reset(uz_context* ctx) {
     return UZ_OK;
 }
 
+// The keyframe behind `handle` leaves the store (uz_store_remove) and the handle will be recycled: its place dies
+// (removePlace), the checked_ pairs naming it go (the next keyframe with this handle is a different node), and its rows are
+// never re-linked again (their memory is about to be reused).
+void places_forget_handle(uz_context* ctx, int32_t handle) {
+    PlacesState& ps = ctx->places;
+    auto it = ps.by_handle.find(handle);
+    if (it != ps.by_handle.end()) {
+        const int32_t place = it->second;
+        PlaceInfo& pi = ps.places[place];
+        pi.live = false;
+        for (uint32_t k = 0; k < pi.ins_count; ++k) ps.inserted[pi.ins_begin + k].n = 0;
+        ps.by_handle.erase(it);
+        if (ps.d_live) cudaMemsetAsync(ps.d_live + place, 0, 1, ctx->stream);
+    }
+    for (auto c = ps.checked.begin(); c != ps.checked.end();) {
+        if ((int32_t)(*c >> 32) == handle || (int32_t)(*c & 0xFFFFFFFFu) == handle) c = ps.checked.erase(c);
+        else ++c;
+    }
+}
+
 bool place_cam_usable(const Cam& c) { return c.n > 0 && c.raw != nullptr && is_binary_type(c.feature_type); }
 
 // The one driver behind search_and_add / add / search.
@@ -130,7 +150,7 @@ uz_status places_run(uz_context* ctx, PlaceMode mode, const int32_t* handles, co
         if (mode != kSearchOnly) {
             if (ps.by_handle.count(h)) continue;          // place_recognizer.cpp:80-84 / :142-144
             place = (int32_t)ps.places.size();
-            ps.places.push_back(PlaceInfo{h, (long long)stamps_ns[i], true});
+            ps.places.push_back(PlaceInfo{h, (long long)stamps_ns[i], true, (uint32_t)(ps.inserted.size() + ins.size()), 0u});
             ps.by_handle[h] = place;
             place_of[i] = place;
         }
@@ -146,6 +166,7 @@ uz_status places_run(uz_context* ctx, PlaceMode mode, const int32_t* handles, co
                 pc.insert_filtered = mode == kSearchAndAdd;
                 new_nodes += (size_t)c.n * 8;
                 ins.push_back(pc);
+                ps.places[place].ins_count++;
             }
             if (mode != kAddOnly) {
                 pc.query_filtered = (mode == kSearchAndAdd && big) ? 1 : 0;

@@ -52,13 +52,11 @@ constexpr int kMmaSmemBytes = 2 * kMmaABytes + 2 * kMmaBBytes + 2 * kMmaItemRows
 
 __host__ __device__ constexpr size_t e8_bytes(int n) { return (size_t)((n + 7) / 8) * kE8GroupBytes; }
 
-struct MmaTask {
-    const uint8_t* q_e8;      // "to" camera (OpenCV query) in E8 layout
-    const uint8_t* t_e8;      // "from" camera (OpenCV train)
-    int32_t nq, nt;
-    uint32_t key_off;         // first row of this matching in the keys scratch
-    int32_t pair;
-};
+// The kernel reads the batch's MatchTask table (uz_knn2.cuh): for a matching that runs here, q_desc / t_desc point at the
+// E8 layouts of the "to" (OpenCV query) and "from" (train) cameras.
+using MmaTask = MatchTask;
+__device__ __forceinline__ const uint8_t* mma_q(const MmaTask* tk) { return reinterpret_cast<const uint8_t*>(tk->q_desc); }
+__device__ __forceinline__ const uint8_t* mma_t(const MmaTask* tk) { return reinterpret_cast<const uint8_t*>(tk->t_desc); }
 
 // Descriptor fields the host passes in (so that the probe can A/B them): see uz_knn2_mma_desc()
 struct MmaDesc {
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
                         mbar_wait_wd(&a_empty[0], (uA[0] & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)e8_bytes(min(kMmaM, nq - q0));
                         mbar_expect_tx(&a_full[0], bytes);
-                        bulk_g2s(sA, tk->q_e8 + (size_t)(q0 >> 3) * kE8GroupBytes, bytes, &a_full[0]);
+                        bulk_g2s(sA, mma_q(tk) + (size_t)(q0 >> 3) * kE8GroupBytes, bytes, &a_full[0]);
                         uA[0]++;
                     }
                     {
@@ -248,14 +246,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
                         mbar_wait_wd(&b_empty[slot], ((uB >> 1) & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)e8_bytes(min(kMmaN, nt - t * kMmaN));
                         mbar_expect_tx(&b_full[slot], bytes);
-                        bulk_g2s(sB + slot * kMmaBBytes, tk->t_e8 + (size_t)t * kMmaBBytes, bytes, &b_full[slot]);
+                        bulk_g2s(sB + slot * kMmaBBytes, mma_t(tk) + (size_t)t * kMmaBBytes, bytes, &b_full[slot]);
                         uB++;
                     }
                     if (t == 0 && nqt == 2) {
                         mbar_wait_wd(&a_empty[1], (uA[1] & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)e8_bytes(min(kMmaM, nq - q0 - kMmaM));
                         mbar_expect_tx(&a_full[1], bytes);
-                        bulk_g2s(sA + kMmaABytes, tk->q_e8 + (size_t)((q0 + kMmaM) >> 3) * kE8GroupBytes, bytes, &a_full[1]);
+                        bulk_g2s(sA + kMmaABytes, mma_q(tk) + (size_t)((q0 + kMmaM) >> 3) * kE8GroupBytes, bytes, &a_full[1]);
                         uA[1]++;
                     }
                 }
