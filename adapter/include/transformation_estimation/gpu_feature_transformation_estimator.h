@@ -57,6 +57,11 @@ protected:
 class GpuFeatureTransformationEstimator : public TransformationEstimator {
 public:
     GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, int device = 0);
+    // Several GPUs of one box behind the same class (uz_group): the node store is replicated on every device (one upload
+    // over PCIe, the other devices pull from the first one's HBM over NVLink), a batch of queued pairs is cut into
+    // contiguous shards, and every device's solve kernel writes its edge records straight into one result buffer.  Edges
+    // are byte-identical to the single-device estimator's.
+    GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, const std::vector<int>& devices);
     ~GpuFeatureTransformationEstimator();
 
     bool estimateEdgeImpl(SlamNode& from, SlamNode& to, SlamEdge& edge);                                  // :38
@@ -84,20 +89,33 @@ public:
     std::mutex& gpuMutex() { return gpu_mutex_; }
     bool residentHandle(const SlamNode& node, int32_t* handle);       // uploads the node if needed; gpuMutex() must be held
 
-    // device-resident keyframe store: nodes are uploaded once and addressed by id_ afterwards
+    // device-resident keyframe store: nodes are uploaded once and addressed by id_ afterwards.  Every call re-validates the
+    // cached copy against the node it is handed (the FEATURE sensor data of a node changes under a fixed id: late sensor
+    // arrivals graph_slam_node.cpp:244, node merge :1010-1026) and re-uploads it under the same handle when it differs.
+    // forgetNode gives the node's device memory back; call it where the reference removes a node (graph.removeNode,
+    // graph_slam_node.cpp:1050) - see INTEGRATION.md.
     void forgetNode(const std::string& id);
+    // Resume (GraphSlamNode::load, graph_slam_node.cpp:875-888: every stored node is re-added): all nodes in ONE bulk upload.
+    bool loadNodes(const std::vector<SlamNode>& nodes);
+    int devices() const { return uz_group_size(grp_); }
+    int64_t storeBytes() const { return uz_store_bytes(ctx_); }
     size_t residentNodes() const { return handles_.size(); }
     const char* lastError() const;
 
 protected:
-    struct Resident { int32_t handle; std::vector<FeatureDataPtr> cams; };
+    struct Resident { int32_t handle = -1; std::vector<FeatureDataPtr> cams; std::vector<int> rows; };
     bool ensureResident(const SlamNode& node, Resident** out);
     void fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to, SlamEdge& edge) const;
     int internFrame(const std::string& frame);
 
-    uz_context* ctx_ = nullptr;
+    void init(const std::vector<int>& devices);
+    void collectCams(const SlamNode& node, std::vector<FeatureDataPtr>& cams) const;
+
+    uz_group* grp_ = nullptr;
+    uz_context* ctx_ = nullptr;           // the group's first device: stage entry points and the place recogniser run there
     transformation_estimation::FeatureLinkEstimationConfig config_;
     std::unordered_map<std::string, Resident> handles_;
     std::unordered_map<std::string, int> frames_;
+    size_t anon_ = 0;
     std::mutex gpu_mutex_;
 };

@@ -76,18 +76,32 @@ void TransformationEstimator::waitIdle() {
 // ---------------------------------------------------------------------------------------------------------
 GpuFeatureTransformationEstimator::GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, int device)
     : TransformationEstimator(callback) {
-    if (uz_create(device, &ctx_) != UZ_OK)
-        throw std::runtime_error(std::string("uz_create failed (no CPU fallback): ") + uz_last_error(nullptr));
+    init(std::vector<int>(1, device));
+}
+
+GpuFeatureTransformationEstimator::GpuFeatureTransformationEstimator(boost::function<void(SlamEdge)> callback, const std::vector<int>& devices)
+    : TransformationEstimator(callback) {
+    init(devices);
+}
+
+void GpuFeatureTransformationEstimator::init(const std::vector<int>& devices) {
+    std::vector<int32_t> dev(devices.begin(), devices.end());
+    if (uz_group_create(dev.data(), (int32_t)dev.size(), &grp_) != UZ_OK)
+        throw std::runtime_error(std::string("uz_group_create failed (no CPU fallback): ") + uz_group_last_error(nullptr));
+    ctx_ = uz_group_context(grp_, 0);
     setConfig(config_);
     startThread();
 }
 
 GpuFeatureTransformationEstimator::~GpuFeatureTransformationEstimator() {
     stopThread();
-    uz_destroy(ctx_);
+    uz_group_destroy(grp_);
 }
 
-const char* GpuFeatureTransformationEstimator::lastError() const { return uz_last_error(ctx_); }
+const char* GpuFeatureTransformationEstimator::lastError() const {
+    const char* g = uz_group_last_error(grp_);
+    return (g && g[0]) ? g : uz_last_error(ctx_);
+}
 
 void GpuFeatureTransformationEstimator::setConfig(transformation_estimation::FeatureLinkEstimationConfig config) {
     std::lock_guard<std::mutex> lk(gpu_mutex_);
@@ -98,7 +112,7 @@ void GpuFeatureTransformationEstimator::setConfig(transformation_estimation::Fea
     p.ransac_iterations = config.ransac_iteration;
     p.break_percentage = config.ransac_break_percentage;
     // link_covariance is unused by the live reference code (:138-144 commented out); use_epnp is ignored (:130)
-    if (uz_set_params(ctx_, &p) != UZ_OK) std::fprintf(stderr, "setConfig: %s\n", uz_last_error(ctx_));
+    if (uz_group_set_params(grp_, &p) != UZ_OK) std::fprintf(stderr, "setConfig: %s\n", lastError());
 }
 
 int GpuFeatureTransformationEstimator::internFrame(const std::string& frame) {
@@ -123,24 +137,85 @@ static void feature_view(const FeatureData& f, int frame_tag, std::vector<uint8_
     out->sensor_frame = frame_tag;
 }
 
-bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Resident** out) {
-    auto it = handles_.find(node.id_);
-    if (it != handles_.end() && !node.id_.empty()) { *out = &it->second; return true; }
-    Resident r;
-    std::vector<uz_features> views;
-    std::vector<std::vector<uint8_t> > valid;
+void GpuFeatureTransformationEstimator::collectCams(const SlamNode& node, std::vector<FeatureDataPtr>& cams) const {
+    cams.clear();
     for (const SensorDataPtr& d : node.sensor_data_)
         if (d->type_ == graph_slam_msgs::SensorData::SENSOR_TYPE_FEATURE) {           // :41,:43
             FeatureDataPtr f = boost::dynamic_pointer_cast<FeatureData>(d);
-            if (f) r.cams.push_back(f);
+            if (f) cams.push_back(f);
         }
-    views.resize(r.cams.size());
-    valid.resize(r.cams.size());
-    for (size_t i = 0; i < r.cams.size(); ++i) feature_view(*r.cams[i], internFrame(r.cams[i]->sensor_frame_), valid[i], &views[i]);
-    if (uz_store_add(ctx_, views.data(), (int32_t)views.size(), &r.handle) != UZ_OK) return false;
-    std::string key = node.id_.empty() ? "#anon" + std::to_string(handles_.size()) : node.id_;
+}
+
+// true when the device copy was made from exactly these FeatureData objects: same objects (FeatureData is immutable once
+// published, sensor_data.h:113-114), same sizes
+static bool same_cams(const std::vector<FeatureDataPtr>& a, const std::vector<FeatureDataPtr>& b, const std::vector<int>& rows) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (a[i].get() != b[i].get() || rows[i] != a[i]->features_.rows) return false;
+    return true;
+}
+
+bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Resident** out) {
+    std::vector<FeatureDataPtr> cams;
+    collectCams(node, cams);
+    auto it = node.id_.empty() ? handles_.end() : handles_.find(node.id_);
+    if (it != handles_.end() && same_cams(cams, it->second.cams, it->second.rows)) { *out = &it->second; return true; }
+    std::vector<uz_features> views(cams.size());
+    std::vector<std::vector<uint8_t> > valid(cams.size());
+    std::vector<int> rows(cams.size());
+    for (size_t i = 0; i < cams.size(); ++i) {
+        feature_view(*cams[i], internFrame(cams[i]->sensor_frame_), valid[i], &views[i]);
+        rows[i] = cams[i]->features_.rows;
+    }
+    if (it != handles_.end()) {
+        // the node's sensor data changed under its id (graph_slam_node.cpp:244, :1010-1026): the reference copies the node on
+        // every estimateEdge (transformation_estimator.cpp:39) and so always matches the current data - re-upload, same handle
+        if (uz_group_store_replace(grp_, it->second.handle, views.data(), (int32_t)views.size()) != UZ_OK) return false;
+        it->second.cams = cams; it->second.rows = rows;
+        *out = &it->second;
+        return true;
+    }
+    Resident r;
+    r.cams = cams; r.rows = rows;
+    if (uz_group_store_add(grp_, views.data(), (int32_t)views.size(), &r.handle) != UZ_OK) return false;
+    std::string key = node.id_.empty() ? "#anon" + std::to_string(anon_++) : node.id_;
     auto ins = handles_.emplace(key, r);
     *out = &ins.first->second;
+    return true;
+}
+
+bool GpuFeatureTransformationEstimator::loadNodes(const std::vector<SlamNode>& nodes) {
+    std::lock_guard<std::mutex> lk(gpu_mutex_);
+    std::vector<uz_features> views;
+    std::vector<std::vector<uint8_t> > valid;
+    std::vector<int32_t> counts;
+    std::vector<Resident> res;
+    std::vector<const SlamNode*> fresh;
+    size_t total = 0;
+    for (const SlamNode& n : nodes) {
+        if (n.id_.empty() || handles_.count(n.id_)) continue;
+        Resident r;
+        collectCams(n, r.cams);
+        total += r.cams.size();
+        res.push_back(r);
+        fresh.push_back(&n);
+    }
+    views.resize(total); valid.resize(total);
+    size_t k = 0;
+    for (Resident& r : res) {
+        r.rows.resize(r.cams.size());
+        for (size_t i = 0; i < r.cams.size(); ++i, ++k) {
+            feature_view(*r.cams[i], internFrame(r.cams[i]->sensor_frame_), valid[k], &views[k]);
+            r.rows[i] = r.cams[i]->features_.rows;
+        }
+        counts.push_back((int32_t)r.cams.size());
+    }
+    std::vector<int32_t> handles(res.size());
+    if (!res.empty() && uz_group_store_add_bulk(grp_, views.data(), counts.data(), (int32_t)res.size(), handles.data()) != UZ_OK) {
+        std::fprintf(stderr, "loadNodes: %s\n", lastError());
+        return false;
+    }
+    for (size_t i = 0; i < res.size(); ++i) { res[i].handle = handles[i]; handles_.emplace(fresh[i]->id_, res[i]); }
     return true;
 }
 
@@ -148,7 +223,7 @@ void GpuFeatureTransformationEstimator::forgetNode(const std::string& id) {
     std::lock_guard<std::mutex> lk(gpu_mutex_);
     auto it = handles_.find(id);
     if (it == handles_.end()) return;
-    uz_store_remove(ctx_, it->second.handle);
+    uz_group_store_remove(grp_, it->second.handle);
     handles_.erase(it);
 }
 
@@ -183,7 +258,7 @@ void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<
     std::vector<Resident*> rf(n), rt(n);
     for (size_t i = 0; i < n; ++i) {
         if (!ensureResident(pairs[i].first, &rf[i]) || !ensureResident(pairs[i].second, &rt[i])) {
-            std::fprintf(stderr, "estimateEdgeBatch: %s\n", uz_last_error(ctx_));
+            std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError());
             for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
             return;
         }
@@ -191,13 +266,13 @@ void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<
         ht[i] = rt[i]->handle;
     }
     std::vector<uz_edge_result> res(n);
-    const uz_status st = uz_estimate_edges(ctx_, hf.data(), ht.data(), (int32_t)n, res.data());
+    const uz_status st = uz_group_estimate_edges(grp_, hf.data(), ht.data(), (int32_t)n, res.data());
     for (size_t i = 0; i < n; ++i) {
         if (st == UZ_OK) { fillEdge(res[i], *rf[i], *rt[i], edges[i]); ok[i] = res[i].ok ? 1 : 0; }
         edges[i].id_from_ = pairs[i].first.id_;          // :168-169, set even on failure
         edges[i].id_to_ = pairs[i].second.id_;
     }
-    if (st != UZ_OK) std::fprintf(stderr, "uz_estimate_edges: %s\n", uz_last_error(ctx_));
+    if (st != UZ_OK) std::fprintf(stderr, "uz_group_estimate_edges: %s\n", lastError());
 }
 
 bool GpuFeatureTransformationEstimator::estimateEdgeImpl(SlamNode& from, SlamNode& to, SlamEdge& edge) {

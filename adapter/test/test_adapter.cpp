@@ -70,7 +70,14 @@ static void make_pair_nodes(int n, const Pose& G, SlamNode& a, SlamNode& b, cons
 int main() {
     std::mutex m;
     std::map<std::string, SlamEdge> got;          // keyed by id_from|id_to
-    GpuFeatureTransformationEstimator est([&](SlamEdge e) { std::lock_guard<std::mutex> lk(m); got[e.id_from_ + "|" + e.id_to_] = e; });
+    // UZ_TEST_DEVICES="0,1,...": the same class on several GPUs (uz_group); default: device 0
+    std::vector<int> devices;
+    if (const char* dv = std::getenv("UZ_TEST_DEVICES")) {
+        for (const char* p = dv; *p;) { devices.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    }
+    if (devices.empty()) devices.push_back(0);
+    GpuFeatureTransformationEstimator est([&](SlamEdge e) { std::lock_guard<std::mutex> lk(m); got[e.id_from_ + "|" + e.id_to_] = e; }, devices);
+    CHECK(est.devices() == (int)devices.size());
     transformation_estimation::FeatureLinkEstimationConfig cfg;
     cfg.ransac_threshold = 0.1; cfg.ransac_iteration = 100; cfg.ransac_break_percentage = 0.6;    // slam.yaml:35-36
     est.setConfig(cfg);
@@ -144,6 +151,67 @@ int main() {
     SlamEdge fe;
     CHECK(!est.estimateEdgeImpl(X, Y, fe) && fe.id_from_ == "x" && fe.id_to_ == "y");
 
+    // 2b. a node's sensor data changes under its id (late sensor arrival graph_slam_node.cpp:244, node merge :1010-1026): the
+    //     reference copies the node on every estimateEdge and matches the CURRENT data; a cached device copy must follow
+    {
+        got.clear();
+        SlamNode U, V, X2, Y2;
+        make_pair_nodes(200, G[2], U, V, "u_new", "v", "/cam0");
+        make_pair_nodes(100, G[3], X2, Y2, "x2", "y2", "/cam1");
+        SlamNode Uold;
+        Uold.id_ = "u";
+        Uold.addSensorData(X2.sensor_data_[0]);                      // only a /cam1 camera so far: nothing comparable with v
+        est.estimateEdge(Uold, V);
+        est.waitIdle();
+        CHECK(got["u|v"].matching_score_ == 0.);
+        const size_t resident = est.residentNodes();
+        SlamNode Unew = Uold;
+        Unew.addSensorData(U.sensor_data_[0]);                       // the /cam0 camera arrives under the same id
+        est.estimateEdge(Unew, V);
+        est.waitIdle();
+        CHECK(got["u|v"].matching_score_ >= 80);
+        CHECK(est.residentNodes() == resident);                      // re-uploaded under the same handle, not added
+        SlamEdge d;
+        CHECK(est.estimateEdgeDirect(Unew.sensor_data_, V.sensor_data_, d));
+        CHECK(d.matching_score_ == got["u|v"].matching_score_);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) CHECK(d.transform_(r, c) == got["u|v"].transform_(r, c));
+        CHECK(got["u|v"].sensor_from_ == "/cam0");
+        est.estimateEdge(Uold, V);                                   // and back: the old copy of the node is handed in again
+        est.waitIdle();
+        CHECK(got["u|v"].matching_score_ == 0.);
+    }
+
+    // 2c. removed nodes give their device memory back (graph.removeNode, graph_slam_node.cpp:1050 -> forgetNode); resume
+    //     re-adds every stored node in one bulk upload (GraphSlamNode::load, :875-888 -> loadNodes)
+    {
+        const int64_t bytes0 = est.storeBytes();
+        const size_t resident0 = est.residentNodes();
+        for (int k = 0; k < 12; ++k) {
+            SlamNode P1, P2;
+            SlamEdge e;
+            make_pair_nodes(150 + 10 * k, G[k % NP], P1, P2, "tmp_a" + std::to_string(k), "tmp_b" + std::to_string(k), "/cam0");
+            CHECK(est.estimateEdgeImpl(P1, P2, e) && e.matching_score_ >= 50);
+            est.forgetNode(P1.id_); est.forgetNode(P2.id_);
+        }
+        CHECK(est.storeBytes() == bytes0 && est.residentNodes() == resident0);
+        std::vector<SlamNode> stored;
+        for (int k = 0; k < 5; ++k) {
+            SlamNode P1, P2;
+            make_pair_nodes(120, G[k], P1, P2, "ld_a" + std::to_string(k), "ld_b" + std::to_string(k), "/cam0");
+            stored.push_back(P1); stored.push_back(P2);
+        }
+        CHECK(est.loadNodes(stored));
+        CHECK(est.residentNodes() == resident0 + 10);
+        SlamEdge e, d;
+        CHECK(est.estimateEdgeImpl(stored[4], stored[5], e));
+        CHECK(est.estimateEdgeDirect(stored[4].sensor_data_, stored[5].sensor_data_, d));
+        CHECK(e.matching_score_ == d.matching_score_ && e.matching_score_ >= 50);
+        CHECK(est.residentNodes() == resident0 + 10);
+        for (const SlamNode& n : stored) est.forgetNode(n.id_);
+        CHECK(est.storeBytes() == bytes0);
+    }
+
     // 3. estimateSVD / consensus3D, the TransformationFilter call shape (transformation_filter.cpp:272,275)
     Eigen::MatrixXd P(3, 80), Q(3, 80);
     for (int i = 0; i < 80; ++i) {
@@ -213,8 +281,9 @@ int main() {
             for (int c = 0; c < 4; ++c) CHECK(Ts[1](r, c) == T(r, c));
     }
 
+    const size_t before = est.residentNodes();
     est.forgetNode("a0");
-    CHECK(est.residentNodes() == (size_t)2 * NP + 13 + 2 - 1);          // + the 13 nodes of section 1b
-    std::printf("ADAPTER OK: %d queued pairs, callbacks delivered, direct/batch identical\n", NP);
+    CHECK(est.residentNodes() == before - 1);
+    std::printf("ADAPTER OK: %d queued pairs on %d device(s), callbacks delivered, direct/batch identical\n", NP, est.devices());
     return 0;
 }

@@ -105,6 +105,13 @@ uz_status uz_set_stream(uz_context* ctx, void* cuda_stream);
 uz_status uz_store_add(uz_context* ctx, const uz_features* cams, int32_t n_cams, int32_t* handle_out);
 uz_status uz_store_add_bulk(uz_context* ctx, const uz_features* cams, const int32_t* cams_per_keyframe,
                             int32_t n_keyframes, int32_t* handles_out);
+/* The node's sensor data changed under a fixed id (late sensor arrivals graph_slam_node.cpp:244, node merge :1010-1026; the
+ * reference copies the whole SlamNode on every estimateEdge, transformation_estimator.cpp:39, so it always sees the current
+ * data): new cameras under the SAME handle.  A place that was built from the old rows keeps reading them, as the reference's
+ * recogniser keeps the copy it was given. */
+uz_status uz_store_replace(uz_context* ctx, int32_t handle, const uz_features* cams, int32_t n_cams);
+/* Gives the keyframe's device memory back to the store (uz_store_bytes drops) and recycles the handle; a place and the
+ * checked_ pairs of that handle are forgotten with it. */
 uz_status uz_store_remove(uz_context* ctx, int32_t handle);
 uz_status uz_store_clear(uz_context* ctx);
 int32_t   uz_store_size(const uz_context* ctx);            /* live keyframes */
@@ -297,6 +304,7 @@ uz_status uz_group_set_params(uz_group* g, const uz_params* p);
 uz_status uz_group_store_add(uz_group* g, const uz_features* cams, int32_t n_cams, int32_t* handle_out);
 uz_status uz_group_store_add_bulk(uz_group* g, const uz_features* cams, const int32_t* cams_per_keyframe,
                                   int32_t n_keyframes, int32_t* handles_out);
+uz_status uz_group_store_replace(uz_group* g, int32_t handle, const uz_features* cams, int32_t n_cams);
 uz_status uz_group_store_remove(uz_group* g, int32_t handle);
 uz_status uz_group_store_clear(uz_group* g);
 int32_t   uz_group_store_size(const uz_group* g);

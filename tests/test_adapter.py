@@ -47,3 +47,16 @@ def test_adapter_end_to_end_on_gpu(built):
     out = subprocess.run([os.path.join(ADAPTER, "test_adapter")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ADAPTER OK" in out.stdout
+
+
+@pytest.mark.gpu
+def test_adapter_on_two_gpus(built):
+    """the same C++ class over a device list (uz_group behind the adapter): same checks, edges identical to one device"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _build()
+    env = dict(os.environ, UZ_TEST_DEVICES="0,1")
+    out = subprocess.run([os.path.join(ADAPTER, "test_adapter")], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ADAPTER OK" in out.stdout and "2 device(s)" in out.stdout

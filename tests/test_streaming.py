@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 
 def _estimator(**env):
     from uzliti_slam_b200 import EdgeEstimator
+    # the streaming solve and the segmented small launches are forms of the INTEGER-PIPE match kernels (a tensor-core match
+    # CTA fills its SM's shared memory, nothing runs beside it): tests of those forms switch the 256-bit rows back to them
+    env.setdefault("UZ_MATCH_MMA", 0)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
@@ -112,8 +115,9 @@ def test_streaming_survives_starvation():
         starved.close()
 
 
-@pytest.mark.parametrize("chunks,alt,stream", [(2, 1, 1), (5, 1, 1), (7, 0, 1), (5, 1, 0), (16, 1, 1)])
-def test_chunked_host_pipeline_equals_store_path(chunks, alt, stream):
+@pytest.mark.parametrize("chunks,alt,stream,mma", [(2, 1, 1, 0), (5, 1, 1, 0), (7, 0, 1, 0), (5, 1, 0, 0), (16, 1, 1, 0),
+                                                   (2, 1, 1, 1), (5, 1, 1, 1), (7, 0, 1, 1), (16, 1, 0, 1)])
+def test_chunked_host_pipeline_equals_store_path(chunks, alt, stream, mma):
     """uz_estimate_edges_host cuts a batch into chunks that upload, match and solve on their own, consecutive chunks on two
     alternating compute streams (UZ_ALT_CHUNKS=0: one stream).  A later chunk reuses cameras an earlier chunk uploaded
     (every keyframe appears in many pairs, pairs shuffled), ragged sizes, both descriptor widths, pageable host memory."""
@@ -123,7 +127,7 @@ def test_chunked_host_pipeline_equals_store_path(chunks, alt, stream):
     kfs = kn + kw
     pairs = np.concatenate([pn, pw + len(kn)])
     pairs = pairs[np.random.default_rng(3).permutation(len(pairs))]
-    est = _estimator(UZ_STREAM_SOLVE=stream, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_HOST_CHUNKS=chunks, UZ_ALT_CHUNKS=alt)
+    est = _estimator(UZ_STREAM_SOLVE=stream, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_HOST_CHUNKS=chunks, UZ_ALT_CHUNKS=alt, UZ_MATCH_MMA=mma)
     try:
         h = est.add_keyframes(kfs)
         a = est.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]])
@@ -145,8 +149,13 @@ def test_small_launch_forms_agree(oracle):
     pairs = np.concatenate([pairs[:40], pw + 36])
     fast = _estimator(UZ_STREAM_SOLVE=0)
     plain = _estimator(UZ_STREAM_SOLVE=0, UZ_SEGMENT=0, UZ_SOLVE_WIDE=0)
+    tensor = _estimator(UZ_MATCH_MMA=1)        # 256-bit rows on the tensor cores, 512-bit rows segmented beside them
     try:
         hf, hp = fast.add_keyframes(kfs), plain.add_keyframes(kfs)
+        ht = tensor.add_keyframes(kfs)
+        for n in (1, 7, len(pairs)):
+            assert tensor.estimateEdges(ht[pairs[:n, 0]], ht[pairs[:n, 1]]).tobytes() == \
+                plain.estimateEdges(hp[pairs[:n, 0]], hp[pairs[:n, 1]]).tobytes()
         for cross in (0, 1):
             fast.setConfig(cross_check=cross)
             plain.setConfig(cross_check=cross)
@@ -160,3 +169,4 @@ def test_small_launch_forms_agree(oracle):
     finally:
         fast.close()
         plain.close()
+        tensor.close()

@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTED_SYMBOLS = [
     "uz_create", "uz_destroy", "uz_last_error", "uz_default_params", "uz_set_params", "uz_get_params",
-    "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_remove", "uz_store_clear",
+    "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_replace", "uz_store_remove", "uz_store_clear",
     "uz_store_size", "uz_store_bytes", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers", "uz_set_stream_solve",
@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
     "uz_group_create", "uz_group_destroy", "uz_group_last_error", "uz_group_size", "uz_group_context", "uz_group_set_params",
-    "uz_group_store_add", "uz_group_store_add_bulk", "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size",
+    "uz_group_store_add", "uz_group_store_add_bulk", "uz_group_store_replace", "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size",
     "uz_group_estimate_edges", "uz_group_estimate_edges_device", "uz_group_set_gather", "uz_group_last_timing",
 ]
 
@@ -107,7 +107,7 @@ def load_library():
     lib.uz_default_params.restype = None
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)
-    for name in ("uz_create", "uz_set_params", "uz_get_params", "uz_set_stream", "uz_store_add", "uz_store_add_bulk",
+    for name in ("uz_create", "uz_set_params", "uz_get_params", "uz_set_stream", "uz_store_add", "uz_store_add_bulk", "uz_store_replace", "uz_group_store_replace",
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
@@ -222,6 +222,11 @@ class EdgeEstimator:
 
     def remove_keyframe(self, handle):
         self._check(self.lib.uz_store_remove(self.ctx, int(handle)))
+
+    def replace_keyframe(self, handle, cams):
+        keep = []
+        arr = features_array(cams, keep)
+        self._check(self.lib.uz_store_replace(self.ctx, int(handle), arr, len(cams)))
 
     def clear(self):
         self._check(self.lib.uz_store_clear(self.ctx))
@@ -616,6 +621,11 @@ class GroupEstimator:
 
     def remove_keyframe(self, handle):
         self._check(self.lib.uz_group_store_remove(self.grp, int(handle)))
+
+    def replace_keyframe(self, handle, cams):
+        keep = []
+        arr = features_array(cams, keep)
+        self._check(self.lib.uz_group_store_replace(self.grp, int(handle), arr, len(cams)))
 
     def clear(self):
         self._check(self.lib.uz_group_store_clear(self.grp))

@@ -38,6 +38,25 @@ void register_keyframes(uz_context* ctx, const std::vector<Cam>& up, const std::
     }
 }
 
+// uz_store_replace: the keyframe's new cameras are placed; its old range goes back to the arena unless a place still reads it
+void swap_keyframe(uz_context* ctx, int32_t handle, const std::vector<Cam>& up, const BlockRef& block) {
+    Keyframe& kf = ctx->kfs[handle];
+    const BlockRef old{kf.block, kf.block_bytes};
+    auto it = ctx->places.by_handle.find(handle);
+    if (it != ctx->places.by_handle.end() && ctx->places.places[it->second].ins_count > 0) ctx->places.retired[it->second].push_back(old);
+    else ctx->store_arena.free(old.p, old.bytes);
+    kf.cams = up;
+    kf.block = block.p; kf.block_bytes = block.bytes;
+    for (const Cam& c : kf.cams) ctx->store_max_n = std::max(ctx->store_max_n, c.n);
+}
+
+uz_status sync_compute_streams(uz_context* ctx) {
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->alt) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->alt));
+    if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
+    return UZ_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -215,6 +234,29 @@ uz_status uz_store_add_bulk(uz_context* ctx, const uz_features* cams, const int3
 uz_status uz_store_add(uz_context* ctx, const uz_features* cams, int32_t n_cams, int32_t* handle_out) {
     if (!handle_out) return UZ_ERR_INVALID;
     return uz_store_add_bulk(ctx, cams, &n_cams, 1, handle_out);
+}
+
+uz_status uz_store_replace(uz_context* ctx, int32_t handle, const uz_features* cams, int32_t n_cams) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (handle < 0 || handle >= (int32_t)ctx->kfs.size() || !ctx->kfs[handle].live) return fail(ctx, UZ_ERR_INVALID, "unknown keyframe handle");
+    if (n_cams < 0 || (n_cams > 0 && !cams)) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    std::vector<const uz_features*> feats((size_t)n_cams);
+    for (int i = 0; i < n_cams; ++i) feats[i] = cams + i;
+    if ((st = sync_compute_streams(ctx)) != UZ_OK) return st;
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
+    std::vector<Cam> up;
+    std::vector<BlockRef> blocks;
+    if ((st = place_cams(ctx, ctx->store_arena, feats, &n_cams, 1, up, blocks)) != UZ_OK) return st;
+    st = fill_cams(ctx, feats, up);
+    if (st == UZ_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "keyframe upload failed");
+    if (st != UZ_OK) {
+        cudaStreamSynchronize(ctx->stream); cudaGetLastError();
+        for (auto& b : blocks) ctx->store_arena.free(b.p, b.bytes);
+        return st;
+    }
+    swap_keyframe(ctx, handle, up, blocks[0]);
+    return UZ_OK;
 }
 
 uz_status uz_store_remove(uz_context* ctx, int32_t handle) {

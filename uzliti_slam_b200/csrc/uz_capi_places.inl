@@ -87,7 +87,7 @@ void places_release(uz_context* ctx) {
     ps.d_slots = nullptr; ps.d_nodes = nullptr; ps.d_stamps = nullptr; ps.d_live = nullptr;
     ps.n_slots = 0; ps.node_cap = 0; ps.n_nodes = 0; ps.place_cap = 0; ps.live_entries = 0;
     ps.d_cams.release(); ps.d_votes.release(); ps.d_out.release(); ps.d_out_votes.release();
-    ps.places.clear(); ps.by_handle.clear(); ps.checked.clear(); ps.inserted.clear();
+    ps.places.clear(); ps.by_handle.clear(); ps.checked.clear(); ps.inserted.clear(); ps.retired.clear();
 }
 
 uz_status places_reset(uz_context* ctx) {
@@ -96,7 +96,8 @@ uz_status places_reset(uz_context* ctx) {
     if (ps.d_slots) UZ_CUDA(ctx, cudaMemsetAsync(ps.d_slots, 0, (size_t)ps.n_slots * sizeof(PlaceSlot), ctx->stream));
     if (ps.d_live) UZ_CUDA(ctx, cudaMemsetAsync(ps.d_live, 0, ps.place_cap, ctx->stream));
     ps.n_nodes = 0; ps.live_entries = 0;
-    ps.places.clear(); ps.by_handle.clear(); ps.checked.clear(); ps.inserted.clear();
+    for (auto& kv : ps.retired) for (auto& b : kv.second) ctx->store_arena.free(b.p, b.bytes);
+    ps.places.clear(); ps.by_handle.clear(); ps.checked.clear(); ps.inserted.clear(); ps.retired.clear();
     return UZ_OK;
 }
 
@@ -111,6 +112,11 @@ void places_forget_handle(uz_context* ctx, int32_t handle) {
         PlaceInfo& pi = ps.places[place];
         pi.live = false;
         for (uint32_t k = 0; k < pi.ins_count; ++k) ps.inserted[pi.ins_begin + k].n = 0;
+        auto rt = ps.retired.find(place);
+        if (rt != ps.retired.end()) {
+            for (auto& b : rt->second) ctx->store_arena.free(b.p, b.bytes);
+            ps.retired.erase(rt);
+        }
         ps.by_handle.erase(it);
         if (ps.d_live) cudaMemsetAsync(ps.d_live + place, 0, 1, ctx->stream);
     }

@@ -85,7 +85,7 @@ void group_shard(int n_pairs, int world, int rank, int* lo, int* hi) {
 }
 
 // replica side of a store add: same layout as on the first device, primary arrays pulled from its HBM
-uz_status group_replicate(uz_context* ctx, const uz_context* src, const int32_t* handles, int32_t n_keyframes) {
+uz_status group_replicate(uz_context* ctx, const uz_context* src, const int32_t* handles, int32_t n_keyframes, bool replace = false) {
     uz_status st = check_ctx(ctx);
     if (st != UZ_OK) return st;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -126,6 +126,14 @@ uz_status group_replicate(uz_context* ctx, const uz_context* src, const int32_t*
         cudaStreamSynchronize(ctx->stream); cudaGetLastError();
         for (auto& b : blocks) ctx->store_arena.free(b.p, b.bytes);
         return st;
+    }
+    if (replace) {                    // uz_group_store_replace: one keyframe, the handle stays
+        if (handles[0] < 0 || handles[0] >= (int32_t)ctx->kfs.size() || !ctx->kfs[handles[0]].live) {
+            ctx->store_arena.free(blocks[0].p, blocks[0].bytes);
+            return fail(ctx, UZ_ERR_INVALID, "replicated store out of step: unknown keyframe handle");
+        }
+        swap_keyframe(ctx, handles[0], up, blocks[0]);
+        return UZ_OK;
     }
     std::vector<int32_t> got((size_t)n_keyframes);
     register_keyframes(ctx, up, blocks, counts.data(), n_keyframes, got.data());
@@ -229,6 +237,18 @@ uz_status uz_group_store_add_bulk(uz_group* g, const uz_features* cams, const in
 uz_status uz_group_store_add(uz_group* g, const uz_features* cams, int32_t n_cams, int32_t* handle_out) {
     if (!handle_out) return UZ_ERR_INVALID;
     return uz_group_store_add_bulk(g, cams, &n_cams, 1, handle_out);
+}
+
+uz_status uz_group_store_replace(uz_group* g, int32_t handle, const uz_features* cams, int32_t n_cams) {
+    if (!g) return UZ_ERR_INVALID;
+    uz_status st = uz_store_replace(g->ctx[0], handle, cams, n_cams);
+    if (st != UZ_OK) { g->err = g->ctx[0]->err; return st; }
+    if (g->ctx.size() == 1) return UZ_OK;
+    const uz_context* src = g->ctx[0];
+    return group_run(g, [g, src, handle](int r) {
+        uz_status s2 = sync_compute_streams(g->ctx[r]);
+        return s2 != UZ_OK ? s2 : group_replicate(g->ctx[r], src, &handle, 1, true);
+    }, 1);
 }
 
 uz_status uz_group_store_remove(uz_group* g, int32_t handle) {

@@ -169,6 +169,8 @@ struct Keyframe {
     size_t block_bytes = 0;
 };
 
+struct BlockRef { void* p; size_t bytes; };
+
 // one keyframe pair as two camera spans (store keyframes or transient uploads)
 struct PairRef { const Cam* from; int n_from; const Cam* to; int n_to; };
 
@@ -180,6 +182,9 @@ struct PlacesState {
     std::unordered_map<int32_t, int32_t> by_handle;     // live places only (place_id_map_.right)
     std::unordered_set<uint64_t> checked;               // checked_: (from handle << 32) | to handle
     std::vector<PlaceCam> inserted;                     // every camera ever inserted (relink on growth); n = 0: its keyframe left the store
+    std::unordered_map<int32_t, std::vector<BlockRef>> retired;   // place -> store ranges it still reads although the keyframe was
+                                                        // replaced since (uz_store_replace): the reference's recogniser keeps its own
+                                                        // copy of the descriptors it was given (lsh_set_recognizer.cpp:253-259)
     PlaceSlot* d_slots = nullptr; uint32_t n_slots = 0;
     PlaceNode* d_nodes = nullptr; size_t node_cap = 0, n_nodes = 0;
     size_t live_entries = 0;                            // upper bound of distinct keys (for the load factor)

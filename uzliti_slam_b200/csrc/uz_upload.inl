@@ -259,7 +259,6 @@ uz_status derive_layouts(uz_context* ctx, const Cam* cams, size_t n_cams) {
 
 // Lays cameras out on the device.  group_sizes == nullptr: ONE range for all cameras (transients; *blocks gets one
 // entry); otherwise one range per keyframe (group_sizes[k] cameras each), so that a keyframe can be freed on its own.
-struct BlockRef { void* p; size_t bytes; };
 uz_status place_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_features*>& feats, const int32_t* group_sizes,
                      size_t n_groups, std::vector<Cam>& out, std::vector<BlockRef>& blocks) {
     out.assign(feats.size(), Cam());
