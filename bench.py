@@ -82,12 +82,49 @@ def _cpu_worker(args):
     lo, hi = args
     from oracle import binding as O
     kfs, pairs = _G["kfs"], _G["pairs"]
-    cons = 0
+    recs = []
     for i in range(lo, hi):
         a, b = pairs[i]
         r = O.estimate_edge([kfs[a]], [kfs[b]], want_debug=False)
-        cons += r["consensus"]
-    return hi - lo, cons
+        recs.append((int(bool(r["ok"])), int(r["n_ratio_matches"]), int(r["n_matches"]), int(r["consensus"]),
+                     np.asarray(r["T"], np.float64).tobytes()))
+    return hi - lo, recs
+
+
+def reference_faithful_1thread(kfs, sample, budget_s=4.0):
+    """the reference's own execution model - ONE thread per estimator
+    (transformation_estimator.cpp:26), OpenCV's BFMatcher for the matching (the call of :38,:58), then ratio test, depth
+    filter, sort, gather and the oracle's RANSAC (PCL/Eigen restated), minus the reference's 1 ms sleep per pair."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    from oracle import binding as O
+    cv2.setNumThreads(1)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    done, t0, checked = 0, time.perf_counter(), 0
+    for a, b in sample:
+        F, T = kfs[a], kfs[b]
+        knn = bf.knnMatch(T["desc"], F["desc"], k=2)                                     # query = to, train = from (:58)
+        m = np.array([(x[0].queryIdx, x[0].trainIdx, x[0].distance, x[1].distance) for x in knn if len(x) == 2], np.float64)
+        keep = m[:, 2] < 0.99 * m[:, 3]                                                  # :65-71
+        q, t, d = m[keep, 0].astype(np.int64), m[keep, 1].astype(np.int64), m[keep, 2]
+        v = (T["valid"][q] != 0) & (F["valid"][t] != 0)                                  # :103-112
+        q, t, d = q[v], t[v], d[v]
+        o = np.lexsort((q, d))                                                           # :114 in the (distance, queryIdx) order
+        P, Q = T["pos"][q[o]], F["pos"][t[o]]                                            # :118-124
+        r = O.estimate_svd(P, Q, 0.1, 100, 0.6) if len(o) >= 3 else None                 # :130
+        if checked < 3 and r is not None:                                                # the composed pipeline IS the oracle's
+            full = O.estimate_edge([F], [T], want_debug=False)
+            assert full["consensus"] == r["consensus"] and full["n_matches"] == len(o)
+            checked += 1
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    secs = time.perf_counter() - t0
+    return dict(value=round(done / secs, 2), unit=UNIT, cores=1, pairs=done, seconds=round(secs, 2),
+                what="cv2.BFMatcher(NORM_HAMMING).knnMatch (OpenCV %s, 1 thread) + ratio/depth filter/sort + oracle RANSAC, one pair "
+                     "after the other (the reference's single estimator thread without its 1 ms sleep)" % cv2.__version__)
 
 
 def cpu_pass(kfs, pairs, pool, ncores, chunk=8):
@@ -119,10 +156,13 @@ def cpu_baseline(kfs, pairs, budget_s=12.0):
         _G["pairs"] = sample
         done, secs, pos = 0, 0.0, 0
         n = ncores * 32
+        records = []
         while secs < budget_s and pos < len(sample):
             jobs = [(i, min(i + 8, pos + n, len(sample))) for i in range(pos, min(pos + n, len(sample)), 8)]
             t0 = time.perf_counter()
-            done += sum(k for k, _ in pool.map(_cpu_worker, jobs))
+            for k, recs in pool.map(_cpu_worker, jobs):
+                done += k
+                records += recs
             secs += time.perf_counter() - t0
             pos += n
     finally:
@@ -142,17 +182,20 @@ def cpu_baseline(kfs, pairs, budget_s=12.0):
         extra["cv2_version"] = cv2.__version__
     except Exception:
         pass
-    return dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port",
-                sample=f"{done} pairs of the same workload (fixed random subsample of the 200000), oracle port "
-                       f"(oracle/uz_oracle.cpp, g++ -O3 x86-64-v3), one process per core, {secs:.1f}s", **extra)
+    faithful = reference_faithful_1thread(kfs, sample[:4000])
+    if faithful:
+        extra["reference_faithful_1thread"] = faithful
+    out = dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port",
+               sample=f"{done} pairs of the same workload (fixed random subsample of the 200000), oracle port "
+                      f"(oracle/uz_oracle.cpp, g++ -O3 x86-64-v3), one process per core, {secs:.1f}s", **extra)
+    return out, sample[:len(records)], records
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_kf = min(N_KEYFRAMES, 2000)      # the sample below never touches more keyframes than this
-    kfs, pairs, _ = build_map(n_kf)
+    kfs, pairs, _ = build_map(N_KEYFRAMES)      # the same 10000-keyframe map and pair list as the GPU arm
     ncores = len(os.sched_getaffinity(0))
     rng = np.random.default_rng(1)
     sample = pairs[rng.permutation(len(pairs))]
@@ -181,12 +224,12 @@ def run_reference(args):
         pool.close()
         pool.join()
     val = done / secs
-    sample_desc = (f"each step = {per_step} pairs of the C4 workload (fixed random subsample), oracle port on "
-                   f"{ncores} host processes")
+    sample_desc = (f"each step = {per_step} pairs of the C4 workload (fixed random subsample of the same 200000 pairs on the "
+                   f"same {N_KEYFRAMES}-keyframe map; per-pair work is identical), oracle port on {ncores} host processes")
     line = dict(impl="reference", metric=METRIC, value=round(val, 2), unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(secs / args.steps * 1e3, 3), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="u32", data="synthetic",
-                config=dict(workload=WORKLOAD, l2="n/a (CPU)", sample=sample_desc),
+                config=dict(workload=WORKLOAD, keyframes=N_KEYFRAMES, features=N_FEATURES, l2="n/a (CPU)", sample=sample_desc),
                 cpu_baseline=dict(value=round(val, 2), unit=UNIT, cores=ncores, kind="port", sample=sample_desc),
                 e2e=dict(value=round(val, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -477,6 +520,21 @@ def measure_other_configs(est, handles, kfs):
     return out
 
 
+def _new_estimator(device, **env):
+    """a context with UZ_* knobs set for its creation only (they are read by uz_create)"""
+    from uzliti_slam_b200 import EdgeEstimator
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return EdgeEstimator(device)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -504,10 +562,11 @@ def run_gpu(args):
     sel = np.arange(lo, hi) % total_pairs
     my_pairs = pairs[sel]
 
-    cpu = None
+    cpu, cpu_pairs, cpu_records = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(kfs, pairs, budget_s=args.cpu_seconds)
-        log(f"[bench] cpu_baseline: {cpu['value']} {UNIT} on {cpu['cores']} cores")
+        cpu, cpu_pairs, cpu_records = cpu_baseline(kfs, pairs, budget_s=args.cpu_seconds)
+        log(f"[bench] cpu_baseline: {cpu['value']} {UNIT} on {cpu['cores']} cores, "
+            f"single thread with cv2: {(cpu.get('reference_faithful_1thread') or {}).get('value')}")
 
     import torch
     import torch.distributed as dist
@@ -515,8 +574,10 @@ def run_gpu(args):
     from uzliti_slam_b200.binding import RESULT_DTYPE
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")        # host-side waits that must not park a kernel on the GPUs
 
     # pinned host copy of the map (the e2e leg DMAs straight out of it)
     t_desc = torch.from_numpy(desc).pin_memory()
@@ -532,7 +593,7 @@ def run_gpu(args):
     assert stream.cuda_stream != 0
     est.set_stream(stream.cuda_stream)
 
-    # integer-pipe peaks, measured here and now (roofline denominators)
+    # integer-pipe peaks, measured here and now (roofline denominators of the integer-pipe kernels)
     peaks = {name: est.microbench(op) for op, name in enumerate(["popc", "lop3", "imad", "vimnmx"])}
 
     t0 = time.time()
@@ -554,6 +615,24 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, steps, warm=1):
+        """device time (ms, CUDA events on the launching stream) of `steps` calls, max over ranks"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t = a.elapsed_time(b)
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt[0])
+        return t / steps
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -594,41 +673,162 @@ def run_gpu(args):
                   max_consensus_false=int(out["consensus"][~same].max()) if (~same).any() else 0,
                   mean_matches=float(out["n_matches"].mean()))
 
-    # ---- e2e: the same batch from pinned host buffers through uz_estimate_edges_host ------------------
-    prep = est.prepare_host_pairs([([pinned_kfs[a]], [pinned_kfs[b]]) for a, b in my_pairs])
+    # C4 parity beyond the test suite's sample: every pair the CPU baseline solved (its records are kept) is solved again on
+    # the GPU and compared field by field, transform bit for bit (untimed)
+    if cpu_records:
+        g = est.estimateEdges(handles[cpu_pairs[:, 0]], handles[cpu_pairs[:, 1]])
+        bad = 0
+        for r, (ok, nr, nm, cons, tb) in zip(g, cpu_records):
+            if (int(r["ok"]), int(r["n_ratio_matches"]), int(r["n_matches"]), int(r["consensus"])) != (ok, nr, nm, cons) or \
+                    (ok and r["T"].tobytes() != tb):
+                bad += 1
+        sanity["cpu_records_compared"] = len(cpu_records)
+        sanity["cpu_records_equal"] = bad == 0
+        sanity["cpu_records_differing"] = bad
+
+    # N GPUs == 1 GPU, byte for byte: the head of the gathered batch, recomputed by rank 0 alone
+    if world > 1:
+        n_chk = min(2500, pairs_per_gpu)
+        gathered = np.frombuffer(res_all.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+        if rank == 0:
+            last = world - 1
+            llo, _ = shard_bounds(world * pairs_per_gpu, world, last)
+            chk = np.concatenate([np.arange(0, n_chk), np.arange(llo, llo + n_chk)])      # rank 0's head and the last rank's head
+            gp = pairs[chk % total_pairs]
+            alone = est.estimateEdges(handles[gp[:, 0]], handles[gp[:, 1]])
+            sanity["gathered_equals_single_gpu"] = bool(alone.tobytes() == gathered[chk].tobytes())
+            sanity["gathered_pairs_compared"] = int(len(chk))
+
+    # ---- e2e: the same batch from HOST buffers through uz_estimate_edges_host ---------------------------
     uniq = np.unique(my_pairs)
     h2d = int(len(uniq)) * N_FEATURES * (32 + 24 + 1)
     d2h = pairs_per_gpu * rec
     e2e_steps = max(2, min(args.steps, 5))
-    est.estimateEdgesHostPrepared(prep)
-    est.estimateEdgesHostPrepared(prep)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        est.estimateEdgesHostPrepared(prep)       # blocks until the edge records are back in host memory
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    e2e_val = world * pairs_per_gpu * e2e_steps / e2e_s
-    assert prep["res"].tobytes() == out.tobytes(), "host path and store path disagree"
 
-    # ---- the two kernels each on their own (not timed, rank 0): in the timed region the solve grid runs BESIDE the
-    # match kernel (streaming form), so the live spans above overlap; this pass gives the un-shared durations
-    alone = None
-    if rank == 0:
-        est.set_stream_solve(0)
-        est.estimateEdgesDevice(hf, ht, res_local.data_ptr())      # (no collective here: rank 0 only)
-        est.enable_timers(True)
-        est.reset_timers()
+    def e2e_leg(source):
+        prep = est.prepare_host_pairs([([source[a]], [source[b]]) for a, b in my_pairs])
+        est.estimateEdgesHostPrepared(prep)
+        est.estimateEdgesHostPrepared(prep)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            est.estimateEdgesHostPrepared(prep)       # blocks until the edge records are back in host memory
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([secs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t[0])
+        assert prep["res"].tobytes() == out.tobytes(), "host path and store path disagree"
+        return world * pairs_per_gpu * e2e_steps / secs
+
+    e2e_val = e2e_leg(pinned_kfs)                      # pinned, device-mapped FeatureData: pulled by the gather kernel
+    e2e_pageable = e2e_leg(kfs) if not args.no_extras else None    # plain malloc'ed arrays (cv::Mat / Eigen): pinned ring first
+
+    # ---- the integer-pipe match kernel on the same batch (the north star's POPC design; UZ_MATCH_MMA=0) -------------
+    int_pipe = None
+    if rank == 0 and not args.no_extras:
+        ep = _new_estimator(local_rank, UZ_MATCH_MMA=0, UZ_STREAM_SOLVE=0)
+        ep.set_stream(stream.cuda_stream)
+        hp = ep.add_keyframes(pinned_kfs)
+        hpf, hpt = np.ascontiguousarray(hp[my_pairs[:, 0]]), np.ascontiguousarray(hp[my_pairs[:, 1]])
+        ep.estimateEdgesDevice(hpf, hpt, res_local.data_ptr())
+        ep.enable_timers(True)
+        ep.reset_timers()
         for _ in range(3):
-            est.estimateEdgesDevice(hf, ht, res_local.data_ptr())
-        ta = est.get_timers()
-        est.enable_timers(False)
-        est.set_stream_solve(STREAM_SOLVE)
-        alone = dict(knn2_ms=ta["match_ms"] / max(ta["match_launches"], 1), solve_ms=ta["solve_ms"] / max(ta["solve_launches"], 1))
+            ep.estimateEdgesDevice(hpf, hpt, res_local.data_ptr())
+        tp = ep.get_timers()
+        torch.cuda.synchronize()
+        same_records = np.frombuffer(res_local.cpu().numpy().tobytes(), dtype=RESULT_DTYPE).tobytes() == out.tobytes()
+        ep.close()
+        kms = tp["match_ms"] / max(tp["match_launches"], 1)
+        g = tp["compares"] / max(tp["match_launches"], 1) / (kms * 1e-3) * 1e-9
+        popc_limit, alu_limit = peaks["popc"] / 4.0, peaks["lop3"] / 14.25
+        int_pipe = dict(kernel="knn2_kernel<256,2> (4 POPC + 13 LOP3 + 4 IMAD + 1.25 VIMNMX.U16x2 per 256-bit compare), solve behind it",
+                        knn2_ms_per_launch=round(kms, 3), solve_ms_per_launch=round(tp["solve_ms"] / max(tp["solve_launches"], 1), 3),
+                        achieved_gcmp_per_s=round(g, 2), popc_ceiling_gcmp_per_s=round(popc_limit, 2),
+                        alu_ceiling_gcmp_per_s=round(alu_limit, 2), frac_of_popc_ceiling=round(g / min(popc_limit, alu_limit), 4),
+                        textbook_8popc_ceiling=round(peaks["popc"] / 8.0, 2), frac_of_textbook=round(g / (peaks["popc"] / 8.0), 4),
+                        pipe_peaks_gops={k: round(v, 1) for k, v in peaks.items()}, records_equal_tensor_core_path=bool(same_records))
+    barrier()
+
+    # ---- strong scaling and the latency-bound end (C3) at this N, through the same step (shards + all-gather) ----------
+    def sharded(total, steps):
+        lo2, hi2 = shard_bounds(total, world, rank)
+        idx = np.arange(lo2, hi2) % total_pairs
+        f2 = np.ascontiguousarray(handles[pairs[idx, 0]])
+        t2 = np.ascontiguousarray(handles[pairs[idx, 1]])
+        per = (total + world - 1) // world
+        loc = torch.empty(max(per, 1) * rec, dtype=torch.uint8, device=dev)
+        allb = torch.empty(world * max(per, 1) * rec, dtype=torch.uint8, device=dev) if world > 1 else loc
+
+        def fn():
+            est.estimateEdgesDevice(f2, t2, loc.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(allb, loc)
+        return timed(fn, steps)
+
+    scaling_extra = None
+    if not args.no_extras:
+        strong_ms = sharded(200000, 2)
+        c3_f = np.ascontiguousarray(handles[1:1001])
+        c3_t = np.full(1000, handles[0], dtype=handles.dtype)
+        lo3, hi3 = shard_bounds(1000, world, rank)
+        per3 = (1000 + world - 1) // world
+        loc3 = torch.empty(per3 * rec, dtype=torch.uint8, device=dev)
+        all3 = torch.empty(world * per3 * rec, dtype=torch.uint8, device=dev) if world > 1 else loc3
+
+        def c3():
+            est.estimateEdgesDevice(c3_f[lo3:hi3], c3_t[lo3:hi3], loc3.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(all3, loc3)
+        c3_ms = timed(c3, 20, warm=3)
+        scaling_extra = dict(
+            strong=dict(what="C4 as ONE job: 200000 pairs fixed, cut into %d contiguous shards, records all-gathered" % world,
+                        ms=round(strong_ms, 3), edges_per_s=round(200000 / (strong_ms * 1e-3), 1)),
+            c3=dict(what="C3: 1 query keyframe vs 1000 candidates (1000 pairs) cut into %d shards, records all-gathered: the "
+                         "latency-bound end of the curve" % world,
+                    ms=round(c3_ms, 4), edges_per_s=round(1000 / (c3_ms * 1e-3), 1)))
+
+    # ---- the same job through ONE process: uz_group over all N devices (rank 0 drives, the other ranks wait on the host) ---
+    group = None
+    if world > 1 and not args.no_extras:
+        if rank == 0:
+            from uzliti_slam_b200 import GroupEstimator
+            g = GroupEstimator(list(range(world)))
+            t0 = time.perf_counter()
+            hg = g.add_keyframes(pinned_kfs)
+            t_store = time.perf_counter() - t0
+            allp = pairs[np.arange(world * pairs_per_gpu) % total_pairs]
+            gf, gt = np.ascontiguousarray(hg[allp[:, 0]]), np.ascontiguousarray(hg[allp[:, 1]])
+            res_g = np.zeros(len(allp), RESULT_DTYPE)
+            modes = {}
+            for mode in (0, 1):
+                g.set_gather(mode)
+                g.estimateEdges(gf, gt, out=res_g)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    g.estimateEdges(gf, gt, out=res_g)
+                modes[mode] = (time.perf_counter() - t0) / 3
+            dev_ms = float(g.last_timing().max())
+            g.set_gather(0)
+            c3g = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                g.estimateEdges(c3_f.astype(np.int32) - handles[0] + hg[0], c3_t.astype(np.int32) - handles[0] + hg[0], out=res_g[:1000])
+                c3g.append(time.perf_counter() - t0)
+            n_chk = min(2500, pairs_per_gpu)
+            chk = np.concatenate([np.arange(0, n_chk), np.arange(len(allp) - n_chk, len(allp))])
+            g.estimateEdges(gf, gt, out=res_g)
+            alone = est.estimateEdges(handles[allp[chk, 0]], handles[allp[chk, 1]])
+            group = dict(what="uz_group_estimate_edges: ONE process, %d devices, replicated store pulled over NVLink, every device's "
+                              "solve kernel writes its records through a host-mapped pointer into one host array (no collective)" % world,
+                         pairs=int(len(allp)), edges_per_s=round(len(allp) / modes[0], 1), ms=round(modes[0] * 1e3, 3),
+                         device_ms_max=round(dev_ms, 3), edges_per_s_copy_per_device=round(len(allp) / modes[1], 1),
+                         store_replication_s=round(t_store, 3), c3_ms=round(float(np.median(c3g[5:])) * 1e3, 4),
+                         records_equal_single_gpu=bool(alone.tobytes() == res_g[chk].tobytes()), pairs_compared=int(len(chk)))
+            g.close()
+        dist.barrier(group=cpu_group)
     barrier()
 
     places = None
@@ -644,63 +844,68 @@ def run_gpu(args):
         knn_ms = tm["match_ms"] / max(tm["match_launches"], 1)
         solve_ms = tm["solve_ms"] / max(tm["solve_launches"], 1)
         gcmp = cmp_per_launch / (knn_ms * 1e-3) * 1e-9
-        # per compare the kernel issues 13 LOP3 + 1.25 VIMNMX(3).U16x2 on the ALU pipe, 4 POPC on the XU pipe and
-        # 4 IMAD on the FMA pipe (SASS of knn2_kernel<256,2,true,true>, profiles/); ncu charges a VIMNMX one ALU slot
-        alu_limit = peaks["lop3"] / 14.25
-        popc_limit = peaks["popc"] / 4.0
-        peak = min(alu_limit, popc_limit)
-        gcmp_alone = cmp_per_launch / (alone["knn2_ms"] * 1e-3) * 1e-9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "knn2_ncu_summary.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        alg_bytes = pairs_per_gpu * (2 * N_FEATURES * 32 + N_FEATURES * 8)
         mp = {}
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = mp.get("hbm_gbs", 6650.0)
+        # tensor roofline: a 256-bit compare is a K = 256 int8 dot product = 512 ops; the int8 peak is 2 x the bf16 peak (same
+        # tcgen05 data path at twice the K per instruction); MEASURED_PEAKS.json holds the measured bf16 figures
+        bf16 = mp.get("bf16_tflops_sustained", 1400.0)
+        bf16_burst = mp.get("bf16_tflops", 1590.0)
+        tops = gcmp * 512e-3
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "knn2_mma_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        alg_bytes = pairs_per_gpu * (2 * N_FEATURES * 256 + N_FEATURES * 8)
+        solve_bytes = int(N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
         line = dict(
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="u32", data="synthetic",
+            dtype="s8 (exact int8 dot products of +-1 bit vectors, int32 accumulate) + u32 keys", data="synthetic",
             config=dict(workload=WORKLOAD, keyframes=n_kf, features=N_FEATURES, pairs_per_gpu=pairs_per_gpu,
                         l2="inputs larger than L2: every step streams the 10000-keyframe store "
-                           f"({est.store_bytes() / 1e6:.0f} MB resident per GPU) through the match kernel; no flush",
+                           f"({est.store_bytes() / 1e6:.0f} MB resident per GPU, 2.6 GB of it the int8 operand layout) through the "
+                           "match kernel; no flush",
                         parallelism=f"pair-list sharding x{world}, store replicated, all-gather of 176 B edge records"),
             g_descriptor_cmp_per_s=round(world * cmp_per_launch / (ms / args.steps * 1e-3) * 1e-9, 2),
-            roofline=dict(bound="int", kernel="knn2_kernel", achieved=round(gcmp, 2), peak=round(peak, 2), unit="Gcmp/s",
-                          frac=round(gcmp / peak, 4), traffic=traffic,
-                          peak_source="min(ALU, POPC) limit of the kernel's own SASS mix (13 LOP3 + 1.25 VIMNMX.U16x2 on the "
-                                      "ALU pipe, 4 POPC on the XU pipe per 256-bit compare) from pipe rates microbenchmarked "
-                                      "in this run; POPC binds",
-                          live_span="knn2_ms_per_launch is the kernel's span in the timed region, where the persistent solve "
-                                    "grid shares the SMs with it (streaming form); 'alone' is the same launch with the "
-                                    "solve behind it (uz_set_stream_solve(0)), measured after the timed region",
-                          alone=dict(knn2_ms_per_launch=round(alone["knn2_ms"], 3), solve_ms_per_launch=round(alone["solve_ms"], 3),
-                                     achieved=round(gcmp_alone, 2), frac=round(gcmp_alone / peak, 4)),
-                          stream_solve_ctas_per_sm=STREAM_SOLVE,
-                          solve=dict(kernel="solve_kernel (one CTA per pair, alone)", bound="latency/issue, not HBM (reported as the north star asks)",
-                                     algorithmic_bytes_per_pair=int(N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec),
-                                     achieved_gbs=round(pairs_per_gpu * (N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
-                                                        / (alone["solve_ms"] * 1e-3) * 1e-9, 2),
-                                     frac_of_hbm=round(pairs_per_gpu * (N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
-                                                       / (alone["solve_ms"] * 1e-3) * 1e-9 / hbm_peak, 5)),
-                          pipe_peaks_gops={k: round(v, 1) for k, v in peaks.items()},
-                          textbook_peak_8popc=round(peaks["popc"] / 8.0, 2), frac_of_textbook=round(gcmp / (peaks["popc"] / 8.0), 4),
-                          knn2_ms_per_launch=round(knn_ms, 3), solve_ms_per_launch=round(solve_ms, 3),
+            roofline=dict(bound="tensor", kernel="knn2_mma_kernel (tcgen05.mma kind::i8, 128x256x32, TMEM accumulators)",
+                          achieved=round(tops, 1), peak=round(2 * bf16, 1), unit="TFLOP/s", frac=round(tops / (2 * bf16), 4),
+                          ops="integer: one int8 multiply-add = 2 ops; a 256-bit compare = 512 ops",
+                          traffic=traffic,
+                          peak_source=("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (the kernel runs inside a seconds-long step; "
+                                       "int8 is the bf16 data path at twice the K per instruction)" if mp else "fallback 2 x 1400 TF/s"),
+                          frac_of_burst_peak=round(tops / (2 * bf16_burst), 4), burst_peak=round(2 * bf16_burst, 1),
+                          frac_of_nominal_4500=round(tops / 4500.0, 4),
+                          achieved_gcmp_per_s=round(gcmp, 2), knn2_ms_per_launch=round(knn_ms, 3), solve_ms_per_launch=round(solve_ms, 3),
                           compares_per_launch=int(cmp_per_launch),
+                          padding="1000 x 1000 matchings run as 4 items x (2 x 128) query rows x 4 x 256 train rows: 95.4 % of the "
+                                  "issued MMA work is real compares",
                           hbm=dict(achieved_gbs=round(alg_bytes / (knn_ms * 1e-3) * 1e-9, 2), peak_gbs=hbm_peak,
                                    frac=round(alg_bytes / (knn_ms * 1e-3) * 1e-9 / hbm_peak, 5),
-                                   peak_source="MEASURED_PEAKS.json" if mp else "fallback")),
+                                   algorithmic_bytes_per_launch=int(alg_bytes),
+                                   peak_source="MEASURED_PEAKS.json" if mp else "fallback"),
+                          solve=dict(kernel="solve_kernel (one CTA per pair, behind the match kernel)",
+                                     bound="latency/issue, not HBM (reported as the north star asks)",
+                                     algorithmic_bytes_per_pair=solve_bytes,
+                                     achieved_gbs=round(pairs_per_gpu * solve_bytes / (solve_ms * 1e-3) * 1e-9, 2),
+                                     frac_of_hbm=round(pairs_per_gpu * solve_bytes / (solve_ms * 1e-3) * 1e-9 / hbm_peak, 5)),
+                          int_pipe_kernel=int_pipe),
             cpu_baseline=cpu,
             e2e=dict(value=round(e2e_val, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                     api="uz_estimate_edges_host (pinned host FeatureData in, host edge records out)"),
-            gpu_launches=launches, clocks=clocks, sanity=sanity, candidate_generation=places, other_configs=others)
+                     api="uz_estimate_edges_host (host FeatureData in, host edge records out)",
+                     pinned=round(e2e_val, 1), pageable=round(e2e_pageable, 1) if e2e_pageable else None,
+                     note="value = pinned, device-mapped host buffers (pulled over PCIe by the gather kernel); pageable = plain "
+                          "malloc'ed arrays as cv::Mat / Eigen hold them (host threads pack them into a pinned ring first)"
+                          + ("; at N > 1 every rank times its own host round trip (max over ranks), records stay in the rank's "
+                             "host memory - the one-array form is `group`" if world > 1 else "")),
+            gpu_launches=launches, clocks=clocks, sanity=sanity, scaling_extra=scaling_extra, group=group,
+            candidate_generation=places, other_configs=others)
         emit(line)
     est.close()
     if world > 1:
