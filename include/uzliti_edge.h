@@ -144,6 +144,30 @@ uz_status uz_store_add_rgbd(uz_context* ctx, const uint8_t* descriptors, int32_t
  * (graph_slam_common/src/rosbag_storage.cpp:135-211).  Descriptor floats are narrowed to bytes as the reference does. */
 uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* features_blob, size_t blob_bytes, int32_t feature_type,
                             int32_t sensor_frame, int32_t* handle_out);
+/* Resume (GraphSlamNode::load, graph_slam_node.cpp:875-888: RosbagStorage::loadGraph reads every stored Node,
+ * rosbag_storage.cpp:135-211, and every node is re-added): many serialised Feature[] fields in ONE decode launch.  blobs are
+ * concatenated per keyframe (cams_per_keyframe[k] of them); each blob is what uz_store_add_wire takes. */
+uz_status uz_store_add_wire_bulk(uz_context* ctx, const uint8_t* const* blobs, const size_t* blob_bytes,
+                                 const int32_t* feature_types, const int32_t* sensor_frames,
+                                 const int32_t* cams_per_keyframe, int32_t n_keyframes, int32_t* handles_out);
+/* Where a sensor's fields sit inside a ROS1-serialised message (byte offsets from the start of the message walked). */
+typedef struct {
+    int32_t sensor_type;           /* SensorData.msg: 1 = SENSOR_TYPE_FEATURE                                        */
+    int32_t descriptor_type;       /* Features.msg descriptor_type (feature_type_)                                   */
+    int32_t n_features;
+    int32_t sensor_frame_len;
+    size_t  sensor_frame_offset;   /* characters of SensorData.sensor_frame (not NUL terminated)                     */
+    size_t  displacement_offset;   /* geometry_msgs/Pose: 7 float64 (position xyz, orientation xyzw)                 */
+    size_t  features_offset;       /* the Feature[] field: uint32 count + elements = the blob of uz_store_add_wire*  */
+    size_t  features_bytes;
+} uz_wire_sensor;
+/* Host-only walks (no device, no context): one graph_slam_msgs/SensorData message (what /sensor_data carries,
+ * graph_slam_msgs/msg/SensorData.msg) ... */
+uz_status uz_wire_walk_sensor_data(const uint8_t* msg, size_t bytes, uz_wire_sensor* sensor_out, size_t* consumed_out);
+/* ... and one graph_slam_msgs/Node message (what a RosbagStorage node record holds, graph_slam_msgs/msg/Node.msg): every
+ * SensorData of its SensorDataArray in order (n_sensors_out may exceed capacity), and where the node's id string sits. */
+uz_status uz_wire_walk_node(const uint8_t* msg, size_t bytes, uz_wire_sensor* sensors_out, int32_t capacity,
+                            int32_t* n_sensors_out, size_t* id_offset_out, int32_t* id_len_out);
 /* The decode alone, results back on the host (uv_out optional: n x 2 int32).  The descriptor width is what the
  * elements carry (32 or 64, all equal): descriptors_out needs capacity x UZ_MAX_DESC_BYTES bytes and receives n packed
  * rows of *desc_bytes_out bytes. */

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
     "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_launch_count", "uz_enable_timers", "uz_reset_timers", "uz_set_stream_solve",
     "uz_get_timers", "uz_microbench", "uz_version",
-    "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
+    "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_store_add_wire_bulk", "uz_wire_walk_sensor_data", "uz_wire_walk_node", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
     "uz_estimate_svd_batch", "uz_default_gate_params", "uz_gate_edges", "uz_gate_edges_device",
     "uz_default_place_params", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
@@ -52,6 +52,35 @@ class GateParams(C.Structure):
 class PlaceParams(C.Structure):
     _fields_ = [("T", C.c_double), ("k_nearest_neighbors", C.c_int32), ("min_rows", C.c_int32),
                 ("min_key_bits", C.c_int32), ("min_gap_ns", C.c_int64)]
+
+
+class WireSensor(C.Structure):
+    _fields_ = [("sensor_type", C.c_int32), ("descriptor_type", C.c_int32), ("n_features", C.c_int32),
+                ("sensor_frame_len", C.c_int32), ("sensor_frame_offset", C.c_size_t), ("displacement_offset", C.c_size_t),
+                ("features_offset", C.c_size_t), ("features_bytes", C.c_size_t)]
+
+
+def wire_walk_node(msg, capacity=16):
+    """where the FEATURE sensors sit inside a ROS1-serialised graph_slam_msgs/Node (host only, no device)"""
+    lib = load_library()
+    b = np.frombuffer(bytes(msg), np.uint8)
+    out = (WireSensor * capacity)()
+    n, ido, idl = C.c_int32(), C.c_size_t(), C.c_int32()
+    st = lib.uz_wire_walk_node(_p(b), C.c_size_t(len(b)), out, capacity, C.byref(n), C.byref(ido), C.byref(idl))
+    if st != 0:
+        raise UzError(f"uz_wire_walk_node: malformed message (status {st})")
+    node_id = bytes(b[ido.value:ido.value + idl.value]).decode()
+    return node_id, [out[i] for i in range(min(n.value, capacity))]
+
+
+def wire_walk_sensor_data(msg):
+    lib = load_library()
+    b = np.frombuffer(bytes(msg), np.uint8)
+    s, used = WireSensor(), C.c_size_t()
+    st = lib.uz_wire_walk_sensor_data(_p(b), C.c_size_t(len(b)), C.byref(s), C.byref(used))
+    if st != 0:
+        raise UzError(f"uz_wire_walk_sensor_data: malformed message (status {st})")
+    return s, used.value
 
 
 class Features(C.Structure):
@@ -111,7 +140,8 @@ def load_library():
                  "uz_store_remove", "uz_store_clear", "uz_match_knn2", "uz_estimate_svd", "uz_consensus3d",
                  "uz_sample_list", "uz_estimate_edges", "uz_estimate_edges_device", "uz_estimate_edges_host",
                  "uz_set_debug", "uz_debug_pair", "uz_debug_counts", "uz_debug_phases", "uz_enable_timers", "uz_reset_timers", "uz_get_timers",
-                 "uz_microbench", "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
+                 "uz_store_add_wire_bulk", "uz_wire_walk_sensor_data", "uz_wire_walk_node",
+                 "uz_microbench", "uz_backproject", "uz_store_add_rgbd", "uz_store_add_wire", "uz_store_add_wire_bulk", "uz_wire_walk_sensor_data", "uz_wire_walk_node", "uz_wire_decode", "uz_wire_encode", "uz_store_read",
                  "uz_estimate_svd_batch", "uz_gate_edges", "uz_gate_edges_device", "uz_places_set_params", "uz_places_clear", "uz_places_search_and_add", "uz_places_add",
                  "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing"):
         getattr(lib, name).restype = C.c_int
@@ -276,6 +306,24 @@ class EdgeEstimator:
         self._check(self.lib.uz_store_add_wire(self.ctx, _p(b), C.c_size_t(len(b)), int(feature_type), int(sensor_frame),
                                                C.byref(h)))
         return h.value
+
+    def add_keyframes_wire(self, keyframes):
+        """keyframes: list of lists of (blob, feature_type, sensor_frame) - one decode launch for all (resume path)"""
+        blobs, types, frames, counts, keep = [], [], [], [], []
+        for kf in keyframes:
+            counts.append(len(kf))
+            for blob, ft, fr in kf:
+                b = blob if isinstance(blob, np.ndarray) else np.frombuffer(bytes(blob), np.uint8)
+                keep.append(b)
+                blobs.append(b.ctypes.data)
+                types.append(int(ft)); frames.append(int(fr))
+        n = len(blobs)
+        ptrs = (C.c_void_p * max(n, 1))(*blobs)
+        sizes = (C.c_size_t * max(n, 1))(*[len(b) for b in keep])
+        types = np.array(types, np.int32); frames = np.array(frames, np.int32); counts = np.array(counts, np.int32)
+        handles = np.empty(len(keyframes), np.int32)
+        self._check(self.lib.uz_store_add_wire_bulk(self.ctx, ptrs, sizes, _p(types), _p(frames), _p(counts), len(keyframes), _p(handles)))
+        return handles
 
     def wire_decode(self, blob, capacity=4096):
         b = np.frombuffer(bytes(blob), np.uint8)

@@ -292,9 +292,12 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
 
     bp.with_solve = d_results != nullptr;
     bp.cross = prm.cross_check != 0 && bp.with_solve;
+    g_stage.start();
     uz_status st = enumerate_tasks(ctx, pairs, sl, bp);
     if (st != UZ_OK) return st;
+    g_stage.stop(4);
     choose_shapes(ctx, bp);
+    g_stage.stop(5);
     MatchTask* tasks = bp.tasks;
     const std::vector<uint8_t>& task_wide = ctx->task_wide;
     const size_t n_tasks = bp.n_tasks, n_fwd = bp.n_fwd;
@@ -374,6 +377,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     }
     int4* h_merges = (int4*)(h_tiles + std::max<size_t>(tiles_bytes, 16));
     if (!merges.empty()) memcpy(h_merges, merges.data(), merges.size() * sizeof(int4));
+    g_stage.stop(6);
 
     // (4) device buffers; small launches: the three tables travel as ONE copy (a copy command costs more than its few KB)
     const size_t all_tiles_bytes = std::max<size_t>(tiles_bytes, 16) + merges.size() * sizeof(int4);
@@ -406,6 +410,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_tiles.p, h_tiles, all_tiles_bytes, cudaMemcpyHostToDevice, ctx->stream));
         UZ_CUDA(ctx, cudaMemcpyAsync(sl.d_pair_tasks.p, bp.pair_tasks, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     }
+    g_stage.stop(7);
     bp.d_tiles_narrow = t_tiles;
     bp.d_tiles_wide = t_tiles + narrow_bytes;
     bp.d_merges = (const int4*)(t_tiles + std::max<size_t>(tiles_bytes, 16));
@@ -544,6 +549,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         }
     }
     if (ctx->timers) ctx->pending.push_back(tm);
+    g_stage.stop(8);
     UZ_CUDA(ctx, cudaEventRecord(sl.done, results_on));     // the slot's tables and keys are free once the solve is through
     sl.used = true;
     if (result_stream) *result_stream = results_on;

@@ -128,6 +128,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (hc) ctx->host_chunks = atoi(hc);
         const char* mm = getenv("UZ_MATCH_MMA");
         if (mm) ctx->match_mma = atoi(mm) != 0;
+        const char* stt = getenv("UZ_STAGE_THREADS");
+        if (stt && atoi(stt) >= 1 && atoi(stt) <= 64) ctx->stage_threads = atoi(stt);
         const char* rm = getenv("UZ_RING_MB");
         if (rm && atoi(rm) >= 1 && atoi(rm) <= 4096) ctx->ring_half = (size_t)atoi(rm) << 20;
     }
@@ -159,6 +161,7 @@ void uz_destroy(uz_context* ctx) {
         if (sl.done) cudaEventDestroy(sl.done);
     }
     for (auto& t : ctx->samples) t.d.release();
+    if (ctx->pool) { ctx->pool->stop(); delete ctx->pool; ctx->pool = nullptr; }
     ctx->ring.release();
     for (int i = 0; i < 2; ++i) if (ctx->ring_free[i]) cudaEventDestroy(ctx->ring_free[i]);
     ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release(); ctx->h_results.release();
@@ -641,18 +644,18 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // stream behind the upload's event, queue its records' way home - so the GPU starts after the host has looked at
     // the FIRST chunk only, uploads of later chunks run beside the matching of earlier ones, and records are copied
     // out to the caller while later chunks still compute.  What stays exposed is the first chunk's upload.
-    // Chunk ends as fractions of the batch: equal chunks of about 768 pairs, between 4 and 40 of them.  Consecutive chunks
-    // compute on two alternating streams (below), so a chunk boundary costs next to nothing and small chunks win: the
-    // exposed first upload shrinks and records go home earlier, until the chunks get too small for the persistent solve
-    // grid.  Measured on C4 (25 000 pairs, store-resident 937 k edges/s): 8 chunks 894 k, 16: 916 k, 32: 926 k, 48: 930 k,
-    // 64: 903 k, 80: 839 k; on one stream the same 9-chunk split that gave 869 k gives 909 k on two.
+    // Chunk ends as fractions of the batch: equal chunks of about 1600 pairs, between 4 and 40 of them.  Consecutive chunks
+    // compute on two alternating streams (below), so a chunk boundary costs little; small chunks shrink the exposed first
+    // upload and send records home earlier, large ones amortise the launches of a chunk.  Measured on C4 (25 000 pairs) with
+    // the tensor-core match kernel (store-resident 3.28 M edges/s): 8 chunks 2.49 M, 16: 2.52 M, 32: 2.37 M, 64: 2.12 M
+    // (with the integer-pipe kernels of round 1, 768-pair chunks were best: 926-930 k against 937 k store-resident).
     // UZ_HOST_CHUNKS = k > 0 forces k equal parts.
     std::vector<double> fracs;
     int want_chunks = 1;
     if (ctx->debug) want_chunks = 1;                            // the parity taps describe ONE launch pair
     else if (ctx->host_chunks > 0) want_chunks = std::min(ctx->host_chunks, n_pairs);
     else if (n_pairs < 2048) want_chunks = 1;
-    else want_chunks = std::min(40, std::max(4, n_pairs / 768));
+    else want_chunks = std::min(40, std::max(4, n_pairs / 1600));
     for (int c = 1; c <= want_chunks; ++c) fracs.push_back((double)c / want_chunks);
     const int n_chunks = (int)fracs.size();
     std::vector<size_t> chunk_pair_end((size_t)n_chunks);
@@ -725,13 +728,15 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         const size_t p0 = chunk_begin(c), p1 = chunk_pair_end[c];
         if (p1 <= p0) continue;
         // (1) intern the chunk's cameras
+        g_stage.start();
         const size_t u0 = uniq.size(), cf0 = cf, ct0 = ct;
         from_u.clear(); to_u.clear();
         for (size_t i = p0; i < p1; ++i) {
             for (int k = 0; k < n_from[i]; ++k, ++cf) from_u.push_back(intern(from_cams + cf));
             for (int k = 0; k < n_to[i]; ++k, ++ct) to_u.push_back(intern(to_cams + ct));
         }
-        // (2) upload (+ CSA pass) of the cameras nobody before this chunk needed, on the side stream
+        g_stage.stop(0);
+        // (2) upload (+ layout pass) of the cameras nobody before this chunk needed, on the side stream
         cudaEvent_t ready = nullptr;
         if (uniq.size() > u0) {
             std::vector<const uz_features*> fresh(uniq.begin() + u0, uniq.end());
@@ -749,6 +754,7 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
             up.insert(up.end(), got.begin(), got.end());
         }
         // (3) match + solve behind the upload, records home behind the solve
+        g_stage.start();
         fcams.resize(cf - cf0); tcams.resize(ct - ct0);
         for (size_t i = 0; i < fcams.size(); ++i) fcams[i] = up[from_u[i]];
         for (size_t i = 0; i < tcams.size(); ++i) tcams[i] = up[to_u[i]];
@@ -762,6 +768,7 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         }
         // odd chunks compute on the second stream: two match kernels of one stream run strictly one after the other, and
         // every such boundary leaves the SMs partly idle while the last CTAs of the earlier kernel finish
+        g_stage.stop(3);
         if (alternate && (c & 1)) ctx->stream = ctx->alt;
         // the upload stream is in order, so the newest upload event covers every camera uploaded so far; a chunk on the
         // other compute stream needs it even when it brought no camera of its own
@@ -777,9 +784,11 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
                                            cudaMemcpyDeviceToHost, rs) != cudaSuccess)
             st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
+        g_stage.start();
         if (st == UZ_OK) { home[c] = ctx->get_event(); cudaEventRecord(home[c], rs); }
         if (c == 0) tr.lap("first chunk enqueued");
         drain(c, false);
+        g_stage.stop(9);
     }
     tr.lap("all chunks enqueued");
     drain(n_chunks, true);
@@ -797,6 +806,11 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     if (ctx->alt) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->alt));
     if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
     tr.lap("wait GPU + records out");
+    {
+        static const char* const names[10] = {"intern cameras", "place cameras", "copy lists + gather + derive", "pair views", "enumerate tasks",
+                                              "choose shapes", "keys + tiles", "table copies", "launches", "records home + drain"};
+        g_stage.report(names, 10);
+    }
     return UZ_OK;
 }
 

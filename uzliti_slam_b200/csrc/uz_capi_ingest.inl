@@ -208,6 +208,157 @@ uz_status uz_store_add_wire(uz_context* ctx, const uint8_t* blob, size_t blob_by
     return UZ_OK;
 }
 
+// ---- resume: many serialised keyframes at once (second half) ------------------------------------------
+uz_status uz_store_add_wire_bulk(uz_context* ctx, const uint8_t* const* blobs, const size_t* blob_bytes, const int32_t* feature_types,
+                                 const int32_t* sensor_frames, const int32_t* cams_per_keyframe, int32_t n_keyframes,
+                                 int32_t* handles_out) {
+    uz_status st = check_ctx(ctx);
+    if (st != UZ_OK) return st;
+    if (n_keyframes < 0 || (n_keyframes > 0 && (!cams_per_keyframe || !handles_out))) return fail(ctx, UZ_ERR_INVALID, "bad arguments");
+    size_t total = 0;
+    for (int i = 0; i < n_keyframes; ++i) {
+        if (cams_per_keyframe[i] < 0) return fail(ctx, UZ_ERR_INVALID, "negative camera count");
+        total += (size_t)cams_per_keyframe[i];
+    }
+    if (total > 0 && (!blobs || !blob_bytes || !feature_types || !sensor_frames)) return fail(ctx, UZ_ERR_INVALID, "null blob arrays");
+    if (n_keyframes == 0) return UZ_OK;
+    // pseudo feature views: only sizes and tags matter for the placement
+    std::vector<uz_features> views(total);
+    std::vector<const uz_features*> feats(total);
+    std::vector<int32_t> ns(total), cols(total);
+    size_t blob_total = 0;
+    static const uint8_t kDummy = 0;
+    for (size_t i = 0; i < total; ++i) {
+        if ((st = wire_prepare(ctx, blobs[i], blob_bytes[i], &ns[i], &cols[i])) != UZ_OK) return st;
+        memset(&views[i], 0, sizeof(uz_features));
+        views[i].n = ns[i]; views[i].desc_bytes = cols[i]; views[i].desc_stride = cols[i];
+        views[i].feature_type = feature_types[i]; views[i].sensor_frame = sensor_frames[i];
+        views[i].descriptors = &kDummy; views[i].positions = (const double*)&kDummy; views[i].valid_3d = &kDummy;
+        feats[i] = &views[i];
+        blob_total += ((size_t)ns[i] * wire_elem_bytes(cols[i]) + 255) & ~(size_t)255;
+    }
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->transient.reset();
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
+    std::vector<Cam> up;
+    std::vector<BlockRef> blocks;
+    if ((st = place_cams(ctx, ctx->store_arena, feats, cams_per_keyframe, (size_t)n_keyframes, up, blocks)) != UZ_OK) return st;
+    auto undo = [&]() { cudaStreamSynchronize(ctx->stream); cudaGetLastError(); for (auto& b : blocks) ctx->store_arena.free(b.p, b.bytes); };
+    // the serialised bodies travel like any other host buffers (pinned sources pulled directly, pageable ones through the ring)
+    uint8_t* d_blobs = (uint8_t*)ctx->transient.alloc(std::max<size_t>(blob_total, 1));
+    int* dstat = (int*)ctx->transient.alloc(4);
+    if (!d_blobs || !dstat) { undo(); return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed"); }
+    std::vector<CopyItem> items;
+    std::vector<WireJob> jobs;
+    size_t at = 0;
+    int max_n = 1;
+    for (size_t i = 0; i < total; ++i) {
+        if (ns[i] == 0) continue;
+        const size_t body = (size_t)ns[i] * wire_elem_bytes(cols[i]);
+        items.push_back(CopyItem{blobs[i] + 4, d_blobs + at, body, 0, 0, 0});
+        jobs.push_back(WireJob{d_blobs + at, (uint8_t*)up[i].raw, up[i].pos, up[i].valid, ns[i], cols[i]});
+        max_n = std::max(max_n, ns[i]);
+        at += (body + 255) & ~(size_t)255;
+    }
+    st = flush_copies(ctx, items);
+    if (st == UZ_OK && cudaMemsetAsync(dstat, 0, 4, ctx->stream) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "cudaMemsetAsync failed");
+    for (size_t j0 = 0; j0 < jobs.size() && st == UZ_OK; j0 += 32768) {
+        const size_t cnt = std::min<size_t>(32768, jobs.size() - j0);
+        WireJob* h = (WireJob*)ctx->h_chunks.alloc(cnt * sizeof(WireJob));
+        WireJob* d = (WireJob*)ctx->d_chunks.alloc(cnt * sizeof(WireJob));
+        if (!h || !d) { st = fail(ctx, UZ_ERR_NOMEM, "wire job table allocation failed"); break; }
+        memcpy(h, jobs.data() + j0, cnt * sizeof(WireJob));
+        if (cudaMemcpyAsync(d, h, cnt * sizeof(WireJob), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync failed"); break; }
+        wire_decode_bulk_kernel<<<dim3((unsigned)std::min((max_n * 32 + 255) / 256, 32), (unsigned)cnt, 1), 256, 0, ctx->stream>>>(d, dstat);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "wire_decode_bulk_kernel launch failed");
+    }
+    if (st == UZ_OK) st = derive_layouts(ctx, up.data(), up.size());
+    int stat = 0;
+    if (st == UZ_OK && cudaMemcpyAsync(&stat, dstat, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync failed");
+    if (st == UZ_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, UZ_ERR_CUDA, "bulk wire ingest failed");
+    if (st == UZ_OK && stat) st = fail(ctx, UZ_ERR_UNSUPPORTED, "an element's descriptor length differs from the first element's");
+    if (st != UZ_OK) { undo(); return st; }
+    register_keyframes(ctx, up, blocks, cams_per_keyframe, n_keyframes, handles_out);
+    return UZ_OK;
+}
+
+// ---- envelope walk (host, no device): where the Feature[] fields sit inside serialised messages -------------------------
+namespace {
+struct WireCursor {
+    const uint8_t* p; size_t n, at; bool ok;
+    bool need(size_t k) { if (!ok || k > n - at) { ok = false; return false; } return true; }
+    uint32_t u32() { if (!need(4)) return 0; uint32_t v; memcpy(&v, p + at, 4); at += 4; return v; }
+    void skip(size_t k) { if (need(k)) at += k; }
+    void str(size_t* off, int32_t* len) { const uint32_t l = u32(); if (off) *off = at; if (len) *len = (int32_t)l; skip(l); }
+    void header() { skip(4 + 8); str(nullptr, nullptr); }                       // std_msgs/Header: seq, stamp, frame_id
+    void arr(size_t elem) { const uint32_t c = u32(); if (ok && (size_t)c > (n - at) / (elem ? elem : 1)) { ok = false; return; } skip((size_t)c * elem); }
+    void image() { header(); skip(4 + 4); str(nullptr, nullptr); skip(1 + 4); arr(1); }   // sensor_msgs/Image
+};
+
+// one graph_slam_msgs/SensorData (SensorData.msg) starting at the cursor
+bool walk_sensor_data(WireCursor& c, uz_wire_sensor* out) {
+    uz_wire_sensor s;
+    memset(&s, 0, sizeof(s));
+    c.header();
+    s.sensor_type = (int32_t)c.u32();
+    s.displacement_offset = c.at; c.skip(56);                                   // geometry_msgs/Pose: 7 float64
+    c.str(&s.sensor_frame_offset, &s.sensor_frame_len);
+    // graph_slam_msgs/Features: header, descriptor_type, Feature[] features, sensor_msgs/CameraInfo camera_model
+    c.header();
+    s.descriptor_type = (int32_t)c.u32();
+    s.features_offset = c.at;
+    const uint32_t nf = c.u32();
+    s.n_features = (int32_t)nf;
+    for (uint32_t i = 0; i < nf && c.ok; ++i) { c.skip(4 + 4 + 1 + 4); c.arr(4); c.skip(24); }     // Feature.msg
+    s.features_bytes = c.at - s.features_offset;
+    c.header(); c.skip(4 + 4); c.str(nullptr, nullptr); c.arr(8); c.skip(8 * (9 + 9 + 12)); c.skip(4 + 4); c.skip(4 * 4 + 1);   // CameraInfo
+    c.image(); c.image();                                                        // graph_slam_msgs/DepthImage: depth, color
+    c.arr(4);                                                                    // float32[] gist_descriptor
+    c.header(); c.skip(7 * 4); c.arr(4); c.arr(4);                               // sensor_msgs/LaserScan
+    c.skip(24);                                                                  // geometry_msgs/Point scan_center
+    if (c.ok && out) *out = s;
+    return c.ok;
+}
+}  // namespace
+
+uz_status uz_wire_walk_sensor_data(const uint8_t* msg, size_t bytes, uz_wire_sensor* sensor_out, size_t* consumed_out) {
+    if (!msg || !sensor_out) return UZ_ERR_INVALID;
+    WireCursor c{msg, bytes, 0, true};
+    if (!walk_sensor_data(c, sensor_out)) return UZ_ERR_INVALID;
+    if (consumed_out) *consumed_out = c.at;
+    return UZ_OK;
+}
+
+uz_status uz_wire_walk_node(const uint8_t* msg, size_t bytes, uz_wire_sensor* sensors_out, int32_t capacity, int32_t* n_sensors_out,
+                            size_t* id_offset_out, int32_t* id_len_out) {
+    if (!msg || !n_sensors_out || capacity < 0 || (capacity > 0 && !sensors_out)) return UZ_ERR_INVALID;
+    WireCursor c{msg, bytes, 0, true};
+    c.arr(8);                                                                    // time[] stamps
+    c.str(id_offset_out, id_len_out);                                            // string id
+    c.skip(56 + 56);                                                             // pose, odom_pose
+    c.header();                                                                  // SensorDataArray.header
+    const uint32_t ns = c.u32();
+    int32_t n = 0;
+    for (uint32_t i = 0; i < ns && c.ok; ++i) {
+        uz_wire_sensor s;
+        const size_t base = c.at;
+        (void)base;
+        if (!walk_sensor_data(c, &s)) break;
+        if (n < capacity) sensors_out[n] = s;
+        ++n;
+    }
+    c.arr(0);                                                                    // string[] edge_ids: count, then the strings
+    if (c.ok) {
+        uint32_t cnt; memcpy(&cnt, msg + c.at - 4, 4);
+        for (uint32_t i = 0; i < cnt && c.ok; ++i) c.str(nullptr, nullptr);
+    }
+    c.skip(1 + 8);                                                               // bool fixed, float64 uncertainty
+    if (!c.ok) return UZ_ERR_INVALID;
+    *n_sensors_out = n;
+    return UZ_OK;
+}
+
 uz_status uz_wire_encode(uz_context* ctx, int32_t handle, int32_t cam, const int32_t* uv, uint8_t* blob_out, size_t capacity,
                          size_t* bytes_out) {
     uz_status st = check_ctx(ctx);

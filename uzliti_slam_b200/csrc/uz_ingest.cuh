@@ -89,6 +89,22 @@ __global__ void __launch_bounds__(256) wire_decode_kernel(const uint8_t* __restr
     if (uv && lane == 4) { uv[2 * f] = (int32_t)load_u32_unaligned(e); uv[2 * f + 1] = (int32_t)load_u32_unaligned(e + 4); }
 }
 
+// Many blobs in one launch (resume: GraphSlamNode::load re-adds every stored node, graph_slam_node.cpp:875-888).
+// blockIdx.y = blob; status[0] is set to 1 if any element's descriptor length differs from its blob's.
+struct WireJob { const uint8_t* blob; uint8_t* desc; double* pos; uint8_t* valid; int32_t n, cols; };
+__global__ void __launch_bounds__(256) wire_decode_bulk_kernel(const WireJob* __restrict__ jobs, int* __restrict__ status) {
+    const WireJob j = jobs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < j.n; f += (gridDim.x * blockDim.x) >> 5) {
+        const uint8_t* e = j.blob + (size_t)f * wire_elem_bytes(j.cols);
+        const uint32_t len = load_u32_unaligned(e + 13);
+        if (len != (uint32_t)j.cols) { if (lane == 0) atomicExch(status, 1); continue; }
+        for (int k = lane; k < j.cols; k += 32) j.desc[(size_t)f * j.cols + k] = narrow_x86(__uint_as_float(load_u32_unaligned(e + 17 + 4 * k)));
+        if (lane < 3) j.pos[3 * (size_t)f + lane] = load_f64_unaligned(e + 17 + 4 * j.cols + 8 * lane);
+        if (lane == 3) j.valid[f] = e[8] ? 1 : 0;
+    }
+}
+
 // FeatureData::toMsg (sensor_data.cpp:77-122): the inverse of wire_decode_kernel, one warp per feature.  blob points at the
 // first element; uv (n x 2, may be null) supplies feature_positions_2d_, keypoint_strength is -1.
 __device__ __forceinline__ void store_u32_unaligned(uint8_t* p, uint32_t v) {

@@ -11,8 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -138,6 +142,51 @@ struct Arena {
     void release() { for (auto& c : chunks) cudaFree(c.base); chunks.clear(); total = 0; used = 0; }
 };
 
+// A few persistent host threads for packing pageable buffers into the pinned staging ring (a single memcpy stream tops out
+// near 10 GB/s; spawning threads per group costs more than a small group's copy).
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(unsigned)> job;
+    unsigned generation = 0, pending = 0;
+    bool quit = false;
+    void start(unsigned n) {
+        for (unsigned i = 0; i < n; ++i)
+            th.emplace_back([this, i]() {
+                unsigned seen = 0;
+                std::unique_lock<std::mutex> lk(m);
+                for (;;) {
+                    cv_go.wait(lk, [&] { return quit || generation != seen; });
+                    if (quit) return;
+                    seen = generation;
+                    auto fn = job;
+                    lk.unlock();
+                    fn(i + 1);
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_all();
+                }
+            });
+    }
+    // runs fn(0) here and fn(1..n) on the workers; returns when all are through
+    void run(const std::function<void(unsigned)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = fn; pending = (unsigned)th.size(); ++generation;
+        }
+        cv_go.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv_go.notify_all();
+        for (auto& t : th) if (t.joinable()) t.join();
+        th.clear();
+    }
+};
+
 struct Cam {
     uint32_t* raw = nullptr;   // n x dbytes/4 words, bytes as given
     uint32_t* csa = nullptr;   // same rows, every 256-bit half in CSA layout (uz_knn2.cuh)
@@ -244,6 +293,8 @@ struct uz_context {
     bool ring_busy[2] = {false, false};
     int ring_cur = 0;
     uintptr_t ring_dev = 0;          // device address of the ring
+    HostPool* pool = nullptr;        // packs pageable buffers into the ring (UZ_STAGE_THREADS, default min(8, cores / 2))
+    int stage_threads = 0;
     PlacesState places;
     double places_ms[3] = {0, 0, 0};
     int host_chunks = 0;             // UZ_HOST_CHUNKS: upload/compute pipeline depth of uz_estimate_edges_host (0 = auto)
@@ -313,6 +364,21 @@ struct Trace {
         t0 = t1;
     }
 };
+
+// UZ_TRACE=1: accumulated host time per stage of the chunked host path (printed by uz_estimate_edges_host)
+struct StageClock {
+    bool on = getenv("UZ_TRACE") != nullptr;
+    double acc[16] = {0};
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on) t = std::chrono::steady_clock::now(); }
+    void stop(int k) { if (on) { auto n = std::chrono::steady_clock::now(); acc[k] += std::chrono::duration<double, std::milli>(n - t).count(); t = n; } }
+    void report(const char* const* names, int n) {
+        if (!on) return;
+        for (int i = 0; i < n; ++i) fprintf(stderr, "[uz trace]   %-28s %.3f ms\n", names[i], acc[i]);
+        for (double& a : acc) a = 0;
+    }
+};
+StageClock g_stage;
 
 std::string g_create_err = "";   // why the last uz_create failed (uz_last_error(NULL))
 

@@ -8,8 +8,6 @@
 //     threads and pulled from there by the same kernel - no per-array cudaMemcpyAsync, no synchronous staging in the driver;
 //   * a handful of large arrays goes through the DMA engines (cudaMemcpyAsync) as before.
 // Then one launch derives the CSA layout (integer-pipe kernels) and the E8 layout (tensor-core kernel) of every camera.
-#include <thread>
-
 namespace {
 
 struct CopyItem {
@@ -165,21 +163,23 @@ uz_status flush_copies(uz_context* ctx, const std::vector<CopyItem>& items) {
     auto flush_group = [&]() -> uz_status {
         const int half = ctx->ring_cur;
         if (!group.empty()) {
-            // pack into the pinned ring with a few host threads (a single memcpy stream tops out near 10 GB/s)
+            // pack into the pinned ring with a few persistent host threads
             size_t bytes = 0;
             for (const auto& g : group) bytes += g.count;
-            const unsigned nthr = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)std::max(1u, std::thread::hardware_concurrency() / 2), bytes >> 20}));
             uint8_t* base = (uint8_t*)ctx->ring.p + (size_t)half * ctx->ring_half;
-            auto work = [&](unsigned t) {
-                for (size_t k = t; k < group.size(); k += nthr) stage_copy(items[group[k].item], group[k].from, group[k].count, base + group[k].ring_off);
-            };
-            if (nthr > 1) {
-                std::vector<std::thread> th;
-                for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work, t);
-                work(0);
-                for (auto& t : th) t.join();
+            if (!ctx->pool && bytes >= ((size_t)1 << 20)) {
+                unsigned want = ctx->stage_threads > 0 ? (unsigned)ctx->stage_threads
+                                                       : std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+                if (want > 1) { ctx->pool = new HostPool(); ctx->pool->start(want - 1); }
+            }
+            if (ctx->pool && bytes >= ((size_t)1 << 20)) {
+                const unsigned nthr = (unsigned)ctx->pool->th.size() + 1;
+                ctx->pool->run([&](unsigned t) {
+                    for (size_t k = t; k < group.size(); k += nthr)
+                        stage_copy(items[group[k].item], group[k].from, group[k].count, base + group[k].ring_off);
+                });
             } else {
-                work(0);
+                for (const auto& g : group) stage_copy(items[g.item], g.from, g.count, base + g.ring_off);
             }
             for (const auto& g : group)
                 push_chunks(cc, ctx->ring_dev + (size_t)half * ctx->ring_half + g.ring_off, items[g.item].dev + g.from, g.count);
@@ -319,9 +319,13 @@ uz_status fill_cams(uz_context* ctx, const std::vector<const uz_features*>& feat
 // transient upload: one range for everything, freed by the arena's reset()
 uz_status upload_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_features*>& feats, std::vector<Cam>& out) {
     std::vector<BlockRef> blocks;
+    g_stage.start();
     uz_status st = place_cams(ctx, arena, feats, nullptr, 0, out, blocks);
+    g_stage.stop(1);
     if (st != UZ_OK) return st;
-    return fill_cams(ctx, feats, out);
+    st = fill_cams(ctx, feats, out);
+    g_stage.stop(2);
+    return st;
 }
 
 // ---- sample tables ---------------------------------------------------------------------------------
