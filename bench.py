@@ -743,7 +743,8 @@ def run_gpu(args):
         ep.close()
         kms = tp["match_ms"] / max(tp["match_launches"], 1)
         g = tp["compares"] / max(tp["match_launches"], 1) / (kms * 1e-3) * 1e-9
-        popc_limit, alu_limit = peaks["popc"] / 4.0, peaks["lop3"] / 14.25
+        from uzliti_slam_b200 import mix
+        popc_limit, alu_limit = peaks["popc"] / mix.KNN2_POPC, peaks["lop3"] / (mix.KNN2_LOP3 + mix.KNN2_MINMAX)
         int_pipe = dict(kernel="knn2_kernel<256,2> (4 POPC + 13 LOP3 + 4 IMAD + 1.25 VIMNMX.U16x2 per 256-bit compare), solve behind it",
                         knn2_ms_per_launch=round(kms, 3), solve_ms_per_launch=round(tp["solve_ms"] / max(tp["solve_launches"], 1), 3),
                         achieved_gcmp_per_s=round(g, 2), popc_ceiling_gcmp_per_s=round(popc_limit, 2),
@@ -854,7 +855,8 @@ def run_gpu(args):
         # tcgen05 data path at twice the K per instruction); MEASURED_PEAKS.json holds the measured bf16 figures
         bf16 = mp.get("bf16_tflops_sustained", 1400.0)
         bf16_burst = mp.get("bf16_tflops", 1590.0)
-        tops = gcmp * 512e-3
+        from uzliti_slam_b200 import mix
+        tops = gcmp * mix.MMA_OPS_PER_COMPARE * 1e-3
         traffic = None
         prof = os.path.join(ROOT, "profiles", "knn2_mma_ncu_summary.json")
         if os.path.exists(prof):

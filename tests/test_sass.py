@@ -1,0 +1,92 @@
+"""CPU: the shipped library's SASS carries the instruction mix the roofline arithmetic assumes (uzliti_slam_b200/mix.py), and
+the match kernels are what DESIGN.md says they are: TMA bulk copies + mbarriers in both, POPC/LOP3 on the integer pipes in
+knn2_kernel, tcgen05.mma (UTCIMMA) + TMEM loads (LDTM) and NO popcount in knn2_mma_kernel."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from uzliti_slam_b200 import binding, mix
+
+
+def _functions(built):
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.check_output(["cuobjdump", "-sass", binding.lib_path()], text=True)
+    funcs, name, body = {}, None, []
+    for ln in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", ln)
+        if m:
+            if name:
+                funcs[name] = body
+            name, body = m.group(1), []
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+        if m and name:
+            body.append((int(m.group(1), 16), m.group(2).strip()))
+    if name:
+        funcs[name] = body
+    return funcs
+
+
+def _op(text):
+    t = text.split()
+    return t[1] if t[0].startswith("@") else t[0]
+
+
+def _hot_loop(body):
+    """the main compare loop: the smallest body of a backward branch with at least 16 POPC and packed (U16x2) min/max"""
+    addr_index = {a: i for i, (a, _) in enumerate(body)}
+    best = None
+    for i, (a, text) in enumerate(body):
+        m = re.search(r"\bBRA(?:\.\w+)*\s+(?:!?\w+,\s*)?(0x[0-9a-f]+)", text)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt < a and tgt in addr_index:
+            j = addr_index[tgt]
+            n = sum(1 for _, t in body[j:i + 1] if _op(t).startswith("POPC"))
+            packed = any("U16x2" in _op(t) for _, t in body[j:i + 1])
+            size = i - j
+            if n >= 16 and packed and (best is None or size < best[1]):
+                best = (n, size, j, i)
+    return best
+
+
+def test_integer_pipe_kernel_mix_matches_the_roofline_constants(built):
+    funcs = _functions(built)
+    # knn2_kernel<256, 2, true, true, false, false>
+    names = [n for n in funcs if "knn2_kernel" in n and "ILi256ELi2ELb1ELb1ELb0ELb0E" in n]
+    assert len(names) == 1, [n for n in funcs if "knn2_kernel" in n][:4]
+    body = funcs[names[0]]
+    hot = _hot_loop(body)
+    assert hot is not None
+    _, _, j, i = hot
+    ops = [_op(t) for _, t in body[j:i + 1]]
+    cnt = lambda p: sum(1 for o in ops if o.startswith(p))          # noqa: E731
+    n = mix.KNN2_COMPARES_PER_ITERATION
+    assert cnt("POPC") == mix.KNN2_POPC * n
+    assert cnt("LOP3") == mix.KNN2_LOP3 * n
+    assert mix.KNN2_IMAD * n <= cnt("IMAD") <= mix.KNN2_IMAD * n + 2
+    assert cnt("VIMNMX") == int(mix.KNN2_MINMAX * n)
+    assert cnt("LDS") == 8 and all("128" in t for _, t in body[j:i + 1] if _op(t).startswith("LDS"))
+    whole = [_op(t) for _, t in body]
+    assert any(o.startswith("UBLKCP") for o in whole) and any(o.startswith("SYNCS") for o in whole)      # TMA bulk copy + mbarrier
+
+
+def test_tensor_core_kernel_is_tcgen05_with_tmem_and_no_popcount(built):
+    funcs = _functions(built)
+    names = [n for n in funcs if "knn2_mma_kernel" in n]
+    assert len(names) == 1
+    ops = [_op(t) for _, t in funcs[names[0]]]
+    cnt = lambda p: sum(1 for o in ops if o.startswith(p))          # noqa: E731
+    assert cnt("UTCIMMA") >= mix.MMA_INSTRUCTIONS_PER_TILE and cnt("UTCIMMA") % mix.MMA_INSTRUCTIONS_PER_TILE == 0
+    assert cnt("LDTM") >= 8                       # four 32-column loads per accumulator in the full path, four in the ragged one
+    assert cnt("UBLKCP") >= 3 and cnt("SYNCS") >= 10 and cnt("UTCBAR") + cnt("UTCCOMMIT") + cnt("UTC") >= 1
+    assert cnt("POPC") <= 2 and cnt("HMMA") == 0      # (a stray POPC of the warp-vote lowering; the compares use none)
+    # the packed-key epilogue: per 128 columns 128 multiply-adds with an immediate (16384 + column pair) and 160 packed min/max
+    body = funcs[names[0]]
+    imm = [t for _, t in body if _op(t).startswith("IMAD") and re.search(r"0x40[0-9a-f]{2}40[0-9a-f]{2}\b", t)]
+    assert len(imm) >= 64 * 2                     # one per column pair, two unrolled accumulators or paths
+    assert cnt("VIMNMX") >= 160

@@ -33,11 +33,15 @@ def _worker(rank, world, port, q):
     # store maintenance: only rank 0 "ingests" the map, every rank ends up with identical keyframes
     from uzliti_slam_b200.sharding import broadcast_keyframes
     ragged = [dict(k, desc=k["desc"][:100 + i], pos=k["pos"][:100 + i], valid=k["valid"][:100 + i], sensor_frame=i % 3) for i, k in enumerate(kfs)]
+    # BRISK / FREAK keyframes (64-byte rows) between the ORB ones: widths travel per keyframe
+    wide, _, _ = S.make_map(3, n_features=50, cluster=3, pool=50, n_shared=30, k_candidates=1, seed=9, desc_bytes=64)
+    ragged = ragged[:5] + wide + ragged[5:]
     got = broadcast_keyframes(ragged if rank == 0 else None, src=0)
     assert len(got) == len(ragged)
     for a, b in zip(got, ragged):
         assert np.array_equal(a["desc"], b["desc"]) and a["pos"].tobytes() == b["pos"].tobytes() and np.array_equal(a["valid"], b["valid"])
         assert a["sensor_frame"] == b["sensor_frame"] and a["feature_type"] == b["feature_type"]
+        assert a["desc"].shape == b["desc"].shape
     mine, lo = shard_pairs(pairs, world, rank)
     rec = np.zeros(len(mine), RESULT_DTYPE)
     for i, (a, b) in enumerate(mine):       # the per-rank compute step, here through the oracle (CPU test)

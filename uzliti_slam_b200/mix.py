@@ -1,0 +1,16 @@
+"""Instruction mix of the match kernels per descriptor compare, as the roofline arithmetic of bench.py uses it.
+tests/test_sass.py disassembles the shipped library (cuobjdump) and checks these numbers against the hot loops, so a
+compiler change cannot move the real ceiling silently."""
+
+# knn2_kernel<256, 2, CSA, PACK16>: integer pipes, per 256-bit compare
+KNN2_POPC = 4          # XU pipe
+KNN2_LOP3 = 13         # ALU pipe
+KNN2_IMAD = 4          # FMA pipe (weighted popcount chain); +1 per iteration of 8 compares for the row index
+KNN2_MINMAX = 1.25     # VIMNMX(.3).U16x2 per compare (5 per 4 compares), ALU pipe
+KNN2_COMPARES_PER_ITERATION = 8      # 4 train rows x 2 queries per thread
+
+# knn2_mma_kernel: tensor cores, per 128 x 256 tile of compares
+MMA_INSTRUCTIONS_PER_TILE = 8        # tcgen05.mma kind::i8, K = 32 each, K = 256 in all
+MMA_OPS_PER_COMPARE = 512            # 256 int8 multiply-adds
+MMA_EPILOGUE_IMAD = 1.0              # per compare: key16 = dot * (-64) + (16384 + column)
+MMA_EPILOGUE_MINMAX = 1.25

@@ -61,25 +61,30 @@ def broadcast_keyframes(keyframes, src=0, group=None):
     nccl = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
     if rank == src:
-        meta = np.array([[len(k["desc"]), int(k.get("feature_type", 2)), int(k.get("sensor_frame", 0))] for k in keyframes],
-                        np.int64).reshape(-1, 3)
+        # per keyframe: rows, feature_type, sensor_frame, descriptor width (32: ORB / BRIEF, 64: BRISK / FREAK)
+        meta = np.array([[len(k["desc"]), int(k.get("feature_type", 2)), int(k.get("sensor_frame", 0)),
+                          int(np.asarray(k["desc"]).shape[1]) if np.asarray(k["desc"]).ndim == 2 else 32] for k in keyframes],
+                        np.int64).reshape(-1, 4)
         head = torch.tensor([len(keyframes)], dtype=torch.int64)
     else:
         meta, head = None, torch.zeros(1, dtype=torch.int64)
     head = head.to(dev)
     dist.broadcast(head, src, group=group)
     n_kf = int(head.item())
-    t_meta = (torch.from_numpy(meta) if rank == src else torch.zeros((n_kf, 3), dtype=torch.int64)).to(dev)
+    t_meta = (torch.from_numpy(meta) if rank == src else torch.zeros((n_kf, 4), dtype=torch.int64)).to(dev)
     dist.broadcast(t_meta, src, group=group)
     meta = t_meta.cpu().numpy()
     total = int(meta[:, 0].sum())
+    desc_total = int((meta[:, 0] * meta[:, 3]).sum())
     if rank == src:
-        desc = np.concatenate([np.ascontiguousarray(k["desc"], np.uint8).reshape(-1, 32) for k in keyframes] + [np.zeros((0, 32), np.uint8)])
+        # descriptors travel as ONE flat byte buffer (rows of different widths cannot share a 2-D tensor)
+        desc = np.concatenate([np.ascontiguousarray(k["desc"], np.uint8).reshape(-1) for k in keyframes] + [np.zeros(0, np.uint8)])
         pos = np.concatenate([np.ascontiguousarray(k["pos"], np.float64).reshape(-1, 3) for k in keyframes] + [np.zeros((0, 3))])
         valid = np.concatenate([np.ascontiguousarray(k["valid"], np.uint8).reshape(-1) for k in keyframes] + [np.zeros(0, np.uint8)])
+        assert desc.size == desc_total
         tens = [torch.from_numpy(desc), torch.from_numpy(pos), torch.from_numpy(valid)]
     else:
-        tens = [torch.zeros((total, 32), dtype=torch.uint8), torch.zeros((total, 3), dtype=torch.float64),
+        tens = [torch.zeros(desc_total, dtype=torch.uint8), torch.zeros((total, 3), dtype=torch.float64),
                 torch.zeros(total, dtype=torch.uint8)]
     out = []
     for t in tens:
@@ -87,9 +92,11 @@ def broadcast_keyframes(keyframes, src=0, group=None):
         dist.broadcast(t, src, group=group)
         out.append(t.cpu().numpy())
     desc, pos, valid = out
-    kfs, o = [], 0
-    for n, ftype, frame in meta:
-        n = int(n)
-        kfs.append(dict(desc=desc[o:o + n], pos=pos[o:o + n], valid=valid[o:o + n], feature_type=int(ftype), sensor_frame=int(frame)))
+    kfs, o, od = [], 0, 0
+    for n, ftype, frame, width in meta:
+        n, width = int(n), int(width)
+        kfs.append(dict(desc=desc[od:od + n * width].reshape(n, width), pos=pos[o:o + n], valid=valid[o:o + n],
+                        feature_type=int(ftype), sensor_frame=int(frame)))
         o += n
+        od += n * width
     return kfs
