@@ -53,6 +53,51 @@ def test_oracle_sample_lists_golden(oracle):
     assert g["rand_seed1_first64"][0] == 1804289383          # the well-known first rand() of glibc
 
 
+REF_STAGE3 = os.path.join(HERE, "golden", "ref_stage3.npz")
+
+
+def _run_oracle_case(oracle, kind, P, Q, par, Tin):
+    thr, it, bp, prosac = float(par[0]), int(par[1]), float(par[2]), bool(par[3])
+    if kind == 0:
+        r = oracle.estimate_svd(P, Q, thr, it, bp, prosac)
+        return r["T"], r["consensus"], r["mse"], r["mask"]
+    if kind == 1:
+        return oracle.pose_svd(P, Q), 0, 0.0, np.zeros(len(P), bool)
+    c, mask = oracle.consensus3d(P, Q, Tin, thr)
+    return Tin, c, 0.0, mask
+
+
+def test_reference_stage3_cases_run_through_the_oracle(oracle):
+    """the Python half of the recipe (oracle/make_ref_golden.py) works here: cases are generated and the oracle solves them"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(os.path.dirname(HERE), "oracle", "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = mod.make_cases()
+    assert len(cases) >= 60 and {c[0] for c in cases} == {0, 1, 2}
+    for kind, P, Q, thr, it, bp, prosac, T in cases[:20] + cases[-14:]:
+        Tout, cons, mse, mask = _run_oracle_case(oracle, kind, P, Q, (thr, it, bp, prosac), T)
+        assert np.isfinite(np.asarray(Tout)).all() and 0 <= cons <= len(P) and mask.sum() == (cons if kind != 1 else 0)
+
+
+def test_oracle_matches_reference_stage3(oracle):
+    """Stage 3 pinned to the reference's own binaries - when someone has produced the vectors (oracle/build_ref.sh needs
+    Eigen 3 / PCL / Boost headers, which this image does not have).  Until then: parity unpinned."""
+    if not os.path.exists(REF_STAGE3):
+        pytest.skip("tests/golden/ref_stage3.npz not present: stage 3 (PCL / Eigen arithmetic) is parity-unpinned; "
+                    "run oracle/build_ref.sh + oracle/make_ref_golden.py where Eigen 3 / PCL headers exist")
+    g = np.load(REF_STAGE3)
+    for i in range(int(g["n_cases"])):
+        kind = int(g[f"c{i}_kind"])
+        Tout, cons, mse, mask = _run_oracle_case(oracle, kind, g[f"c{i}_P"], g[f"c{i}_Q"], g[f"c{i}_par"], g[f"c{i}_Tin"])
+        assert np.array_equal(np.asarray(Tout), g[f"c{i}_T"]), f"case {i}: transform differs from the reference's"
+        if kind != 1:
+            assert cons == int(g[f"c{i}_consensus"]) and np.array_equal(mask.astype(np.uint8), g[f"c{i}_mask"]), f"case {i}"
+        if kind == 0:
+            ref_mse = float(g[f"c{i}_mse"])
+            assert (np.isnan(mse) and np.isnan(ref_mse)) or mse == ref_mse, f"case {i}"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", EDGE_FILES, ids=lambda p: os.path.basename(p)[5:-4])
 def test_gpu_reproduces_golden(est, path):
