@@ -544,7 +544,8 @@ def run_gpu(args):
             log(f"[bench] --gpus {args.gpus} needs torchrun (one process per GPU); re-launching")
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
-            sys.exit(subprocess.call(cmd))
+            # (descriptor 1 of this process already points at stderr: hand the children the REAL stdout for the result line)
+            sys.exit(subprocess.call(cmd, stdout=_RESULT_OUT or sys.stdout))
         raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
 
     n_kf = args.keyframes

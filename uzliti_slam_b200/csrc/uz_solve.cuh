@@ -47,7 +47,7 @@ constexpr int kSolveThreads = 128;
 constexpr int kHistPerLane = 17;                   // counting sort by distance: 0..512 (64-byte descriptors) in 32 x 17 bins
 constexpr int kHistBins = 32 * kHistPerLane;
 static_assert(kHistBins > 8 * UZ_MAX_DESC_BYTES, "one bin per possible Hamming distance");
-static_assert(kHistBins * 4 <= kSolveThreads * 12 * 8, "the histogram lives in the hypothesis buffer");
+static_assert((kSolveThreads / 32 + 1) * kHistBins * 4 <= kSolveThreads * 12 * 8, "the histograms live in the hypothesis buffer");
 #ifndef UZ_SOLVE_H
 #define UZ_SOLVE_H 2
 #endif
@@ -241,7 +241,17 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    uz_edge_result* res = results + pair;              // batch-wide index; pair_tasks/results are indexed by it
+    // The record is put together in shared memory by one thread and leaves as eleven 16-byte stores: `results` may be peer
+    // memory (NVLink) or mapped host memory (PCIe) in group mode, where 22 separate 8-byte stores per record are what costs.
+    __shared__ __align__(16) uz_edge_result s_rec;
+    uz_edge_result* const out_rec = results + pair;    // batch-wide index; pair_tasks/results are indexed by it
+    uz_edge_result* res = &s_rec;
+    static_assert(sizeof(uz_edge_result) == 11 * 16, "the record leaves as eleven uint4");
+#define UZ_PUBLISH_RECORD()                                                                                             \
+    do {                                                                                                                \
+        __syncthreads();                                                                                                \
+        if (tid < 11) reinterpret_cast<uint4*>(out_rec)[tid] = reinterpret_cast<const uint4*>(&s_rec)[tid];            \
+    } while (0)
 #define UZ_PHASE(k) do { if (prm.dbg_phase && tid == 0) prm.dbg_phase[(size_t)pair * 8 + (k)] = clock64(); } while (0)
     UZ_PHASE(0);
     int M = 0;
@@ -273,6 +283,7 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
                 res->consensus = 0; res->best_iteration = -1; res->iterations_run = 0; res->mse = 0.0;
                 res->info_scale = 1.0; write_identity(res->T);
             }
+            UZ_PUBLISH_RECORD();
             return;
         }
         const MatchTask* tk = tasks + pt.x + best;
@@ -284,46 +295,97 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         // ratio test (:65-71) + valid_3d filter (:103-112) + the sort of :114 as a STABLE COUNTING SORT by
         // distance: matches are produced in query order, so equal distances keep ascending queryIdx, which
         // is exactly the (distance, queryIdx) order.  Pass 1 (all warps): per-query distance + histogram.
-        int* hist = reinterpret_cast<int*>(Th);                 // [kHistBins] bins (distances 0..512); Th is not used before K3
+        // The histogram is kept per PARTITION of the query rows (one partition of `part` consecutive rows per warp), so that
+        // the placement pass below runs on all warps at once: hist[w][d], then tot[d]; Th is not used before K3.
+        int* hist = reinterpret_cast<int*>(Th);                 // [NW][kHistBins] + [kHistBins]
+        int* tot = hist + NW * kHistBins;
+        static_assert((NW + 1) * kHistBins * 4 <= THREADS * 12 * 8, "the histograms live in the hypothesis buffer");
         uint16_t* dq = reinterpret_cast<uint16_t*>(pf);         // [cap] distance of query i, 0xFFFF = dropped
-        for (int bidx = tid; bidx < kHistBins; bidx += THREADS) hist[bidx] = 0;
+        const int part = (((nq + NW - 1) / NW) + 31) & ~31;     // rows per partition, a multiple of 32
+        for (int bidx = tid; bidx < (NW + 1) * kHistBins; bidx += THREADS) hist[bidx] = 0;
         if (tid == 0) { s_nvalid = 0; s_nratio = 0; }
         __syncthreads();
-        for (int i = tid; i < nq; i += THREADS) {
-            const uint2 m = load_key(k + i);
-            const bool pass = match_survives(m, i, prm.ratio_num, prm.ratio_den, keys, tk->rev_key_off);
-            uint16_t d = 0xFFFFu;
-            if (pass) {
-                atomicAdd(&s_nratio, 1);
-                if (vq[i] && vt[m.x & 0xFFFFu]) { d = (uint16_t)(m.x >> 16); atomicAdd(&hist[d], 1); }
+        // Pass 1 (all warps): ratio test, valid flags, distance + histogram.  The loads of a thread's rows go out together,
+        // level by level (row keys + query flags, then the dependent cross-check keys and train flags): two global-memory
+        // latencies per four rows instead of two per row.
+        {
+            constexpr int U = 4;
+            int my_ratio = 0;
+            for (int base = 0; base < nq; base += THREADS * U) {
+                uint2 m[U];
+                uint8_t a[U], b[U];
+                uint32_t rk[U];
+                bool pass[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    m[u] = i < nq ? load_key(k + i) : make_uint2(kNoKey, kNoKey);
+                    a[u] = i < nq ? vq[i] : (uint8_t)0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    pass[u] = i < nq && m[u].y != kNoKey && ((int)(m[u].x >> 16) * prm.ratio_den < (int)(m[u].y >> 16) * prm.ratio_num);
+                    rk[u] = (uint32_t)i;
+                    b[u] = 0;
+                    if (pass[u]) {
+                        if (tk->rev_key_off != kNoRev) rk[u] = load_key(keys + tk->rev_key_off + (m[u].x & 0xFFFFu)).x & 0xFFFFu;
+                        if (a[u]) b[u] = vt[m[u].x & 0xFFFFu];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    if (i >= nq) continue;
+                    uint16_t d = 0xFFFFu;
+                    if (pass[u] && (int)rk[u] == i) {           // (without the cross-check rk is i itself)
+                        ++my_ratio;
+                        if (a[u] && b[u]) { d = (uint16_t)(m[u].x >> 16); atomicAdd(&hist[(i / part) * kHistBins + d], 1); }
+                    }
+                    dq[i] = d;
+                }
             }
-            dq[i] = d;
+            if (my_ratio) atomicAdd(&s_nratio, my_ratio);
         }
         __syncthreads();
         n_ratio = s_nratio;
         UZ_PHASE(1);
+        // per bin: where each partition starts inside the bin, and the bin's total
+        for (int bidx = tid; bidx < kHistBins; bidx += THREADS) {
+            int run = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const int c = hist[w * kHistBins + bidx]; hist[w * kHistBins + bidx] = run; run += c; }
+            tot[bidx] = run;
+        }
+        __syncthreads();
         if (warp == 0) {
             // exclusive prefix over the 513 bins: kHistPerLane consecutive bins per lane
             int loc[kHistPerLane], sum = 0;
 #pragma unroll
-            for (int j = 0; j < kHistPerLane; ++j) { loc[j] = hist[lane * kHistPerLane + j]; sum += loc[j]; }
+            for (int j = 0; j < kHistPerLane; ++j) { loc[j] = tot[lane * kHistPerLane + j]; sum += loc[j]; }
             int inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             int run = inc - sum;
 #pragma unroll
-            for (int j = 0; j < kHistPerLane; ++j) { hist[lane * kHistPerLane + j] = run; run += loc[j]; }
+            for (int j = 0; j < kHistPerLane; ++j) { tot[lane * kHistPerLane + j] = run; run += loc[j]; }
             if (lane == 31) s_nvalid = inc;
-            __syncwarp();
-            // pass 2 (one warp, query order): slot = bin offset + rank among equal distances seen so far
-            for (int base = 0; base < nq; base += 32) {
+        }
+        __syncthreads();
+        for (int bidx = tid; bidx < NW * kHistBins; bidx += THREADS) hist[bidx] += tot[bidx % kHistBins];
+        __syncthreads();
+        {
+            // pass 2 (every warp its partition, in query order): slot = bin offset + rank among equal distances seen so far
+            int* myhist = hist + warp * kHistBins;
+            const int q_end = min(nq, (warp + 1) * part);
+            for (int base = warp * part; base < q_end; base += 32) {
                 const int q = base + lane;
-                const unsigned d = q < nq ? dq[q] : 0xFFFFu;
+                const unsigned d = q < q_end ? dq[q] : 0xFFFFu;
                 const unsigned peers = __match_any_sync(0xffffffffu, d);
                 const int rank = __popc(peers & ((1u << lane) - 1u));
-                if (d != 0xFFFFu) skeys[hist[d] + rank] = (d << 16) | (unsigned)q;
+                if (d != 0xFFFFu) skeys[myhist[d] + rank] = (d << 16) | (unsigned)q;
                 __syncwarp();
-                if (d != 0xFFFFu && rank == 0) hist[d] += __popc(peers);
+                if (d != 0xFFFFu && rank == 0) myhist[d] += __popc(peers);
                 __syncwarp();
             }
         }
@@ -332,19 +394,44 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         UZ_PHASE(2);
         gP = tk->q_pos;
         gQ = tk->t_pos;
-        for (int i = tid; i < M; i += THREADS) {
-            const uint32_t key = skeys[i];
-            const int q = key & 0xFFFFu;
-            const int t = load_key(k + q).x & 0xFFFFu;
-            const float x = (float)gP[3 * q], y = (float)gP[3 * q + 1], z = (float)gP[3 * q + 2];
-            const float u = (float)gQ[3 * t], v = (float)gQ[3 * t + 1], w = (float)gQ[3 * t + 2];
-            const int pi = pidx(i);
-            pxf[pi] = x; pyf[pi] = y; pzf[pi] = z; qxf[pi] = u; qyf[pi] = v; qzf[pi] = w;
-            kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(u) + fabsf(v) + fabsf(w)));
-            tq[i] = ((uint32_t)t << 16) | (uint32_t)q;
-            if (prm.dbg_matches) {
-                int32_t* d = prm.dbg_matches + ((size_t)pair * cap + i) * 3;
-                d[0] = q; d[1] = t; d[2] = (int)(key >> 16);
+        {
+            // gather of the matched 3-D points, two matches per thread at a time: train indices first, then all 12 doubles
+            constexpr int U = 2;
+            for (int base = 0; base < M; base += THREADS * U) {
+                uint32_t key[U];
+                int tt[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    key[u] = i < M ? skeys[i] : 0u;
+                    tt[u] = i < M ? (int)(load_key(k + (key[u] & 0xFFFFu)).x & 0xFFFFu) : 0;
+                }
+                double pv[U][6];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    const int q = key[u] & 0xFFFFu;
+                    if (i < M) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { pv[u][c] = gP[3 * q + c]; pv[u][3 + c] = gQ[3 * tt[u] + c]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * THREADS + tid;
+                    if (i >= M) continue;
+                    const int q = key[u] & 0xFFFFu, t = tt[u];
+                    const float x = (float)pv[u][0], y = (float)pv[u][1], z = (float)pv[u][2];
+                    const float uu = (float)pv[u][3], v = (float)pv[u][4], w = (float)pv[u][5];
+                    const int pi = pidx(i);
+                    pxf[pi] = x; pyf[pi] = y; pzf[pi] = z; qxf[pi] = uu; qyf[pi] = v; qzf[pi] = w;
+                    kp_local = fmaxf(kp_local, 4.5f * (fabsf(x) + fabsf(y) + fabsf(z)) + 1.5f * (fabsf(uu) + fabsf(v) + fabsf(w)));
+                    tq[i] = ((uint32_t)t << 16) | (uint32_t)q;
+                    if (prm.dbg_matches) {
+                        int32_t* d = prm.dbg_matches + ((size_t)pair * cap + i) * 3;
+                        d[0] = q; d[1] = t; d[2] = (int)(key[u] >> 16);
+                    }
+                }
             }
         }
     } else {
@@ -379,6 +466,7 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
             res->n_matches = M; res->consensus = 0; res->best_iteration = -1; res->iterations_run = 0;
             res->mse = 0.0; res->info_scale = 1.0; write_identity(res->T);
         }
+        UZ_PUBLISH_RECORD();
         if (prm.dbg_mask) for (int i = tid; i < M; i += THREADS) prm.dbg_mask[(size_t)pair * cap + i] = 0;
         return;
     }
@@ -496,6 +584,7 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
             res->best_iteration = s_best; res->iterations_run = s_run; res->mse = 0.0; res->info_scale = 1.0;
             write_identity(res->T);
         }
+        UZ_PUBLISH_RECORD();
         if (prm.dbg_mask) for (int i = tid; i < M; i += THREADS) prm.dbg_mask[(size_t)pair * cap + i] = 0;
         return;
     }
@@ -606,8 +695,10 @@ __device__ __forceinline__ void solve_pair(const MatchTask* __restrict__ tasks, 
         for (int e = 0; e < 12; ++e) res->T[e] = Tfin[e];
         res->T[12] = 0.0; res->T[13] = 0.0; res->T[14] = 0.0; res->T[15] = 1.0;
     }
+    UZ_PUBLISH_RECORD();
     UZ_PHASE(7);
 #undef UZ_PHASE
+#undef UZ_PUBLISH_RECORD
 }
 
 // One CTA per pair: the launch form of small batches, of the direct entry points (uz_estimate_svd, cluster RANSAC) and of
