@@ -756,6 +756,8 @@ def run_gpu(args):
 
     # ---- strong scaling and the latency-bound end (C3) at this N, through the same step (shards + all-gather) ----------
     def sharded(total, steps):
+        """`total` pairs as one job over the ranks: every rank takes its contiguous shard in calls of at most 25000 pairs (the
+        calls are asynchronous: the host prepares call k+1 while the GPU runs call k), then the records are all-gathered"""
         lo2, hi2 = shard_bounds(total, world, rank)
         idx = np.arange(lo2, hi2) % total_pairs
         f2 = np.ascontiguousarray(handles[pairs[idx, 0]])
@@ -763,9 +765,11 @@ def run_gpu(args):
         per = (total + world - 1) // world
         loc = torch.empty(max(per, 1) * rec, dtype=torch.uint8, device=dev)
         allb = torch.empty(world * max(per, 1) * rec, dtype=torch.uint8, device=dev) if world > 1 else loc
+        cuts = list(range(0, len(f2), 25000)) + [len(f2)]
 
         def fn():
-            est.estimateEdgesDevice(f2, t2, loc.data_ptr())
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                est.estimateEdgesDevice(f2[a:b], t2[a:b], loc.data_ptr() + a * rec)
             if world > 1:
                 dist.all_gather_into_tensor(allb, loc)
         return timed(fn, steps)
@@ -813,7 +817,16 @@ def run_gpu(args):
                     g.estimateEdges(gf, gt, out=res_g)
                 modes[mode] = (time.perf_counter() - t0) / 3
             dev_ms = float(g.last_timing().max())
-            g.set_gather(0)
+            # records into device 0's memory: written by every device's solve kernel through the peer-mapped pointer (NVLink)
+            buf_g = torch.empty(len(allp) * rec, dtype=torch.uint8, device=dev)
+            g.estimateEdgesDevice(gf, gt, buf_g.data_ptr())
+            t0 = time.perf_counter()
+            for _ in range(3):
+                g.estimateEdgesDevice(gf, gt, buf_g.data_ptr())
+            peer_s = (time.perf_counter() - t0) / 3
+            peer_ms = float(g.last_timing().max())
+            peer_equal = bool(buf_g.cpu().numpy().tobytes() == res_g.tobytes())
+            g.set_gather(1)
             c3g = []
             for _ in range(30):
                 t0 = time.perf_counter()
@@ -823,10 +836,16 @@ def run_gpu(args):
             chk = np.concatenate([np.arange(0, n_chk), np.arange(len(allp) - n_chk, len(allp))])
             g.estimateEdges(gf, gt, out=res_g)
             alone = est.estimateEdges(handles[allp[chk, 0]], handles[allp[chk, 1]])
-            group = dict(what="uz_group_estimate_edges: ONE process, %d devices, replicated store pulled over NVLink, every device's "
-                              "solve kernel writes its records through a host-mapped pointer into one host array (no collective)" % world,
-                         pairs=int(len(allp)), edges_per_s=round(len(allp) / modes[0], 1), ms=round(modes[0] * 1e3, 3),
-                         device_ms_max=round(dev_ms, 3), edges_per_s_copy_per_device=round(len(allp) / modes[1], 1),
+            group = dict(what="uz_group_estimate_edges: ONE process, %d devices, replicated store pulled over NVLink, contiguous pair "
+                              "shards, records delivered into ONE host array by one copy per device (no collective)" % world,
+                         pairs=int(len(allp)), edges_per_s=round(len(allp) / modes[1], 1), ms=round(modes[1] * 1e3, 3),
+                         device_ms_max=round(dev_ms, 3),
+                         host_mapped_sink=dict(edges_per_s=round(len(allp) / modes[0], 1), ms=round(modes[0] * 1e3, 3),
+                                               what="measured alternative: solve kernels write through a host-mapped pointer"),
+                         peer_write=dict(edges_per_s=round(len(allp) / peer_s, 1), ms=round(peer_s * 1e3, 3), device_ms_max=round(peer_ms, 3),
+                                         records_equal=peer_equal,
+                                         what="uz_group_estimate_edges_device: records written into device 0's memory by every device's "
+                                              "solve kernel over NVLink (gather fused into the solve)"),
                          store_replication_s=round(t_store, 3), c3_ms=round(float(np.median(c3g[5:])) * 1e3, 4),
                          records_equal_single_gpu=bool(alone.tobytes() == res_g[chk].tobytes()), pairs_compared=int(len(chk)))
             g.close()

@@ -313,9 +313,9 @@ uz_status uz_places_last_timing(uz_context* ctx, double* insert_ms, double* vote
  *     keyframe from that device's HBM over NVLink (peer memory) and derives its layouts locally; handles are identical
  *     on all devices;
  *   - uz_group_estimate_edges* cuts the pair list into contiguous shards (rank r of n takes [lo, hi) with
- *     lo = r * (N / n) + min(r, N % n)) and every device's solve kernel writes its 176-byte records straight into ONE result
- *     buffer at the pair's batch-wide index, through a host-mapped pointer (results on the host) or a peer-mapped pointer
- *     (results in devices[0]'s memory): the gather is fused into the solve, no collective runs.
+ *     lo = r * (N / n) + min(r, N % n)); records land in ONE result array at the pair's batch-wide index: in devices[0]'s
+ *     memory every device's solve kernel writes them itself through a peer-mapped pointer over NVLink (the gather is fused
+ *     into the solve), on the host every device delivers its shard over its own PCIe link.  No collective runs.
  * Results are byte-identical to uz_estimate_edges on one device.  Devices need peer access to devices[0]. */
 typedef struct uz_group uz_group;
 uz_status uz_group_create(const int32_t* devices, int32_t n_devices, uz_group** out);
@@ -338,8 +338,9 @@ uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, cons
 /* Same, records land in devices[0]'s memory (n_pairs records), e.g. for uz_gate_edges_device.  Blocks until done. */
 uz_status uz_group_estimate_edges_device(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
                                          int32_t n_pairs, void* results_on_first_device);
-/* 0 (default): records written by the solve kernels through the mapped pointer.  1: records stay local and travel with
- * one cudaMemcpyAsync per device (the measured alternative; host results only). */
+/* Host results only.  1 (default): records stay local and every device copies its shard into the pinned result array over its
+ * own PCIe link.  0: the solve kernels write through a host-mapped pointer (the measured alternative: slower).  Device
+ * results (uz_group_estimate_edges_device) are always written by the solve kernels through the peer-mapped pointer. */
 uz_status uz_group_set_gather(uz_group* g, int32_t mode);
 /* Device time (ms, CUDA events per device) of the last uz_group_estimate_edges* call, one value per device. */
 uz_status uz_group_last_timing(const uz_group* g, double* ms_per_device, int32_t capacity);

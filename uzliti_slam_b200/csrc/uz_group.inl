@@ -7,11 +7,13 @@
 //     reading peer memory, and derives the CSA / E8 layouts locally.  Handles are the same on every device.
 //   * batch: the from-sorted pair list is cut into contiguous shards (shard_bounds, the rule of
 //     uzliti_slam_b200/sharding.py); every device runs its shard.
-//   * gather: FUSED INTO THE SOLVE.  Each device's solve kernel writes its 176-byte records straight into ONE result
-//     buffer at the pair's batch-wide index - device memory of the first device through a peer-mapped pointer over NVLink
-//     (uz_group_estimate_edges_device), or pinned host memory through a host-mapped pointer (uz_group_estimate_edges) - so
-//     no collective and no second copy per device remain.  gather mode 1 keeps the measured alternative: records stay
-//     local and travel with one cudaMemcpyAsync per device.
+//   * gather: no collective.  Results wanted in device memory (uz_group_estimate_edges_device): FUSED INTO THE SOLVE - each
+//     device's solve kernel writes its 176-byte records (eleven 16-byte stores) straight into the first device's buffer at the
+//     pair's batch-wide index through a peer-mapped pointer over NVLink.  Results wanted on the host
+//     (uz_group_estimate_edges): every device copies its shard of records into one pinned array over its OWN PCIe link
+//     (gather mode 1, default); the solve kernels writing through a host-mapped pointer (mode 0) is the measured
+//     alternative - small posted writes over PCIe cost more than one DMA per device (2 GPUs, 50 000 pairs: 9.7 against
+//     11-20 ms).
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -29,7 +31,7 @@ struct uz_group {
     std::vector<uz_context*> ctx;
     std::vector<Worker*> workers;
     std::string err;
-    int gather_mode = 0;
+    int gather_mode = 1;              // host results: 1 = local records + one copy per device (default, measured faster), 0 = host-mapped sink
     PinBuf h_results;                 // portable + mapped: every device may write into it
     uz_edge_result* h_results_dev = nullptr;
     std::vector<double> last_ms;      // device time of the last batch per rank
