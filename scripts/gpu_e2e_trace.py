@@ -9,7 +9,7 @@ kfs, pairs, _ = bench.build_map(10000, out=(desc, pos, valid))
 td, tp, tv = torch.from_numpy(desc).pin_memory(), torch.from_numpy(pos).pin_memory(), torch.from_numpy(valid).pin_memory()
 pinned = [dict(kf, desc=td.numpy()[i], pos=tp.numpy()[i], valid=tv.numpy()[i]) for i, kf in enumerate(kfs)]
 my = pairs[:25000]
-os.environ["UZ_TRACE"] = "1"
+os.environ["UZ_TRACE"] = os.environ.get("UZ_TRACE", "1")
 from uzliti_slam_b200 import EdgeEstimator
 est = EdgeEstimator(0)
 for name, src in (("pinned", pinned), ("pageable", kfs)):

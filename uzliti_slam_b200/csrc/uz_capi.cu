@@ -644,23 +644,30 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // stream behind the upload's event, queue its records' way home - so the GPU starts after the host has looked at
     // the FIRST chunk only, uploads of later chunks run beside the matching of earlier ones, and records are copied
     // out to the caller while later chunks still compute.  What stays exposed is the first chunk's upload.
-    // Chunk ends as fractions of the batch: equal chunks of about 1600 pairs, between 4 and 40 of them.  Consecutive chunks
+    // Chunks of about 1600 pairs, between 4 and 40 of them.  Consecutive chunks
     // compute on two alternating streams (below), so a chunk boundary costs little; small chunks shrink the exposed first
     // upload and send records home earlier, large ones amortise the launches of a chunk.  Measured on C4 (25 000 pairs) with
     // the tensor-core match kernel (store-resident 3.28 M edges/s): 8 chunks 2.49 M, 16: 2.52 M, 32: 2.37 M, 64: 2.12 M
     // (with the integer-pipe kernels of round 1, 768-pair chunks were best: 926-930 k against 937 k store-resident).
     // UZ_HOST_CHUNKS = k > 0 forces k equal parts.
-    std::vector<double> fracs;
+    // A chunk is a whole number of solve waves (5 CTAs per SM; that is also a whole number of tensor-core items per match
+    // CTA): the next chunk's match CTAs need SMs that are completely free, so a last wave that fills a quarter of the
+    // chip costs a tenth of a millisecond per chunk.
     int want_chunks = 1;
+    const int wave = 5 * ctx->sm_count;
+    int per_chunk = std::max(wave, ((1600 + wave / 2) / wave) * wave);          // 1480 pairs on a B200
     if (ctx->debug) want_chunks = 1;                            // the parity taps describe ONE launch pair
-    else if (ctx->host_chunks > 0) want_chunks = std::min(ctx->host_chunks, n_pairs);
+    else if (ctx->host_chunks > 0) { want_chunks = std::min(ctx->host_chunks, n_pairs); per_chunk = (n_pairs + want_chunks - 1) / want_chunks; }
     else if (n_pairs < 2048) want_chunks = 1;
-    else want_chunks = std::min(40, std::max(4, n_pairs / 1600));
-    for (int c = 1; c <= want_chunks; ++c) fracs.push_back((double)c / want_chunks);
-    const int n_chunks = (int)fracs.size();
+    else {
+        want_chunks = (n_pairs + per_chunk - 1) / per_chunk;
+        if (want_chunks > 40) { per_chunk = ((n_pairs / 40 + wave - 1) / wave) * wave; want_chunks = (n_pairs + per_chunk - 1) / per_chunk; }
+        if (want_chunks < 4) { want_chunks = 4; per_chunk = (n_pairs + 3) / 4; }
+    }
+    const int n_chunks = want_chunks;
     std::vector<size_t> chunk_pair_end((size_t)n_chunks);
     for (int c = 0; c < n_chunks; ++c)
-        chunk_pair_end[c] = c + 1 == n_chunks ? (size_t)n_pairs : std::min<size_t>((size_t)n_pairs, (size_t)(fracs[c] * n_pairs + 0.5));
+        chunk_pair_end[c] = c + 1 == n_chunks ? (size_t)n_pairs : std::min<size_t>((size_t)n_pairs, (size_t)(c + 1) * (size_t)per_chunk);
 
     // unique cameras (a keyframe that appears in many pairs - one query vs many candidates - is uploaded once),
     // numbered in order of first use so that every chunk uploads exactly the cameras nobody before it needed
@@ -724,6 +731,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     };
     size_t cf = 0, ct = 0;
     cudaEvent_t last_ready = nullptr;
+    // UZ_TRACE=2: device timeline of the chunks (upload begin/end on the side stream, compute begin/end)
+    const bool tl_on = getenv("UZ_TRACE") != nullptr && atoi(getenv("UZ_TRACE")) >= 2;
+    std::vector<cudaEvent_t> tl(tl_on ? (size_t)n_chunks * 4 : 0, nullptr);
     for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
         const size_t p0 = chunk_begin(c), p1 = chunk_pair_end[c];
         if (p1 <= p0) continue;
@@ -743,7 +753,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
             std::vector<Cam> got;
             if (piped) ctx->stream = ctx->side;
             ctx->copy_beside_compute = piped && c > 0;       // chunk 0 has the chip to itself
+            if (tl_on) { tl[4 * c] = ctx->get_event(); cudaEventRecord(tl[4 * c], ctx->stream); }
             st = upload_cams(ctx, ctx->transient, fresh, got);
+            if (tl_on) { tl[4 * c + 1] = ctx->get_event(); cudaEventRecord(tl[4 * c + 1], ctx->stream); }
             ctx->copy_beside_compute = 0;
             if (st == UZ_OK && piped) {
                 ready = ctx->get_event();
@@ -778,7 +790,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         }
         if (last_ready && (ready || alternate)) cudaStreamWaitEvent(ctx->stream, last_ready, 0);
         cudaStream_t rs = ctx->stream;
+        if (tl_on) { tl[4 * c + 2] = ctx->get_event(); cudaEventRecord(tl[4 * c + 2], ctx->stream); }
         st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0, /*join=*/false, &rs);
+        if (tl_on) { tl[4 * c + 3] = ctx->get_event(); cudaEventRecord(tl[4 * c + 3], rs); }
         ctx->stream = main_stream;
         // into pinned memory: a pageable destination would make the copy synchronous and stall the next chunk's enqueue
         if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
@@ -806,6 +820,16 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     if (ctx->alt) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->alt));
     if (ctx->solve_stream) UZ_CUDA(ctx, cudaStreamSynchronize(ctx->solve_stream));
     tr.lap("wait GPU + records out");
+    if (tl_on) {
+        cudaEvent_t base = nullptr;
+        for (auto e : tl) if (e) { base = e; break; }
+        for (int c = 0; c < n_chunks && base; ++c) {
+            float t[4] = {-1, -1, -1, -1};
+            for (int k = 0; k < 4; ++k) if (tl[4 * c + k]) cudaEventElapsedTime(&t[k], base, tl[4 * c + k]);
+            fprintf(stderr, "[uz timeline] chunk %2d: upload %7.3f .. %7.3f ms   compute %7.3f .. %7.3f ms\n", c, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : tl) if (e) ctx->event_pool.push_back(e);
+    }
     {
         static const char* const names[10] = {"intern cameras", "place cameras", "copy lists + gather + derive", "pair views", "enumerate tasks",
                                               "choose shapes", "keys + tiles", "table copies", "launches", "records home + drain"};
