@@ -18,8 +18,12 @@ def main():
     td, tp, tv = torch.from_numpy(desc).pin_memory(), torch.from_numpy(pos).pin_memory(), torch.from_numpy(valid).pin_memory()
     pinned = [dict(kf, desc=td.numpy()[i], pos=tp.numpy()[i], valid=tv.numpy()[i]) for i, kf in enumerate(kfs)]
     my = pairs[:n_pairs]
-    for env in ({}, {"UZ_COPY_CTAS": "148"}, {"UZ_COPY_CTAS": "296"}, {"UZ_COPY_CTAS": "32"}, {"UZ_HOST_CHUNKS": "8"}, {"UZ_HOST_CHUNKS": "16"},
-                {"UZ_HOST_CHUNKS": "64"}, {"UZ_ALT_CHUNKS": "0"}, {"UZ_TRACE": "1"}):
+    knobs = [{}, {"UZ_HOST_SLOTS": "2"}, {"UZ_HOST_SLOTS": "3"}, {"UZ_HOST_SLOTS": "4"}, {"UZ_COPY_CTAS": "32"}, {"UZ_COPY_CTAS": "148"},
+             {"UZ_HOST_CHUNKS": "8"}, {"UZ_HOST_CHUNKS": "32"}, {"UZ_ALT_CHUNKS": "0"}, {"UZ_TRACE": "2"}]
+    if os.environ.get("UZ_PROBE_KNOBS"):
+        import json
+        knobs = json.loads(os.environ["UZ_PROBE_KNOBS"])
+    for env in knobs:
         est = bench._new_estimator(0, **env)
         os.environ.update(env)
         for name, src in (("pinned", pinned), ("pageable", kfs)):

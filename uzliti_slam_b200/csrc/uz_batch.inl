@@ -285,7 +285,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     if (result_stream) *result_stream = ctx->stream;
     if (n_pairs == 0) return UZ_OK;
     cudaStream_t results_on = ctx->stream;
-    ctx->cur_slot ^= 1;
+    ctx->cur_slot = (ctx->cur_slot + 1) % std::max(2, std::min(ctx->slot_depth, (int)uz_context::kSlots));
     uz_context::Slot& sl = ctx->slots[ctx->cur_slot];
     if (!sl.done) UZ_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     if (sl.used) UZ_CUDA(ctx, cudaEventSynchronize(sl.done));      // normally long complete

@@ -124,6 +124,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (gu) ctx->gather_upload = atoi(gu);
         const char* cc = getenv("UZ_COPY_CTAS");
         if (cc && atoi(cc) > 0) ctx->copy_ctas = atoi(cc);
+        const char* hs = getenv("UZ_HOST_SLOTS");
+        if (hs && atoi(hs) >= 2) ctx->host_slots = std::min(atoi(hs), (int)uz_context::kSlots);
         const char* hc = getenv("UZ_HOST_CHUNKS");
         if (hc) ctx->host_chunks = atoi(hc);
         const char* mm = getenv("UZ_MATCH_MMA");
@@ -647,7 +649,8 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     // Chunks of about 1600 pairs, between 4 and 40 of them.  Consecutive chunks
     // compute on two alternating streams (below), so a chunk boundary costs little; small chunks shrink the exposed first
     // upload and send records home earlier, large ones amortise the launches of a chunk.  Measured on C4 (25 000 pairs) with
-    // the tensor-core match kernel (store-resident 3.28 M edges/s): 8 chunks 2.49 M, 16: 2.52 M, 32: 2.37 M, 64: 2.12 M
+    // the tensor-core match kernel (store-resident 3.28 M edges/s): 8 chunks 2.49 M, 16: 2.52 M, 32: 2.37 M, 64: 2.12 M;
+    // chunks that grow by 15-60 % each (short first upload, fewer launches later) measured the same as equal ones
     // (with the integer-pipe kernels of round 1, 768-pair chunks were best: 926-930 k against 937 k store-resident).
     // UZ_HOST_CHUNKS = k > 0 forces k equal parts.
     // A chunk is a whole number of solve waves (5 CTAs per SM; that is also a whole number of tensor-core items per match
@@ -733,7 +736,11 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
     cudaEvent_t last_ready = nullptr;
     // UZ_TRACE=2: device timeline of the chunks (upload begin/end on the side stream, compute begin/end)
     const bool tl_on = getenv("UZ_TRACE") != nullptr && atoi(getenv("UZ_TRACE")) >= 2;
-    std::vector<cudaEvent_t> tl(tl_on ? (size_t)n_chunks * 4 : 0, nullptr);
+    std::vector<cudaEvent_t> tl(tl_on ? (size_t)n_chunks * 5 : 0, nullptr);
+    // the host runs several chunks ahead of the compute streams (a two-deep ring made every upload wait for the compute
+    // of the chunk three before it: 3 chunks per 1.6 ms on C4, measured with UZ_TRACE=2)
+    struct DepthGuard { uz_context* c; ~DepthGuard() { c->slot_depth = 2; } } depth_guard{ctx};
+    if (n_chunks > 2) ctx->slot_depth = ctx->host_slots;
     for (int c = 0; c < n_chunks && st == UZ_OK; ++c) {
         const size_t p0 = chunk_begin(c), p1 = chunk_pair_end[c];
         if (p1 <= p0) continue;
@@ -753,9 +760,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
             std::vector<Cam> got;
             if (piped) ctx->stream = ctx->side;
             ctx->copy_beside_compute = piped && c > 0;       // chunk 0 has the chip to itself
-            if (tl_on) { tl[4 * c] = ctx->get_event(); cudaEventRecord(tl[4 * c], ctx->stream); }
+            if (tl_on) { tl[5 * c] = ctx->get_event(); cudaEventRecord(tl[5 * c], ctx->stream); ctx->trace_mid = tl[5 * c + 4] = ctx->get_event(); }
             st = upload_cams(ctx, ctx->transient, fresh, got);
-            if (tl_on) { tl[4 * c + 1] = ctx->get_event(); cudaEventRecord(tl[4 * c + 1], ctx->stream); }
+            if (tl_on) { tl[5 * c + 1] = ctx->get_event(); cudaEventRecord(tl[5 * c + 1], ctx->stream); ctx->trace_mid = nullptr; }
             ctx->copy_beside_compute = 0;
             if (st == UZ_OK && piped) {
                 ready = ctx->get_event();
@@ -790,9 +797,9 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         }
         if (last_ready && (ready || alternate)) cudaStreamWaitEvent(ctx->stream, last_ready, 0);
         cudaStream_t rs = ctx->stream;
-        if (tl_on) { tl[4 * c + 2] = ctx->get_event(); cudaEventRecord(tl[4 * c + 2], ctx->stream); }
+        if (tl_on) { tl[5 * c + 2] = ctx->get_event(); cudaEventRecord(tl[5 * c + 2], ctx->stream); }
         st = run_pairs(ctx, part, (uz_edge_result*)ctx->d_results.p + p0, /*join=*/false, &rs);
-        if (tl_on) { tl[4 * c + 3] = ctx->get_event(); cudaEventRecord(tl[4 * c + 3], rs); }
+        if (tl_on) { tl[5 * c + 3] = ctx->get_event(); cudaEventRecord(tl[5 * c + 3], rs); }
         ctx->stream = main_stream;
         // into pinned memory: a pageable destination would make the copy synchronous and stall the next chunk's enqueue
         if (st == UZ_OK && cudaMemcpyAsync(h_res + p0, (uz_edge_result*)ctx->d_results.p + p0, (p1 - p0) * sizeof(uz_edge_result),
@@ -824,9 +831,10 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         cudaEvent_t base = nullptr;
         for (auto e : tl) if (e) { base = e; break; }
         for (int c = 0; c < n_chunks && base; ++c) {
-            float t[4] = {-1, -1, -1, -1};
-            for (int k = 0; k < 4; ++k) if (tl[4 * c + k]) cudaEventElapsedTime(&t[k], base, tl[4 * c + k]);
-            fprintf(stderr, "[uz timeline] chunk %2d: upload %7.3f .. %7.3f ms   compute %7.3f .. %7.3f ms\n", c, t[0], t[1], t[2], t[3]);
+            float t[5] = {-1, -1, -1, -1, -1};
+            for (int k = 0; k < 5; ++k)
+                if (tl[5 * c + k] && cudaEventElapsedTime(&t[k], base, tl[5 * c + k]) != cudaSuccess) { cudaGetLastError(); t[k] = -1; }
+            fprintf(stderr, "[uz timeline] chunk %2d: upload %7.3f .. (gathered %7.3f) .. %7.3f ms   compute %7.3f .. %7.3f ms\n", c, t[0], t[4], t[1], t[2], t[3]);
         }
         for (auto e : tl) if (e) ctx->event_pool.push_back(e);
     }

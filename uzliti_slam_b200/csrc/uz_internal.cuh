@@ -285,6 +285,7 @@ struct uz_context {
     int gather_upload = 1;           // UZ_GATHER_UPLOAD=0 forces the cudaMemcpyAsync path
     int copy_beside_compute = 0;     // set while uploads are enqueued that overlap the match kernel
     int copy_ctas = 64;              // UZ_COPY_CTAS
+    cudaEvent_t trace_mid = nullptr; // UZ_TRACE=2: recorded between the gather and the layout pass of an upload
     // pageable sources are staged through this pinned ring (two halves, an event each) and pulled by the same gather kernel
     PinBuf ring;
     size_t ring_half = (size_t)32 << 20;          // UZ_RING_MB
@@ -316,8 +317,12 @@ struct uz_context {
         cudaEvent_t done = nullptr;
         bool used = false;
     };
-    Slot slots[2];
-    int cur_slot = 0;
+    // Ring of launch slots: a batch waits for the batch that used its slot `slot_depth` launches ago.  Two deep for
+    // store-resident calls (their tables are large); the chunked host path runs kSlots deep so that the host can enqueue
+    // uploads several chunks ahead of the compute streams.
+    static constexpr int kSlots = 6;
+    Slot slots[kSlots];
+    int cur_slot = 0, slot_depth = 2, host_slots = kSlots;
     DevBuf d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
 
     // where the solve kernel writes the records of the batch being launched (group mode: a peer-mapped buffer)

@@ -313,6 +313,7 @@ uz_status fill_cams(uz_context* ctx, const std::vector<const uz_features*>& feat
     }
     uz_status st = flush_copies(ctx, items);
     if (st != UZ_OK) return st;
+    if (ctx->trace_mid) cudaEventRecord(ctx->trace_mid, ctx->stream);
     return derive_layouts(ctx, cams.data(), cams.size());
 }
 
