@@ -64,7 +64,8 @@ def emit(line):
 
 
 def build_map(n_keyframes, out=None):
-    from uzliti_slam_b200 import synthetic as S
+    # the splitmix64 generator that include/uz_synth.h mirrors byte for byte: a C++ host builds the same map
+    from uzliti_slam_b200 import synth_splitmix as S
     t0 = time.time()
     kfs, pairs, poses = S.make_map(n_keyframes, n_features=N_FEATURES, cluster=25, pool=1000, n_shared=600,
                                    k_candidates=K_CAND, cross_cluster=4, seed=4, out=out)

@@ -1,31 +1,35 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench, ncu launch list, ncu --set full of the two kernels.
-# Usage (from the repo root, via gpurun): bash scripts/gpu_round.sh <tag>
-TAG=${1:-r01}
+# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list, ncu --set full of the kernels of the step.
+# Usage (from the repo root, via gpurun): bash scripts/gpu_round.sh <tag> [quick]
+TAG=${1:-r02}
+QUICK=${2:-}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
 tail -3 gpurun_out/pytest_$TAG.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; tail -1 gpurun_out/smoke_$TAG.log
-timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
+timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
 cat gpurun_out/bench_$TAG.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_ref_$TAG.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout 600 adapter/bench_adapter 10000 25000 3 > gpurun_out/bench_adapter_$TAG.json 2>> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_adapter_$TAG.json
+[ -n "$QUICK" ] && exit 0
+# launch list of the default step: the tensor-core match kernel, then the solve kernel behind it on the same stream, so
+# the per-kernel shares of this (serialised, cold-cache) list are comparable with a live step
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench_$TAG.log 2>&1
-# the same list with the solve BEHIND the match kernel (UZ_STREAM_SOLVE=0): under ncu kernels are serialised, so only this
-# form's per-kernel shares are comparable with a live step
-UZ_STREAM_SOLVE=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches_serial_$TAG.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --no-places > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 3 -c 1 -f -o gpurun_out/knn2_full_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mma_kernel -s 3 -c 1 -f -o gpurun_out/knn2_mma_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
-# streaming form (persistent grid; under ncu it is serialised behind the match kernel) and the one-CTA-per-pair form
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_stream_kernel -s 6 -c 1 -f -o gpurun_out/solve_stream_full_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 3 -c 1 -f -o gpurun_out/solve_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -c 1 -f -o gpurun_out/solve_full_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:derive_layouts_kernel -c 1 -f -o gpurun_out/derive_layouts_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
+# the integer-pipe kernels that remain: 512-bit rows, and the 256-bit fallback (UZ_MATCH_MMA=0)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_wide_kernel -s 2 -c 1 -f -o gpurun_out/knn2_wide_full_$TAG \
     python scripts/gpu_wide_probe.py 200 > /dev/null 2>&1
+UZ_MATCH_MMA=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_kernel -s 3 -c 1 -f -o gpurun_out/knn2_full_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 for k in places_insert_kernel places_vote_kernel places_select_kernel; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/${k}_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1

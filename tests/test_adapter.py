@@ -2,6 +2,7 @@
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -60,3 +61,26 @@ def test_adapter_on_two_gpus(built):
     out = subprocess.run([os.path.join(ADAPTER, "test_adapter")], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ADAPTER OK" in out.stdout and "2 device(s)" in out.stdout
+
+
+@pytest.mark.gpu
+def test_adapter_bench_on_the_benchmark_map(built):
+    """bench_adapter generates the benchmark's map in C++ (include/uz_synth.h) and drives it through the adapter's queue:
+    the map must be the one the Python generator builds, every edge must come back, and resident == cold answers"""
+    import json
+    from uzliti_slam_b200 import synth_splitmix as SM
+    _build()
+    out = subprocess.run([os.path.join(ADAPTER, "bench_adapter"), "150", "2000", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    kfs, pairs, _ = SM.make_map(150, native=False)
+    assert d["map_checksum_desc"] == SM.checksum(np.stack([k["desc"] for k in kfs]))
+    assert d["map_checksum_pos"] == SM.checksum(np.stack([k["pos"] for k in kfs]))
+    assert d["pairs"] == 2000 and d["same_edges"] is True and d["edges_score_ge_15"] > 1000
+    # the same pairs through the Python binding: the sum of matching scores agrees (scores are integers)
+    from uzliti_slam_b200 import EdgeEstimator
+    est = EdgeEstimator(0)
+    h = est.add_keyframes(kfs)
+    res = est.estimateEdges(h[pairs[:2000, 0]], h[pairs[:2000, 1]])
+    est.close()
+    assert int(np.where(res["ok"] != 0, res["consensus"], 0).sum()) == d["score_sum_resident"]
