@@ -161,7 +161,7 @@ public:
     double age_ = 0.;
     double error_ = 0.;
     double matching_score_ = 0.;
-    bool valid_ = true;
+    bool valid_ = false;                                             // slam_edge.cpp:47
     ros::Duration diff_time_;
 };
 #endif  // UZ_ADAPTER_REAL_HEADERS

@@ -9,8 +9,9 @@
 // on false the worker zeroes matching_score_ and STILL fires the callback, transformation_estimator.cpp:53-56).
 // What changes is the execution model: the reference pops ONE pair per 1 ms tick on its worker thread; here
 // the worker drains the whole queue and hands it to the GPU as one batch (estimateEdgeBatch), with the
-// nodes' FeatureData cached in the device-resident keyframe store.  Callbacks are fired from the worker
-// thread, never while the caller of estimateEdge() is on the stack (the reference's callers hold graph_mutex_).
+// nodes' FeatureData cached in the device-resident keyframe store.  Callbacks are fired from a delivery thread (in
+// estimation order, while the next chunk is being estimated), never while the caller of estimateEdge() is on the stack
+// (the reference's callers hold graph_mutex_).
 #pragma once
 #ifdef UZ_ADAPTER_REAL_HEADERS
 #include <graph_slam_common/slam_node.h>
@@ -44,7 +45,14 @@ protected:
     void startThread();                               // called by the most-derived constructor
     void stopThread();
     void estimationThread();
+    void deliveryThread();
 
+    // edges of one chunk on their way to the callback; two slots, filled and delivered in turn
+    struct Delivery { std::vector<SlamEdge> edges; std::vector<char> ok; };
+    static const int kDeliveryChunk = 4096;
+    Delivery slots_[2];
+    bool slot_full_[2] = {false, false};
+    std::thread delivery_thread_;
     std::thread estimation_thread_;
     std::mutex estimation_mutex_;
     std::condition_variable cv_;
@@ -105,6 +113,7 @@ public:
 protected:
     struct Resident { int32_t handle = -1; std::vector<FeatureDataPtr> cams; std::vector<int> rows; };
     bool ensureResident(const SlamNode& node, Resident** out);
+    bool loadNodesLocked(const std::vector<const SlamNode*>& nodes);      // gpuMutex() held
     void fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to, SlamEdge& edge) const;
     int internFrame(const std::string& frame);
 

@@ -3,8 +3,10 @@
 // transformation_estimation/src/feature_transformation_estimator.cpp:32-171,178-184,337-353.
 #include <transformation_estimation/gpu_feature_transformation_estimator.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <stdexcept>
+#include <unordered_set>
 
 // ---------------------------------------------------------------------------------------------------------
 // TransformationEstimator: queue + worker thread (transformation_estimator.cpp:22-62)
@@ -16,6 +18,7 @@ TransformationEstimator::~TransformationEstimator() { stopThread(); }
 void TransformationEstimator::startThread() {
     running_ = true;
     estimation_thread_ = std::thread(&TransformationEstimator::estimationThread, this);
+    delivery_thread_ = std::thread(&TransformationEstimator::deliveryThread, this);
 }
 
 void TransformationEstimator::stopThread() {
@@ -26,14 +29,17 @@ void TransformationEstimator::stopThread() {
     }
     cv_.notify_all();
     if (estimation_thread_.joinable()) estimation_thread_.join();
+    if (delivery_thread_.joinable()) delivery_thread_.join();
 }
 
 void TransformationEstimator::estimateEdge(SlamNode& from, SlamNode& to) {
+    bool wake;
     {   // cheap and non-blocking: callers hold graph_mutex_ (graph_slam_node.cpp:207,448)
         std::lock_guard<std::mutex> lk(estimation_mutex_);
-        est_queue_.push_back(std::make_pair(from, to));   // copies the nodes; FeatureData is shared (shared_ptr)
+        wake = est_queue_.empty();                        // the worker only sleeps on an empty queue: one wake-up per burst
+        est_queue_.emplace_back(from, to);                // copies the nodes; FeatureData is shared (shared_ptr)
     }
-    cv_.notify_one();
+    if (wake) cv_.notify_all();
 }
 
 void TransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs,
@@ -43,32 +49,70 @@ void TransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, 
     for (size_t i = 0; i < pairs.size(); ++i) ok[i] = estimateEdgeImpl(pairs[i].first, pairs[i].second, edges[i]);
 }
 
+// Two threads: the estimation thread turns queued pairs into edges, the delivery thread fires the callbacks.  A drained queue
+// is worked off in chunks, and while chunk c's edges are being delivered (edge copies, strings, the caller's callback) chunk
+// c + 1 is already being estimated.  Order of delivery is the order of estimation (LIFO per drained queue, :49-50).
 void TransformationEstimator::estimationThread() {
     std::unique_lock<std::mutex> lk(estimation_mutex_);
+    // the queue and the batch being worked on are two vectors that change roles, and the edge vectors live across batches:
+    // their capacity is kept, so a steady stream of estimateEdge calls neither regrows the queue nor touches fresh pages
+    std::vector<std::pair<SlamNode, SlamNode> > batch, chunk;
+    int fill = 0;
     while (running_) {
         if (est_queue_.empty()) { cv_.wait(lk); continue; }
-        std::vector<std::pair<SlamNode, SlamNode> > batch;
-        batch.swap(est_queue_);
-        // the reference pops the NEWEST pair first (LIFO, :49-50): deliver in that order
-        std::vector<std::pair<SlamNode, SlamNode> > lifo(batch.rbegin(), batch.rend());
+        batch.swap(est_queue_);                          // est_queue_ gets the (cleared) vector of the previous batch
         busy_ = true;
         lk.unlock();
-        std::vector<SlamEdge> edges;
-        std::vector<char> ok;
-        estimateEdgeBatch(lifo, edges, ok);
-        for (size_t i = 0; i < edges.size(); ++i) {
-            if (!ok[i]) edges[i].matching_score_ = 0.;   // :53-55
-            callback_(edges[i]);                         // :56 — fired even on failure
+        // the reference pops the NEWEST pair first (LIFO, :49-50): deliver in that order
+        std::reverse(batch.begin(), batch.end());
+        for (size_t at = 0; at < batch.size(); at += kDeliveryChunk) {
+            const size_t end = std::min(batch.size(), at + (size_t)kDeliveryChunk);
+            std::vector<std::pair<SlamNode, SlamNode> >* part = &batch;
+            if (batch.size() > (size_t)kDeliveryChunk) {
+                chunk.assign(std::make_move_iterator(batch.begin() + at), std::make_move_iterator(batch.begin() + end));
+                part = &chunk;
+            }
+            lk.lock();
+            cv_.wait(lk, [&] { return !slot_full_[fill]; });
+            lk.unlock();
+            estimateEdgeBatch(*part, slots_[fill].edges, slots_[fill].ok);
+            lk.lock();
+            slot_full_[fill] = true;
+            lk.unlock();
+            cv_.notify_all();
+            fill ^= 1;
         }
+        batch.clear();
+        chunk.clear();
         lk.lock();
         busy_ = false;
         cv_.notify_all();
     }
 }
 
+void TransformationEstimator::deliveryThread() {
+    std::unique_lock<std::mutex> lk(estimation_mutex_);
+    int cur = 0;
+    for (;;) {
+        cv_.wait(lk, [&] { return slot_full_[cur] || (!running_ && !busy_); });
+        if (!slot_full_[cur]) return;                    // stopped and nothing left to deliver
+        lk.unlock();
+        std::vector<SlamEdge>& edges = slots_[cur].edges;
+        const std::vector<char>& ok = slots_[cur].ok;
+        for (size_t i = 0; i < edges.size(); ++i) {
+            if (!ok[i]) edges[i].matching_score_ = 0.;   // :53-55
+            callback_(edges[i]);                         // :56 - fired even on failure
+        }
+        lk.lock();
+        slot_full_[cur] = false;
+        cv_.notify_all();
+        cur ^= 1;
+    }
+}
+
 void TransformationEstimator::waitIdle() {
     std::unique_lock<std::mutex> lk(estimation_mutex_);
-    cv_.wait(lk, [this] { return est_queue_.empty() && !busy_; });
+    cv_.wait(lk, [this] { return est_queue_.empty() && !busy_ && !slot_full_[0] && !slot_full_[1]; });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -146,20 +190,26 @@ void GpuFeatureTransformationEstimator::collectCams(const SlamNode& node, std::v
         }
 }
 
-// true when the device copy was made from exactly these FeatureData objects: same objects (FeatureData is immutable once
-// published, sensor_data.h:113-114), same sizes
-static bool same_cams(const std::vector<FeatureDataPtr>& a, const std::vector<FeatureDataPtr>& b, const std::vector<int>& rows) {
-    if (a.size() != b.size()) return false;
-    for (size_t i = 0; i < a.size(); ++i)
-        if (a[i].get() != b[i].get() || rows[i] != a[i]->features_.rows) return false;
-    return true;
+// true when the device copy was made from exactly the node's FeatureData objects: same objects (FeatureData is immutable
+// once published, sensor_data.h:113-114), same sizes.  The common case - node resident and unchanged -
+// allocates nothing.
+static bool node_matches(const SlamNode& node, const std::vector<FeatureDataPtr>& have, const std::vector<int>& rows) {
+    size_t k = 0;
+    for (const SensorDataPtr& d : node.sensor_data_) {
+        if (d->type_ != graph_slam_msgs::SensorData::SENSOR_TYPE_FEATURE) continue;
+        const FeatureData* f = dynamic_cast<const FeatureData*>(d.get());
+        if (!f) continue;
+        if (k >= have.size() || have[k].get() != f || rows[k] != f->features_.rows) return false;
+        ++k;
+    }
+    return k == have.size();
 }
 
 bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Resident** out) {
+    auto it = node.id_.empty() ? handles_.end() : handles_.find(node.id_);
+    if (it != handles_.end() && node_matches(node, it->second.cams, it->second.rows)) { *out = &it->second; return true; }
     std::vector<FeatureDataPtr> cams;
     collectCams(node, cams);
-    auto it = node.id_.empty() ? handles_.end() : handles_.find(node.id_);
-    if (it != handles_.end() && same_cams(cams, it->second.cams, it->second.rows)) { *out = &it->second; return true; }
     std::vector<uz_features> views(cams.size());
     std::vector<std::vector<uint8_t> > valid(cams.size());
     std::vector<int> rows(cams.size());
@@ -186,13 +236,21 @@ bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Res
 
 bool GpuFeatureTransformationEstimator::loadNodes(const std::vector<SlamNode>& nodes) {
     std::lock_guard<std::mutex> lk(gpu_mutex_);
+    std::vector<const SlamNode*> ptrs;
+    ptrs.reserve(nodes.size());
+    for (const SlamNode& n : nodes) ptrs.push_back(&n);
+    return loadNodesLocked(ptrs);
+}
+
+bool GpuFeatureTransformationEstimator::loadNodesLocked(const std::vector<const SlamNode*>& nodes) {
     std::vector<uz_features> views;
     std::vector<std::vector<uint8_t> > valid;
     std::vector<int32_t> counts;
     std::vector<Resident> res;
     std::vector<const SlamNode*> fresh;
     size_t total = 0;
-    for (const SlamNode& n : nodes) {
+    for (const SlamNode* np : nodes) {
+        const SlamNode& n = *np;
         if (n.id_.empty() || handles_.count(n.id_)) continue;
         Resident r;
         collectCams(n, r.cams);
@@ -227,12 +285,31 @@ void GpuFeatureTransformationEstimator::forgetNode(const std::string& id) {
     handles_.erase(it);
 }
 
+static void set_identity6(Eigen::MatrixXd& m) {
+    if (m.rows() != 6 || m.cols() != 6) { m = Eigen::MatrixXd::Identity(6, 6); return; }
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) m(a, b) = a == b ? 1.0 : 0.0;
+}
+
+// the state of SlamEdge() (slam_edge.cpp:22-25 / slam_edge.h:47-93), in place
+static void resetEdge(SlamEdge& e) {
+    e.id_.clear(); e.id_from_.clear(); e.id_to_.clear();
+    e.transform_ = Eigen::Isometry3d::Identity();
+    e.displacement_from_ = Eigen::Isometry3d::Identity();
+    e.displacement_to_ = Eigen::Isometry3d::Identity();
+    set_identity6(e.information_);
+    e.type_ = 0;
+    e.sensor_from_.clear(); e.sensor_to_.clear();
+    e.age_ = 0.; e.error_ = 0.; e.matching_score_ = 0.; e.valid_ = false;        // init(): slam_edge.cpp:33-48
+    e.diff_time_ = ros::Duration(1);
+}
+
 void GpuFeatureTransformationEstimator::fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to,
                                                  SlamEdge& edge) const {
     if (!r.ok) return;                                   // on failure the edge keeps its default-constructed fields
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) edge.transform_(a, b) = r.T[4 * a + b];               // :147
-    edge.information_ = Eigen::MatrixXd::Identity(6, 6);
+    set_identity6(edge.information_);
     if (r.consensus > 0 && r.mse > 0) {                                                     // :134-137
         edge.information_ *= r.info_scale;
         for (int a = 3; a < 6; ++a)
@@ -252,10 +329,22 @@ void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<
                                                           std::vector<SlamEdge>& edges, std::vector<char>& ok) {
     std::lock_guard<std::mutex> lk(gpu_mutex_);
     const size_t n = pairs.size();
-    edges.assign(n, SlamEdge());
+    edges.resize(n);
+    for (SlamEdge& e : edges) resetEdge(e);               // == default constructed, without giving the 6 x 6 matrix back to the heap
     ok.assign(n, 0);
     std::vector<int32_t> hf(n), ht(n);
     std::vector<Resident*> rf(n), rt(n);
+    {   // nodes this batch sees for the first time travel in ONE bulk upload (a cold queue otherwise pays one upload call per node)
+        std::vector<const SlamNode*> fresh;
+        std::unordered_set<std::string> seen;
+        for (size_t i = 0; i < n; ++i)
+            for (const SlamNode* nd : {&pairs[i].first, &pairs[i].second})
+                if (!nd->id_.empty() && !handles_.count(nd->id_) && seen.insert(nd->id_).second) fresh.push_back(nd);
+        if (fresh.size() > 1 && !loadNodesLocked(fresh)) {
+            for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
+            return;
+        }
+    }
     for (size_t i = 0; i < n; ++i) {
         if (!ensureResident(pairs[i].first, &rf[i]) || !ensureResident(pairs[i].second, &rt[i])) {
             std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError());

@@ -861,6 +861,21 @@ def run_gpu(args):
     if rank == 0 and not args.no_extras:
         others = measure_other_configs(est, handles, kfs)
 
+    adapter_queue = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        # the same map and pair list through the C++ adapter's queue interface (the class a maintainer swaps in,
+        # INTEGRATION.md): adapter/bench_adapter builds the map with include/uz_synth.h - the generator of build_map
+        exe = os.path.join(ROOT, "adapter", "bench_adapter")
+        if os.path.exists(exe):
+            try:
+                from uzliti_slam_b200 import synth_splitmix as SM
+                out = subprocess.run([exe, str(n_kf), str(pairs_per_gpu), "3"], capture_output=True, text=True, timeout=300)
+                adapter_queue = json.loads(out.stdout.strip().splitlines()[-1])
+                adapter_queue["same_map_as_this_bench"] = bool(
+                    adapter_queue.get("map_checksum_desc") == SM.checksum(np.stack([k["desc"] for k in kfs])))
+            except Exception as e:  # noqa: BLE001
+                adapter_queue = {"error": repr(e)[:200]}
+
     if rank == 0:
         cmp_per_launch = tm["compares"] / max(tm["match_launches"], 1)
         knn_ms = tm["match_ms"] / max(tm["match_launches"], 1)
@@ -928,7 +943,7 @@ def run_gpu(args):
                           + ("; at N > 1 every rank times its own host round trip (max over ranks), records stay in the rank's "
                              "host memory - the one-array form is `group`" if world > 1 else "")),
             gpu_launches=launches, clocks=clocks, sanity=sanity, scaling_extra=scaling_extra, group=group,
-            candidate_generation=places, other_configs=others)
+            candidate_generation=places, other_configs=others, adapter_queue=adapter_queue)
         emit(line)
     est.close()
     if world > 1:
