@@ -14,13 +14,16 @@ SIZES = [(1000, 1000), (400, 300), (65, 129), (1, 5), (513, 4096), (130, 127), (
          (7, 1), (129, 257), (1000, 31), (9, 700)]
 
 
-def _est(mma):
+def _est(mma, cfg=None):
     from uzliti_slam_b200 import EdgeEstimator
     os.environ["UZ_MATCH_MMA"] = str(mma)
+    if cfg is not None:
+        os.environ["UZ_MMA2_CFG"] = str(cfg)
     try:
         return EdgeEstimator(0)
     finally:
         os.environ.pop("UZ_MATCH_MMA", None)
+        os.environ.pop("UZ_MMA2_CFG", None)
 
 
 def test_mma_neighbours_equal_oracle_and_popc_kernel(oracle):
@@ -98,3 +101,72 @@ def test_whole_path_records_identical_on_both_match_kernels(oracle):
         assert a[0]["consensus"] == o["consensus"] and a[0]["cam_from"] == o["cam_from"]
     finally:
         em.close(); ep.close()
+
+
+@pytest.mark.parametrize("variant", [4, 7])
+def test_alternative_tensor_core_kernels_equal_oracle(oracle, variant):
+    """the measured alternatives that stay selectable (UZ_MATCH_MMA=4: 16 epilogue warps, 7: the IMAD epilogue of knn2_mma_kernel)"""
+    e = _est(variant)
+    try:
+        for nq, nt in SIZES:
+            for mode in range(3):
+                rng = np.random.default_rng(55 * nq + nt + mode)
+                q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+                t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+                if mode == 1:
+                    q[:, 2:] = 0; t[:, 2:] = 0
+                if mode == 2 and nt > 4:
+                    t[nt - 1] = q[0]; t[nt // 2] = q[0]; t[1] = q[nq // 2]; t[min(130, nt - 1)] = q[nq // 2]
+                idx, dist = e.knnMatch(q, t)
+                oi, od = oracle.knn2(q, t)
+                assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt, mode)
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_cta_pair_kernel_neighbours_equal_oracle(oracle, cfg):
+    """knn2_mma2_kernel (tcgen05.mma.cta_group::2 on CTA pairs; UZ_MATCH_MMA=3 forces it for every launch): the same shapes,
+    both pipeline configurations"""
+    e2 = _est(3, cfg)
+    try:
+        for nq, nt in SIZES + [(512, 256), (511, 513), (1024, 1000), (640, 128), (2000, 1500)]:
+            for mode in range(3):
+                rng = np.random.default_rng(99 * nq + nt + mode)
+                q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+                t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+                if mode == 1:
+                    q[:, 2:] = 0; t[:, 2:] = 0
+                if mode == 2 and nt > 4:
+                    t[nt - 1] = q[0]; t[nt // 2] = q[0]; t[1] = q[nq // 2]; t[min(130, nt - 1)] = q[nq // 2]
+                idx, dist = e2.knnMatch(q, t)
+                oi, od = oracle.knn2(q, t)
+                assert np.array_equal(idx, oi), (nq, nt, mode)
+                assert np.array_equal(dist, od), (nq, nt, mode)
+    finally:
+        e2.close()
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_cta_pair_kernel_whole_batches_identical(oracle, cfg):
+    """batches large enough to keep every CTA pair busy for many items (ragged sizes, rigs, cross-check): records byte-identical
+    to the one-CTA tensor-core kernel's"""
+    e2, e1 = _est(2, cfg), _est(1)
+    try:
+        kfs, pairs, _ = S.make_map(120, n_features=1000, cluster=10, pool=1000, n_shared=600, k_candidates=10, cross_cluster=2, seed=23)
+        ragged, rp, _ = S.make_map(60, n_features=700, cluster=6, pool=700, n_shared=400, k_candidates=6, cross_cluster=2, seed=21)
+        for cross in (0, 1):
+            for ks, ps in ((kfs, pairs), (ragged, rp)):
+                recs = []
+                for e in (e2, e1):
+                    e.setConfig(cross_check=cross)
+                    e.clear()
+                    h = e.add_keyframes(ks)
+                    recs.append(e.estimateEdges(h[ps[:, 0]], h[ps[:, 1]]))
+                assert recs[0].tobytes() == recs[1].tobytes()
+                assert (recs[0]["ok"] == 1).any()
+        host = e2.estimateEdgesHost([([kfs[a]], [kfs[b]]) for a, b in pairs[:300]])
+        e1.setConfig(cross_check=1)
+        assert host.tobytes() == e1.estimateEdgesHost([([kfs[a]], [kfs[b]]) for a, b in pairs[:300]]).tobytes()
+    finally:
+        e2.close(); e1.close()

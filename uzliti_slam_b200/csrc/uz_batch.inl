@@ -78,6 +78,10 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma16_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmak_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel<2, 3>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel<1, 4>);
     if (e == cudaSuccess) e = max_shared_carveout(derive_layouts_kernel);
     return e;
 }
@@ -97,6 +101,7 @@ struct BatchPlan {
     int max_nq = 0, cap = 0;
     int64_t compares = 0;
     bool mma = false;                    // 256-bit matchings on the tensor cores (knn2_mma_kernel)
+    bool mma2 = false;                   // ... on CTA pairs (knn2_mma2_kernel): launches that keep every pair of SMs busy
     int best_cfg = 3, wide_cfg = 0;      // integer-pipe tile shapes
     int tile_rows = 512, wide_threads = 256, wide_tile_rows = 512;
     bool fused = false;                  // cross-check inside the match kernel (integer-pipe kernels only)
@@ -236,7 +241,14 @@ void choose_shapes(uz_context* ctx, BatchPlan& bp) {
         if (bp.n_wide) bp.wide_cfg = pick(kWideCand, 2, wth, wqp, wsp, 32, true);
         if (ctx->force_wide_cfg >= 0 && ctx->force_wide_cfg < 2) bp.wide_cfg = ctx->force_wide_cfg;
     }
-    bp.tile_rows = bp.mma ? kMmaItemRows : kKnnConfigs[bp.best_cfg].threads * kKnnConfigs[bp.best_cfg].qpt;
+    if (bp.mma && (ctx->match_mma == 2 || ctx->match_mma == 3)) {
+        // CTA pairs take 512-row items; worth it only when there are at least as many items as pairs of SMs
+        size_t items2 = 0;
+        for (size_t t = 0; t < bp.n_tasks; ++t)
+            if (!task_wide[t]) items2 += ((size_t)tasks[t].nq + kMma2ItemRows - 1) / kMma2ItemRows;
+        bp.mma2 = items2 >= (size_t)(ctx->sm_count / 2) || (ctx->match_mma == 3 && items2 > 0);     // 3: always (tests)
+    }
+    bp.tile_rows = bp.mma2 ? kMma2ItemRows : bp.mma ? kMmaItemRows : kKnnConfigs[bp.best_cfg].threads * kKnnConfigs[bp.best_cfg].qpt;
     bp.wide_threads = bp.wide_cfg == 0 ? 256 : 64;
     bp.wide_tile_rows = 2 * bp.wide_threads;
 
@@ -482,11 +494,34 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) ctx->match_launches++;
         }
-        if (nt > 0 && bp.mma) {
+        if (nt > 0 && bp.mma2) {
+            // persistent grid of CTA pairs (clusters of two = one TPC), items dealt round-robin
+            cudaLaunchConfig_t cfg = {};
+            const int clusters = std::min(nt, ctx->sm_count / 2);
+            cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(kMmaThreads); cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const MmaTask* mt = reinterpret_cast<const MmaTask*>(d_tk);
+            if (ctx->mma2_cfg == 1) {
+                cfg.dynamicSmemBytes = mma2_smem_bytes(1, 4);
+                UZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, knn2_mma2_kernel<1, 4>, mt, d_t, nt, d_k, uz_knn2_mma_desc()));
+            } else {
+                cfg.dynamicSmemBytes = mma2_smem_bytes(2, 3);
+                UZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, knn2_mma2_kernel<2, 3>, mt, d_t, nt, d_k, uz_knn2_mma_desc()));
+            }
+            ctx->mma_launches++;
+        } else if (nt > 0 && bp.mma) {
             // persistent grid, one CTA per SM; items are dealt round-robin, so neighbouring SMs work on the same pair and
             // share its train rows in L2
-            knn2_mma_kernel<<<std::min(nt, ctx->sm_count), kMmaThreads, kMmaSmemBytes, ctx->stream>>>(
-                reinterpret_cast<const MmaTask*>(d_tk), d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
+            const MmaTask* mt = reinterpret_cast<const MmaTask*>(d_tk);
+            const int grid = std::min(nt, ctx->sm_count);
+            if (ctx->match_mma == 4)         // measured alternatives, kept for A/B (profiles/mma_experiments_r02.txt)
+                knn2_mma16_kernel<<<grid, kMma16Threads, kMma16SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
+            else if (ctx->match_mma == 7)
+                knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
+            else                             // default: the keys come out of the tensor core
+                knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
             ctx->mma_launches++;
         } else if (nt > 0) switch (bp.best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, bp.seg_narrow); break;

@@ -44,6 +44,8 @@ constexpr int kMmaM = 128;                 // query rows per MMA / per TMEM accu
 constexpr int kMmaN = 256;                 // train rows per stage / accumulator columns
 constexpr int kMmaItemRows = 2 * kMmaM;    // query rows per item (two accumulators)
 constexpr int kE8RowBytes = 256;           // one int8 per descriptor bit
+constexpr uint32_t kE8Set = 0x08u, kE8Clear = 0xF8u;   // +8 / -8: a product is +-64, so <q, t> arrives as 64 x (agreements - disagreements)
+constexpr int kE8Dot = 64;                 // ... and the key unit 64 x 2 per bit of distance needs no multiply (uz_knn2_mmak.cuh)
 constexpr int kE8GroupBytes = 8 * kE8RowBytes;
 constexpr int kMmaThreads = 320;
 constexpr int kMmaABytes = kMmaM * kE8RowBytes;     // 32 KB
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) expand_e8_kernel(const uint32_t* __restri
     for (int k = 0; k < 4; ++k) {
         uint32_t v = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) v |= (((bits >> (4 * k + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+        for (int b = 0; b < 4; ++b) v |= (((bits >> (4 * k + b)) & 1u) ? kE8Set : kE8Clear) << (8 * b);
         o[k] = v;
     }
     *reinterpret_cast<uint4*>(e8 + (size_t)(row >> 3) * kE8GroupBytes + c * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -157,7 +159,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
 
 // Epilogue multipliers from the constant bank: with immediate powers of two ptxas turns the multiply-add into
 // ALU-pipe shifts/LEAs, and the ALU pipe carries the packed min/max
-__constant__ int32_t kMmaKeyMul[2] = {-64, -64 * 65536};
+__constant__ int32_t kMmaKeyMul[2] = {-1, -65536};        // accumulators hold 64 x dot (operands are +-8)
 
 // two columns (ja even lane, jb odd lane) of one query row -> packed key16 pair
 __device__ __forceinline__ uint32_t mma_pack2(uint32_t dot_a, uint32_t dot_b, const int ja /* a constant after unrolling */) {
@@ -181,11 +183,22 @@ __device__ __forceinline__ void mma_chunk_masked(const uint32_t (&d)[32], int va
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         if (j < valid) {
-            const uint32_t ham = (uint32_t)(256 - (int32_t)d[j]) >> 1;
+            const uint32_t ham = (uint32_t)(256 * kE8Dot - (int32_t)d[j]) >> 7;       // (256 - dot) / 2, accumulator = 64 dot
             top2_update(m1, m2, (ham << 16) | (t_first + (uint32_t)j));
         }
     }
 }
+
+// UZ_MMA_PROF (probe builds only): per CTA, clocks the MMA issuer spent waiting for train tiles, query tiles and free
+// accumulators, and its whole loop
+#ifdef UZ_MMA_PROF
+__device__ long long g_mma_prof[256][4];
+#define UZ_PROF_T(x) const long long x = clock64()
+#define UZ_PROF_ADD(k, a, b) prof[k] += (b) - (a)
+#else
+#define UZ_PROF_T(x)
+#define UZ_PROF_ADD(k, a, b)
+#endif
 
 // items[k] = (task, first query row); CTA b takes items b, b + gridDim.x, ...
 __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask* __restrict__ tasks, const int2* __restrict__ items,
@@ -262,6 +275,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         uint32_t uB = 0, uA[2] = {0, 0}, uAcc[2] = {0, 0};
+#ifdef UZ_MMA_PROF
+        long long prof[4] = {0, 0, 0, 0};
+        const long long prof_begin = clock64();
+#endif
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int2 item = items[it];
             const MmaTask* tk = tasks + item.x;
@@ -270,13 +287,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
             const int T = (nt + kMmaN - 1) / kMmaN;
             for (int t = 0; t < T; ++t) {
                 const uint32_t slot = uB & 1u;
+                UZ_PROF_T(p0);
                 mbar_wait_wd(&b_full[slot], (uB >> 1) & 1u);
+                UZ_PROF_T(p1);
+                UZ_PROF_ADD(0, p0, p1);
                 const int rows = min(kMmaN, nt - t * kMmaN);
                 const uint32_t n_mma = (uint32_t)((rows + 15) & ~15);            // N: multiple of 16 at M = 128
                 const uint32_t idesc = dsc.idesc_base | ((n_mma >> 3) << 17);
                 for (int i = 0; i < nqt; ++i) {
+                    UZ_PROF_T(p2);
                     if (t == 0) mbar_wait_wd(&a_full[i], uA[i] & 1u);
+                    UZ_PROF_T(p3);
                     mbar_wait_wd(&acc_empty[i], (uAcc[i] & 1u) ^ 1u);
+                    UZ_PROF_T(p4);
+                    UZ_PROF_ADD(1, p2, p3);
+                    UZ_PROF_ADD(2, p3, p4);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a_addr = smem_u32(sA + i * kMmaABytes), b_addr = smem_u32(sB + slot * kMmaBBytes);
@@ -296,6 +321,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
             }
             if (T > 0) for (int i = 0; i < nqt; ++i) uA[i]++;
         }
+#ifdef UZ_MMA_PROF
+        if (lane == 0 && blockIdx.x < 256) {
+            prof[3] = clock64() - prof_begin;
+            for (int k = 0; k < 4; ++k) g_mma_prof[blockIdx.x][k] = prof[k];
+        }
+#endif
     } else {
         // ===================== epilogue =====================
         const int ew = warp - 2;                   // 0..7

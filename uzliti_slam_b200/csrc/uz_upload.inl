@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
         for (int k = 0; k < 4; ++k) {
             uint32_t v = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) v |= (((bits >> (4 * k + b)) & 1u) ? 0x01u : 0xFFu) << (8 * b);
+            for (int b = 0; b < 4; ++b) v |= (((bits >> (4 * k + b)) & 1u) ? kE8Set : kE8Clear) << (8 * b);
             o[k] = v;
         }
         *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kE8GroupBytes + c * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
