@@ -14,7 +14,6 @@
 
 #include "../uzliti_slam_b200/csrc/uz_knn2_mma.cuh"
 #include "../uzliti_slam_b200/csrc/uz_knn2_mma2.cuh"
-#include "../uzliti_slam_b200/csrc/uz_knn2_mma16.cuh"
 #include "../uzliti_slam_b200/csrc/uz_knn2_mmak.cuh"
 
 using namespace uz;
@@ -69,7 +68,6 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     CK(cudaMemcpy(d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_keys, 0xEE, std::max<size_t>(key_rows, 1) * sizeof(uint2)));
     CK(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
-    CK(cudaFuncSetAttribute(knn2_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma16SmemBytes));
     CK(cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes));
     const int grid = (int)std::min<size_t>(items.size(), (size_t)g_sms);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -77,7 +75,6 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
         if (grid > 0 && variant == 2) knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
-        else if (grid > 0 && variant == 1) knn2_mma16_kernel<<<grid, kMma16Threads, kMma16SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         else if (grid > 0) knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         cudaEventRecord(e1);
         cudaError_t e = cudaGetLastError();
@@ -101,7 +98,6 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     return best;
 }
 
-template <int ASETS, int NS>
 static float run_mma2(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc dsc, std::vector<uint2>* out, int reps) {
     std::vector<int2> items;
     for (size_t t = 0; t < tasks.size(); ++t)
@@ -113,10 +109,10 @@ static float run_mma2(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDes
     CK(cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(MmaTask), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_keys, 0xEE, std::max<size_t>(key_rows, 1) * sizeof(uint2)));
-    CK(cudaFuncSetAttribute(knn2_mma2_kernel<ASETS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma2_smem_bytes(ASETS, NS)));
+    CK(cudaFuncSetAttribute(knn2_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma2SmemBytes));
     const int clusters = (int)std::min<size_t>(items.size(), (size_t)g_sms / 2);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kMmaThreads); cfg.dynamicSmemBytes = mma2_smem_bytes(ASETS, NS);
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kMmaThreads); cfg.dynamicSmemBytes = kMma2SmemBytes;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -124,7 +120,7 @@ static float run_mma2(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDes
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        if (clusters > 0) CK(cudaLaunchKernelEx(&cfg, knn2_mma2_kernel<ASETS, NS>, (const MmaTask*)d_tasks, (const int2*)d_items, (int)items.size(), d_keys, dsc));
+        if (clusters > 0) CK(cudaLaunchKernelEx(&cfg, knn2_mma2_kernel, (const MmaTask*)d_tasks, (const int2*)d_items, (int)items.size(), d_keys, dsc));
         cudaEventRecord(e1);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("knn2_mma2_kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
@@ -138,17 +134,8 @@ static float run_mma2(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDes
         CK(cudaMemcpyFromSymbol(h, g_mma_prof, sizeof(h)));
         double s[4] = {0, 0, 0, 0};
         for (int b = 0; b < clusters; ++b) for (int k = 0; k < 4; ++k) s[k] += (double)h[b][k] / clusters;
-        printf("  pair kernel <%d,%d> issuer, mean clocks per cluster: loop %.0f, waiting for train tiles %.0f (%.1f %%), query tiles %.0f (%.1f %%), free accumulators %.0f (%.1f %%)\n",
-               ASETS, NS, s[3], s[0], 100 * s[0] / s[3], s[1], 100 * s[1] / s[3], s[2], 100 * s[2] / s[3]);
-        static long long h2[256][16];
-        CK(cudaMemcpyFromSymbol(h2, g_mma_prof2, sizeof(h2)));
-        double s2[16];
-        for (int k = 0; k < 16; ++k) { s2[k] = 0; for (int b = 0; b < clusters; ++b) s2[k] += (double)h2[b][k] / clusters; }
-        const double per_item = (double)items.size() / clusters;
-        printf("    per item (clocks): train tile t=0..3: %.0f %.0f %.0f %.0f | query block 0,1: %.0f %.0f | accumulator (t,i): ", s2[0] / per_item, s2[1] / per_item,
-               s2[2] / per_item, s2[3] / per_item, s2[4] / per_item, s2[5] / per_item);
-        for (int k = 8; k < 16; ++k) printf("%.0f ", s2[k] / per_item);
-        printf("\n");
+        printf("  pair kernel issuer, mean clocks per cluster: loop %.0f, waiting for train tiles %.0f (%.1f %%), query tiles %.0f (%.1f %%), free accumulators %.0f (%.1f %%)\n",
+               s[3], s[0], 100 * s[0] / s[3], s[1], 100 * s[1] / s[3], s[2], 100 * s[2] / s[3]);
     }
 #endif
     cudaFree(d_tasks); cudaFree(d_items); cudaFree(d_keys);
@@ -180,6 +167,7 @@ static float run_popc(const std::vector<MatchTask>& tasks, size_t key_rows, std:
     return best;
 }
 
+static float run_mma2(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc dsc, std::vector<uint2>* out, int reps);
 static int check(MmaDesc dsc, const char* name) {
     std::mt19937 rng(1234);
     const int shapes[][3] = {{128, 256, 0}, {256, 256, 0}, {500, 500, 0}, {1000, 1000, 0}, {1000, 1000, 1}, {777, 333, 2},
@@ -200,7 +188,8 @@ static int check(MmaDesc dsc, const char* name) {
     }
     CK(cudaDeviceSynchronize());
     std::vector<uint2> got;
-    run_mma(tasks, key_rows, dsc, &got, 1, getenv("PROBE_VARIANT") ? atoi(getenv("PROBE_VARIANT")) : 0);
+    const int variant = getenv("PROBE_VARIANT") ? atoi(getenv("PROBE_VARIANT")) : 0;
+    if (variant == 3) run_mma2(tasks, key_rows, dsc, &got, 1); else run_mma(tasks, key_rows, dsc, &got, 1, variant);
     for (size_t k = 0; k < tasks.size(); ++k) {
         int bad = 0;
         for (int i = 0; i < tasks[k].nq; ++i) {
@@ -249,23 +238,18 @@ int main(int argc, char** argv) {
     std::vector<uint2> k_mma, k_popc;
     const float ms_popc = run_popc(pt, key_rows, &k_popc, 4);
     const float ms_mma = run_mma(mt, key_rows, dsc, &k_mma, 4);
-    std::vector<uint2> k16;
-    const float ms_16 = run_mma(mt, key_rows, dsc, &k16, 4, 1);
     std::vector<uint2> kk;
     const float ms_k = run_mma(mt, key_rows, dsc, &kk, 4, 2);
     size_t diffk = 0;
     for (size_t i = 0; i < key_rows; ++i) diffk += (kk[i].x != k_popc[i].x || kk[i].y != k_popc[i].y);
     printf("keys from the MMA: %.3f ms, rows differing %zu\n", ms_k, diffk);
-    size_t diff16 = 0;
-    for (size_t i = 0; i < key_rows; ++i) diff16 += (k16[i].x != k_popc[i].x || k16[i].y != k_popc[i].y);
-    printf("16 epilogue warps: %.3f ms, rows differing %zu\n", ms_16, diff16);
     std::vector<uint2> k2a, k2b;
-    const float ms_2a = run_mma2<2, 3>(mt, key_rows, dsc, &k2a, 4);
-    const float ms_2b = run_mma2<1, 4>(mt, key_rows, dsc, &k2b, 4);
+    const float ms_2a = run_mma2(mt, key_rows, dsc, &k2a, 4);
+    k2b = k2a;
     size_t diff = 0, diff2 = 0;
     for (size_t i = 0; i < key_rows; ++i) diff += (k_mma[i].x != k_popc[i].x || k_mma[i].y != k_popc[i].y);
     for (size_t i = 0; i < key_rows; ++i) diff2 += (k2a[i].x != k_popc[i].x || k2a[i].y != k_popc[i].y) + (k2b[i].x != k_popc[i].x || k2b[i].y != k_popc[i].y);
-    printf("pair kernel: <2,3> %.3f ms, <1,4> %.3f ms, rows differing %zu\n", ms_2a, ms_2b, diff2);
+    printf("pair kernel: %.3f ms, rows differing %zu\n", ms_2a, diff2 / 2);
     const double cmp = (double)P * N * N;
     printf("TIME pairs=%d N=%d pool=%d: popc %.3f ms (%.0f G cmp/s)  mma %.3f ms (%.0f G cmp/s)  speedup %.2fx  rows differing %zu of %zu\n",
            P, N, pool, ms_popc, cmp / ms_popc * 1e-6, ms_mma, cmp / ms_mma * 1e-6, ms_popc / ms_mma, diff, key_rows);

@@ -78,10 +78,8 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = max_shared_carveout(gather_copy_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma_kernel);
-    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma16_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmak_kernel);
-    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel<2, 3>);
-    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel<1, 4>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(derive_layouts_kernel);
     return e;
 }
@@ -503,22 +501,15 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             const MmaTask* mt = reinterpret_cast<const MmaTask*>(d_tk);
-            if (ctx->mma2_cfg == 1) {
-                cfg.dynamicSmemBytes = mma2_smem_bytes(1, 4);
-                UZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, knn2_mma2_kernel<1, 4>, mt, d_t, nt, d_k, uz_knn2_mma_desc()));
-            } else {
-                cfg.dynamicSmemBytes = mma2_smem_bytes(2, 3);
-                UZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, knn2_mma2_kernel<2, 3>, mt, d_t, nt, d_k, uz_knn2_mma_desc()));
-            }
+            cfg.dynamicSmemBytes = kMma2SmemBytes;
+            UZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, knn2_mma2_kernel, mt, d_t, nt, d_k, uz_knn2_mma_desc()));
             ctx->mma_launches++;
         } else if (nt > 0 && bp.mma) {
             // persistent grid, one CTA per SM; items are dealt round-robin, so neighbouring SMs work on the same pair and
             // share its train rows in L2
             const MmaTask* mt = reinterpret_cast<const MmaTask*>(d_tk);
             const int grid = std::min(nt, ctx->sm_count);
-            if (ctx->match_mma == 4)         // measured alternatives, kept for A/B (profiles/mma_experiments_r02.txt)
-                knn2_mma16_kernel<<<grid, kMma16Threads, kMma16SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
-            else if (ctx->match_mma == 7)
+            if (ctx->match_mma == 7)         // measured alternative, kept for A/B (profiles/mma_experiments_r02.txt)
                 knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
             else                             // default: the keys come out of the tensor core
                 knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);

@@ -130,8 +130,7 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (hc) ctx->host_chunks = atoi(hc);
         const char* mm = getenv("UZ_MATCH_MMA");
         if (mm) ctx->match_mma = atoi(mm);
-        const char* m2 = getenv("UZ_MMA2_CFG");
-        if (m2) ctx->mma2_cfg = atoi(m2);
+
         const char* stt = getenv("UZ_STAGE_THREADS");
         if (stt && atoi(stt) >= 1 && atoi(stt) <= 64) ctx->stage_threads = atoi(stt);
         const char* rm = getenv("UZ_RING_MB");
@@ -147,12 +146,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
                                  (int)solve_smem_bytes(1024));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma16SmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(knn2_mma2_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma2_smem_bytes(2, 3));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(knn2_mma2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mma2_smem_bytes(1, 4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma2SmemBytes);
     if (e == cudaSuccess) e = set_carveouts();
     if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
     *out = ctx;

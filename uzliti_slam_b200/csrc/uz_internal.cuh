@@ -26,7 +26,6 @@
 #include "uz_knn2.cuh"
 #include "uz_knn2_mma.cuh"
 #include "uz_knn2_mma2.cuh"
-#include "uz_knn2_mma16.cuh"
 #include "uz_knn2_mmak.cuh"
 #include "uz_places.cuh"
 #include "uz_samples.h"
@@ -264,8 +263,7 @@ struct uz_context {
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
     int match_mma = 1;               // UZ_MATCH_MMA: 0 = 256-bit rows on the integer pipes (knn2_kernel); 1 = tensor cores, keys formed by the
                                      // MMA (knn2_mmak_kernel, default); measured alternatives: 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches
-                                     // that fill the chip / always, 4 = 16 epilogue warps, 7 = IMAD epilogue (knn2_mma_kernel)
-    int mma2_cfg = 0;                // UZ_MMA2_CFG: 0 = two query-tile sets + 3 train stages, 1 = one set + 4 stages
+                                     // that fill the chip / always, 7 = IMAD epilogue (knn2_mma_kernel)
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments
     int solve_wide = 1;              // UZ_SOLVE_WIDE=0: never use the 512-thread solve CTA for small launches

@@ -305,4 +305,5 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mmak_kernel(const MmaTask
     }
 }
 
+
 }  // namespace uz
