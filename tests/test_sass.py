@@ -77,16 +77,22 @@ def test_integer_pipe_kernel_mix_matches_the_roofline_constants(built):
 
 def test_tensor_core_kernel_is_tcgen05_with_tmem_and_no_popcount(built):
     funcs = _functions(built)
-    names = [n for n in funcs if "knn2_mma_kernel" in n]
+    names = [n for n in funcs if "knn2_mmak_kernel" in n]
     assert len(names) == 1
-    ops = [_op(t) for _, t in funcs[names[0]]]
+    body = funcs[names[0]]
+    ops = [_op(t) for _, t in body]
     cnt = lambda p: sum(1 for o in ops if o.startswith(p))          # noqa: E731
-    assert cnt("UTCIMMA") >= mix.MMA_INSTRUCTIONS_PER_TILE and cnt("UTCIMMA") % mix.MMA_INSTRUCTIONS_PER_TILE == 0
-    assert cnt("LDTM") >= 8                       # four 32-column loads per accumulator in the full path, four in the ragged one
+    per_step = mix.MMA_INSTRUCTIONS_PER_TILE + mix.MMA_KEY_SLICE_INSTRUCTIONS
+    assert cnt("UTCIMMA") >= per_step and cnt("UTCIMMA") % per_step == 0          # 8 x K = 32 of the descriptor + the constant key slice
+    assert cnt("LDTM") >= 4 and sum(1 for o in ops if o.startswith("LDTM") and "PACK16BIT" in o) >= 2   # packed loads: two columns per register
     assert cnt("UBLKCP") >= 3 and cnt("SYNCS") >= 10 and cnt("UTCBAR") + cnt("UTCCOMMIT") + cnt("UTC") >= 1
     assert cnt("POPC") <= 2 and cnt("HMMA") == 0      # (a stray POPC of the warp-vote lowering; the compares use none)
-    # the packed-key epilogue: per 128 columns 128 multiply-adds with an immediate (16384 + column pair) and 160 packed min/max
-    body = funcs[names[0]]
-    imm = [t for _, t in body if _op(t).startswith("IMAD") and re.search(r"0x40[0-9a-f]{2}40[0-9a-f]{2}\b", t)]
-    assert len(imm) >= 64 * 2                     # one per column pair, two unrolled accumulators or paths
-    assert cnt("VIMNMX") >= 160
+    # the epilogue is packed max only: per 128 columns of the full path 64 registers x 2.5 packed min/max, and NO multiply-add
+    # that builds a key (the IMAD epilogue of knn2_mma_kernel carries immediates 0x40xx40xx = 16384 + column pair)
+    packed = sum(1 for o in ops if o.startswith("VIMNMX") and "U16x2" in o)
+    assert packed >= int(64 * 2 * mix.MMA_EPILOGUE_MINMAX)
+    assert not [t for _, t in body if _op(t).startswith("IMAD") and re.search(r"0x40[0-9a-f]{2}40[0-9a-f]{2}\b", t)]
+    # the measured alternative still has them
+    alt = [n for n in funcs if "knn2_mma_kernel" in n]
+    assert len(alt) == 1
+    assert len([t for _, t in funcs[alt[0]] if _op(t).startswith("IMAD") and re.search(r"0x40[0-9a-f]{2}40[0-9a-f]{2}\b", t)]) >= 64 * 2

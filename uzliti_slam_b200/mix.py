@@ -9,8 +9,9 @@ KNN2_IMAD = 4          # FMA pipe (weighted popcount chain); +1 per iteration of
 KNN2_MINMAX = 1.25     # VIMNMX(.3).U16x2 per compare (5 per 4 compares), ALU pipe
 KNN2_COMPARES_PER_ITERATION = 8      # 4 train rows x 2 queries per thread
 
-# knn2_mma_kernel: tensor cores, per 128 x 256 tile of compares
+# knn2_mmak_kernel: tensor cores, per 128 x 256 tile of compares
 MMA_INSTRUCTIONS_PER_TILE = 8        # tcgen05.mma kind::i8, K = 32 each, K = 256 in all
+MMA_KEY_SLICE_INSTRUCTIONS = 1       # + the constant K-slice that turns the accumulator into the packed key (overhead, not counted as work)
 MMA_OPS_PER_COMPARE = 512            # 256 int8 multiply-adds
-MMA_EPILOGUE_IMAD = 1.0              # per compare: key16 = dot * (-64) + (16384 + column)
+MMA_EPILOGUE_IMAD = 0.0              # per compare: none (knn2_mma_kernel, UZ_MATCH_MMA=7, needed 1: key16 = dot * (-64) + (16384 + column))
 MMA_EPILOGUE_MINMAX = 1.25
