@@ -374,10 +374,30 @@ def measure_places(est, handles, kfs, my_pairs=None, cpu_keyframes=1500):
     want = np.concatenate([w for w in want if len(w)] + [np.zeros((0, 2), np.int64)])
     got_head = pairs[pairs[:, 1] < handles[m - 1] + 1] if m < n else pairs
     same = bool(np.array_equal(got_head.astype(np.int64), want))
+    # HBM view of the two table kernels (random 16 B slots + 8 B nodes: bound by DRAM sectors, not bytes): algorithmic bytes per
+    # bucket entry = 4 B key + 16 B slot + 8 B node; `traffic` = what ncu saw (profiles/places_ncu_summary.json)
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        mp = {}
+    hbm_peak = mp.get("hbm_gbs", 6650.0)
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "places_ncu_summary.json")))
+    except Exception:
+        ncu = {}
+    alg = entries * 28.0
+    roof = {}
+    for name, ms_k in (("insert", tm["insert_ms"]), ("vote", tm["vote_ms"])):
+        gbs = alg / (ms_k * 1e-3) * 1e-9 if ms_k > 0 else 0.0
+        traffic = ncu.get(name + "_dram_bytes_per_launch") if n == N_KEYFRAMES else None
+        roof[name] = dict(bound="hbm", achieved=round(gbs, 1), peak=hbm_peak, unit="GB/s", frac=round(gbs / hbm_peak, 4),
+                          algorithmic_bytes=int(alg), traffic=traffic,
+                          traffic_gbs=round(traffic / (ms_k * 1e-3) * 1e-9, 1) if traffic and ms_k > 0 else None,
+                          note="random 32 B sectors: traffic / algorithmic bytes is the sector overfetch of an open-addressing table")
     return dict(what="searchAndAddPlace x %d keyframes (LSH-bucket voting, T=2, k=20), one batch" % n,
                 keyframes_per_s=round(n / dt, 1), wall_ms=round(dt * 1e3, 2), insert_ms=round(tm["insert_ms"], 3),
                 vote_ms=round(tm["vote_ms"], 3), select_ms=round(tm["select_ms"], 3), bucket_entries=entries,
-                pairs=int(len(pairs)), true_pair_frac=round(float(true.mean()), 4) if len(pairs) else None,
+                pairs=int(len(pairs)), true_pair_frac=round(float(true.mean()), 4) if len(pairs) else None, roofline=roof,
                 cpu_oracle=dict(keyframes=m, keyframes_per_s=round(m / cpu_dt, 1), cores=1, kind="port",
                                 same_pairs_as_gpu=same))
 
