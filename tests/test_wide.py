@@ -43,10 +43,45 @@ def test_knn2_wide_random(est, oracle, nq, nt):
     assert np.array_equal(dist, od)
 
 
+def test_knn2_wide_integer_pipe_kernel_equals_tensor_core_kernel(est, oracle):
+    """the default for 64-byte rows is knn2_mmaw_kernel (tensor cores, two 256-bit planes); UZ_MATCH_MMA_WIDE=0 keeps
+    knn2_wide_kernel: same neighbours on random, tie-heavy and extreme rows, and byte-identical edge records"""
+    e = _estimator(UZ_MATCH_MMA_WIDE=0)
+    try:
+        for nq, nt in [(500, 500), (1000, 1000), (257, 511), (129, 64), (3, 1000), (1, 1), (4096, 4096), (1000, 127), (130, 129)]:
+            for mode in range(3):
+                rng = np.random.default_rng(nq * 31 + nt + mode)
+                q = rng.integers(0, 256, (nq, 64), dtype=np.uint8)
+                t = rng.integers(0, 256, (nt, 64), dtype=np.uint8)
+                if mode == 1:
+                    q[:, 1:] = 0; t[:, 1:] = 0                   # ties everywhere
+                if mode == 2:
+                    q[0] = 0; t[0] = 255; t[nt - 1] = 0; q[nq - 1] = 255      # distances 0 and 512
+                a = est.knnMatch(q, t)
+                b = e.knnMatch(q, t)
+                o = oracle.knn2(q, t)
+                assert np.array_equal(a[0], o[0]) and np.array_equal(a[1], o[1]), (nq, nt, mode)
+                assert np.array_equal(b[0], o[0]) and np.array_equal(b[1], o[1]), (nq, nt, mode)
+        kfs, pairs, _ = S.make_map(60, n_features=700, cluster=6, pool=700, n_shared=400, k_candidates=6, cross_cluster=2, seed=8, desc_bytes=64)
+        for cross in (0, 1):
+            recs = []
+            for x in (est, e):
+                x.setConfig(cross_check=cross)
+                x.clear()
+                h = x.add_keyframes(kfs)
+                recs.append(x.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]]))
+            assert recs[0].tobytes() == recs[1].tobytes()
+            assert (recs[0]["ok"] == 1).any()
+        est.setConfig(cross_check=0)
+        est.clear()
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("cfg", [0, 1])
 def test_knn2_wide_both_shapes(oracle, cfg):
     """256 x 2 and 64 x 2 query CTAs (UZ_KNN_WIDE_CFG forces one)"""
-    e = _estimator(UZ_KNN_WIDE_CFG=cfg)
+    e = _estimator(UZ_KNN_WIDE_CFG=cfg, UZ_MATCH_MMA_WIDE=0)
     try:
         for nq, nt in [(700, 900), (130, 70), (1000, 1000)]:
             rng = np.random.default_rng(nq + nt + cfg)
@@ -166,7 +201,7 @@ def test_mixed_widths_in_one_batch(oracle):
         pairs = pairs[rng.permutation(len(pairs))]
         n0 = e.launch_count()
         res = e.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]])
-        assert e.launch_count() - n0 == 4                # narrow match + wide match + segment merge (a small launch) + solve
+        assert e.launch_count() - n0 == 3                # narrow match + wide match (both on the tensor cores) + solve
         for r, (a, b) in zip(res, pairs):
             if kfs[a]["desc"].shape[1] != kfs[b]["desc"].shape[1]:
                 assert r["ok"] == 0 and r["consensus"] == 0 and r["cam_from"] == -1
@@ -195,8 +230,8 @@ def test_wide_streaming_equals_one_cta_per_pair():
                                desc_bytes=64)
     kfs = [{k: (v[:[600, 520, 300, 64, 5][i % 5]] if isinstance(v, np.ndarray) else v) for k, v in kf.items()}
            for i, kf in enumerate(kfs)]
-    plain = _estimator(UZ_STREAM_SOLVE=0)
-    stream = _estimator(UZ_STREAM_SOLVE=1, UZ_STREAM_SOLVE_MIN_PAIRS=1)
+    plain = _estimator(UZ_STREAM_SOLVE=0, UZ_MATCH_MMA_WIDE=0)      # the streaming solve runs beside the integer-pipe kernels only
+    stream = _estimator(UZ_STREAM_SOLVE=1, UZ_STREAM_SOLVE_MIN_PAIRS=1, UZ_MATCH_MMA_WIDE=0)
     try:
         hp = plain.add_keyframes(kfs)
         hs = stream.add_keyframes(kfs)

@@ -79,6 +79,7 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmak_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaw_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(derive_layouts_kernel);
     return e;
@@ -99,6 +100,7 @@ struct BatchPlan {
     int max_nq = 0, cap = 0;
     int64_t compares = 0;
     bool mma = false;                    // 256-bit matchings on the tensor cores (knn2_mma_kernel)
+    bool mma_wide = false;               // 512-bit matchings on the tensor cores (knn2_mmaw_kernel)
     bool mma2 = false;                   // ... on CTA pairs (knn2_mma2_kernel): launches that keep every pair of SMs busy
     int best_cfg = 3, wide_cfg = 0;      // integer-pipe tile shapes
     int tile_rows = 512, wide_threads = 256, wide_tile_rows = 512;
@@ -134,10 +136,13 @@ uz_status enumerate_tasks(uz_context* ctx, const std::vector<PairRef>& pairs, uz
     size_t n_tasks = 0, key_rows = 0;
     // the tensor-core form needs the E8 layout of both cameras; the measured alternatives (UZ_KNN_VARIANT) stay on the integer pipes
     bp.mma = ctx->match_mma && ctx->variant_csa && ctx->variant_pack16 && ctx->force_cfg < 0;
-    for (int i = 0; i < bp.n_pairs && bp.mma; ++i) {
-        for (int a = 0; a < pairs[i].n_from && bp.mma; ++a) if (pairs[i].from[a].dbytes == UZ_DESC_BYTES && pairs[i].from[a].n > 0 && !pairs[i].from[a].e8) bp.mma = false;
-        for (int b = 0; b < pairs[i].n_to && bp.mma; ++b) if (pairs[i].to[b].dbytes == UZ_DESC_BYTES && pairs[i].to[b].n > 0 && !pairs[i].to[b].e8) bp.mma = false;
+    bp.mma_wide = bp.mma && ctx->match_mma_wide != 0;
+    auto lacks_e8 = [](const Cam& c, bool wide) { return (c.dbytes != UZ_DESC_BYTES) == wide && c.n > 0 && !c.e8; };
+    for (int i = 0; i < bp.n_pairs && (bp.mma || bp.mma_wide); ++i) {
+        for (int a = 0; a < pairs[i].n_from; ++a) { if (lacks_e8(pairs[i].from[a], false)) bp.mma = false; if (lacks_e8(pairs[i].from[a], true)) bp.mma_wide = false; }
+        for (int b = 0; b < pairs[i].n_to; ++b) { if (lacks_e8(pairs[i].to[b], false)) bp.mma = false; if (lacks_e8(pairs[i].to[b], true)) bp.mma_wide = false; }
     }
+    bp.mma_wide = bp.mma_wide && bp.mma;
     for (int i = 0; i < bp.n_pairs; ++i) {
         const int first = (int)n_tasks;
         const Cam* fc = pairs[i].from;
@@ -152,7 +157,7 @@ uz_status enumerate_tasks(uz_context* ctx, const std::vector<PairRef>& pairs, uz
                     if (wide) { task_wide[n_tasks] = 1; ++bp.n_wide; }
                     MatchTask& tk = bp.tasks[n_tasks++];
                     const bool bin = is_binary_type(F.feature_type);   // unknown type: empty matches (:60-62)
-                    if (!wide && bp.mma) {
+                    if (wide ? bp.mma_wide : bp.mma) {
                         tk.q_desc = (const uint32_t*)T.e8; tk.t_desc = (const uint32_t*)F.e8;
                     } else {
                         const bool use_csa = ctx->variant_csa || wide;     // the wide kernel has the CSA form only
@@ -176,7 +181,7 @@ uz_status enumerate_tasks(uz_context* ctx, const std::vector<PairRef>& pairs, uz
     // the minimum over the queries (uz_knn2.cuh, col_update16); the matching's column keys live behind the row keys in
     // the same scratch.  Reversed form (tensor-core kernel, UZ_XCHECK_FUSED=0, and the kernel variants without the
     // packed-key shapes): every matching runs a second time with query and train swapped.
-    const bool narrow_on_mma = bp.mma && bp.n_wide < bp.n_fwd;
+    const bool narrow_on_mma = (bp.mma && bp.n_wide < bp.n_fwd) || (bp.mma_wide && bp.n_wide > 0);       // anything on the tensor cores
     bp.fused = bp.cross && ctx->xcheck_fused && ctx->variant_csa && ctx->variant_pack16 && !narrow_on_mma &&
                !(ctx->force_cfg >= 0 && ctx->force_cfg < 2);
     if (!bp.fused && bp.cross) {
@@ -248,13 +253,13 @@ void choose_shapes(uz_context* ctx, BatchPlan& bp) {
     }
     bp.tile_rows = bp.mma2 ? kMma2ItemRows : bp.mma ? kMmaItemRows : kKnnConfigs[bp.best_cfg].threads * kKnnConfigs[bp.best_cfg].qpt;
     bp.wide_threads = bp.wide_cfg == 0 ? 256 : 64;
-    bp.wide_tile_rows = 2 * bp.wide_threads;
+    bp.wide_tile_rows = bp.mma_wide ? kMmaItemRows : 2 * bp.wide_threads;
 
     // the persistent streaming solve runs beside the INTEGER-PIPE match kernels only: a tensor-core match CTA owns its SM's
     // shared memory (200 KB of operand stages), no solve CTA fits next to it
     bp.cap = bp.with_solve ? std::max(128, pow2ceil(std::max(bp.max_nq, 1))) : 0;
     const int stream_ctas = ctx->stream_solve_ctas * ctx->sm_count;
-    const bool narrow_on_mma = bp.mma && bp.n_wide < bp.n_tasks;
+    const bool narrow_on_mma = (bp.mma && bp.n_wide < bp.n_tasks) || (bp.mma_wide && bp.n_wide > 0);     // anything on the tensor cores
     bp.may_stream = bp.with_solve && !narrow_on_mma && ctx->solve_stream != nullptr && ctx->stream_solve_ctas > 0 && bp.cap <= 1024 &&
                     bp.n_pairs >= (ctx->stream_min_pairs > 0 ? ctx->stream_min_pairs : 2 * stream_ctas);
 
@@ -268,15 +273,15 @@ void choose_shapes(uz_context* ctx, BatchPlan& bp) {
         (bp.mma || kKnnConfigs[bp.best_cfg].qpt == 2)) {
         double warps = 0;
         for (size_t t = 0; t < bp.n_tasks; ++t) {
-            if (bp.mma && !task_wide[t]) continue;
+            if (task_wide[t] ? bp.mma_wide : bp.mma) continue;
             const int rows = bp.rows_of(t, task_wide);
             warps += (double)(((size_t)tasks[t].nq + rows - 1) / rows) * (task_wide[t] ? bp.wide_threads : kKnnConfigs[bp.best_cfg].threads) / 32.0;
         }
         const double capacity = (double)ctx->sm_count * 32.0;
         if (warps > 0 && warps * 2 <= capacity) bp.seg_target = (int)std::min(16.0, std::floor(capacity / warps));
     }
-    bp.seg_wide = bp.seg_target > 1;
-    bp.seg_narrow = bp.seg_wide && !bp.mma;
+    bp.seg_wide = bp.seg_target > 1 && !bp.mma_wide;
+    bp.seg_narrow = bp.seg_target > 1 && !bp.mma;
     bp.narrow_tile_bytes = bp.seg_narrow ? sizeof(int4) : sizeof(int2);
     bp.wide_tile_bytes = bp.seg_wide ? sizeof(int4) : sizeof(int2);
 }
@@ -485,7 +490,14 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         uint2* d_k = (uint2*)sl.d_keys.p;
         const int nt = (int)bp.n_tiles_narrow;
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
-        if (bp.n_tiles_wide > 0) {
+        if (bp.n_tiles_wide > 0 && bp.mma_wide) {
+            const int ntw = (int)bp.n_tiles_wide;
+            knn2_mmaw_kernel<<<std::min(ntw, ctx->sm_count), kMmaThreads, kMmawSmemBytes, ctx->stream>>>(
+                reinterpret_cast<const MmaTask*>(d_tk), d_tw, ntw, d_k, uz_knn2_mma_desc());
+            ctx->launches++; ctx->mma_launches++;
+            UZ_CUDA(ctx, cudaGetLastError());
+            if (ctx->timers) ctx->match_launches++;
+        } else if (bp.n_tiles_wide > 0) {
             if (bp.wide_cfg == 0) launch_knn2_wide<256>(ctx, d_tk, d_tw, (int)bp.n_tiles_wide, d_k, d_pending, d_prog, fused, bp.seg_wide);
             else launch_knn2_wide<64>(ctx, d_tk, d_tw, (int)bp.n_tiles_wide, d_k, d_pending, d_prog, fused, bp.seg_wide);
             ctx->launches++;

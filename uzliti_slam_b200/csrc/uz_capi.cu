@@ -130,6 +130,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (hc) ctx->host_chunks = atoi(hc);
         const char* mm = getenv("UZ_MATCH_MMA");
         if (mm) ctx->match_mma = atoi(mm);
+        const char* mw = getenv("UZ_MATCH_MMA_WIDE");
+        if (mw) ctx->match_mma_wide = atoi(mw);
 
         const char* stt = getenv("UZ_STAGE_THREADS");
         if (stt && atoi(stt) >= 1 && atoi(stt) <= 64) ctx->stage_threads = atoi(stt);
@@ -147,6 +149,7 @@ uz_status uz_create(int32_t device, uz_context** out) {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmawSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma2SmemBytes);
     if (e == cudaSuccess) e = set_carveouts();
     if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
@@ -318,6 +321,7 @@ uz_status uz_match_knn2(uz_context* ctx, int32_t desc_bytes, const uint8_t* quer
     if (q_stride < db || (nt > 0 && t_stride < db)) return fail(ctx, UZ_ERR_INVALID, "descriptor stride < descriptor width");
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->transient.reset();
+    ctx->h_chunks.reset(); ctx->d_chunks.reset();
     // two position-less cameras
     Keyframe kq, kt;
     kq.cams.resize(1); kt.cams.resize(1);
@@ -327,14 +331,13 @@ uz_status uz_match_knn2(uz_context* ctx, int32_t desc_bytes, const uint8_t* quer
         const int halves = n * (db / 32);
         c.raw = (uint32_t*)ctx->transient.alloc((size_t)n * db);
         c.csa = (uint32_t*)ctx->transient.alloc((size_t)n * db);
-        if (db == UZ_DESC_BYTES) c.e8 = (uint8_t*)ctx->transient.alloc(e8_bytes(n));
+        c.e8 = (uint8_t*)ctx->transient.alloc(db == UZ_DESC_BYTES ? e8_bytes(n) : e8w_bytes(n));
         uint8_t* stage = (uint8_t*)ctx->transient.alloc((size_t)n * stride);
-        if (!c.raw || !c.csa || !stage || (db == UZ_DESC_BYTES && !c.e8)) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
+        if (!c.raw || !c.csa || !stage || !c.e8) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
         UZ_CUDA(ctx, cudaMemcpyAsync(stage, h, (size_t)(n - 1) * stride + db, cudaMemcpyHostToDevice, ctx->stream));
         pack_descriptors_kernel<<<(halves + 255) / 256, 256, 0, ctx->stream>>>(stage, halves, stride, c.raw, c.csa, db / 32);
         ctx->launches++;
-        if (c.e8) { expand_e8_kernel<<<(n * 16 + 255) / 256, 256, 0, ctx->stream>>>(c.raw, n, c.e8); ctx->launches++; }
-        return UZ_OK;
+        return derive_layouts(ctx, &c, 1);        // (recomputes the CSA form too; one launch)
     };
     if ((st = up(query, nq, q_stride, kq.cams[0])) != UZ_OK) return st;
     if ((st = up(train, nt, t_stride, kt.cams[0])) != UZ_OK) return st;

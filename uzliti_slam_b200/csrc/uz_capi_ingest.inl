@@ -36,7 +36,7 @@ uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int dbytes, int featur
     if (n == 0) return UZ_OK;
     c.raw = (uint32_t*)(base + L.raw); c.pos = (double*)(base + L.pos); c.valid = base + L.valid;
     c.csa = (uint32_t*)(base + L.csa);
-    c.e8 = dbytes == UZ_DESC_BYTES ? base + L.e8 : nullptr;
+    c.e8 = base + L.e8;
     return UZ_OK;
 }
 

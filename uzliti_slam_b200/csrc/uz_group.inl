@@ -114,7 +114,7 @@ uz_status group_replicate(uz_context* ctx, const uz_context* src, const int32_t*
             if (s.n > 0) {
                 o.raw = (uint32_t*)(base + lay[c].raw); o.pos = (double*)(base + lay[c].pos); o.valid = base + lay[c].valid;
                 o.csa = (uint32_t*)(base + lay[c].csa);
-                o.e8 = s.dbytes == UZ_DESC_BYTES ? base + lay[c].e8 : nullptr;
+                o.e8 = base + lay[c].e8;
                 push_chunks(cc, (uintptr_t)s.raw, (uint8_t*)o.raw, (size_t)s.n * s.dbytes);      // peer reads over NVLink
                 push_chunks(cc, (uintptr_t)s.pos, (uint8_t*)o.pos, (size_t)s.n * 24);
                 push_chunks(cc, (uintptr_t)s.valid, o.valid, (size_t)s.n);

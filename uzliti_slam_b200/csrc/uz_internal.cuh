@@ -27,6 +27,7 @@
 #include "uz_knn2_mma.cuh"
 #include "uz_knn2_mma2.cuh"
 #include "uz_knn2_mmak.cuh"
+#include "uz_knn2_mmaw.cuh"
 #include "uz_places.cuh"
 #include "uz_samples.h"
 #include "uz_solve.cuh"
@@ -192,7 +193,7 @@ struct HostPool {
 struct Cam {
     uint32_t* raw = nullptr;   // n x dbytes/4 words, bytes as given
     uint32_t* csa = nullptr;   // same rows, every 256-bit half in CSA layout (uz_knn2.cuh)
-    uint8_t* e8 = nullptr;     // 32-byte rows only: one int8 per bit in the UMMA canonical layout (uz_knn2_mma.cuh)
+    uint8_t* e8 = nullptr;     // one int8 per bit in the UMMA canonical layout (uz_knn2_mma.cuh); 64-byte rows: two planes (uz_knn2_mmaw.cuh)
     double* pos = nullptr;     // 3 x n column-major
     uint8_t* valid = nullptr;  // n
     int32_t n = 0, feature_type = 0, sensor_frame = 0;
@@ -209,7 +210,7 @@ inline CamLayout cam_layout(size_t at, int n, int dbytes) {
     L.valid = up(L.pos + (size_t)n * 24);
     L.csa = up(L.valid + (size_t)n);
     L.e8 = up(L.csa + (size_t)n * dbytes);
-    L.end = up(L.e8 + (dbytes == UZ_DESC_BYTES ? e8_bytes(n) : 0));
+    L.end = up(L.e8 + (dbytes == UZ_DESC_BYTES ? e8_bytes(n) : e8w_bytes(n)));
     return L;
 }
 
@@ -261,6 +262,7 @@ struct uz_context {
     int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
     int xcheck_fused = 1;            // UZ_XCHECK_FUSED=0: cross-check by a second, reversed matching (the measured alternative)
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
+    int match_mma_wide = 1;          // UZ_MATCH_MMA_WIDE=0: 512-bit rows stay on the integer pipes (knn2_wide_kernel)
     int match_mma = 1;               // UZ_MATCH_MMA: 0 = 256-bit rows on the integer pipes (knn2_kernel); 1 = tensor cores, keys formed by the
                                      // MMA (knn2_mmak_kernel, default); measured alternatives: 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches
                                      // that fill the chip / always, 7 = IMAD epilogue (knn2_mma_kernel)

@@ -33,9 +33,12 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
         c[0] = make_uint4(o[0], o[1], o[2], o[3]); c[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
     if (j.e8 == nullptr) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n * 16; i += gridDim.x * blockDim.x) {
-        const int row = i >> 4, c = i & 15;
-        const uint32_t w = j.raw[(size_t)row * 8 + (c >> 1)];
+    // one thread per (row, 16-bit chunk): 16 int8 = one uint4 store.  64-byte rows: chunk 16..31 goes to the second plane.
+    const int chunks = 16 * j.halves_per_row;
+    const size_t plane = e8_bytes(j.n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n * chunks; i += gridDim.x * blockDim.x) {
+        const int row = i / chunks, c = i % chunks;
+        const uint32_t w = j.raw[(size_t)row * (8 * j.halves_per_row) + (c >> 1)];
         const uint32_t bits = (c & 1) ? (w >> 16) : (w & 0xFFFFu);
         uint32_t o[4];
 #pragma unroll
@@ -45,7 +48,8 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
             for (int b = 0; b < 4; ++b) v |= (((bits >> (4 * k + b)) & 1u) ? kE8Set : kE8Clear) << (8 * b);
             o[k] = v;
         }
-        *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kE8GroupBytes + c * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(j.e8 + (size_t)(c >> 4) * plane + (size_t)(row >> 3) * kE8GroupBytes + (c & 15) * 128 + (row & 7) * 16) =
+            make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -241,7 +245,7 @@ uz_status derive_layouts(uz_context* ctx, const Cam* cams, size_t n_cams) {
         const Cam& c = cams[i];
         if (c.n == 0) continue;
         jobs.push_back(DeriveJob{c.raw, c.csa, c.e8, c.n, c.dbytes / 32});
-        max_units = std::max(max_units, c.n * 16);
+        max_units = std::max(max_units, c.n * 16 * (c.dbytes / 32));
     }
     for (size_t j0 = 0; j0 < jobs.size(); j0 += 32768) {
         const size_t cnt = std::min<size_t>(32768, jobs.size() - j0);
@@ -292,7 +296,7 @@ uz_status place_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_f
             if (f->n == 0) continue;
             o.raw = (uint32_t*)(base + lay[c].raw); o.pos = (double*)(base + lay[c].pos); o.valid = base + lay[c].valid;
             o.csa = (uint32_t*)(base + lay[c].csa);
-            o.e8 = o.dbytes == UZ_DESC_BYTES ? base + lay[c].e8 : nullptr;
+            o.e8 = base + lay[c].e8;
         }
         k += cnt;
     }
