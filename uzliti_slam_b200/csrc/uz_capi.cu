@@ -126,6 +126,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (cc && atoi(cc) > 0) ctx->copy_ctas = atoi(cc);
         const char* hs = getenv("UZ_HOST_SLOTS");
         if (hs && atoi(hs) >= 2) ctx->host_slots = std::min(atoi(hs), (int)uz_context::kSlots);
+        const char* hf = getenv("UZ_HOST_FIRST_WAVES");
+        if (hf) ctx->host_first_waves = atoi(hf);
         const char* hc = getenv("UZ_HOST_CHUNKS");
         if (hc) ctx->host_chunks = atoi(hc);
         const char* mm = getenv("UZ_MATCH_MMA");
@@ -673,10 +675,18 @@ uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, 
         if (want_chunks > 40) { per_chunk = ((n_pairs / 40 + wave - 1) / wave) * wave; want_chunks = (n_pairs + per_chunk - 1) / per_chunk; }
         if (want_chunks < 4) { want_chunks = 4; per_chunk = (n_pairs + 3) / 4; }
     }
-    const int n_chunks = want_chunks;
-    std::vector<size_t> chunk_pair_end((size_t)n_chunks);
-    for (int c = 0; c < n_chunks; ++c)
-        chunk_pair_end[c] = c + 1 == n_chunks ? (size_t)n_pairs : std::min<size_t>((size_t)n_pairs, (size_t)(c + 1) * (size_t)per_chunk);
+    if (want_chunks <= 1) per_chunk = n_pairs;
+    // the first chunk is ONE solve wave (UZ_HOST_FIRST_WAVES): its upload is the only one nothing overlaps
+    const int first = (ctx->host_first_waves > 0 && !ctx->debug && ctx->host_chunks <= 0 && want_chunks >= 4 &&
+                       ctx->host_first_waves * wave < per_chunk) ? ctx->host_first_waves * wave : 0;
+    std::vector<size_t> chunk_pair_end;
+    if (first > 0) chunk_pair_end.push_back((size_t)first);
+    for (size_t at = (size_t)first; at < (size_t)n_pairs;) {
+        at = std::min<size_t>((size_t)n_pairs, at + (size_t)per_chunk);
+        if ((size_t)n_pairs - at < (size_t)wave / 2) at = (size_t)n_pairs;          // no crumb at the end
+        chunk_pair_end.push_back(at);
+    }
+    const int n_chunks = (int)chunk_pair_end.size();
 
     // unique cameras (a keyframe that appears in many pairs - one query vs many candidates - is uploaded once),
     // numbered in order of first use so that every chunk uploads exactly the cameras nobody before it needed

@@ -329,6 +329,7 @@ struct uz_context {
     static constexpr int kSlots = 6;
     Slot slots[kSlots];
     int cur_slot = 0, slot_depth = 2, host_slots = kSlots;
+    int host_first_waves = 1;        // UZ_HOST_FIRST_WAVES: size of the first chunk of uz_estimate_edges_host in solve waves (0: like the others)
     DevBuf d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
 
     // where the solve kernel writes the records of the batch being launched (group mode: a peer-mapped buffer)
