@@ -290,7 +290,8 @@ struct uz_context {
     void* pfn_ptr_attr = nullptr;    // cuPointerGetAttribute via cudaGetDriverEntryPoint (no link-time libcuda)
     int gather_upload = 1;           // UZ_GATHER_UPLOAD=0 forces the cudaMemcpyAsync path
     int copy_beside_compute = 0;     // set while uploads are enqueued that overlap the match kernel
-    int copy_ctas = 64;              // UZ_COPY_CTAS
+    int copy_ctas = 24;              // UZ_COPY_CTAS: gather CTAs beside the compute kernels.  16 CTAs already pull 49 GB/s over PCIe; every one
+                                     // takes a solve CTA's place on its SM (C4 end to end: 8: 2.21 M, 16: 2.75 M, 24: 2.81 M, 32: 2.75 M, 64: 2.64 M edges/s)
     cudaEvent_t trace_mid = nullptr; // UZ_TRACE=2: recorded between the gather and the layout pass of an upload
     // pageable sources are staged through this pinned ring (two halves, an event each) and pulled by the same gather kernel
     PinBuf ring;
