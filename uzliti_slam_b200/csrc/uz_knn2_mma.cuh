@@ -1,4 +1,7 @@
 // uz_knn2_mma.cuh — K1 on the 5th-generation tensor cores: Hamming kNN-2 as an exact int8 contraction.
+// This file: the operand layout, the tcgen05 helpers every tensor-core match kernel shares, and the FIRST kernel of the family
+// (knn2_mma_kernel, IMAD epilogue; UZ_MATCH_MMA=7).  The default kernel is knn2_mmak_kernel (uz_knn2_mmak.cuh), 512-bit rows run
+// in knn2_mmaw_kernel (uz_knn2_mmaw.cuh), the CTA-pair experiment is knn2_mma2_kernel (uz_knn2_mma2.cuh).
 //
 // Same contract as knn2_kernel (uz_knn2.cuh): cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k = 2)
 // (/root/reference/transformation_estimation/src/feature_transformation_estimator.cpp:38,58), two packed keys per
@@ -12,7 +15,8 @@
 // kernel deliberately steps outside that sentence and is kept only because it is bit-exact and measured faster
 // (DESIGN.md section 4).
 //
-// Data.  Descriptors are expanded ONCE at ingestion into the "E8 layout": one int8 per bit (+1 set, -1 clear), stored
+// Data.  Descriptors are expanded ONCE at ingestion into the "E8 layout": one int8 per bit (+8 set, -8 clear: the accumulator
+// holds 64 <q, t>, which is what lets knn2_mmak_kernel form the packed key inside the MMA), stored
 // directly in the no-swizzle K-major canonical layout of the UMMA shared-memory descriptor, so that any run of 8-row
 // groups is one contiguous byte range and a tile arrives with ONE 1-D TMA bulk copy (no tensor map):
 //   byte(row i, k) = (i >> 3) * 2048 + (k >> 4) * 128 + (i & 7) * 16 + (k & 15),   k = bit index 0..255
@@ -27,7 +31,7 @@
 //   warps 2..9  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (its hardware lane quarter) and one 128-column half
 //               of every accumulator; a thread is ONE query row.  tcgen05.ld 32 columns at a time, then per compare
 //               1 IMAD (FMA pipe) + 1.25 VIMNMX.U16x2 (ALU pipe):
-//                 key16 = (hamming << 7) | (column & 127) = dot * (-64) + (16384 + column)     exact, no shift needed
+//                 key16 = (hamming << 7) | (column & 127) = (16384 + column) - accumulator     (accumulator = 64 dot)
 //               two columns share a register (low half: even columns, high half: odd columns), running top-2 per half
 //               with the packed min/max of knn2_kernel, widened into the 32-bit keys every 128 columns.
 // An item is 256 query rows of one matching against all of its train rows; each train tile is used by both query tiles
