@@ -77,7 +77,7 @@ int main(int argc, char** argv) {
     };
 
     // 3. cold: nothing resident, every node travels from pageable memory inside the timed region
-    double cold_s, load_s, best = 1e30;
+    double first_s, cold_s, load_s, best = 1e30;
     long long score_cold, score_warm = 0;
     {
         GpuFeatureTransformationEstimator est(cb, devices);
@@ -88,7 +88,11 @@ int main(int argc, char** argv) {
             for (long p = 0; p < std::min<long>(n_pairs, 64); ++p) { est.forgetNode(nodes[pairs[2 * p]].id_); est.forgetNode(nodes[pairs[2 * p + 1]].id_); }
             delivered = 0; accepted = 0; score_sum = 0;
         }
-        cold_s = run_queue(est);
+        first_s = run_queue(est);               // first use: the store arena and the pinned staging ring grow inside this pass
+        if (delivered != n_pairs) { std::printf("{\"error\": \"%ld of %ld edges delivered\"}\n", (long)delivered, n_pairs); return 1; }
+        for (int i = 0; i < n_kf; ++i) est.forgetNode(nodes[i].id_);
+        delivered = 0; accepted = 0; score_sum = 0;
+        cold_s = run_queue(est);                // cold data, warm allocator: every node travels again
         score_cold = score_sum;
         if (delivered != n_pairs) { std::printf("{\"error\": \"%ld of %ld edges delivered\"}\n", (long)delivered, n_pairs); return 1; }
     }
@@ -109,10 +113,10 @@ int main(int argc, char** argv) {
         }
     }
     std::printf("{\"bench\": \"adapter queue, C++ host\", \"devices\": %d, \"keyframes\": %d, \"pairs\": %ld, \"generator_s\": %.2f, "
-                "\"map_checksum_desc\": %llu, \"map_checksum_pos\": %llu, \"edges_per_s_cold_pageable\": %.1f, \"cold_ms\": %.3f, "
+                "\"map_checksum_desc\": %llu, \"map_checksum_pos\": %llu, \"first_use_ms\": %.3f, \"edges_per_s_cold_pageable\": %.1f, \"cold_ms\": %.3f, "
                 "\"load_nodes_s\": %.3f, \"keyframes_per_s_load\": %.1f, \"edges_per_s_resident\": %.1f, \"resident_ms\": %.3f, "
                 "\"edges_score_ge_15\": %ld, \"score_sum_cold\": %lld, \"score_sum_resident\": %lld, \"same_edges\": %s}\n",
-                (int)devices.size(), n_kf, n_pairs, gen_s, ck_desc, ck_pos, n_pairs / cold_s, cold_s * 1e3, load_s, n_kf / load_s,
+                (int)devices.size(), n_kf, n_pairs, gen_s, ck_desc, ck_pos, first_s * 1e3, n_pairs / cold_s, cold_s * 1e3, load_s, n_kf / load_s,
                 n_pairs / best, best * 1e3, acc_warm, score_cold, score_warm, score_cold == score_warm ? "true" : "false");
     return 0;
 }
