@@ -100,3 +100,28 @@ def test_small_ring_wraps(oracle):
             assert rec["consensus"] == o["consensus"] and rec["n_matches"] == o["n_matches"]
     finally:
         e.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_synchronous_call_equals_one_launch_pair(built):
+    """uz_estimate_edges cuts a large store-resident batch into chunks that double in size (the host prepares chunk c + 1
+    while chunk c runs); UZ_PIPELINE_CALLS=0 keeps one launch pair: byte-identical records, more launches"""
+    import os
+    from uzliti_slam_b200 import EdgeEstimator
+    kfs, pairs, _ = S.make_map(420, n_features=300, cluster=10, pool=300, n_shared=180, k_candidates=20, cross_cluster=4, seed=71)
+    assert len(pairs) >= 8 * 5 * 148
+    os.environ["UZ_PIPELINE_CALLS"] = "0"
+    try:
+        one = EdgeEstimator(0)
+    finally:
+        os.environ.pop("UZ_PIPELINE_CALLS", None)
+    piped = EdgeEstimator(0)
+    try:
+        ho, hp = one.add_keyframes(kfs), piped.add_keyframes(kfs)
+        n0, n1 = one.launch_count(), piped.launch_count()
+        a = one.estimateEdges(ho[pairs[:, 0]], ho[pairs[:, 1]])
+        b = piped.estimateEdges(hp[pairs[:, 0]], hp[pairs[:, 1]])
+        assert a.tobytes() == b.tobytes() and (a["ok"] == 1).sum() > 1000
+        assert one.launch_count() - n0 == 2 and piped.launch_count() - n1 >= 6
+    finally:
+        one.close(); piped.close()

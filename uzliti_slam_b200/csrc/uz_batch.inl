@@ -594,6 +594,35 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
     return UZ_OK;
 }
 
+// A synchronous store-resident call (uz_estimate_edges, a group's shard) as a short pipeline: the batch is cut into chunks
+// that double in size, so the GPU starts after the host has prepared the FIRST chunk (1480 pairs) and the tables of chunk
+// c + 1 are built while chunk c runs.  One launch pair for 25 000 pairs leaves the GPU idle for the ~1.3 ms the host needs to
+// enumerate tasks and tiles.  Tensor-core match path only (the integer-pipe kernels overlap their own solve per launch), not
+// with the parity taps (they describe one launch pair).
+// after_chunk(first pair, pairs): called when a chunk has been enqueued (e.g. to queue its records' way home).
+uz_status run_pairs_pipelined(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_results,
+                              const std::function<uz_status(size_t, size_t)>& after_chunk = nullptr) {
+    const size_t n = pairs.size();
+    const size_t wave = (size_t)5 * (size_t)ctx->sm_count;
+    if (ctx->debug || !ctx->match_mma || !ctx->pipeline_calls || n < 8 * wave) {
+        const uz_status st = run_pairs(ctx, pairs, d_results);
+        return st != UZ_OK || !after_chunk ? st : after_chunk(0, n);
+    }
+    std::vector<PairRef> part;
+    size_t at = 0, take = 2 * wave;
+    while (at < n) {
+        size_t k = std::min(take, n - at);
+        if (n - at - k < wave) k = n - at;              // no crumb at the end
+        part.assign(pairs.begin() + at, pairs.begin() + at + k);
+        uz_status st = run_pairs(ctx, part, d_results + at);
+        if (st == UZ_OK && after_chunk) st = after_chunk(at, k);
+        if (st != UZ_OK) return st;
+        at += k;
+        take *= 2;
+    }
+    return UZ_OK;
+}
+
 uz_status resolve_timers(uz_context* ctx) {
     if (ctx->pending.empty()) return UZ_OK;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

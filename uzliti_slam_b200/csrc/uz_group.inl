@@ -281,11 +281,11 @@ static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const 
             st = pairs_from_handles(ctx, from_handles + lo, to_handles + lo, hi - lo, pairs);
             if (st != UZ_OK) return st;
             if (g->gather_mode == 0 || !host_out) {
-                st = run_pairs(ctx, pairs, sink + lo);                   // the solve writes through the peer- / host-mapped pointer
+                st = run_pairs_pipelined(ctx, pairs, sink + lo);         // the solve writes through the peer- / host-mapped pointer
                 if (st != UZ_OK) return st;
             } else {                                                     // measured alternative: local records, one copy per device
                 UZ_CUDA(ctx, ctx->d_results.ensure((size_t)(hi - lo) * sizeof(uz_edge_result)));
-                st = run_pairs(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
+                st = run_pairs_pipelined(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
                 if (st != UZ_OK) return st;
                 UZ_CUDA(ctx, cudaMemcpyAsync((uz_edge_result*)g->h_results.p + lo, ctx->d_results.p, (size_t)(hi - lo) * sizeof(uz_edge_result),
                                              cudaMemcpyDeviceToHost, ctx->stream));
