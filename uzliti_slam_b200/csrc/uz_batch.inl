@@ -623,6 +623,38 @@ uz_status run_pairs_pipelined(uz_context* ctx, const std::vector<PairRef>& pairs
     return UZ_OK;
 }
 
+// run_pairs_pipelined with the records delivered to a host array: every chunk's records are copied into pinned memory behind
+// its solve and from there into the caller's array while later chunks compute.  Returns with the stream idle.
+uz_status run_pairs_to_host(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_result* d_res, uz_edge_result* h_pinned,
+                            uz_edge_result* results) {
+    struct Home { size_t at, k; cudaEvent_t ev; };
+    std::vector<Home> home;
+    size_t drained = 0;
+    auto drain = [&](bool wait) {
+        for (; drained < home.size(); ++drained) {
+            const Home& hm = home[drained];
+            if (wait) { if (cudaEventSynchronize(hm.ev) != cudaSuccess) return; }
+            else if (cudaEventQuery(hm.ev) != cudaSuccess) { cudaGetLastError(); return; }
+            memcpy(results + hm.at, h_pinned + hm.at, hm.k * sizeof(uz_edge_result));
+        }
+    };
+    uz_status st = run_pairs_pipelined(ctx, pairs, d_res, [&](size_t at, size_t k) -> uz_status {
+        if (cudaMemcpyAsync(h_pinned + at, d_res + at, k * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            return fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
+        cudaEvent_t ev = ctx->get_event();
+        cudaEventRecord(ev, ctx->stream);
+        home.push_back(Home{at, k, ev});
+        drain(false);
+        return UZ_OK;
+    });
+    if (st == UZ_OK) drain(true);
+    for (auto& hm : home) ctx->event_pool.push_back(hm.ev);
+    if (st != UZ_OK) { cudaStreamSynchronize(ctx->stream); return st; }
+    if (drained != home.size()) return fail(ctx, UZ_ERR_CUDA, "cudaEventSynchronize failed");
+    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UZ_OK;
+}
+
 uz_status resolve_timers(uz_context* ctx) {
     if (ctx->pending.empty()) return UZ_OK;
     UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -635,40 +635,10 @@ uz_status uz_estimate_edges(uz_context* ctx, const int32_t* from_handles, const 
         return UZ_OK;
     }
     UZ_CUDA(ctx, ctx->h_results.ensure((size_t)n_pairs * sizeof(uz_edge_result)));
-    uz_edge_result* d_res = (uz_edge_result*)ctx->d_results.p;
-    uz_edge_result* h_res = (uz_edge_result*)ctx->h_results.p;
-    // records travel chunk by chunk into pinned memory and from there into the caller's array while later chunks compute
-    struct Home { size_t at, k; cudaEvent_t ev; };
-    std::vector<Home> home;
-    size_t drained = 0;
-    auto drain = [&](bool wait) {
-        for (; drained < home.size(); ++drained) {
-            const Home& hm = home[drained];
-            if (wait) { if (cudaEventSynchronize(hm.ev) != cudaSuccess) return; }
-            else if (cudaEventQuery(hm.ev) != cudaSuccess) { cudaGetLastError(); return; }
-            memcpy(results + hm.at, h_res + hm.at, hm.k * sizeof(uz_edge_result));
-        }
-    };
-    {
-        std::vector<PairRef> pairs;
-        st = pairs_from_handles(ctx, from_handles, to_handles, n_pairs, pairs);
-        if (st == UZ_OK)
-            st = run_pairs_pipelined(ctx, pairs, d_res, [&](size_t at, size_t k) -> uz_status {
-                if (cudaMemcpyAsync(h_res + at, d_res + at, k * sizeof(uz_edge_result), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-                    return fail(ctx, UZ_ERR_CUDA, "cudaMemcpyAsync(results) failed");
-                cudaEvent_t ev = ctx->get_event();
-                cudaEventRecord(ev, ctx->stream);
-                home.push_back(Home{at, k, ev});
-                drain(false);
-                return UZ_OK;
-            });
-    }
-    if (st == UZ_OK) drain(true);
-    for (auto& hm : home) ctx->event_pool.push_back(hm.ev);
-    if (st != UZ_OK) { cudaStreamSynchronize(ctx->stream); return st; }
-    if (drained != home.size()) return fail(ctx, UZ_ERR_CUDA, "cudaEventSynchronize failed");
-    UZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return UZ_OK;
+    std::vector<PairRef> pairs;
+    st = pairs_from_handles(ctx, from_handles, to_handles, n_pairs, pairs);
+    if (st != UZ_OK) return st;
+    return run_pairs_to_host(ctx, pairs, (uz_edge_result*)ctx->d_results.p, (uz_edge_result*)ctx->h_results.p, results);
 }
 
 uz_status uz_estimate_edges_host(uz_context* ctx, const uz_features* from_cams, const int32_t* n_from,

@@ -276,6 +276,7 @@ static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const 
         int lo, hi;
         group_shard(n_pairs, world, r, &lo, &hi);
         cudaEventRecord(g->ev0[r], ctx->stream);
+        bool copied_home = false;
         if (hi > lo) {
             std::vector<PairRef> pairs;
             st = pairs_from_handles(ctx, from_handles + lo, to_handles + lo, hi - lo, pairs);
@@ -283,12 +284,11 @@ static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const 
             if (g->gather_mode == 0 || !host_out) {
                 st = run_pairs_pipelined(ctx, pairs, sink + lo);         // the solve writes through the peer- / host-mapped pointer
                 if (st != UZ_OK) return st;
-            } else {                                                     // measured alternative: local records, one copy per device
+            } else {                                                     // local records, copied home chunk by chunk over the device's own PCIe link
                 UZ_CUDA(ctx, ctx->d_results.ensure((size_t)(hi - lo) * sizeof(uz_edge_result)));
-                st = run_pairs_pipelined(ctx, pairs, (uz_edge_result*)ctx->d_results.p);
+                st = run_pairs_to_host(ctx, pairs, (uz_edge_result*)ctx->d_results.p, (uz_edge_result*)g->h_results.p + lo, host_out + lo);
                 if (st != UZ_OK) return st;
-                UZ_CUDA(ctx, cudaMemcpyAsync((uz_edge_result*)g->h_results.p + lo, ctx->d_results.p, (size_t)(hi - lo) * sizeof(uz_edge_result),
-                                             cudaMemcpyDeviceToHost, ctx->stream));
+                copied_home = true;
             }
         }
         cudaEventRecord(g->ev1[r], ctx->stream);
@@ -296,7 +296,7 @@ static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const 
         float ms = 0;
         cudaEventElapsedTime(&ms, g->ev0[r], g->ev1[r]);
         g->last_ms[r] = ms;
-        if (host_out && hi > lo)       // every worker carries its own shard from the pinned landing zone to the caller's array
+        if (host_out && hi > lo && !copied_home)       // host-mapped sink: every worker carries its own shard from the landing zone to the caller's array
             memcpy(host_out + lo, (const uz_edge_result*)g->h_results.p + lo, (size_t)(hi - lo) * sizeof(uz_edge_result));
         return UZ_OK;
     });
