@@ -29,8 +29,8 @@ def test_reference_arm_prints_one_contract_line(built):
 
 
 def test_latest_gpu_profile_line_carries_the_contract_keys():
-    """the newest committed GPU bench line (profiles/bench_r01h.json) has what the contract asks of the GPU arm"""
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r01h.json")))
+    """the newest committed GPU bench line (profiles/bench_r02f.json) has what the contract asks of the GPU arm"""
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r02f.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -40,3 +40,11 @@ def test_latest_gpu_profile_line_carries_the_contract_keys():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and 0.5 < r["frac"] <= 1.0      # north star: >= 50 % of the INT roofline
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] <= d["value"] * 1.01
     assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == []
+    assert r["bound"] == "tensor" and r["traffic"] and d["sanity"]["cpu_records_equal"] is True and d["sanity"]["cpu_records_compared"] > 40000
+    assert d["cpu_baseline"]["reference_faithful_1thread"]["value"] > 0 and d["adapter_queue"]["same_map_as_this_bench"] is True
+    assert d["roofline"]["int_pipe_kernel"]["records_equal_tensor_core_path"] is True
+    # the multi-GPU line of the same tree: gathered records equal one GPU's, also through the one-process group
+    d8 = json.load(open(os.path.join(ROOT, "profiles", "bench_r02g_n8.json")))
+    assert d8["n_gpus"] == 8 and d8["sanity"]["gathered_equals_single_gpu"] is True
+    assert d8["group"]["records_equal_single_gpu"] is True and d8["group"]["peer_write"]["records_equal"] is True
+    assert d8["value"] > 7.5 * d["value"]
