@@ -36,6 +36,13 @@ public:
     // batch hook: default = one estimateEdgeImpl per pair; the GPU estimator overrides it
     virtual void estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
                                    std::vector<char>& ok);
+    // the worker's form of the same, in three steps per chunk of a drained queue (slot = 0 / 1, two chunks alternate):
+    // prepare(c + 1) runs while chunk c is still in flight, then finish(c), then submit(c + 1); endOfBurst() after the last
+    // finish.  Defaults: submit = estimateEdgeBatch, the rest nothing.
+    virtual void prepareEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, int slot);
+    virtual void submitEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges, std::vector<char>& ok, int slot);
+    virtual void finishEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges, std::vector<char>& ok, int slot);
+    virtual void endOfBurst();
 
     std::map<std::string, Eigen::Isometry3d> sensor_transforms_;                       // :56 (unused by this path)
 
@@ -49,7 +56,7 @@ protected:
 
     // edges of one chunk on their way to the callback; two slots, filled and delivered in turn
     struct Delivery { std::vector<SlamEdge> edges; std::vector<char> ok; };
-    static const int kDeliveryChunk = 4096;
+    int delivery_chunk_ = 4096;                       // pairs per estimateEdgeBatch call of a drained queue (UZ_ADAPTER_CHUNK)
     Delivery slots_[2];
     bool slot_full_[2] = {false, false};
     std::thread delivery_thread_;
@@ -81,6 +88,11 @@ public:
                     Eigen::Array<bool, 1, Eigen::Dynamic>& consensusSet);                                   // :53
     void estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
                            std::vector<char>& ok);
+    // look-ups of chunk c + 1 beside the device work of chunk c (uz_group_estimate_edges_begin / _end)
+    void prepareEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, int slot);
+    void submitEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges, std::vector<char>& ok, int slot);
+    void finishEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges, std::vector<char>& ok, int slot);
+    void endOfBurst();
 
     // the steps after the path, batched
     // GraphSlamNode::newEdgeCallback's numeric gate (graph_slam_node.cpp:798-804) for many edges at once
@@ -113,6 +125,19 @@ public:
 protected:
     struct Resident { int32_t handle = -1; std::vector<FeatureDataPtr> cams; std::vector<int> rows; };
     bool ensureResident(const SlamNode& node, Resident** out);
+    Resident* lookupResident(const SlamNode& node);                       // resident and unchanged, or nullptr; no upload
+    bool residentsOf(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<int32_t>& hf, std::vector<int32_t>& ht,
+                     std::vector<Resident*>& rf, std::vector<Resident*>& rt);
+    struct Flight {                                                       // one chunk between prepare and finish
+        std::vector<int32_t> hf, ht;
+        std::vector<Resident*> rf, rt;
+        std::vector<uz_edge_result> res;
+        bool all_resident = false, failed = false;
+        unsigned long long epoch = 0;
+    };
+    Flight flights_[2];
+    bool holding_ = false;                // the worker thread holds gpu_mutex_ (prepare .. endOfBurst)
+    unsigned long long store_epoch_ = 0;  // bumped by everything that changes handles_
     bool loadNodesLocked(const std::vector<const SlamNode*>& nodes);      // gpuMutex() held
     void fillEdge(const uz_edge_result& r, const Resident& from, const Resident& to, SlamEdge& edge) const;
     int internFrame(const std::string& frame);

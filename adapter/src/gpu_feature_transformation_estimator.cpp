@@ -5,13 +5,16 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <unordered_set>
 
 // ---------------------------------------------------------------------------------------------------------
 // TransformationEstimator: queue + worker thread (transformation_estimator.cpp:22-62)
 // ---------------------------------------------------------------------------------------------------------
-TransformationEstimator::TransformationEstimator(boost::function<void(SlamEdge)> callback) : callback_(callback) {}
+TransformationEstimator::TransformationEstimator(boost::function<void(SlamEdge)> callback) : callback_(callback) {
+    if (const char* c = std::getenv("UZ_ADAPTER_CHUNK")) { if (std::atoi(c) >= 64) delivery_chunk_ = std::atoi(c); }
+}
 
 TransformationEstimator::~TransformationEstimator() { stopThread(); }
 
@@ -52,11 +55,20 @@ void TransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, 
 // Two threads: the estimation thread turns queued pairs into edges, the delivery thread fires the callbacks.  A drained queue
 // is worked off in chunks, and while chunk c's edges are being delivered (edge copies, strings, the caller's callback) chunk
 // c + 1 is already being estimated.  Order of delivery is the order of estimation (LIFO per drained queue, :49-50).
+// An estimator may split a chunk's work in three (prepare / submit / finish): chunk c + 1 is PREPARED (host-side look-ups)
+// while chunk c is still running on the device, then c is finished and c + 1 submitted.  The defaults make that the plain
+// synchronous estimateEdgeBatch.
+void TransformationEstimator::prepareEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >&, int) {}
+void TransformationEstimator::submitEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
+                                              std::vector<char>& ok, int) { estimateEdgeBatch(pairs, edges, ok); }
+void TransformationEstimator::finishEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >&, std::vector<SlamEdge>&, std::vector<char>&, int) {}
+void TransformationEstimator::endOfBurst() {}
+
 void TransformationEstimator::estimationThread() {
     std::unique_lock<std::mutex> lk(estimation_mutex_);
-    // the queue and the batch being worked on are two vectors that change roles, and the edge vectors live across batches:
-    // their capacity is kept, so a steady stream of estimateEdge calls neither regrows the queue nor touches fresh pages
-    std::vector<std::pair<SlamNode, SlamNode> > batch, chunk;
+    // the queue and the batch being worked on are two vectors that change roles, and the chunk / edge vectors live across
+    // batches: their capacity is kept, so a steady stream of estimateEdge calls neither regrows the queue nor touches fresh pages
+    std::vector<std::pair<SlamNode, SlamNode> > batch, chunk[2];
     int fill = 0;
     while (running_) {
         if (est_queue_.empty()) { cv_.wait(lk); continue; }
@@ -65,25 +77,30 @@ void TransformationEstimator::estimationThread() {
         lk.unlock();
         // the reference pops the NEWEST pair first (LIFO, :49-50): deliver in that order
         std::reverse(batch.begin(), batch.end());
-        for (size_t at = 0; at < batch.size(); at += kDeliveryChunk) {
-            const size_t end = std::min(batch.size(), at + (size_t)kDeliveryChunk);
-            std::vector<std::pair<SlamNode, SlamNode> >* part = &batch;
-            if (batch.size() > (size_t)kDeliveryChunk) {
-                chunk.assign(std::make_move_iterator(batch.begin() + at), std::make_move_iterator(batch.begin() + end));
-                part = &chunk;
-            }
+        int inflight = -1;
+        auto finish = [&](int slot) {
+            finishEdgeBatch(chunk[slot], slots_[slot].edges, slots_[slot].ok, slot);
+            lk.lock();
+            slot_full_[slot] = true;
+            lk.unlock();
+            cv_.notify_all();
+        };
+        for (size_t at = 0; at < batch.size(); at += (size_t)delivery_chunk_) {
+            const size_t end = std::min(batch.size(), at + (size_t)delivery_chunk_);
             lk.lock();
             cv_.wait(lk, [&] { return !slot_full_[fill]; });
             lk.unlock();
-            estimateEdgeBatch(*part, slots_[fill].edges, slots_[fill].ok);
-            lk.lock();
-            slot_full_[fill] = true;
-            lk.unlock();
-            cv_.notify_all();
+            chunk[fill].assign(std::make_move_iterator(batch.begin() + at), std::make_move_iterator(batch.begin() + end));
+            prepareEdgeBatch(chunk[fill], fill);         // beside the device work of the chunk in flight
+            if (inflight >= 0) finish(inflight);
+            submitEdgeBatch(chunk[fill], slots_[fill].edges, slots_[fill].ok, fill);
+            inflight = fill;
             fill ^= 1;
         }
+        if (inflight >= 0) finish(inflight);
+        endOfBurst();
         batch.clear();
-        chunk.clear();
+        chunk[0].clear(); chunk[1].clear();
         lk.lock();
         busy_ = false;
         cv_.notify_all();
@@ -221,6 +238,7 @@ bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Res
         // the node's sensor data changed under its id (graph_slam_node.cpp:244, :1010-1026): the reference copies the node on
         // every estimateEdge (transformation_estimator.cpp:39) and so always matches the current data - re-upload, same handle
         if (uz_group_store_replace(grp_, it->second.handle, views.data(), (int32_t)views.size()) != UZ_OK) return false;
+        ++store_epoch_;
         it->second.cams = cams; it->second.rows = rows;
         *out = &it->second;
         return true;
@@ -228,6 +246,7 @@ bool GpuFeatureTransformationEstimator::ensureResident(const SlamNode& node, Res
     Resident r;
     r.cams = cams; r.rows = rows;
     if (uz_group_store_add(grp_, views.data(), (int32_t)views.size(), &r.handle) != UZ_OK) return false;
+    ++store_epoch_;
     std::string key = node.id_.empty() ? "#anon" + std::to_string(anon_++) : node.id_;
     auto ins = handles_.emplace(key, r);
     *out = &ins.first->second;
@@ -274,6 +293,7 @@ bool GpuFeatureTransformationEstimator::loadNodesLocked(const std::vector<const 
         return false;
     }
     for (size_t i = 0; i < res.size(); ++i) { res[i].handle = handles[i]; handles_.emplace(fresh[i]->id_, res[i]); }
+    if (!res.empty()) ++store_epoch_;
     return true;
 }
 
@@ -283,6 +303,7 @@ void GpuFeatureTransformationEstimator::forgetNode(const std::string& id) {
     if (it == handles_.end()) return;
     uz_group_store_remove(grp_, it->second.handle);
     handles_.erase(it);
+    ++store_epoch_;
 }
 
 static void set_identity6(Eigen::MatrixXd& m) {
@@ -325,6 +346,86 @@ void GpuFeatureTransformationEstimator::fillEdge(const uz_edge_result& r, const 
     edge.matching_score_ = r.consensus;                                                     // :155
 }
 
+// ---- the worker's three-step form ------------------------------------------------------------------------------------------
+// The worker thread owns gpu_mutex_ from the first prepare of a burst to endOfBurst(), with a yield after every finished
+// chunk; store_epoch_ tells submit whether somebody changed the store during such a yield.
+GpuFeatureTransformationEstimator::Resident* GpuFeatureTransformationEstimator::lookupResident(const SlamNode& node) {
+    if (node.id_.empty()) return nullptr;
+    auto it = handles_.find(node.id_);
+    return (it != handles_.end() && node_matches(node, it->second.cams, it->second.rows)) ? &it->second : nullptr;
+}
+
+void GpuFeatureTransformationEstimator::prepareEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, int slot) {
+    if (!holding_) { gpu_mutex_.lock(); holding_ = true; }
+    Flight& F = flights_[slot];
+    const size_t n = pairs.size();
+    F.hf.resize(n); F.ht.resize(n); F.rf.resize(n); F.rt.resize(n);
+    F.all_resident = true; F.failed = false; F.epoch = store_epoch_;
+    for (size_t i = 0; i < n; ++i) {
+        Resident* a = lookupResident(pairs[i].first);
+        Resident* b = lookupResident(pairs[i].second);
+        if (!a || !b) { F.all_resident = false; break; }
+        F.rf[i] = a; F.rt[i] = b; F.hf[i] = a->handle; F.ht[i] = b->handle;
+    }
+}
+
+void GpuFeatureTransformationEstimator::submitEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
+                                                        std::vector<char>& ok, int slot) {
+    Flight& F = flights_[slot];
+    const size_t n = pairs.size();
+    edges.resize(n);
+    for (SlamEdge& e : edges) resetEdge(e);               // == default constructed, without giving the 6 x 6 matrix back to the heap
+    ok.assign(n, 0);
+    if (!F.all_resident || F.epoch != store_epoch_) {     // nodes to upload (nothing is in flight now), or the store changed during a yield
+        if (!residentsOf(pairs, F.hf, F.ht, F.rf, F.rt)) { F.failed = true; std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError()); return; }
+    }
+    F.res.resize(n);
+    if (n > 0 && uz_group_estimate_edges_begin(grp_, F.hf.data(), F.ht.data(), (int32_t)n, F.res.data()) != UZ_OK) {
+        F.failed = true;
+        std::fprintf(stderr, "uz_group_estimate_edges_begin: %s\n", lastError());
+    }
+}
+
+void GpuFeatureTransformationEstimator::finishEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
+                                                        std::vector<char>& ok, int slot) {
+    Flight& F = flights_[slot];
+    const size_t n = pairs.size();
+    uz_status st = F.failed ? UZ_ERR_INVALID : uz_group_estimate_edges_end(grp_);
+    if (!F.failed && st != UZ_OK) std::fprintf(stderr, "uz_group_estimate_edges_end: %s\n", lastError());
+    for (size_t i = 0; i < n; ++i) {
+        if (st == UZ_OK) { fillEdge(F.res[i], *F.rf[i], *F.rt[i], edges[i]); ok[i] = F.res[i].ok ? 1 : 0; }
+        edges[i].id_from_ = pairs[i].first.id_;          // :168-169, set even on failure
+        edges[i].id_to_ = pairs[i].second.id_;
+    }
+    gpu_mutex_.unlock();                                  // nothing is in flight: let the place recogniser / forgetNode in
+    gpu_mutex_.lock();
+}
+
+void GpuFeatureTransformationEstimator::endOfBurst() {
+    if (holding_) { holding_ = false; gpu_mutex_.unlock(); }
+}
+
+// handles and device copies of every node of a batch (uploads what is missing or stale); gpu_mutex_ held
+bool GpuFeatureTransformationEstimator::residentsOf(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<int32_t>& hf,
+                                                    std::vector<int32_t>& ht, std::vector<Resident*>& rf, std::vector<Resident*>& rt) {
+    const size_t n = pairs.size();
+    hf.resize(n); ht.resize(n); rf.resize(n); rt.resize(n);
+    {   // nodes this batch sees for the first time travel in ONE bulk upload (a cold queue otherwise pays one upload call per node)
+        std::vector<const SlamNode*> fresh;
+        std::unordered_set<std::string> seen;
+        for (size_t i = 0; i < n; ++i)
+            for (const SlamNode* nd : {&pairs[i].first, &pairs[i].second})
+                if (!nd->id_.empty() && !handles_.count(nd->id_) && seen.insert(nd->id_).second) fresh.push_back(nd);
+        if (fresh.size() > 1 && !loadNodesLocked(fresh)) return false;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (!ensureResident(pairs[i].first, &rf[i]) || !ensureResident(pairs[i].second, &rt[i])) return false;
+        hf[i] = rf[i]->handle;
+        ht[i] = rt[i]->handle;
+    }
+    return true;
+}
+
 void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs,
                                                           std::vector<SlamEdge>& edges, std::vector<char>& ok) {
     std::lock_guard<std::mutex> lk(gpu_mutex_);
@@ -332,27 +433,12 @@ void GpuFeatureTransformationEstimator::estimateEdgeBatch(std::vector<std::pair<
     edges.resize(n);
     for (SlamEdge& e : edges) resetEdge(e);               // == default constructed, without giving the 6 x 6 matrix back to the heap
     ok.assign(n, 0);
-    std::vector<int32_t> hf(n), ht(n);
-    std::vector<Resident*> rf(n), rt(n);
-    {   // nodes this batch sees for the first time travel in ONE bulk upload (a cold queue otherwise pays one upload call per node)
-        std::vector<const SlamNode*> fresh;
-        std::unordered_set<std::string> seen;
-        for (size_t i = 0; i < n; ++i)
-            for (const SlamNode* nd : {&pairs[i].first, &pairs[i].second})
-                if (!nd->id_.empty() && !handles_.count(nd->id_) && seen.insert(nd->id_).second) fresh.push_back(nd);
-        if (fresh.size() > 1 && !loadNodesLocked(fresh)) {
-            for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
-            return;
-        }
-    }
-    for (size_t i = 0; i < n; ++i) {
-        if (!ensureResident(pairs[i].first, &rf[i]) || !ensureResident(pairs[i].second, &rt[i])) {
-            std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError());
-            for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
-            return;
-        }
-        hf[i] = rf[i]->handle;
-        ht[i] = rt[i]->handle;
+    std::vector<int32_t> hf, ht;
+    std::vector<Resident*> rf, rt;
+    if (!residentsOf(pairs, hf, ht, rf, rt)) {
+        std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError());
+        for (size_t k = 0; k < n; ++k) { edges[k].id_from_ = pairs[k].first.id_; edges[k].id_to_ = pairs[k].second.id_; }
+        return;
     }
     std::vector<uz_edge_result> res(n);
     const uz_status st = uz_group_estimate_edges(grp_, hf.data(), ht.data(), (int32_t)n, res.data());

@@ -336,6 +336,13 @@ int32_t   uz_group_store_size(const uz_group* g);
 uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
                                   int32_t n_pairs, uz_edge_result* results);
 /* Same, records land in devices[0]'s memory (n_pairs records), e.g. for uz_gate_edges_device.  Blocks until done. */
+/* The same in two halves, for a host that has work of its own to do meanwhile (the adapter prepares the next chunk of its
+ * queue): _begin hands the batch to the group's device workers and returns, _end waits for them and returns the first failure.
+ * from_handles, to_handles and results must stay valid until _end; no other call on the group or its contexts in between
+ * (they answer UZ_ERR_INVALID).  _end without a batch in flight is a no-op. */
+uz_status uz_group_estimate_edges_begin(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
+                                        int32_t n_pairs, uz_edge_result* results);
+uz_status uz_group_estimate_edges_end(uz_group* g);
 uz_status uz_group_estimate_edges_device(uz_group* g, const int32_t* from_handles, const int32_t* to_handles,
                                          int32_t n_pairs, void* results_on_first_device);
 /* Host results only.  1 (default): records stay local and every device copies its shard into the pinned result array over its

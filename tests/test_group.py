@@ -70,3 +70,32 @@ def test_group_records_equal_single_gpu_byte_for_byte(est, ndev):
     finally:
         g.close()
     est.clear()
+
+
+@pytest.mark.gpu
+def test_group_begin_end_equals_the_synchronous_call(built):
+    """uz_group_estimate_edges_begin / _end: the batch runs on the group's device workers while the caller does something else;
+    same records as the one-call form, and the group refuses other work in between"""
+    import torch
+    from uzliti_slam_b200 import GroupEstimator
+    from uzliti_slam_b200.binding import UzError
+    n = min(torch.cuda.device_count(), 2)
+    kfs, pairs, _ = S.make_map(60, n_features=500, cluster=6, pool=500, n_shared=300, k_candidates=6, cross_cluster=2, seed=35)
+    g = GroupEstimator(list(range(n)))
+    try:
+        h = g.add_keyframes(kfs)
+        f, t = h[pairs[:, 0]], h[pairs[:, 1]]
+        want = g.estimateEdges(f, t)
+        g.estimateEdgesBegin(f, t)
+        with pytest.raises(UzError):
+            g.estimateEdges(f[:4], t[:4])                # a batch is in flight
+        with pytest.raises(UzError):
+            g.add_keyframes(kfs[:1])
+        busy = sum(i * i for i in range(20000))          # the caller's own work
+        got = g.estimateEdgesEnd()
+        assert busy > 0 and got.tobytes() == want.tobytes() and (got["ok"] == 1).any()
+        g.estimateEdgesBegin(f[:0], t[:0])               # empty batch: nothing in flight
+        assert len(g.estimateEdgesEnd()) == 0
+        assert g.estimateEdges(f, t).tobytes() == want.tobytes()
+    finally:
+        g.close()

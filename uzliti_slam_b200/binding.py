@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "uz_places_search", "uz_places_remove", "uz_places_count", "uz_places_votes", "uz_places_last_timing",
     "uz_group_create", "uz_group_destroy", "uz_group_last_error", "uz_group_size", "uz_group_context", "uz_group_set_params",
     "uz_group_store_add", "uz_group_store_add_bulk", "uz_group_store_replace", "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size",
-    "uz_group_estimate_edges", "uz_group_estimate_edges_device", "uz_group_set_gather", "uz_group_last_timing",
+    "uz_group_estimate_edges", "uz_group_estimate_edges_begin", "uz_group_estimate_edges_end", "uz_group_estimate_edges_device",
+    "uz_group_set_gather", "uz_group_last_timing",
 ]
 
 
@@ -152,6 +153,7 @@ def load_library():
     lib.uz_group_context.restype = C.c_void_p
     for name in ("uz_group_create", "uz_group_size", "uz_group_set_params", "uz_group_store_add", "uz_group_store_add_bulk",
                  "uz_group_store_remove", "uz_group_store_clear", "uz_group_store_size", "uz_group_estimate_edges",
+                 "uz_group_estimate_edges_begin", "uz_group_estimate_edges_end",
                  "uz_group_estimate_edges_device", "uz_group_set_gather", "uz_group_last_timing"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -692,6 +694,20 @@ class GroupEstimator:
         f = np.ascontiguousarray(from_handles, np.int32)
         t = np.ascontiguousarray(to_handles, np.int32)
         self._check(self.lib.uz_group_estimate_edges_device(self.grp, _p(f), _p(t), len(f), C.c_void_p(results_device_ptr)))
+
+    def estimateEdgesBegin(self, from_handles, to_handles, out=None):
+        """first half of estimateEdges: returns at once; the arrays are kept alive here until estimateEdgesEnd()"""
+        f = np.ascontiguousarray(from_handles, np.int32)
+        t = np.ascontiguousarray(to_handles, np.int32)
+        res = out if out is not None else np.zeros(len(f), RESULT_DTYPE)
+        self._in_flight = (f, t, res)
+        self._check(self.lib.uz_group_estimate_edges_begin(self.grp, _p(f), _p(t), len(f), _p(res)))
+
+    def estimateEdgesEnd(self):
+        self._check(self.lib.uz_group_estimate_edges_end(self.grp))
+        f, t, res = self._in_flight
+        self._in_flight = None
+        return res
 
     def last_timing(self):
         out = np.zeros(len(self.devices), np.float64)

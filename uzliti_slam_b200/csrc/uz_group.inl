@@ -36,6 +36,7 @@ struct uz_group {
     uz_edge_result* h_results_dev = nullptr;
     std::vector<double> last_ms;      // device time of the last batch per rank
     std::vector<cudaEvent_t> ev0, ev1;
+    bool in_flight = false;           // between uz_group_estimate_edges_begin and _end
 };
 
 namespace {
@@ -57,8 +58,8 @@ void group_worker_loop(uz_group::Worker* w) {
     }
 }
 
-// runs fn(rank) on every device's worker thread and waits; returns the first failure
-uz_status group_run(uz_group* g, const std::function<uz_status(int)>& fn, int first_rank = 0) {
+// hands fn(rank) to every device's worker thread
+void group_dispatch(uz_group* g, const std::function<uz_status(int)>& fn, int first_rank = 0) {
     const int n = (int)g->ctx.size();
     for (int r = first_rank; r < n; ++r) {
         uz_group::Worker* w = g->workers[r];
@@ -67,6 +68,10 @@ uz_status group_run(uz_group* g, const std::function<uz_status(int)>& fn, int fi
         w->has_job = true; w->done = false;
         w->cv.notify_all();
     }
+}
+// waits for the workers; returns the first failure
+uz_status group_wait(uz_group* g, int first_rank = 0) {
+    const int n = (int)g->ctx.size();
     uz_status out = UZ_OK;
     for (int r = first_rank; r < n; ++r) {
         uz_group::Worker* w = g->workers[r];
@@ -78,6 +83,11 @@ uz_status group_run(uz_group* g, const std::function<uz_status(int)>& fn, int fi
         }
     }
     return out;
+}
+// runs fn(rank) on every device's worker thread and waits; returns the first failure
+uz_status group_run(uz_group* g, const std::function<uz_status(int)>& fn, int first_rank = 0) {
+    group_dispatch(g, fn, first_rank);
+    return group_wait(g, first_rank);
 }
 
 void group_shard(int n_pairs, int world, int rank, int* lo, int* hi) {
@@ -213,6 +223,7 @@ uz_context* uz_group_context(uz_group* g, int32_t rank) { return (g && rank >= 0
 
 uz_status uz_group_set_params(uz_group* g, const uz_params* p) {
     if (!g || !p) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     for (auto* c : g->ctx) {
         const uz_status st = uz_set_params(c, p);
         if (st != UZ_OK) { g->err = c->err; return st; }
@@ -229,6 +240,7 @@ uz_status uz_group_set_gather(uz_group* g, int32_t mode) {
 uz_status uz_group_store_add_bulk(uz_group* g, const uz_features* cams, const int32_t* cams_per_keyframe, int32_t n_keyframes,
                                   int32_t* handles_out) {
     if (!g) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     uz_status st = uz_store_add_bulk(g->ctx[0], cams, cams_per_keyframe, n_keyframes, handles_out);      // the one trip over PCIe
     if (st != UZ_OK) { g->err = g->ctx[0]->err; return st; }
     if (g->ctx.size() == 1 || n_keyframes == 0) return UZ_OK;
@@ -243,6 +255,7 @@ uz_status uz_group_store_add(uz_group* g, const uz_features* cams, int32_t n_cam
 
 uz_status uz_group_store_replace(uz_group* g, int32_t handle, const uz_features* cams, int32_t n_cams) {
     if (!g) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     uz_status st = uz_store_replace(g->ctx[0], handle, cams, n_cams);
     if (st != UZ_OK) { g->err = g->ctx[0]->err; return st; }
     if (g->ctx.size() == 1) return UZ_OK;
@@ -255,21 +268,23 @@ uz_status uz_group_store_replace(uz_group* g, int32_t handle, const uz_features*
 
 uz_status uz_group_store_remove(uz_group* g, int32_t handle) {
     if (!g) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     return group_run(g, [g, handle](int r) { return uz_store_remove(g->ctx[r], handle); });
 }
 
 uz_status uz_group_store_clear(uz_group* g) {
     if (!g) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     return group_run(g, [g](int r) { return uz_store_clear(g->ctx[r]); });
 }
 
 int32_t uz_group_store_size(const uz_group* g) { return g ? uz_store_size(g->ctx[0]) : 0; }
 
 // shard r of the batch on device r; records go to `sink + pair index` (any address every device can write)
-static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
-                                uz_edge_result* sink, uz_edge_result* host_out) {
+static void group_estimate_dispatch(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
+                                    uz_edge_result* sink, uz_edge_result* host_out) {
     const int world = (int)g->ctx.size();
-    return group_run(g, [=](int r) -> uz_status {
+    group_dispatch(g, [=](int r) -> uz_status {
         uz_context* ctx = g->ctx[r];
         uz_status st = check_ctx(ctx);
         if (st != UZ_OK) return st;
@@ -301,11 +316,13 @@ static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const 
         return UZ_OK;
     });
 }
+static uz_status group_estimate(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
+                                uz_edge_result* sink, uz_edge_result* host_out) {
+    group_estimate_dispatch(g, from_handles, to_handles, n_pairs, sink, host_out);
+    return group_wait(g);
+}
 
-uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
-                                  uz_edge_result* results) {
-    if (!g || n_pairs < 0 || (n_pairs > 0 && (!from_handles || !to_handles || !results))) return UZ_ERR_INVALID;
-    if (n_pairs == 0) return UZ_OK;
+static uz_status group_result_zone(uz_group* g, int32_t n_pairs) {
     const size_t need = (size_t)n_pairs * sizeof(uz_edge_result);
     if (need > g->h_results.cap) {
         if (g->h_results.p) cudaFreeHost(g->h_results.p);
@@ -323,12 +340,42 @@ uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, cons
         cudaHostGetDevicePointer(&d, p, 0);       // unified addressing: the same address on every device
         g->h_results_dev = (uz_edge_result*)d;
     }
+    return UZ_OK;
+}
+
+uz_status uz_group_estimate_edges(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
+                                  uz_edge_result* results) {
+    if (!g || n_pairs < 0 || (n_pairs > 0 && (!from_handles || !to_handles || !results))) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
+    if (n_pairs == 0) return UZ_OK;
+    const uz_status st = group_result_zone(g, n_pairs);
+    if (st != UZ_OK) return st;
     return group_estimate(g, from_handles, to_handles, n_pairs, g->h_results_dev, results);
+}
+
+uz_status uz_group_estimate_edges_begin(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
+                                        uz_edge_result* results) {
+    if (!g || n_pairs < 0 || (n_pairs > 0 && (!from_handles || !to_handles || !results))) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
+    if (n_pairs == 0) return UZ_OK;
+    const uz_status st = group_result_zone(g, n_pairs);
+    if (st != UZ_OK) return st;
+    group_estimate_dispatch(g, from_handles, to_handles, n_pairs, g->h_results_dev, results);
+    g->in_flight = true;
+    return UZ_OK;
+}
+
+uz_status uz_group_estimate_edges_end(uz_group* g) {
+    if (!g) return UZ_ERR_INVALID;
+    if (!g->in_flight) return UZ_OK;
+    g->in_flight = false;
+    return group_wait(g);
 }
 
 uz_status uz_group_estimate_edges_device(uz_group* g, const int32_t* from_handles, const int32_t* to_handles, int32_t n_pairs,
                                          void* results_on_first_device) {
     if (!g || n_pairs < 0 || (n_pairs > 0 && (!from_handles || !to_handles || !results_on_first_device))) return UZ_ERR_INVALID;
+    if (g->in_flight) { g->err = "a batch is in flight: call uz_group_estimate_edges_end first"; return UZ_ERR_INVALID; }
     if (n_pairs == 0) return UZ_OK;
     return group_estimate(g, from_handles, to_handles, n_pairs, (uz_edge_result*)results_on_first_device, nullptr);
 }
