@@ -168,3 +168,26 @@ def test_cta_pair_kernel_whole_batches_identical(oracle, cfg=None):
         assert host.tobytes() == e1.estimateEdgesHost([([kfs[a]], [kfs[b]]) for a, b in pairs[:300]]).tobytes()
     finally:
         e2.close(); e1.close()
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_tensor_core_kernels_fuzz(oracle, width):
+    """random shapes and bit densities (sparse / dense rows move the distances towards 0 and towards the maximum), both widths:
+    the tensor-core kernels against the oracle"""
+    from uzliti_slam_b200 import EdgeEstimator
+    est = EdgeEstimator(0)
+    rng = np.random.default_rng(20260 + width)
+    try:
+        for trial in range(48):
+            nq = int(rng.integers(1, 1400)) if trial % 6 else int(rng.choice([127, 128, 129, 255, 256, 257, 511, 512, 513, 1024]))
+            nt = int(rng.integers(1, 1400)) if trial % 5 else int(rng.choice([127, 128, 129, 255, 256, 257, 383, 384, 385, 1025]))
+            p = float(rng.choice([0.02, 0.3, 0.5, 0.5, 0.7, 0.98]))
+            q = np.packbits(rng.random((nq, width * 8)) < p, axis=1)
+            t = np.packbits(rng.random((nt, width * 8)) < (1.0 - p if trial % 3 == 0 else p), axis=1)
+            if trial % 4 == 0 and nt > 8:                          # duplicated train rows: ties on (distance, index)
+                t[rng.integers(0, nt, 8)] = t[rng.integers(0, nt)]
+            idx, dist = est.knnMatch(q, t)
+            oi, od = oracle.knn2(q, t)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (width, nq, nt, p)
+    finally:
+        est.close()
