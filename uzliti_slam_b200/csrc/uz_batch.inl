@@ -44,7 +44,7 @@ void launch_solve(uz_context* ctx, int n_ctas, int cap, cudaStream_t st, const M
     if (ctx->solve_wide && n_ctas <= ctx->sm_count)
         solve_kernel<kSolveThreadsWide><<<n_ctas, kSolveThreadsWide, solve_smem_bytes(cap, kSolveThreadsWide), st>>>(d_tasks, d_pair_tasks, d_keys, sp, d_results);
     else
-        solve_kernel<kSolveThreads><<<n_ctas, kSolveThreads, solve_smem_bytes(cap), st>>>(d_tasks, d_pair_tasks, d_keys, sp, d_results);
+        solve_kernel<kSolveThreads><<<n_ctas, kSolveThreads, solve_smem_bytes(cap) + (size_t)ctx->solve_smem_pad, st>>>(d_tasks, d_pair_tasks, d_keys, sp, d_results);
 }
 
 // Kernels of one library that are meant to run beside each other must agree on the shared-memory carve-out of the SM:

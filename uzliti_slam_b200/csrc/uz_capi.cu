@@ -126,6 +126,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
         if (cc && atoi(cc) > 0) ctx->copy_ctas = atoi(cc);
         const char* hs = getenv("UZ_HOST_SLOTS");
         if (hs && atoi(hs) >= 2) ctx->host_slots = std::min(atoi(hs), (int)uz_context::kSlots);
+        const char* sp = getenv("UZ_SOLVE_SMEM_PAD");
+        if (sp) ctx->solve_smem_pad = std::max(0, atoi(sp));
         const char* pc = getenv("UZ_PIPELINE_CALLS");
         if (pc) ctx->pipeline_calls = atoi(pc);
         const char* hf = getenv("UZ_HOST_FIRST_WAVES");

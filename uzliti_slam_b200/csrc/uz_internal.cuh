@@ -330,6 +330,7 @@ struct uz_context {
     static constexpr int kSlots = 6;
     Slot slots[kSlots];
     int cur_slot = 0, slot_depth = 2, host_slots = kSlots;
+    int solve_smem_pad = 0;          // UZ_SOLVE_SMEM_PAD (measurement only): extra dynamic shared memory per solve CTA = fewer CTAs per SM
     int pipeline_calls = 1;          // UZ_PIPELINE_CALLS=0: synchronous store-resident calls run as one launch pair (run_pairs_pipelined)
     int host_first_waves = 1;        // UZ_HOST_FIRST_WAVES: size of the first chunk of uz_estimate_edges_host in solve waves (0: like the others)
     DevBuf d_results, d_dbg_matches, d_dbg_mask, d_dbg_counts, d_dbg_phase, d_misc;
