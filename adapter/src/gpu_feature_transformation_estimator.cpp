@@ -87,12 +87,14 @@ void TransformationEstimator::estimationThread() {
         };
         for (size_t at = 0; at < batch.size(); at += (size_t)delivery_chunk_) {
             const size_t end = std::min(batch.size(), at + (size_t)delivery_chunk_);
-            lk.lock();
-            cv_.wait(lk, [&] { return !slot_full_[fill]; });
-            lk.unlock();
             chunk[fill].assign(std::make_move_iterator(batch.begin() + at), std::make_move_iterator(batch.begin() + end));
             prepareEdgeBatch(chunk[fill], fill);         // beside the device work of the chunk in flight
             if (inflight >= 0) finish(inflight);
+            // wait for the delivery slot with nothing in flight and no estimator lock held: a callback that calls back into
+            // the estimator (forgetNode, estimateEdgeDirect) must not find the worker sitting on gpuMutex()
+            lk.lock();
+            cv_.wait(lk, [&] { return !slot_full_[fill]; });
+            lk.unlock();
             submitEdgeBatch(chunk[fill], slots_[fill].edges, slots_[fill].ok, fill);
             inflight = fill;
             fill ^= 1;
@@ -347,8 +349,8 @@ void GpuFeatureTransformationEstimator::fillEdge(const uz_edge_result& r, const 
 }
 
 // ---- the worker's three-step form ------------------------------------------------------------------------------------------
-// The worker thread owns gpu_mutex_ from the first prepare of a burst to endOfBurst(), with a yield after every finished
-// chunk; store_epoch_ tells submit whether somebody changed the store during such a yield.
+// The worker thread owns gpu_mutex_ while a chunk is in flight (submit .. finish, with the look-ups of the next chunk in
+// between) and gives it up after every finished chunk; store_epoch_ tells submit whether somebody changed the store meanwhile.
 GpuFeatureTransformationEstimator::Resident* GpuFeatureTransformationEstimator::lookupResident(const SlamNode& node) {
     if (node.id_.empty()) return nullptr;
     auto it = handles_.find(node.id_);
@@ -356,7 +358,8 @@ GpuFeatureTransformationEstimator::Resident* GpuFeatureTransformationEstimator::
 }
 
 void GpuFeatureTransformationEstimator::prepareEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, int slot) {
-    if (!holding_) { gpu_mutex_.lock(); holding_ = true; }
+    const bool own = !holding_;            // first chunk of a burst: nothing in flight, take the lock for the look-ups only
+    if (own) gpu_mutex_.lock();
     Flight& F = flights_[slot];
     const size_t n = pairs.size();
     F.hf.resize(n); F.ht.resize(n); F.rf.resize(n); F.rt.resize(n);
@@ -367,6 +370,7 @@ void GpuFeatureTransformationEstimator::prepareEdgeBatch(std::vector<std::pair<S
         if (!a || !b) { F.all_resident = false; break; }
         F.rf[i] = a; F.rt[i] = b; F.hf[i] = a->handle; F.ht[i] = b->handle;
     }
+    if (own) gpu_mutex_.unlock();
 }
 
 void GpuFeatureTransformationEstimator::submitEdgeBatch(std::vector<std::pair<SlamNode, SlamNode> >& pairs, std::vector<SlamEdge>& edges,
@@ -376,6 +380,7 @@ void GpuFeatureTransformationEstimator::submitEdgeBatch(std::vector<std::pair<Sl
     edges.resize(n);
     for (SlamEdge& e : edges) resetEdge(e);               // == default constructed, without giving the 6 x 6 matrix back to the heap
     ok.assign(n, 0);
+    if (!holding_) { gpu_mutex_.lock(); holding_ = true; }
     if (!F.all_resident || F.epoch != store_epoch_) {     // nodes to upload (nothing is in flight now), or the store changed during a yield
         if (!residentsOf(pairs, F.hf, F.ht, F.rf, F.rt)) { F.failed = true; std::fprintf(stderr, "estimateEdgeBatch: %s\n", lastError()); return; }
     }
@@ -397,8 +402,8 @@ void GpuFeatureTransformationEstimator::finishEdgeBatch(std::vector<std::pair<Sl
         edges[i].id_from_ = pairs[i].first.id_;          // :168-169, set even on failure
         edges[i].id_to_ = pairs[i].second.id_;
     }
-    gpu_mutex_.unlock();                                  // nothing is in flight: let the place recogniser / forgetNode in
-    gpu_mutex_.lock();
+    holding_ = false;
+    gpu_mutex_.unlock();                                  // nothing is in flight: the place recogniser / forgetNode get their turn
 }
 
 void GpuFeatureTransformationEstimator::endOfBurst() {

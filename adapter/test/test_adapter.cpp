@@ -112,6 +112,39 @@ int main() {
             for (int c = 0; c < 4; ++c) CHECK(d.transform_(r, c) == e.transform_(r, c));
     }
 
+    // 1c. a callback that calls back into the estimator (forgetNode of an unknown id and estimateEdgeDirect both take
+    //     gpuMutex()) while a burst of many small chunks is being worked off: every edge arrives, nothing deadlocks, and the
+    //     answers are the ones of section 1
+    {
+        setenv("UZ_ADAPTER_CHUNK", "64", 1);
+        std::mutex m2;
+        std::map<std::string, SlamEdge> got2;
+        GpuFeatureTransformationEstimator* self = nullptr;
+        int direct_ok = 0;
+        GpuFeatureTransformationEstimator est2([&](SlamEdge e) {
+            self->forgetNode("no such node");
+            if (e.id_from_ == "a0") { SlamEdge d; direct_ok += self->estimateEdgeDirect(A[1].sensor_data_, B[1].sensor_data_, d) ? 1 : 0; }
+            std::lock_guard<std::mutex> lk(m2);
+            got2[e.id_from_ + "|" + e.id_to_ + "#" + std::to_string(got2.size())] = e;
+        }, devices);
+        unsetenv("UZ_ADAPTER_CHUNK");
+        self = &est2;
+        est2.setConfig(cfg);
+        const int reps = 40;                                   // 40 x 24 pairs = 15 chunks of 64
+        for (int r = 0; r < reps; ++r)
+            for (int i = 0; i < NP; ++i) est2.estimateEdge(A[i], B[i]);
+        est2.waitIdle();
+        CHECK((int)got2.size() == reps * NP);
+        CHECK(direct_ok >= 1);
+        for (auto& kv : got2) {
+            const SlamEdge& e = kv.second;
+            const SlamEdge& want = got[e.id_from_ + "|" + e.id_to_];
+            CHECK(e.matching_score_ == want.matching_score_);
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) CHECK(e.transform_(r, c) == want.transform_(r, c));
+        }
+    }
+
     // 1b. BRISK keyframes (64-byte rows; cv::BRISK is FeatureExtractionCore's default, feature_extraction_core.cpp:46-49)
     //     through the same queue, and one BRISK-vs-ORB pair: never compared (cv::BFMatcher would throw), score 0
     {
