@@ -914,8 +914,9 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak = mp.get("hbm_gbs", 6650.0)
-        # tensor roofline: a 256-bit compare is a K = 256 int8 dot product = 512 ops; the int8 peak is 2 x the bf16 peak (same
-        # tcgen05 data path at twice the K per instruction); MEASURED_PEAKS.json holds the measured bf16 figures
+        # tensor roofline: a 256-bit compare is a K = 256 dot product of 4-bit operands = 512 ops; the block-scaled fp4 peak is
+        # 4 x the bf16 peak (same tcgen05 data path at four times the K per instruction); MEASURED_PEAKS.json holds the
+        # measured bf16 figures
         bf16 = mp.get("bf16_tflops_sustained", 1400.0)
         bf16_burst = mp.get("bf16_tflops", 1590.0)
         from uzliti_slam_b200 import mix
@@ -932,28 +933,32 @@ def run_gpu(args):
         line = dict(
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="s8 (exact int8 dot products of +-1 bit vectors, int32 accumulate) + u32 keys", data="synthetic",
+            dtype="e2m1 (exact dot products of +-4 four-bit operands, block scale 2, fp32 accumulate below 2^24) + u32 keys", data="synthetic",
             config=dict(workload=WORKLOAD, keyframes=n_kf, features=N_FEATURES, pairs_per_gpu=pairs_per_gpu,
                         l2="inputs larger than L2: every step streams the 10000-keyframe store "
-                           f"({est.store_bytes() / 1e6:.0f} MB resident per GPU, 2.6 GB of it the int8 operand layout) through the "
+                           f"({est.store_bytes() / 1e6:.0f} MB resident per GPU, 1.3 GB of it the 4-bit operand layout) through the "
                            "match kernel; no flush",
                         parallelism=f"pair-list sharding x{world}, store replicated, all-gather of 176 B edge records"),
             g_descriptor_cmp_per_s=round(world * cmp_per_launch / (ms / args.steps * 1e-3) * 1e-9, 2),
-            roofline=dict(bound="tensor", kernel="knn2_mmak_kernel (tcgen05.mma kind::i8, 128x256x32, TMEM accumulators; the accumulator is the packed key)",
-                          achieved=round(tops, 1), peak=round(2 * bf16_burst, 1), unit="TFLOP/s", frac=round(tops / (2 * bf16_burst), 4),
-                          ops="integer: one int8 multiply-add = 2 ops; a 256-bit compare = 512 ops",
+            roofline=dict(bound="tensor", kernel="knn2_mmaf_kernel (tcgen05.mma kind::mxf4.block_scale, 128x240x64 on 4-bit operands, TMEM "
+                                                 "accumulators; the low half of the fp32 accumulator is the packed key)",
+                          achieved=round(tops, 1), peak=round(4 * bf16_burst, 1), unit="TFLOP/s", frac=round(tops / (4 * bf16_burst), 4),
+                          ops="one 4-bit multiply-add = 2 ops; a 256-bit compare = 512 ops",
                           traffic=traffic,
-                          peak_source=("2 x bf16_tflops (burst) of MEASURED_PEAKS.json: int8 is the bf16 data path at twice the K per instruction; the "
-                                       "match kernel runs in 4 ms bursts between solve launches that leave the tensor pipe idle, and it exceeds "
-                                       "2 x the SUSTAINED bf16 figure (frac_of_sustained_peak > 1), so the sustained number is not its ceiling"
-                                       if mp else "fallback 2 x 1590 TF/s"),
-                          frac_of_sustained_peak=round(tops / (2 * bf16), 4), sustained_peak=round(2 * bf16, 1),
-                          frac_of_nominal_4500=round(tops / 4500.0, 4),
+                          peak_source=("4 x bf16_tflops (burst) of MEASURED_PEAKS.json: block-scaled fp4 is the bf16 data path at four times the K "
+                                       "per instruction (nominal 9 PFLOP/s dense); the match kernel runs in 3 ms bursts between solve "
+                                       "launches that leave the tensor pipe idle, hence the burst figure.  scripts/mxf4_probe.cu measures "
+                                       "141-155 clocks per 128x256x64 instruction against 128 nominal: the pipe itself tops out at ~0.87 of "
+                                       "this peak" if mp else "fallback 4 x 1590 TF/s"),
+                          frac_of_sustained_peak=round(tops / (4 * bf16), 4), sustained_peak=round(4 * bf16, 1),
+                          frac_of_nominal_9000=round(tops / 9000.0, 4),
+                          frac_of_int8_peak=round(tops / (2 * bf16_burst), 4),
                           achieved_gcmp_per_s=round(gcmp, 2), knn2_ms_per_launch=round(knn_ms, 3), solve_ms_per_launch=round(solve_ms, 3),
                           compares_per_launch=int(cmp_per_launch),
-                          padding="1000 x 1000 matchings run as 4 items x (2 x 128) query rows x 4 x 256 train rows (95.4 % of the tile "
-                                  "area is real compares), 8 + 1 instructions per tile (the ninth K-slice forms the key): 84.8 % of the "
-                                  "issued MMA work is counted",
+                          padding="1000 x 1000 matchings run as 4 items x (2 x 128) query rows x (4 x 240 + 48) train rows (96.9 % of the "
+                                  "tile area is real compares), 4 + 1 instructions per tile (a kind::f8f6f4 K = 32 instruction starts the "
+                                  "accumulator at the key offset and takes as long as one of the four): 77.5 % of the issued MMA time is "
+                                  "counted",
                           hbm=dict(achieved_gbs=round(alg_bytes / (knn_ms * 1e-3) * 1e-9, 2), peak_gbs=hbm_peak,
                                    frac=round(alg_bytes / (knn_ms * 1e-3) * 1e-9 / hbm_peak, 5),
                                    algorithmic_bytes_per_launch=int(alg_bytes),

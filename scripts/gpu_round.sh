@@ -19,7 +19,7 @@ cat gpurun_out/bench_adapter_$TAG.json
 # the per-kernel shares of this (serialised, cold-cache) list are comparable with a live step
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mmak_kernel -s 3 -c 1 -f -o gpurun_out/knn2_mmak_full_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mmaf_kernel -s 3 -c 1 -f -o gpurun_out/knn2_mmaf_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 3 -c 1 -f -o gpurun_out/solve_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
@@ -42,6 +42,6 @@ ls -la gpurun_out
 for rep in gpurun_out/*_full_$TAG.ncu-rep; do
   name=$(basename $rep .ncu-rep); name=${name%_full_$TAG}
   python scripts/ncu_summary.py $rep gpurun_out/${name}_${TAG}_ncu_full.json
-  case $name in knn2_mmak) ;; *) rm -f $rep ;; esac
+  case $name in knn2_mmaf) ;; *) rm -f $rep ;; esac
 done
 du -sh gpurun_out

@@ -15,6 +15,7 @@
 #include "../uzliti_slam_b200/csrc/uz_knn2_mma.cuh"
 #include "../uzliti_slam_b200/csrc/uz_knn2_mma2.cuh"
 #include "../uzliti_slam_b200/csrc/uz_knn2_mmak.cuh"
+#include "../uzliti_slam_b200/csrc/uz_knn2_mmaf.cuh"
 
 using namespace uz;
 
@@ -34,7 +35,7 @@ static void cpu_knn2(const uint32_t* q, int nq, const uint32_t* t, int nt, std::
     }
 }
 
-struct Cam { uint32_t* raw; uint32_t* csa; uint8_t* e8; int n; std::vector<uint32_t> h; };
+struct Cam { uint32_t* raw; uint32_t* csa; uint8_t* e8; uint8_t* e4; int n; std::vector<uint32_t> h; };
 
 static Cam make_cam(int n, std::mt19937& rng, int mode) {
     Cam c; c.n = n; c.h.resize((size_t)std::max(n, 1) * 8);
@@ -45,10 +46,13 @@ static Cam make_cam(int n, std::mt19937& rng, int mode) {
     CK(cudaMalloc(&c.csa, (size_t)std::max(n, 1) * 32));
     CK(cudaMalloc(&c.e8, e8_bytes(std::max(n, 1))));
     CK(cudaMemset(c.e8, 0x7F, e8_bytes(std::max(n, 1))));     // garbage in the padding rows on purpose
+    CK(cudaMalloc(&c.e4, e4_bytes(std::max(n, 1))));
+    CK(cudaMemset(c.e4, 0x7F, e4_bytes(std::max(n, 1))));
     if (n) {
         CK(cudaMemcpy(c.raw, c.h.data(), (size_t)n * 32, cudaMemcpyHostToDevice));
         pack_descriptors_kernel<<<(n + 255) / 256, 256>>>((const uint8_t*)c.raw, n, 32, c.raw, c.csa, 1);
         expand_e8_kernel<<<(n * 16 + 255) / 256, 256>>>(c.raw, n, c.e8);
+        expand_e4_kernel<<<(n * 8 + 255) / 256, 256>>>(c.raw, n, c.e4);
         CK(cudaGetLastError());
     }
     return c;
@@ -69,12 +73,14 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     CK(cudaMemset(d_keys, 0xEE, std::max<size_t>(key_rows, 1) * sizeof(uint2)));
     CK(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
     CK(cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes));
+    CK(cudaFuncSetAttribute(knn2_mmaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF4SmemBytes));
     const int grid = (int)std::min<size_t>(items.size(), (size_t)g_sms);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        if (grid > 0 && variant == 2) knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
+        if (grid > 0 && variant == 5) knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
+        else if (grid > 0 && variant == 2) knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         else if (grid > 0) knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         cudaEventRecord(e1);
         cudaError_t e = cudaGetLastError();
@@ -84,6 +90,17 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
         if (r > 0 || reps == 1) best = std::min(best, ms);
     }
     if (out) { out->resize(key_rows); CK(cudaMemcpy(out->data(), d_keys, key_rows * sizeof(uint2), cudaMemcpyDeviceToHost)); }
+#ifdef UZ_F4_TRACE
+    if (variant == 5) {
+        static long long h[2][128][8];
+        CK(cudaMemcpyFromSymbol(h, g_f4_trace, sizeof(h)));
+        const long long z = h[0][0][0];
+        printf("  acc | issuer: tile loop top, tile seen, free seen, committed | epilogue: full seen, read + released, swept   (clocks since the first issue)\n");
+        for (int a = 40; a < 60; ++a)
+            printf("  %3d | %7lld %7lld %7lld %7lld | %7lld %7lld %7lld\n", a, h[0][a][2] - z, h[0][a][3] - z, h[0][a][0] - z,
+                   h[0][a][1] - z, h[1][a][0] - z, h[1][a][1] - z, h[1][a][2] - z);
+    }
+#endif
 #ifdef UZ_MMA_PROF
     {
         static long long h[256][4];
@@ -189,6 +206,7 @@ static int check(MmaDesc dsc, const char* name) {
     CK(cudaDeviceSynchronize());
     std::vector<uint2> got;
     const int variant = getenv("PROBE_VARIANT") ? atoi(getenv("PROBE_VARIANT")) : 0;
+    if (variant == 5) for (size_t k = 0; k < tasks.size(); ++k) { tasks[k].q_desc = (const uint32_t*)cams[2 * k].e4; tasks[k].t_desc = (const uint32_t*)cams[2 * k + 1].e4; }
     if (variant == 3) run_mma2(tasks, key_rows, dsc, &got, 1); else run_mma(tasks, key_rows, dsc, &got, 1, variant);
     for (size_t k = 0; k < tasks.size(); ++k) {
         int bad = 0;
@@ -202,7 +220,7 @@ static int check(MmaDesc dsc, const char* name) {
         printf("[%s] %4d x %4d mode %d: %s (%d bad rows)\n", name, tasks[k].nq, tasks[k].nt, shapes[k][2], bad ? "MISMATCH" : "ok", bad);
         bad_total += bad;
     }
-    for (auto& c : cams) { cudaFree(c.raw); cudaFree(c.csa); cudaFree(c.e8); }
+    for (auto& c : cams) { cudaFree(c.raw); cudaFree(c.csa); cudaFree(c.e8); cudaFree(c.e4); }
     return bad_total;
 }
 
@@ -225,6 +243,7 @@ int main(int argc, char** argv) {
     std::vector<Cam> cams;
     for (int i = 0; i < pool; ++i) cams.push_back(make_cam(N, rng, 0));
     std::vector<MmaTask> mt; std::vector<MatchTask> pt;
+    std::vector<int> tq_of, tf_of;
     size_t key_rows = 0;
     for (int p = 0; p < P; ++p) {
         const int f = (p / 20) % pool, t = (int)(rng() % pool);        // 20 candidates per from-keyframe, as in C4
@@ -232,7 +251,7 @@ int main(int argc, char** argv) {
         MatchTask b; memset(&b, 0, sizeof(b));
         b.q_desc = cams[t].csa; b.t_desc = cams[f].csa; b.nq = N; b.nt = N; b.key_off = (uint32_t)key_rows; b.pair = p; b.rev_key_off = kNoRev;
         key_rows += N;
-        mt.push_back(a); pt.push_back(b);
+        mt.push_back(a); pt.push_back(b); tq_of.push_back(t); tf_of.push_back(f);
     }
     CK(cudaDeviceSynchronize());
     std::vector<uint2> k_mma, k_popc;
@@ -243,6 +262,13 @@ int main(int argc, char** argv) {
     size_t diffk = 0;
     for (size_t i = 0; i < key_rows; ++i) diffk += (kk[i].x != k_popc[i].x || kk[i].y != k_popc[i].y);
     printf("keys from the MMA: %.3f ms, rows differing %zu\n", ms_k, diffk);
+    std::vector<MmaTask> ft = mt;
+    for (size_t k = 0; k < ft.size(); ++k) { ft[k].q_desc = (const uint32_t*)cams[tq_of[k]].e4; ft[k].t_desc = (const uint32_t*)cams[tf_of[k]].e4; }
+    std::vector<uint2> kf;
+    const float ms_f = run_mma(ft, key_rows, dsc, &kf, 4, 5);
+    size_t difff = 0;
+    for (size_t i = 0; i < key_rows; ++i) difff += (kf[i].x != k_popc[i].x || kf[i].y != k_popc[i].y);
+    printf("4-bit operands (kind::mxf4): %.3f ms, rows differing %zu\n", ms_f, difff);
     std::vector<uint2> k2a, k2b;
     const float ms_2a = run_mma2(mt, key_rows, dsc, &k2a, 4);
     k2b = k2a;

@@ -1,6 +1,7 @@
-"""The tensor-core match kernel (knn2_mma_kernel, uz_knn2_mma.cuh: Hamming distance as an exact int8 contraction) is the
-default for 256-bit rows.  It must return exactly what cv::BFMatcher / the oracle / the integer-pipe kernel return: same
-neighbours, same tie rule (lowest train index), on ragged query tiles, ragged train tiles, tiny and maximum sizes."""
+"""The tensor-core match kernel (knn2_mmaf_kernel, uz_knn2_mmaf.cuh: Hamming distance as an exact contraction of 4-bit
+operands, tcgen05.mma kind::mxf4) is the default for 256-bit rows; the int8 kernels before it stay selectable.  Each must
+return exactly what cv::BFMatcher / the oracle / the integer-pipe kernel return: same neighbours, same tie rule (lowest train
+index), on ragged query tiles, ragged train tiles (240-row tiles for the 4-bit kernel, 256 for int8), tiny and maximum sizes."""
 import os
 
 import numpy as np
@@ -11,7 +12,9 @@ from uzliti_slam_b200 import synthetic as S
 pytestmark = pytest.mark.gpu
 
 SIZES = [(1000, 1000), (400, 300), (65, 129), (1, 5), (513, 4096), (130, 127), (64, 2), (256, 256), (257, 255), (4096, 4096),
-         (7, 1), (129, 257), (1000, 31), (9, 700)]
+         (7, 1), (129, 257), (1000, 31), (9, 700),
+         # the 240-row train tiles of the 4-bit kernel: full tiles, one row either side, both column halves ragged
+         (256, 240), (300, 241), (300, 239), (128, 480), (200, 368), (260, 369), (31, 304), (500, 960), (256, 1201), (40, 112), (40, 113)]
 
 
 def _est(mma, cfg=None):
@@ -103,9 +106,10 @@ def test_whole_path_records_identical_on_both_match_kernels(oracle):
         em.close(); ep.close()
 
 
-@pytest.mark.parametrize("variant", [7])
+@pytest.mark.parametrize("variant", [4, 7])
 def test_alternative_tensor_core_kernels_equal_oracle(oracle, variant):
-    """the measured alternative that stays selectable (UZ_MATCH_MMA=7: the IMAD epilogue of knn2_mma_kernel)"""
+    """the measured alternatives that stay selectable (UZ_MATCH_MMA=4: int8 operands, keys formed by the MMA, knn2_mmak_kernel;
+    7: the IMAD epilogue of knn2_mma_kernel)"""
     e = _est(variant)
     try:
         for nq, nt in SIZES:

@@ -75,7 +75,31 @@ def test_integer_pipe_kernel_mix_matches_the_roofline_constants(built):
     assert any(o.startswith("UBLKCP") for o in whole) and any(o.startswith("SYNCS") for o in whole)      # TMA bulk copy + mbarrier
 
 
-def test_tensor_core_kernel_is_tcgen05_with_tmem_and_no_popcount(built):
+def test_default_match_kernel_is_block_scaled_fp4_tcgen05(built):
+    """knn2_mmaf_kernel: tcgen05.mma kind::mxf4 (UTCOMMA) started by one kind::f8f6f4 instruction (UTCQMMA), issued back to
+    back by an elected lane, packed TMEM loads, an epilogue of three-input packed max and one multiply-add per register"""
+    funcs = _functions(built)
+    names = [n for n in funcs if "knn2_mmaf_kernel" in n]
+    assert len(names) == 1
+    body = funcs[names[0]]
+    ops = [_op(t) for _, t in body]
+    cnt = lambda p: sum(1 for o in ops if o.startswith(p))          # noqa: E731
+    assert cnt("UTCOMMA") >= mix.F4_INSTRUCTIONS_PER_TILE and cnt("UTCOMMA") % mix.F4_INSTRUCTIONS_PER_TILE == 0
+    assert cnt("UTCQMMA") * mix.F4_INSTRUCTIONS_PER_TILE == cnt("UTCOMMA") * mix.F4_START_INSTRUCTIONS
+    assert cnt("UTCIMMA") == 0 and cnt("HMMA") == 0 and cnt("POPC") <= 2
+    assert sum(1 for o in ops if o.startswith("LDTM") and "PACK16BIT" in o) >= 2 and cnt("UBLKCP") >= 3 and cnt("UTCBAR") >= 3
+    # the instructions of one accumulator come out back to back: nothing but uniform-datapath moves between them
+    idx = [k for k, o in enumerate(ops) if o.startswith("UTCOMMA")]
+    for a, b in zip(idx[:-1], idx[1:]):
+        if b - a < 40:                                    # same accumulator
+            assert all(o.startswith(("UMOV", "UIADD3", "ULOP3", "USHF", "ULEA", "USEL", "NOP")) for o in ops[a + 1:b]), ops[a + 1:b]
+    # per accumulator half of 128 columns (64 registers): 2 x 32 three-input packed max and 64 multiply-adds
+    max3 = sum(1 for o in ops if o.startswith("VIMNMX3") and "U16x2" in o)
+    assert max3 >= int((64 + 56) * 2 * 2 * mix.F4_EPILOGUE_MINMAX3)
+    assert cnt("IMAD") >= int((64 + 56) * 2 * mix.F4_EPILOGUE_IMAD)
+
+
+def test_int8_tensor_core_kernel_is_tcgen05_with_tmem_and_no_popcount(built):
     funcs = _functions(built)
     names = [n for n in funcs if "knn2_mmak_kernel" in n]
     assert len(names) == 1

@@ -79,6 +79,7 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmak_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaf_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaw_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(derive_layouts_kernel);
@@ -99,7 +100,7 @@ struct BatchPlan {
     size_t n_tasks = 0, n_fwd = 0, n_wide = 0;
     int max_nq = 0, cap = 0;
     int64_t compares = 0;
-    bool mma = false;                    // 256-bit matchings on the tensor cores (knn2_mma_kernel)
+    bool mma = false;                    // 256-bit matchings on the tensor cores (knn2_mmaf_kernel; int8 alternatives)
     bool mma_wide = false;               // 512-bit matchings on the tensor cores (knn2_mmaw_kernel)
     bool mma2 = false;                   // ... on CTA pairs (knn2_mma2_kernel): launches that keep every pair of SMs busy
     int best_cfg = 3, wide_cfg = 0;      // integer-pipe tile shapes
@@ -521,10 +522,12 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             // share its train rows in L2
             const MmaTask* mt = reinterpret_cast<const MmaTask*>(d_tk);
             const int grid = std::min(nt, ctx->sm_count);
-            if (ctx->match_mma == 7)         // measured alternative, kept for A/B (profiles/mma_experiments_r02.txt)
+            if (ctx->match_mma == 7)         // measured alternatives, kept for A/B (profiles/mma_experiments_r02.txt)
                 knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
-            else                             // default: the keys come out of the tensor core
+            else if (!ctx->narrow_e4)        // int8 operands, keys out of the tensor core
                 knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
+            else                             // default: 4-bit operands, keys out of the tensor core
+                knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
             ctx->mma_launches++;
         } else if (nt > 0) switch (bp.best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, bp.seg_narrow); break;

@@ -27,6 +27,7 @@
 #include "uz_knn2_mma.cuh"
 #include "uz_knn2_mma2.cuh"
 #include "uz_knn2_mmak.cuh"
+#include "uz_knn2_mmaf.cuh"
 #include "uz_knn2_mmaw.cuh"
 #include "uz_places.cuh"
 #include "uz_samples.h"
@@ -193,7 +194,8 @@ struct HostPool {
 struct Cam {
     uint32_t* raw = nullptr;   // n x dbytes/4 words, bytes as given
     uint32_t* csa = nullptr;   // same rows, every 256-bit half in CSA layout (uz_knn2.cuh)
-    uint8_t* e8 = nullptr;     // one int8 per bit in the UMMA canonical layout (uz_knn2_mma.cuh); 64-byte rows: two planes (uz_knn2_mmaw.cuh)
+    uint8_t* e8 = nullptr;     // the tensor-core operand layout: 32-byte rows one 4-bit value per bit (uz_knn2_mmaf.cuh; one int8 per bit,
+                               // uz_knn2_mma.cuh, when the context runs an int8 kernel); 64-byte rows two int8 planes (uz_knn2_mmaw.cuh)
     double* pos = nullptr;     // 3 x n column-major
     uint8_t* valid = nullptr;  // n
     int32_t n = 0, feature_type = 0, sensor_frame = 0;
@@ -202,7 +204,8 @@ struct Cam {
 
 // where the layouts of one camera live inside a block (offsets are multiples of 256)
 struct CamLayout { size_t raw, csa, e8, pos, valid, end; };
-inline CamLayout cam_layout(size_t at, int n, int dbytes) {
+inline size_t operand_bytes(int n, int dbytes, bool e4) { return dbytes == UZ_DESC_BYTES ? (e4 ? e4_bytes(n) : e8_bytes(n)) : e8w_bytes(n); }
+inline CamLayout cam_layout(size_t at, int n, int dbytes, bool e4) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     CamLayout L;
     L.raw = at;
@@ -210,7 +213,7 @@ inline CamLayout cam_layout(size_t at, int n, int dbytes) {
     L.valid = up(L.pos + (size_t)n * 24);
     L.csa = up(L.valid + (size_t)n);
     L.e8 = up(L.csa + (size_t)n * dbytes);
-    L.end = up(L.e8 + (dbytes == UZ_DESC_BYTES ? e8_bytes(n) : e8w_bytes(n)));
+    L.end = up(L.e8 + operand_bytes(n, dbytes, e4));
     return L;
 }
 
@@ -263,9 +266,11 @@ struct uz_context {
     int xcheck_fused = 1;            // UZ_XCHECK_FUSED=0: cross-check by a second, reversed matching (the measured alternative)
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
     int match_mma_wide = 1;          // UZ_MATCH_MMA_WIDE=0: 512-bit rows stay on the integer pipes (knn2_wide_kernel)
-    int match_mma = 1;               // UZ_MATCH_MMA: 0 = 256-bit rows on the integer pipes (knn2_kernel); 1 = tensor cores, keys formed by the
-                                     // MMA (knn2_mmak_kernel, default); measured alternatives: 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches
-                                     // that fill the chip / always, 7 = IMAD epilogue (knn2_mma_kernel)
+    int match_mma = 1;               // UZ_MATCH_MMA: 0 = 256-bit rows on the integer pipes (knn2_kernel); 1 = tensor cores, 4-bit operands
+                                     // (kind::mxf4, knn2_mmaf_kernel, default); measured alternatives on int8 operands: 4 = keys formed
+                                     // by the MMA (knn2_mmak_kernel), 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches that fill the
+                                     // chip / always, 7 = IMAD epilogue (knn2_mma_kernel)
+    bool narrow_e4 = true;           // 32-byte rows keep the 4-bit operand layout (match_mma == 1), else the int8 one
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments
     int solve_wide = 1;              // UZ_SOLVE_WIDE=0: never use the 512-thread solve CTA for small launches

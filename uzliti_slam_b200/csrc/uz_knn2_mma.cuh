@@ -144,6 +144,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, const Mma
 #ifndef UZ_MMA_WATCHDOG
 #define UZ_MMA_WATCHDOG 1
 #endif
+// one lane of a converged warp, in the form ptxas recognises as "a single thread": tcgen05 instructions issued under it keep
+// their descriptors in uniform registers and come out back to back.  Behind a `lane == 0` test every one of them is wrapped
+// in a per-thread loop with R2UR moves (~70 clocks apiece next to busy epilogue warps).
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
 #if UZ_MMA_WATCHDOG
     uint32_t done = 0;
@@ -307,7 +320,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
                     UZ_PROF_ADD(1, p2, p3);
                     UZ_PROF_ADD(2, p3, p4);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (tc_elect_one()) {
                         const uint32_t a_addr = smem_u32(sA + i * kMmaABytes), b_addr = smem_u32(sB + slot * kMmaBBytes);
 #pragma unroll
                         for (int k = 0; k < kE8RowBytes / 32; ++k)
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma_kernel(const MmaTask*
                     __syncwarp();
                     uAcc[i]++;
                 }
-                if (lane == 0) tc_commit(&b_empty[slot]);
+                if (tc_elect_one()) tc_commit(&b_empty[slot]);
                 __syncwarp();
                 uB++;
             }

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mma2_kernel(const MmaTask
                         UZ_PROF_T(p3);
                         UZ_PROF_ADD(0, p0, p1); UZ_PROF_ADD(1, p1, p2); UZ_PROF_ADD(2, p2, p3);
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (tc_elect_one()) {
                             const uint32_t a_addr = smem_u32(sA + i * kMmaABytes), b_addr = smem_u32(sB + slot * kMma2BBytes);
 #pragma unroll
                             for (int k = 0; k < kE8RowBytes / 32; ++k)

@@ -1,0 +1,451 @@
+// uz_knn2_mmaf.cuh — the tensor-core match kernel on the 4-BIT path: tcgen05.mma kind::mxf4 (e2m1 operands, UE8M0 block scales,
+// fp32 accumulate), 128 x 240 x 64 per instruction.
+//
+// scripts/mxf4_probe.cu: +-4 operands with constant block scales 2^1 (a product is +-64, as in the int8 kernels) accumulate
+// EXACTLY onto an fp32 accumulator pre-loaded with 2^23 + 16384 - every bit - and the instruction takes 141 clocks for twice
+// the K of an int8 one: 566 clocks per 128 x 256 accumulator of 256-bit compares against 1152 in knn2_mmak_kernel.
+//
+// Operand layout ("E4"): one NIBBLE per descriptor bit (0x6 = +4 set, 0xE = -4 clear), K-major canonical layout with 16-byte
+// core-matrix rows: byte(row i, bit k) = (i >> 3) * 1024 + (k >> 5) * 128 + (i & 7) * 16 + ((k >> 1) & 15), low nibble = even k.
+// Half the bytes of E8: 16 KB query tiles, 30 KB train tiles - four stages fit.
+// Keys.  Every accumulator is STARTED by one kind::f8f6f4 instruction (e5m2 x e5m2, K = 32, not accumulating) over two constant
+// shared-memory blocks - query side [2048, 2048, 128, 64, 8, 1, 0 ...], train side [2048, 2048, 128, d2, d1, d0, 0 ...] with
+// 127 - (row & 127) = 64 d2 + 8 d1 + d0 - which sets it to 2^23 + 16384 + 127 - (column & 127); the four mxf4 instructions add
+// 64 dot on top, exactly (scripts/mxf4_probe.cu).  The low 16 bits of that fp32 value ARE the integer
+// 32895 - ((hamming << 7) | (column & 127)), so the packed 16-bit TMEM load and the packed-max epilogue of knn2_mmak_kernel work
+// unchanged.  640 clocks of tensor pipe per 128 x 256 accumulator against 1152.
+// TMEM.  The block scales live in TMEM next to the accumulators, so a train tile is 240 rows, not 256: accumulators at
+// columns 0 and 240, scales at 480.  1000 train rows are four tiles of 240 and one of 40.
+#pragma once
+#include "uz_knn2_mmak.cuh"
+
+namespace uz {
+
+constexpr int kF4N = 240;                              // train rows per tile / accumulator columns
+constexpr int kF4RowBytes = 128;                       // one nibble per descriptor bit
+constexpr int kF4GroupBytes = 8 * kF4RowBytes;
+constexpr int kF4ABytes = kMmaM * kF4RowBytes;         // 16 KB
+constexpr int kF4BBytes = kF4N * kF4RowBytes;          // 30 KB
+constexpr int kF4Stages = 4;
+constexpr int kF4SfCol = 480;                          // TMEM column of the block scales
+constexpr int kF4TailABytes = kMmaM * 32, kF4TailBBytes = kF4N * 32;
+constexpr int kF4SmemBytes = 2 * kF4ABytes + kF4Stages * kF4BBytes + kF4TailABytes + kF4TailBBytes + 2 * kMmaItemRows * 8 + 256;
+static_assert(kF4SmemBytes <= 232448, "CTA exceeds the 227 KB of shared memory");
+
+constexpr uint32_t kE4Set = 0x6u, kE4Clear = 0xEu;      // e2m1: +4 for a set bit, -4 for a clear one
+__host__ __device__ constexpr size_t e4_bytes(int n) { return (size_t)((n + 7) / 8) * kF4GroupBytes; }
+
+// bits -> E4 layout (ingestion): one thread per (row, 32-bit word): 32 nibbles = one uint4 store
+__global__ void __launch_bounds__(256) expand_e4_kernel(const uint32_t* __restrict__ raw, int n, uint8_t* __restrict__ e4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 8) return;
+    const int row = i >> 3, w = i & 7;
+    const uint32_t bits = raw[(size_t)row * 8 + w];
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) v |= (((bits >> (8 * k + b)) & 1u) ? kE4Set : kE4Clear) << (4 * b);
+        o[k] = v;
+    }
+    *reinterpret_cast<uint4*>(e4 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ void tc_mma_mxf4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t sfa, uint32_t sfb) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%4], [%5], p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(sfa), "r"(sfb) : "memory");
+}
+// 32 lanes x 32 columns, every cell the same value (the block scales)
+__device__ __forceinline__ void f4_fill32(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(taddr), "r"(v) : "memory");
+}
+// the instruction that starts an accumulator: kind::f8f6f4, K = 32, D = A B (no accumulate)
+__device__ __forceinline__ void tc_mma_f8_start(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 0, 0;\n"                  // false: D = A B, the accumulator is not read
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, {%4, %4, %4, %4}, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
+}
+// the packed max network over the first REGS registers of a 64-column group
+template <int REGS>
+__device__ __forceinline__ void f4_group(const uint32_t (&d)[32], uint32_t& p1, uint32_t& p2) {
+#pragma unroll
+    for (int m = 0; m < REGS; m += 2) top2max_update2_u16x2(p1, p2, d[m], d[m + 1]);
+}
+// A whole 128-column block (dA: 64 columns, dB: the first 2 * REGSB columns of the next 64) in two sweeps instead of the
+// five-operation insertion network, because the epilogue is bound by the ALU pipe (every packed min / max, 2 clocks each):
+//   sweep 1  P = the packed maximum of the block, three-input max                                  0.5 ALU operations / register
+//   sweep 2  y = x - P + 65536 as ONE 32-bit multiply-add (fma pipe), then the packed maximum of y   0.5 ALU + 1 FMA / register
+// In 16-bit lanes y is (x - P) mod 2^16: the winner becomes the smallest value, everybody else keeps its order just below
+// 2^16, so max(y) is the runner-up.  The 32-bit form is exact for the low lane; the low lane's borrow reaches the high lane
+// in every register except the one holding the low lane's winner, which the +65536 pre-pays: there the high lane is one too
+// large.  High-lane keys are those of odd columns and 32895 is odd, so they are all even and two of them differ by at
+// least 2: the stray +1 can neither reorder them nor wrap, and is masked off when the runner-up is rebuilt.
+__device__ __forceinline__ uint32_t f4_mad(uint32_t a, uint32_t one, uint32_t c) {
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c)); return d;
+}
+template <int REGSB>
+__device__ __forceinline__ void f4_block(const uint32_t (&dA)[32], const uint32_t (&dB)[32], uint32_t one,
+                                         uint32_t& m1, uint32_t& m2, uint32_t tbase) {
+    uint32_t g0 = 0u, g1 = 0u;
+#pragma unroll
+    for (int m = 0; m < 32; m += 4) {
+        g0 = max_u16x2(max_u16x2(g0, dA[m]), dA[m + 1]);
+        g1 = max_u16x2(max_u16x2(g1, dA[m + 2]), dA[m + 3]);
+    }
+#pragma unroll
+    for (int m = 0; m < REGSB; m += 4) {
+        g0 = max_u16x2(max_u16x2(g0, dB[m]), dB[m + 1]);
+        g1 = max_u16x2(max_u16x2(g1, dB[m + 2]), dB[m + 3]);
+    }
+    uint32_t P = max_u16x2(g0, g1);
+    const uint32_t c = 65536u - P;
+    uint32_t y0 = 0u, y1 = 0u;
+#pragma unroll
+    for (int m = 0; m < 32; m += 4) {
+        y0 = max_u16x2(max_u16x2(y0, f4_mad(dA[m], one, c)), f4_mad(dA[m + 1], one, c));
+        y1 = max_u16x2(max_u16x2(y1, f4_mad(dA[m + 2], one, c)), f4_mad(dA[m + 3], one, c));
+    }
+#pragma unroll
+    for (int m = 0; m < REGSB; m += 4) {
+        y0 = max_u16x2(max_u16x2(y0, f4_mad(dB[m], one, c)), f4_mad(dB[m + 1], one, c));
+        y1 = max_u16x2(max_u16x2(y1, f4_mad(dB[m + 2], one, c)), f4_mad(dB[m + 3], one, c));
+    }
+    uint32_t S = (max_u16x2(y0, y1) - c) & 0xFFFEFFFFu;
+    mmak_merge(m1, m2, P, S, tbase);
+}
+// unpacked columns (ragged end of the train rows): the first `valid` of 32, first column = train row t_first
+__device__ __forceinline__ void f4_masked(const uint32_t (&d)[32], int valid, uint32_t t_first, uint32_t& m1, uint32_t& m2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < valid) {
+            const uint32_t ham = (kMmakTop - (d[j] & 0x7FFFFFu)) >> 7;        // the low bits of 2^23 + x are x = 32895 - key16
+            top2_update(m1, m2, (ham << 16) | (t_first + (uint32_t)j));
+        }
+    }
+}
+
+// 20 warps: the producer, two MMA issuers, a spare, and two groups of eight epilogue warps, one group per accumulator, so that
+// the load latency of one accumulator hides behind the sweeps of the other.  Five warps share a sub-partition's 16384
+// registers: 96 each.
+#ifdef UZ_F4_TRACE
+__device__ long long g_f4_trace[2][128][8];      // probe builds: CTA 0's first 128 accumulators, issuer and epilogue clocks
+#endif
+#ifndef F4_EPI_GROUPS
+#define F4_EPI_GROUPS 2
+#endif
+constexpr int kF4EpiGroups = F4_EPI_GROUPS;   // 2: eight epilogue warps per accumulator; 1: eight warps serve both in turn
+constexpr int kF4Threads = (4 + 8 * kF4EpiGroups) * 32;
+#ifndef F4_ISSUERS
+#define F4_ISSUERS 2
+#endif
+constexpr int kF4Issuers = F4_ISSUERS;        // 1: warp 1 issues for both accumulators; 2: warp 1 for the first, warp 2 for the second
+constexpr int kF4MaxRegs = kF4EpiGroups == 2 ? 96 : 128;
+
+// items[k] = (task, first query row); CTA b takes items b, b + gridDim.x, ...
+__global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restrict__ tasks, const int2* __restrict__ items,
+                                                                  int n_items, uint2* __restrict__ keys, MmaDesc dsc,
+                                                                  int* __restrict__ pair_pending, unsigned int* __restrict__ progress) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;                                    // [2][16 KB]  query tiles, 128 rows x 128 B of nibbles
+    uint8_t* sB = smem + 2 * kF4ABytes;                    // [kF4Stages][30 KB]  train tiles, 240 rows
+    uint8_t* sTailA = sB + kF4Stages * kF4BBytes;           // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
+    uint8_t* sTailB = sTailA + kF4TailABytes;               // [240 rows x 32 B]
+    uint2* xchg = reinterpret_cast<uint2*>(sTailB + kF4TailBBytes);         // [2 parities][256 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kMmaItemRows);
+    uint64_t* a_full = bars;          // [2]
+    uint64_t* a_empty = bars + 2;     // [2]
+    uint64_t* b_full = bars + 4;      // [kF4Stages]
+    uint64_t* b_empty = b_full + kF4Stages;
+    uint64_t* acc_full = b_empty + kF4Stages;    // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
+        for (int s = 0; s < kF4Stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kF4Issuers); }       // every issuer returns a train tile
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the constant operands of the starting instruction (e5m2 bytes; compact canonical layout, 8-row groups of 256 B)
+    for (int r = tid; r < kMmaM + kF4N; r += kF4Threads) {
+        const bool isB = r >= kMmaM;
+        const int row = isB ? r - kMmaM : r;
+        const int v = 127 - (row & 127);
+        const uint32_t dig[8] = {0x00u, 0x3Cu, 0x40u, 0x42u, 0x44u, 0x45u, 0x46u, 0x47u};      // e5m2 of 0..7
+        const uint32_t w0 = 0x68u | (0x68u << 8) | (0x58u << 16) | ((isB ? dig[v >> 6] : 0x54u) << 24);     // 2048, 2048, 128, d2 | 64
+        const uint32_t w1 = isB ? (dig[(v >> 3) & 7] | (dig[v & 7] << 8)) : (0x48u | (0x3Cu << 8));        // d1, d0 | 8, 1
+        uint8_t* dst = (isB ? sTailB : sTailA) + (row >> 3) * 256 + (row & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {          // the whole TMEM: two 240-column accumulators, the block scales behind them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 4 && warp < 8) {
+        // every block scale is 2^1 (UE8M0 128): operands +-4 count as +-8, a product is +-64
+        f4_fill32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kF4SfCol, 0x80808080u);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t uB = 0, uA[2] = {0, 0};
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int2 item = items[it];
+                const MmaTask* tk = tasks + item.x;
+                const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+                const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
+                const int T = (nt + kF4N - 1) / kF4N;
+                for (int t = 0; t < T; ++t) {
+                    if (t == 0) {
+                        mbar_wait_wd(&a_empty[0], (uA[0] & 1u) ^ 1u);
+                        const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0));
+                        mbar_expect_tx(&a_full[0], bytes);
+                        bulk_g2s(sA, mma_q(tk) + (size_t)(q0 >> 3) * kF4GroupBytes, bytes, &a_full[0]);
+                        uA[0]++;
+                    }
+                    {
+                        const uint32_t slot = uB % kF4Stages;
+                        mbar_wait_wd(&b_empty[slot], ((uB / kF4Stages) & 1u) ^ 1u);
+                        const uint32_t bytes = (uint32_t)e4_bytes(min(kF4N, nt - t * kF4N));
+                        mbar_expect_tx(&b_full[slot], bytes);
+                        bulk_g2s(sB + slot * kF4BBytes, mma_t(tk) + (size_t)t * kF4BBytes, bytes, &b_full[slot]);
+                        uB++;
+                    }
+                    if (t == 0 && nqt == 2) {
+                        mbar_wait_wd(&a_empty[1], (uA[1] & 1u) ^ 1u);
+                        const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0 - kMmaM));
+                        mbar_expect_tx(&a_full[1], bytes);
+                        bulk_g2s(sA + kF4ABytes, mma_q(tk) + (size_t)((q0 + kMmaM) >> 3) * kF4GroupBytes, bytes, &a_full[1]);
+                        uA[1]++;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 1 && warp <= kF4Issuers) {
+        // ===================== MMA issuer(s) =====================
+        // The five instructions of an accumulator and their commits are issued by ONE ELECTED lane of the converged warp
+        // (elect.sync): ptxas then keeps every descriptor in uniform registers and emits the tcgen05 instructions back to
+        // back.  Behind a `lane == 0` test it wraps each of them in a per-thread loop with R2UR moves, ~70 clocks apiece
+        // next to busy epilogue warps - as long as the instruction runs - and the issue, not the tensor pipe, bounds the kernel.
+        const int i_first = kF4Issuers == 2 ? warp - 1 : 0, i_end = kF4Issuers == 2 ? warp : 2;
+        uint32_t uB = 0, uA[2] = {0, 0}, uAcc[2] = {0, 0};
+#ifdef UZ_F4_TRACE
+        int tr = 0;
+#endif
+        MmaDesc fdsc = dsc;
+        fdsc.lbo16 = 128 >> 4; fdsc.sbo16 = kF4GroupBytes >> 4;
+        const uint32_t sfa = tmem_base + kF4SfCol, sfb = tmem_base + kF4SfCol + 4;
+        MmaDesc tdsc = dsc;
+        tdsc.lbo16 = 128 >> 4; tdsc.sbo16 = 256 >> 4;
+        const uint64_t tail_a = make_smem_desc(smem_u32(sTailA), tdsc), tail_b = make_smem_desc(smem_u32(sTailB), tdsc);
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int2 item = items[it];
+            const MmaTask* tk = tasks + item.x;
+            const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+            const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
+            const int T = (nt + kF4N - 1) / kF4N;
+            for (int t = 0; t < T; ++t) {
+                const uint32_t slot = uB % kF4Stages;
+#ifdef UZ_F4_TRACE
+                const long long trA = clock64();
+#endif
+                mbar_wait_wd(&b_full[slot], (uB / kF4Stages) & 1u);
+#ifdef UZ_F4_TRACE
+                const long long trB = clock64();
+#endif
+                const int rows = min(kF4N, nt - t * kF4N);
+                const uint32_t n_mma = (uint32_t)((rows + 15) & ~15);            // N: multiple of 16
+                // a, b format E2M1 (MXF4Format 1) | K-major | N >> 3 at [17,23) | scale format UE8M0 at 23 | M >> 4 at [24,29)
+                const uint32_t idesc = (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | (1u << 23) | ((uint32_t)(kMmaM >> 4) << 24);
+                // the starting instruction: c format F32 | a, b format E5M2 | K-major | N | M
+                const uint32_t idesc_start = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);
+                bool issued = false;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i >= i_first && i < i_end && i < nqt) {
+                        if (t == 0) mbar_wait_wd(&a_full[i], uA[i] & 1u);
+                        mbar_wait_wd(&acc_empty[i], (uAcc[i] & 1u) ^ 1u);
+                        tc_fence_after();
+#ifdef UZ_F4_TRACE
+                        const long long tr0 = clock64();
+#endif
+                        if (tc_elect_one()) {
+                            const uint32_t a_addr = smem_u32(sA + i * kF4ABytes), b_addr = smem_u32(sB + slot * kF4BBytes);
+                            const uint32_t d_acc = tmem_base + (uint32_t)i * kF4N;
+                            tc_mma_f8_start(d_acc, tail_a, tail_b, idesc_start);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)       // K = 64 nibbles = 32 bytes of a row per instruction, on top of the start value
+                                tc_mma_mxf4(d_acc, make_smem_desc(a_addr + k * 256, fdsc), make_smem_desc(b_addr + k * 256, fdsc), idesc, sfa, sfb);
+                            tc_commit(&acc_full[i]);
+                            if (t == T - 1) tc_commit(&a_empty[i]);
+                        }
+#ifdef UZ_F4_TRACE
+                        if (lane == 0 && blockIdx.x == 0 && 2 * tr + i < 128) {
+                            long long* row = g_f4_trace[0][2 * tr + i];
+                            row[0] = tr0; row[1] = clock64(); row[2] = trA; row[3] = trB;
+                        }
+#endif
+                        __syncwarp();
+                        uAcc[i]++;
+                        issued = true;
+                    }
+                }
+                // the train tile goes back to the producer when this issuer's instructions on it are done (an issuer with
+                // nothing to do on an item of one query tile returns its share at once)
+                if (tc_elect_one()) { if (issued) tc_commit(&b_empty[slot]); else mbar_arrive(&b_empty[slot]); }
+                __syncwarp();
+#ifdef UZ_F4_TRACE
+                ++tr;
+#endif
+                uB++;
+            }
+            if (T > 0) for (int i = 0; i < nqt; ++i) uA[i]++;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                   // 0 .. 8 * kF4EpiGroups - 1
+        const int quarter = warp & 3;              // the TMEM lanes this warp may touch: 32 * (warp % 4) ..
+        const int half = (ew >> 2) & 1;            // which 128 columns of the accumulator
+        // which accumulators (query tiles of the item) this group of eight warps serves
+        const int i_first = kF4EpiGroups == 2 ? ew >> 3 : 0, i_end = kF4EpiGroups == 2 ? i_first + 1 : 2;
+        const int row_in_tile = quarter * 32 + lane;
+        uint32_t uAcc[2] = {0, 0};
+        uint32_t item_parity = 0;
+#ifdef UZ_F4_TRACE
+        int tr = 0;
+#endif
+        const uint32_t one = 1u + (uint32_t)(n_items < 0);        // 1, but not a constant ptxas could fold the multiply-add with
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, item_parity ^= 1u) {
+            const int2 item = items[it];
+            const MmaTask* tk = tasks + item.x;
+            const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+            const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
+            const int T = (nt + kF4N - 1) / kF4N;
+            if (i_first >= nqt) continue;          // a group with nothing to do on an item of one query tile
+            uint32_t m1[2] = {kNoKey, kNoKey}, m2[2] = {kNoKey, kNoKey};
+            for (int t = 0; t < T; ++t) {
+                const int hw = half ? kF4N - 128 : 128;                                        // columns of this warp's half
+                const int cvalid = min(hw, min(kF4N, nt - t * kF4N) - half * 128);             // valid ones
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i >= i_first && i < i_end && i < nqt) {
+                        mbar_wait_wd(&acc_full[i], uAcc[i] & 1u);
+                        tc_fence_after();
+#ifdef UZ_F4_TRACE
+                        const long long tr0 = clock64();
+                        long long tr1 = 0;
+#endif
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * kF4N + half * 128);
+                        const uint32_t tbase = (uint32_t)(t * kF4N + half * 128);        // global train row of column 0
+                        // low 16 bits of the fp32 accumulator = 32895 - ((hamming << 7) | (column & 127)): the key of knn2_mmak_kernel
+                        uint32_t dA[32], dB[32];
+                        if (cvalid >= hw) {
+                            tc_ld64p(taddr, dA);
+                            tc_ld64p(taddr + 64, dB);            // (half 1: its last 16 columns belong to nobody and are not looked at)
+                            tc_wait_ld(); tc_pin(dA); tc_pin(dB);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[i]);
+#ifdef UZ_F4_TRACE
+                            tr1 = clock64();
+#endif
+                            if (half == 0) f4_block<32>(dA, dB, one, m1[i], m2[i], tbase); else f4_block<24>(dA, dB, one, m1[i], m2[i], tbase);
+                        } else {
+                            // ragged last tile: a whole 64-column group packed, the rest column by column
+                            uint32_t p1 = 0u, p2 = 0u;
+                            const int n64 = cvalid > 0 ? cvalid >> 6 : 0;
+                            const int rem = cvalid > 0 ? cvalid & 63 : 0;
+                            if (n64 > 0) { tc_ld64p(taddr, dA); tc_wait_ld(); tc_pin(dA); f4_group<32>(dA, p1, p2); mmak_merge(m1[i], m2[i], p1, p2, tbase); }
+                            if (rem > 0) {
+                                tc_ld32(taddr + n64 * 64, dA); tc_wait_ld(); tc_pin(dA);
+                                f4_masked(dA, min(rem, 32), tbase + n64 * 64, m1[i], m2[i]);
+                            }
+                            if (rem > 32) {
+                                tc_ld32(taddr + n64 * 64 + 32, dA); tc_wait_ld(); tc_pin(dA);
+                                f4_masked(dA, rem - 32, tbase + n64 * 64 + 32, m1[i], m2[i]);
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[i]);
+                        }
+#ifdef UZ_F4_TRACE
+                        if (lane == 0 && blockIdx.x == 0 && (ew & 7) == 0 && 2 * tr + i < 128) {
+                            long long* row = g_f4_trace[1][2 * tr + i];
+                            row[0] = tr0; row[1] = tr1; row[2] = clock64();
+                        }
+#endif
+                        uAcc[i]++;
+                    }
+                }
+#ifdef UZ_F4_TRACE
+                ++tr;
+#endif
+            }
+            // fold the two column halves of every row (half 1 -> shared memory -> half 0) and publish the keys
+            uint2* xc = xchg + item_parity * kMmaItemRows;
+            if (half == 1) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (i >= i_first && i < i_end && i < nqt) xc[i * kMmaM + row_in_tile] = make_uint2(m1[i], m2[i]);
+            }
+            if (i_first == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int q = q0 + i * kMmaM + row_in_tile;
+                    if (i >= i_first && i < i_end && i < nqt && q < nq) {
+                        const uint2 o = xc[i * kMmaM + row_in_tile];
+                        const uint32_t hi = max(m1[i], o.x);
+                        const uint32_t a = min(m1[i], o.x);
+                        const uint32_t b = min(hi, min(m2[i], o.y));
+                        keys[(size_t)tk->key_off + q] = make_uint2(a, b);
+                    }
+                }
+            }
+            if (pair_pending != nullptr && half == 0) {            // streaming hand-over, as in knn2_kernel (one count per item)
+                // the half-0 warps of every group at work on this item: their key stores are done
+                if (kF4EpiGroups == 2 && nqt == 2) asm volatile("bar.sync 3, 256;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+                if (i_first == 0 && row_in_tile == 0) {
+                    __threadfence();
+                    atomicSub(pair_pending + tk->pair, 1);
+                    atomicAdd(progress, 1u);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+}  // namespace uz

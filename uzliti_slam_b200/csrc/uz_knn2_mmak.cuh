@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mmak_kernel(const MmaTask
                     UZ_PROF_ADD(1, p2, p3);
                     UZ_PROF_ADD(2, p3, p4);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (tc_elect_one()) {
                         const uint32_t a_addr = smem_u32(sA + i * kMmaABytes), b_addr = smem_u32(sB + slot * kMmaBBytes);
 #pragma unroll
                         for (int k = 0; k < kE8RowBytes / 32; ++k)
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mmak_kernel(const MmaTask
                     __syncwarp();
                     uAcc[i]++;
                 }
-                if (lane == 0) tc_commit(&b_empty[slot]);
+                if (tc_elect_one()) tc_commit(&b_empty[slot]);
                 __syncwarp();
                 uB++;
             }

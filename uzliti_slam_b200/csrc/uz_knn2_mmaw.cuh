@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mmaw_kernel(const MmaTask
                             mbar_wait_wd(&acc_empty[ai], (uAcc[ai] & 1u) ^ 1u);
                         }
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (tc_elect_one()) {
                             const uint32_t a_addr = smem_u32(sA + (i * 2 + p) * kMmaABytes), b_addr = smem_u32(sB + slot * kMmawStageBytes);
                             const uint32_t d = tmem_base + (uint32_t)ai * kMmawN;
 #pragma unroll
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) knn2_mmaw_kernel(const MmaTask
                         __syncwarp();
                         if (p == 1) uAcc[ai]++;
                     }
-                    if (lane == 0) tc_commit(&b_empty[slot]);
+                    if (tc_elect_one()) tc_commit(&b_empty[slot]);
                     __syncwarp();
                     uB++;
                 }

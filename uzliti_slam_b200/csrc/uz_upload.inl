@@ -16,10 +16,10 @@ struct CopyItem {
     int32_t rows, row_bytes, stride;   // strided source (cv::Mat with padded rows): rows > 0
 };
 
-struct DeriveJob { const uint32_t* raw; uint32_t* csa; uint8_t* e8; int32_t n; int32_t halves_per_row; };
+struct DeriveJob { const uint32_t* raw; uint32_t* csa; uint8_t* e8; int32_t n; int16_t halves_per_row; int16_t e4; };
 
-// blockIdx.y = camera.  CSA transform of every 256-bit half (uz_knn2.cuh) and, for 32-byte rows, the int8 expansion in
-// the UMMA canonical layout (uz_knn2_mma.cuh).
+// blockIdx.y = camera.  CSA transform of every 256-bit half (uz_knn2.cuh) and the tensor-core operand layout: 4-bit values
+// (uz_knn2_mmaf.cuh) or int8 (uz_knn2_mma.cuh) in the UMMA canonical layout.
 __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __restrict__ jobs) {
     const DeriveJob j = jobs[blockIdx.y];
     const int halves = j.n * j.halves_per_row;
@@ -33,6 +33,23 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
         c[0] = make_uint4(o[0], o[1], o[2], o[3]); c[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
     if (j.e8 == nullptr) return;
+    if (j.e4) {
+        // 32-byte rows, 4-bit operands (uz_knn2_mmaf.cuh): one thread per (row, 32-bit word): 32 nibbles = one uint4 store
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n * 8; i += gridDim.x * blockDim.x) {
+            const int row = i >> 3, w = i & 7;
+            const uint32_t bits = j.raw[(size_t)row * 8 + w];
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v |= (((bits >> (8 * k + b)) & 1u) ? kE4Set : kE4Clear) << (4 * b);
+                o[k] = v;
+            }
+            *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     // one thread per (row, 16-bit chunk): 16 int8 = one uint4 store.  64-byte rows: chunk 16..31 goes to the second plane.
     const int chunks = 16 * j.halves_per_row;
     const size_t plane = e8_bytes(j.n);
@@ -244,7 +261,7 @@ uz_status derive_layouts(uz_context* ctx, const Cam* cams, size_t n_cams) {
     for (size_t i = 0; i < n_cams; ++i) {
         const Cam& c = cams[i];
         if (c.n == 0) continue;
-        jobs.push_back(DeriveJob{c.raw, c.csa, c.e8, c.n, c.dbytes / 32});
+        jobs.push_back(DeriveJob{c.raw, c.csa, c.e8, c.n, (int16_t)(c.dbytes / 32), (int16_t)(ctx->narrow_e4 && c.dbytes == UZ_DESC_BYTES)});
         max_units = std::max(max_units, c.n * 16 * (c.dbytes / 32));
     }
     for (size_t j0 = 0; j0 < jobs.size(); j0 += 32768) {
@@ -279,7 +296,7 @@ uz_status place_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_f
         std::vector<CamLayout> lay(cnt);
         for (size_t c = 0; c < cnt; ++c) {
             const uz_features* f = feats[k + c];
-            lay[c] = cam_layout(at, f->n, desc_width(f->desc_bytes));
+            lay[c] = cam_layout(at, f->n, desc_width(f->desc_bytes), ctx->narrow_e4);
             at = lay[c].end;
         }
         uint8_t* base = (uint8_t*)arena.alloc(std::max<size_t>(at, 1));

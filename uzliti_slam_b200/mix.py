@@ -9,7 +9,14 @@ KNN2_IMAD = 4          # FMA pipe (weighted popcount chain); +1 per iteration of
 KNN2_MINMAX = 1.25     # VIMNMX(.3).U16x2 per compare (5 per 4 compares), ALU pipe
 KNN2_COMPARES_PER_ITERATION = 8      # 4 train rows x 2 queries per thread
 
-# knn2_mmak_kernel: tensor cores, per 128 x 256 tile of compares
+# knn2_mmaf_kernel (default): tensor cores on 4-bit operands, per 128 x 240 tile of compares
+F4_INSTRUCTIONS_PER_TILE = 4         # tcgen05.mma kind::mxf4.block_scale, K = 64 each, K = 256 in all
+F4_START_INSTRUCTIONS = 1            # + the kind::f8f6f4 instruction that starts the accumulator at 2^23 + 16384 + 127 - column (overhead)
+F4_TILE_ROWS = 240                   # train rows per accumulator (two accumulators + the block scales fill the 512 TMEM columns)
+F4_EPILOGUE_MINMAX3 = 0.5            # per compare: two sweeps of three-input packed max, each over two compares per register
+F4_EPILOGUE_IMAD = 0.5               # per compare: the 32-bit multiply-add of the second sweep (two compares per register)
+
+# knn2_mmak_kernel (UZ_MATCH_MMA=4): tensor cores on int8 operands, per 128 x 256 tile of compares
 MMA_INSTRUCTIONS_PER_TILE = 8        # tcgen05.mma kind::i8, K = 32 each, K = 256 in all
 MMA_KEY_SLICE_INSTRUCTIONS = 1       # + the constant K-slice that turns the accumulator into the packed key (overhead, not counted as work)
 MMA_OPS_PER_COMPARE = 512            # 256 int8 multiply-adds
