@@ -35,6 +35,11 @@ static void cpu_knn2(const uint32_t* q, int nq, const uint32_t* t, int nt, std::
     }
 }
 
+static const uint8_t* zero_page() {
+    static uint8_t* z = nullptr;
+    if (!z) { CK(cudaMalloc(&z, kF4ZeroPageBytes)); CK(cudaMemset(z, 0, kF4ZeroPageBytes)); }
+    return z;
+}
 struct Cam { uint32_t* raw; uint32_t* csa; uint8_t* e8; uint8_t* e4; int n; std::vector<uint32_t> h; };
 
 static Cam make_cam(int n, std::mt19937& rng, int mode) {
@@ -52,7 +57,7 @@ static Cam make_cam(int n, std::mt19937& rng, int mode) {
         CK(cudaMemcpy(c.raw, c.h.data(), (size_t)n * 32, cudaMemcpyHostToDevice));
         pack_descriptors_kernel<<<(n + 255) / 256, 256>>>((const uint8_t*)c.raw, n, 32, c.raw, c.csa, 1);
         expand_e8_kernel<<<(n * 16 + 255) / 256, 256>>>(c.raw, n, c.e8);
-        expand_e4_kernel<<<(n * 8 + 255) / 256, 256>>>(c.raw, n, c.e4);
+        expand_e4_kernel<<<(((n + 7) & ~7) * 8 + 255) / 256, 256>>>(c.raw, n, c.e4);
         CK(cudaGetLastError());
     }
     return c;
@@ -79,7 +84,7 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        if (grid > 0 && variant == 5) knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
+        if (grid > 0 && variant == 5) knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr, zero_page());
         else if (grid > 0 && variant == 2) knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         else if (grid > 0) knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         cudaEventRecord(e1);
@@ -96,7 +101,7 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
         CK(cudaMemcpyFromSymbol(h, g_f4_trace, sizeof(h)));
         const long long z = h[0][0][0];
         printf("  acc | issuer: tile loop top, tile seen, free seen, committed | epilogue: full seen, read + released, swept   (clocks since the first issue)\n");
-        for (int a = 40; a < 60; ++a)
+        for (int a = 40; a < 72; ++a)
             printf("  %3d | %7lld %7lld %7lld %7lld | %7lld %7lld %7lld\n", a, h[0][a][2] - z, h[0][a][3] - z, h[0][a][0] - z,
                    h[0][a][1] - z, h[1][a][0] - z, h[1][a][1] - z, h[1][a][2] - z);
     }

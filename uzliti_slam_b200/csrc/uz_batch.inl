@@ -527,7 +527,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             else if (!ctx->narrow_e4)        // int8 operands, keys out of the tensor core
                 knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
             else                             // default: 4-bit operands, keys out of the tensor core
-                knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
+                knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr, ctx->f4_zeros);
             ctx->mma_launches++;
         } else if (nt > 0) switch (bp.best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, bp.seg_narrow); break;

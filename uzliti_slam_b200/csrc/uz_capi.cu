@@ -160,6 +160,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmawSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma2SmemBytes);
     if (e == cudaSuccess) e = set_carveouts();
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->f4_zeros, kF4ZeroPageBytes);
+    if (e == cudaSuccess) e = cudaMemset(ctx->f4_zeros, 0, kF4ZeroPageBytes);
     if (e != cudaSuccess) { cudaGetLastError(); uz_destroy(ctx); return fail(nullptr, UZ_ERR_CUDA, std::string("cudaFuncSetAttribute(solve_kernel smem): ") + cudaGetErrorString(e)); }
     *out = ctx;
     return UZ_OK;
@@ -182,6 +184,7 @@ void uz_destroy(uz_context* ctx) {
     for (int i = 0; i < 2; ++i) if (ctx->ring_free[i]) cudaEventDestroy(ctx->ring_free[i]);
     ctx->d_results.release(); ctx->d_dbg_matches.release(); ctx->d_dbg_mask.release(); ctx->d_dbg_counts.release(); ctx->d_dbg_phase.release(); ctx->d_chunks.release(); ctx->h_chunks.release(); ctx->h_results.release();
     ctx->d_misc.release();
+    if (ctx->f4_zeros) cudaFree(ctx->f4_zeros);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& t : ctx->pending) for (int i = 0; i < 4; ++i) if (t.e[i]) cudaEventDestroy(t.e[i]);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }

@@ -270,6 +270,7 @@ struct uz_context {
                                      // (kind::mxf4, knn2_mmaf_kernel, default); measured alternatives on int8 operands: 4 = keys formed
                                      // by the MMA (knn2_mmak_kernel), 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches that fill the
                                      // chip / always, 7 = IMAD epilogue (knn2_mma_kernel)
+    uint8_t* f4_zeros = nullptr;     // kF4ZeroPageBytes of zeros: what knn2_mmaf_kernel completes a ragged train tile from
     bool narrow_e4 = true;           // 32-byte rows keep the 4-bit operand layout (match_mma == 1), else the int8 one
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments

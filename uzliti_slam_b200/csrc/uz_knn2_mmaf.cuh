@@ -29,17 +29,23 @@ constexpr int kF4BBytes = kF4N * kF4RowBytes;          // 30 KB
 constexpr int kF4Stages = 4;
 constexpr int kF4SfCol = 480;                          // TMEM column of the block scales
 constexpr int kF4TailABytes = kMmaM * 32, kF4TailBBytes = kF4N * 32;
-constexpr int kF4SmemBytes = 2 * kF4ABytes + kF4Stages * kF4BBytes + kF4TailABytes + kF4TailBBytes + 2 * kMmaItemRows * 8 + 256;
+constexpr int kF4SmemBytes = 4 * kF4ABytes + kF4Stages * kF4BBytes + kF4TailABytes + 3 * kF4TailBBytes + 2 * kMmaItemRows * 8 + 256;
 static_assert(kF4SmemBytes <= 232448, "CTA exceeds the 227 KB of shared memory");
 
 constexpr uint32_t kE4Set = 0x6u, kE4Clear = 0xEu;      // e2m1: +4 for a set bit, -4 for a clear one
 __host__ __device__ constexpr size_t e4_bytes(int n) { return (size_t)((n + 7) / 8) * kF4GroupBytes; }
+// The rows [n, round_up(n, 8)) of the last 8-row group hold zero nibbles (value +0), and a ragged train tile is completed to
+// 128 or 240 rows from a page of zeros: a missing row contributes nothing to any sum.
+constexpr size_t kF4ZeroPageBytes = kF4BBytes;
+// train rows the instructions of a tile with `rows` real rows cover
+__host__ __device__ constexpr int f4_tile_cols(int rows) { return rows <= 128 ? 128 : kF4N; }
 
 // bits -> E4 layout (ingestion): one thread per (row, 32-bit word): 32 nibbles = one uint4 store
 __global__ void __launch_bounds__(256) expand_e4_kernel(const uint32_t* __restrict__ raw, int n, uint8_t* __restrict__ e4) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * 8) return;
+    if (i >= ((n + 7) & ~7) * 8) return;
     const int row = i >> 3, w = i & 7;
+    if (row >= n) { *reinterpret_cast<uint4*>(e4 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u); return; }
     const uint32_t bits = raw[(size_t)row * 8 + w];
     uint32_t o[4];
 #pragma unroll
@@ -74,12 +80,6 @@ __device__ __forceinline__ void tc_mma_f8_start(uint32_t d_tmem, uint64_t adesc,
         "setp.ne.b32 p, 0, 0;\n"                  // false: D = A B, the accumulator is not read
         "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, {%4, %4, %4, %4}, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
-}
-// the packed max network over the first REGS registers of a 64-column group
-template <int REGS>
-__device__ __forceinline__ void f4_group(const uint32_t (&d)[32], uint32_t& p1, uint32_t& p2) {
-#pragma unroll
-    for (int m = 0; m < REGS; m += 2) top2max_update2_u16x2(p1, p2, d[m], d[m + 1]);
 }
 // A whole 128-column block (dA: 64 columns, dB: the first 2 * REGSB columns of the next 64) in two sweeps instead of the
 // five-operation insertion network, because the epilogue is bound by the ALU pipe (every packed min / max, 2 clocks each):
@@ -123,20 +123,16 @@ __device__ __forceinline__ void f4_block(const uint32_t (&dA)[32], const uint32_
     uint32_t S = (max_u16x2(y0, y1) - c) & 0xFFFEFFFFu;
     mmak_merge(m1, m2, P, S, tbase);
 }
-// unpacked columns (ragged end of the train rows): the first `valid` of 32, first column = train row t_first
-__device__ __forceinline__ void f4_masked(const uint32_t (&d)[32], int valid, uint32_t t_first, uint32_t& m1, uint32_t& m2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (j < valid) {
-            const uint32_t ham = (kMmakTop - (d[j] & 0x7FFFFFu)) >> 7;        // the low bits of 2^23 + x are x = 32895 - key16
-            top2_update(m1, m2, (ham << 16) | (t_first + (uint32_t)j));
-        }
-    }
-}
-
-// 20 warps: the producer, two MMA issuers, a spare, and two groups of eight epilogue warps, one group per accumulator, so that
-// the load latency of one accumulator hides behind the sweeps of the other.  Five warps share a sub-partition's 16384
-// registers: 96 each.
+// 20 warps: the producer, two MMA issuers, the writer of the ragged tiles' start operands, and two groups of eight epilogue
+// warps, one group per accumulator, so that the load latency of one accumulator hides behind the sweeps of the other.  Five
+// warps share a sub-partition's 16384 registers: 96 each.
+//
+// Ragged train tiles (the last of a matching: `rows` < 240 real rows) are made whole instead of being masked in the epilogue:
+// the producer completes the operand tile to 128 or 240 rows from a page of zeros, and warp 3 writes a copy of the start
+// operand whose rows >= `rows` are [2048, 2048, 0, ...]: the accumulator of such a column is exactly 2^23, its key 0.  A real
+// key of a block with missing columns is never 0 (that is distance 256 in column 127), and a lane with fewer than two real
+// columns can only surface a key-0 "row" whose index is >= the number of train rows: it loses every tie against real rows and
+// is dropped when the keys are published.  The epilogue therefore knows one path.
 #ifdef UZ_F4_TRACE
 __device__ long long g_f4_trace[2][128][8];      // probe builds: CTA 0's first 128 accumulators, issuer and epilogue clocks
 #endif
@@ -151,32 +147,60 @@ constexpr int kF4Threads = (4 + 8 * kF4EpiGroups) * 32;
 constexpr int kF4Issuers = F4_ISSUERS;        // 1: warp 1 issues for both accumulators; 2: warp 1 for the first, warp 2 for the second
 constexpr int kF4MaxRegs = kF4EpiGroups == 2 ? 96 : 128;
 
+// What a role needs to know about an item, fetched one item ahead (and the item's (task, row) pair two ahead): the two
+// dependent global loads at the top of an item cost every role ~1000 clocks otherwise, with the tensor pipe idle behind them.
+struct F4Item { const uint8_t* q; const uint8_t* t; int nq, nt, q0; uint32_t key_off; int pair; };
+__device__ __forceinline__ int2 f4_item_id(const int2* __restrict__ items, int it, int n_items) {
+    return it < n_items ? items[it] : make_int2(-1, 0);
+}
+__device__ __forceinline__ F4Item f4_item(const MmaTask* __restrict__ tasks, int2 id) {
+    F4Item m = {nullptr, nullptr, 0, 0, 0, 0u, 0};
+    if (id.x >= 0) {
+        const MmaTask* tk = tasks + id.x;
+        m.q = mma_q(tk); m.t = mma_t(tk); m.nq = tk->nq; m.nt = tk->nt; m.q0 = id.y; m.key_off = tk->key_off; m.pair = tk->pair;
+    }
+    return m;
+}
+#define F4_ITEM_LOOP_BEGIN                                                                                   \
+    int2 id1 = f4_item_id(items, blockIdx.x + gridDim.x, n_items);                                           \
+    F4Item cur = f4_item(tasks, f4_item_id(items, blockIdx.x, n_items));                                     \
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {                                               \
+        const F4Item nxt = f4_item(tasks, id1);                                                              \
+        const int2 id2 = f4_item_id(items, it + 2 * gridDim.x, n_items);                                     \
+        const int nq = cur.nq, nt = cur.nt, q0 = cur.q0;
+#define F4_ITEM_LOOP_END                                                                                     \
+        cur = nxt; id1 = id2;                                                                                \
+    }
+
 // items[k] = (task, first query row); CTA b takes items b, b + gridDim.x, ...
 __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restrict__ tasks, const int2* __restrict__ items,
                                                                   int n_items, uint2* __restrict__ keys, MmaDesc dsc,
-                                                                  int* __restrict__ pair_pending, unsigned int* __restrict__ progress) {
+                                                                  int* __restrict__ pair_pending, unsigned int* __restrict__ progress,
+                                                                  const uint8_t* __restrict__ zero_page) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;                                    // [2][16 KB]  query tiles, 128 rows x 128 B of nibbles
-    uint8_t* sB = smem + 2 * kF4ABytes;                    // [kF4Stages][30 KB]  train tiles, 240 rows
+    uint8_t* sA = smem;                                    // [2 items][2][16 KB]  query tiles, 128 rows x 128 B of nibbles: the next
+                                                           // item's are fetched while this one's are in use
+    uint8_t* sB = smem + 4 * kF4ABytes;                    // [kF4Stages][30 KB]  train tiles, 240 rows
     uint8_t* sTailA = sB + kF4Stages * kF4BBytes;           // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
     uint8_t* sTailB = sTailA + kF4TailABytes;               // [240 rows x 32 B]
-    uint2* xchg = reinterpret_cast<uint2*>(sTailB + kF4TailBBytes);         // [2 parities][256 rows]
+    uint8_t* sTailR = sTailB + kF4TailBBytes;               // [2][240 rows x 32 B]  start operands of ragged tiles
+    uint2* xchg = reinterpret_cast<uint2*>(sTailR + 2 * kF4TailBBytes);     // [2 parities][256 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kMmaItemRows);
-    uint64_t* a_full = bars;          // [2]
-    uint64_t* a_empty = bars + 2;     // [2]
-    uint64_t* b_full = bars + 4;      // [kF4Stages]
+    uint64_t* a_full = bars;          // [2 items][2]
+    uint64_t* a_empty = bars + 4;     // [2 items][2]
+    uint64_t* b_full = bars + 8;      // [kF4Stages]
     uint64_t* b_empty = b_full + kF4Stages;
     uint64_t* acc_full = b_empty + kF4Stages;    // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* rag_full = acc_empty + 2;          // [2]
+    uint64_t* rag_empty = rag_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rag_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
-        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); mbar_init(&rag_full[i], 1); mbar_init(&rag_empty[i], kF4Issuers); }
         for (int s = 0; s < kF4Stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kF4Issuers); }       // every issuer returns a train tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,6 +215,10 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
         uint8_t* dst = (isB ? sTailB : sTailA) + (row >> 3) * 256 + (row & 7) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, 0u, 0u);
         *reinterpret_cast<uint4*>(dst + 128) = make_uint4(0u, 0u, 0u, 0u);
+        if (isB) {           // the upper K half of the ragged copies never changes
+            *reinterpret_cast<uint4*>(sTailR + (row >> 3) * 256 + (row & 7) * 16 + 128) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sTailR + kF4TailBBytes + (row >> 3) * 256 + (row & 7) * 16 + 128) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 1) {          // the whole TMEM: two 240-column accumulators, the block scales behind them
@@ -213,38 +241,39 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     if (warp == 0) {
         // ===================== producer =====================
         if (lane == 0) {
-            uint32_t uB = 0, uA[2] = {0, 0};
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const int2 item = items[it];
-                const MmaTask* tk = tasks + item.x;
-                const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+            uint32_t uB = 0, phA = 0, k = 0;          // phA: one phase bit per query-tile buffer
+            F4_ITEM_LOOP_BEGIN
                 const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
                 const int T = (nt + kF4N - 1) / kF4N;
+                const uint32_t ab = (k & 1u) * 2u;
                 for (int t = 0; t < T; ++t) {
                     if (t == 0) {
-                        mbar_wait_wd(&a_empty[0], (uA[0] & 1u) ^ 1u);
+                        mbar_wait_wd(&a_empty[ab], ((phA >> ab) & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0));
-                        mbar_expect_tx(&a_full[0], bytes);
-                        bulk_g2s(sA, mma_q(tk) + (size_t)(q0 >> 3) * kF4GroupBytes, bytes, &a_full[0]);
-                        uA[0]++;
+                        mbar_expect_tx(&a_full[ab], bytes);
+                        bulk_g2s(sA + ab * kF4ABytes, cur.q + (size_t)(q0 >> 3) * kF4GroupBytes, bytes, &a_full[ab]);
+                        phA ^= 1u << ab;
                     }
                     {
                         const uint32_t slot = uB % kF4Stages;
                         mbar_wait_wd(&b_empty[slot], ((uB / kF4Stages) & 1u) ^ 1u);
-                        const uint32_t bytes = (uint32_t)e4_bytes(min(kF4N, nt - t * kF4N));
-                        mbar_expect_tx(&b_full[slot], bytes);
-                        bulk_g2s(sB + slot * kF4BBytes, mma_t(tk) + (size_t)t * kF4BBytes, bytes, &b_full[slot]);
+                        const int rows = min(kF4N, nt - t * kF4N);
+                        const uint32_t bytes = (uint32_t)e4_bytes(rows), fill = (uint32_t)e4_bytes(f4_tile_cols(rows)) - bytes;
+                        mbar_expect_tx(&b_full[slot], bytes + fill);
+                        bulk_g2s(sB + slot * kF4BBytes, cur.t + (size_t)t * kF4BBytes, bytes, &b_full[slot]);
+                        if (fill) bulk_g2s(sB + slot * kF4BBytes + bytes, zero_page, fill, &b_full[slot]);
                         uB++;
                     }
                     if (t == 0 && nqt == 2) {
-                        mbar_wait_wd(&a_empty[1], (uA[1] & 1u) ^ 1u);
+                        mbar_wait_wd(&a_empty[ab + 1], ((phA >> (ab + 1)) & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0 - kMmaM));
-                        mbar_expect_tx(&a_full[1], bytes);
-                        bulk_g2s(sA + kF4ABytes, mma_q(tk) + (size_t)((q0 + kMmaM) >> 3) * kF4GroupBytes, bytes, &a_full[1]);
-                        uA[1]++;
+                        mbar_expect_tx(&a_full[ab + 1], bytes);
+                        bulk_g2s(sA + (ab + 1) * kF4ABytes, cur.q + (size_t)((q0 + kMmaM) >> 3) * kF4GroupBytes, bytes, &a_full[ab + 1]);
+                        phA ^= 1u << (ab + 1);
                     }
                 }
-            }
+                ++k;
+            F4_ITEM_LOOP_END
         }
     } else if (warp >= 1 && warp <= kF4Issuers) {
         // ===================== MMA issuer(s) =====================
@@ -253,7 +282,7 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
         // back.  Behind a `lane == 0` test it wraps each of them in a per-thread loop with R2UR moves, ~70 clocks apiece
         // next to busy epilogue warps - as long as the instruction runs - and the issue, not the tensor pipe, bounds the kernel.
         const int i_first = kF4Issuers == 2 ? warp - 1 : 0, i_end = kF4Issuers == 2 ? warp : 2;
-        uint32_t uB = 0, uA[2] = {0, 0}, uAcc[2] = {0, 0};
+        uint32_t uB = 0, phA = 0, k = 0, nrag = 0, uAcc[2] = {0, 0};
 #ifdef UZ_F4_TRACE
         int tr = 0;
 #endif
@@ -263,12 +292,10 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
         MmaDesc tdsc = dsc;
         tdsc.lbo16 = 128 >> 4; tdsc.sbo16 = 256 >> 4;
         const uint64_t tail_a = make_smem_desc(smem_u32(sTailA), tdsc), tail_b = make_smem_desc(smem_u32(sTailB), tdsc);
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const int2 item = items[it];
-            const MmaTask* tk = tasks + item.x;
-            const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+        F4_ITEM_LOOP_BEGIN
             const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
             const int T = (nt + kF4N - 1) / kF4N;
+            const uint32_t ab = (k & 1u) * 2u;
             for (int t = 0; t < T; ++t) {
                 const uint32_t slot = uB % kF4Stages;
 #ifdef UZ_F4_TRACE
@@ -279,7 +306,12 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                 const long long trB = clock64();
 #endif
                 const int rows = min(kF4N, nt - t * kF4N);
-                const uint32_t n_mma = (uint32_t)((rows + 15) & ~15);            // N: multiple of 16
+                const uint32_t n_mma = (uint32_t)f4_tile_cols(rows);
+                // a ragged tile starts from its own copy of the start operand (written by warp 3)
+                const bool ragged = rows < kF4N;
+                const uint32_t rb = nrag & 1u;
+                if (ragged) mbar_wait_wd(&rag_full[rb], (nrag >> 1) & 1u);
+                const uint64_t tail_bt = ragged ? make_smem_desc(smem_u32(sTailR + rb * kF4TailBBytes), tdsc) : tail_b;
                 // a, b format E2M1 (MXF4Format 1) | K-major | N >> 3 at [17,23) | scale format UE8M0 at 23 | M >> 4 at [24,29)
                 const uint32_t idesc = (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | (1u << 23) | ((uint32_t)(kMmaM >> 4) << 24);
                 // the starting instruction: c format F32 | a, b format E5M2 | K-major | N | M
@@ -288,21 +320,21 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (i >= i_first && i < i_end && i < nqt) {
-                        if (t == 0) mbar_wait_wd(&a_full[i], uA[i] & 1u);
+                        if (t == 0) mbar_wait_wd(&a_full[ab + i], (phA >> (ab + i)) & 1u);
                         mbar_wait_wd(&acc_empty[i], (uAcc[i] & 1u) ^ 1u);
                         tc_fence_after();
 #ifdef UZ_F4_TRACE
                         const long long tr0 = clock64();
 #endif
                         if (tc_elect_one()) {
-                            const uint32_t a_addr = smem_u32(sA + i * kF4ABytes), b_addr = smem_u32(sB + slot * kF4BBytes);
+                            const uint32_t a_addr = smem_u32(sA + (ab + i) * kF4ABytes), b_addr = smem_u32(sB + slot * kF4BBytes);
                             const uint32_t d_acc = tmem_base + (uint32_t)i * kF4N;
-                            tc_mma_f8_start(d_acc, tail_a, tail_b, idesc_start);
+                            tc_mma_f8_start(d_acc, tail_a, tail_bt, idesc_start);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)       // K = 64 nibbles = 32 bytes of a row per instruction, on top of the start value
                                 tc_mma_mxf4(d_acc, make_smem_desc(a_addr + k * 256, fdsc), make_smem_desc(b_addr + k * 256, fdsc), idesc, sfa, sfb);
                             tc_commit(&acc_full[i]);
-                            if (t == T - 1) tc_commit(&a_empty[i]);
+                            if (t == T - 1) tc_commit(&a_empty[ab + i]);
                         }
 #ifdef UZ_F4_TRACE
                         if (lane == 0 && blockIdx.x == 0 && 2 * tr + i < 128) {
@@ -315,17 +347,45 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                         issued = true;
                     }
                 }
-                // the train tile goes back to the producer when this issuer's instructions on it are done (an issuer with
-                // nothing to do on an item of one query tile returns its share at once)
-                if (tc_elect_one()) { if (issued) tc_commit(&b_empty[slot]); else mbar_arrive(&b_empty[slot]); }
+                // the train tile (and a ragged tile's start operand) goes back when this issuer's instructions on it are done
+                // (an issuer with nothing to do on an item of one query tile returns its share at once)
+                if (tc_elect_one()) {
+                    if (issued) tc_commit(&b_empty[slot]); else mbar_arrive(&b_empty[slot]);
+                    if (ragged) { if (issued) tc_commit(&rag_empty[rb]); else mbar_arrive(&rag_empty[rb]); }
+                }
                 __syncwarp();
+                if (ragged) ++nrag;
 #ifdef UZ_F4_TRACE
                 ++tr;
 #endif
                 uB++;
             }
-            if (T > 0) for (int i = 0; i < nqt; ++i) uA[i]++;
-        }
+            if (T > 0) for (int i = 0; i < nqt; ++i) phA ^= 1u << (ab + i);
+            ++k;
+        F4_ITEM_LOOP_END
+    } else if (warp == 3) {
+        // ===================== start operands of the ragged tiles =====================
+        uint32_t nrag = 0;
+        F4_ITEM_LOOP_BEGIN
+            (void)nq; (void)q0;
+            const int rows = nt % kF4N;          // real rows of the last tile, if it is ragged
+            if (rows != 0) {
+            const uint32_t rb = nrag & 1u;
+            mbar_wait_wd(&rag_empty[rb], ((nrag >> 1) & 1u) ^ 1u);
+            const uint32_t dig[8] = {0x00u, 0x3Cu, 0x40u, 0x42u, 0x44u, 0x45u, 0x46u, 0x47u};      // e5m2 of 0..7
+            for (int row = lane; row < kF4N; row += 32) {
+                const int v = 127 - (row & 127);
+                const bool real = row < rows;
+                const uint32_t w0 = 0x68u | (0x68u << 8) | (real ? (0x58u << 16) | (dig[v >> 6] << 24) : 0u);       // 2048, 2048, 128 | 0, d2 | 0
+                const uint32_t w1 = real ? (dig[(v >> 3) & 7] | (dig[v & 7] << 8)) : 0u;
+                *reinterpret_cast<uint4*>(sTailR + rb * kF4TailBBytes + (row >> 3) * 256 + (row & 7) * 16) = make_uint4(w0, w1, 0u, 0u);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rag_full[rb]);
+            ++nrag;
+            }
+        F4_ITEM_LOOP_END
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int ew = warp - 4;                   // 0 .. 8 * kF4EpiGroups - 1
@@ -340,17 +400,13 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
         int tr = 0;
 #endif
         const uint32_t one = 1u + (uint32_t)(n_items < 0);        // 1, but not a constant ptxas could fold the multiply-add with
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x, item_parity ^= 1u) {
-            const int2 item = items[it];
-            const MmaTask* tk = tasks + item.x;
-            const int nq = tk->nq, nt = tk->nt, q0 = item.y;
+        F4_ITEM_LOOP_BEGIN
             const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
             const int T = (nt + kF4N - 1) / kF4N;
-            if (i_first >= nqt) continue;          // a group with nothing to do on an item of one query tile
+            if (i_first < nqt) {                   // (a group has nothing to do on an item of one query tile)
             uint32_t m1[2] = {kNoKey, kNoKey}, m2[2] = {kNoKey, kNoKey};
             for (int t = 0; t < T; ++t) {
-                const int hw = half ? kF4N - 128 : 128;                                        // columns of this warp's half
-                const int cvalid = min(hw, min(kF4N, nt - t * kF4N) - half * 128);             // valid ones
+                const bool active = half == 0 || nt - t * kF4N > 128;        // a tile of <= 128 rows has no second half
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (i >= i_first && i < i_end && i < nqt) {
@@ -360,11 +416,12 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                         const long long tr0 = clock64();
                         long long tr1 = 0;
 #endif
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * kF4N + half * 128);
-                        const uint32_t tbase = (uint32_t)(t * kF4N + half * 128);        // global train row of column 0
-                        // low 16 bits of the fp32 accumulator = 32895 - ((hamming << 7) | (column & 127)): the key of knn2_mmak_kernel
-                        uint32_t dA[32], dB[32];
-                        if (cvalid >= hw) {
+                        if (active) {
+                            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * kF4N + half * 128);
+                            const uint32_t tbase = (uint32_t)(t * kF4N + half * 128);        // global train row of column 0
+                            // low 16 bits of the fp32 accumulator = 32895 - ((hamming << 7) | (column & 127)): the key of
+                            // knn2_mmak_kernel; 0 in the columns a ragged tile does not have
+                            uint32_t dA[32], dB[32];
                             tc_ld64p(taddr, dA);
                             tc_ld64p(taddr + 64, dB);            // (half 1: its last 16 columns belong to nobody and are not looked at)
                             tc_wait_ld(); tc_pin(dA); tc_pin(dB);
@@ -376,20 +433,6 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
 #endif
                             if (half == 0) f4_block<32>(dA, dB, one, m1[i], m2[i], tbase); else f4_block<24>(dA, dB, one, m1[i], m2[i], tbase);
                         } else {
-                            // ragged last tile: a whole 64-column group packed, the rest column by column
-                            uint32_t p1 = 0u, p2 = 0u;
-                            const int n64 = cvalid > 0 ? cvalid >> 6 : 0;
-                            const int rem = cvalid > 0 ? cvalid & 63 : 0;
-                            if (n64 > 0) { tc_ld64p(taddr, dA); tc_wait_ld(); tc_pin(dA); f4_group<32>(dA, p1, p2); mmak_merge(m1[i], m2[i], p1, p2, tbase); }
-                            if (rem > 0) {
-                                tc_ld32(taddr + n64 * 64, dA); tc_wait_ld(); tc_pin(dA);
-                                f4_masked(dA, min(rem, 32), tbase + n64 * 64, m1[i], m2[i]);
-                            }
-                            if (rem > 32) {
-                                tc_ld32(taddr + n64 * 64 + 32, dA); tc_wait_ld(); tc_pin(dA);
-                                f4_masked(dA, rem - 32, tbase + n64 * 64 + 32, m1[i], m2[i]);
-                            }
-                            tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[i]);
                         }
@@ -422,8 +465,9 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                         const uint2 o = xc[i * kMmaM + row_in_tile];
                         const uint32_t hi = max(m1[i], o.x);
                         const uint32_t a = min(m1[i], o.x);
-                        const uint32_t b = min(hi, min(m2[i], o.y));
-                        keys[(size_t)tk->key_off + q] = make_uint2(a, b);
+                        uint32_t b = min(hi, min(m2[i], o.y));
+                        if ((b & 0xFFFFu) >= (uint32_t)nt) b = kNoKey;          // a key-0 column of a ragged tile (one train row in all)
+                        keys[(size_t)cur.key_off + q] = make_uint2(a, b);
                     }
                 }
             }
@@ -432,11 +476,13 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                 if (kF4EpiGroups == 2 && nqt == 2) asm volatile("bar.sync 3, 256;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
                 if (i_first == 0 && row_in_tile == 0) {
                     __threadfence();
-                    atomicSub(pair_pending + tk->pair, 1);
+                    atomicSub(pair_pending + cur.pair, 1);
                     atomicAdd(progress, 1u);
                 }
             }
-        }
+            }
+            item_parity ^= 1u;
+        F4_ITEM_LOOP_END
     }
 
     tc_fence_before();

@@ -35,8 +35,13 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
     if (j.e8 == nullptr) return;
     if (j.e4) {
         // 32-byte rows, 4-bit operands (uz_knn2_mmaf.cuh): one thread per (row, 32-bit word): 32 nibbles = one uint4 store
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n * 8; i += gridDim.x * blockDim.x) {
+        // (the rows that complete the last 8-row group hold zero nibbles: they add nothing to a sum)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((j.n + 7) & ~7) * 8; i += gridDim.x * blockDim.x) {
             const int row = i >> 3, w = i & 7;
+            if (row >= j.n) {
+                *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                continue;
+            }
             const uint32_t bits = j.raw[(size_t)row * 8 + w];
             uint32_t o[4];
 #pragma unroll
