@@ -928,7 +928,7 @@ def run_gpu(args):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        alg_bytes = pairs_per_gpu * (2 * N_FEATURES * 256 + N_FEATURES * 8)
+        alg_bytes = pairs_per_gpu * (2 * N_FEATURES * 128 + N_FEATURES * 8)
         solve_bytes = int(N_FEATURES * 8 + sanity["mean_matches"] * 48 + rec)
         line = dict(
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
