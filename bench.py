@@ -514,8 +514,9 @@ def measure_other_configs(est, handles, kfs):
         est.remove_keyframe(int(x))
 
     # BRISK / FREAK rows (64 bytes; cv::BRISK is FeatureExtractionCore's default, feature_extraction_core.cpp:46-49): the same
-    # loop-closure batch shape on a small map of 512-bit descriptors, through knn2_mmaw_kernel (tensor cores: two 256-bit
-    # planes, K = 512; UZ_MATCH_MMA_WIDE=0 selects knn2_wide_kernel on the integer pipes, 8 POPC per compare)
+    # loop-closure batch shape on a small map of 512-bit descriptors, through knn2_mmaf_kernel<true> (tensor cores, 4-bit
+    # operands, K = 512 in eight instructions; UZ_MATCH_MMA_WIDE=2 selects knn2_mmaw_kernel on two int8 planes,
+    # UZ_MATCH_MMA_WIDE=0 knn2_wide_kernel on the integer pipes, 8 POPC per compare)
     kw, pw, _ = S.make_map(400, n_features=1000, k_candidates=20, seed=77, desc_bytes=64)
     hw = est.add_keyframes(kw)
     est.estimateEdges(hw[pw[:, 0]], hw[pw[:, 1]])
@@ -537,9 +538,11 @@ def measure_other_configs(est, handles, kfs):
     except Exception:
         bf16_burst = 1590.0
     out["BRISK512_loop_closure"] = dict(pairs=int(len(pw)), edges_per_s=round(len(pw) / dt, 1),
-                                        kernel="knn2_mmaw_kernel (tcgen05.mma kind::i8, 128x128x32, K = 512 over two planes)",
+                                        kernel=("knn2_mmaf_kernel<true> (tcgen05.mma kind::mxf4.block_scale, 128x240x64 on 4-bit operands, "
+                                                "K = 512 in eight instructions)" if os.environ.get("UZ_MATCH_MMA_WIDE", "1") == "1" else
+                                                "UZ_MATCH_MMA_WIDE=" + os.environ["UZ_MATCH_MMA_WIDE"]),
                                         knn2_wide_gcmp512_per_s=round(gcmp, 1), knn2_wide_ms=round(tm["match_ms"] / 3, 3),
-                                        tops=round(gcmp * 1024 * 1e-3, 1), frac_of_2x_bf16_burst=round(gcmp * 1024 * 1e-3 / (2 * bf16_burst), 4),
+                                        tops=round(gcmp * 1024 * 1e-3, 1), frac_of_4x_bf16_burst=round(gcmp * 1024 * 1e-3 / (4 * bf16_burst), 4),
                                         x_integer_pipe_popc_ceiling=round(gcmp * 8 / popc, 3),
                                         cpu_port_1thread_edges_per_s=round(1.0 / cpuw, 2),
                                         same_consensus_as_cpu=bool(int(rw[0]["consensus"]) == int(ow["consensus"])))

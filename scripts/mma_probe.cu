@@ -78,13 +78,13 @@ static float run_mma(const std::vector<MmaTask>& tasks, size_t key_rows, MmaDesc
     CK(cudaMemset(d_keys, 0xEE, std::max<size_t>(key_rows, 1) * sizeof(uint2)));
     CK(cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
     CK(cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes));
-    CK(cudaFuncSetAttribute(knn2_mmaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF4SmemBytes));
+    CK(cudaFuncSetAttribute(knn2_mmaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF4SmemBytes));
     const int grid = (int)std::min<size_t>(items.size(), (size_t)g_sms);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        if (grid > 0 && variant == 5) knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr, zero_page());
+        if (grid > 0 && variant == 5) knn2_mmaf_kernel<false><<<grid, kF4Threads, kF4SmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr, zero_page());
         else if (grid > 0 && variant == 2) knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         else if (grid > 0) knn2_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes>>>(d_tasks, d_items, (int)items.size(), d_keys, dsc, nullptr, nullptr);
         cudaEventRecord(e1);

@@ -79,8 +79,12 @@ def test_default_match_kernel_is_block_scaled_fp4_tcgen05(built):
     """knn2_mmaf_kernel: tcgen05.mma kind::mxf4 (UTCOMMA) started by one kind::f8f6f4 instruction (UTCQMMA), issued back to
     back by an elected lane, packed TMEM loads, an epilogue of three-input packed max and one multiply-add per register"""
     funcs = _functions(built)
-    names = [n for n in funcs if "knn2_mmaf_kernel" in n]
+    names = [n for n in funcs if "knn2_mmaf_kernelILb0E" in n]          # <false>: 32-byte rows
     assert len(names) == 1
+    wide = [n for n in funcs if "knn2_mmaf_kernelILb1E" in n]           # <true>: 64-byte rows, eight instructions per accumulator
+    assert len(wide) == 1
+    wops = [_op(t) for _, t in funcs[wide[0]]]
+    assert sum(1 for o in wops if o.startswith("UTCOMMA")) == 2 * sum(1 for o in wops if o.startswith("UTCQMMA")) * mix.F4_INSTRUCTIONS_PER_TILE
     body = funcs[names[0]]
     ops = [_op(t) for _, t in body]
     cnt = lambda p: sum(1 for o in ops if o.startswith(p))          # noqa: E731

@@ -43,12 +43,15 @@ def test_knn2_wide_random(est, oracle, nq, nt):
     assert np.array_equal(dist, od)
 
 
-def test_knn2_wide_integer_pipe_kernel_equals_tensor_core_kernel(est, oracle):
-    """the default for 64-byte rows is knn2_mmaw_kernel (tensor cores, two 256-bit planes); UZ_MATCH_MMA_WIDE=0 keeps
-    knn2_wide_kernel: same neighbours on random, tie-heavy and extreme rows, and byte-identical edge records"""
-    e = _estimator(UZ_MATCH_MMA_WIDE=0)
+@pytest.mark.parametrize("other", [0, 2])
+def test_knn2_wide_integer_pipe_kernel_equals_tensor_core_kernel(est, oracle, other):
+    """the default for 64-byte rows is knn2_mmaf_kernel<true> (tensor cores, 4-bit operands, K = 512); UZ_MATCH_MMA_WIDE=0 keeps
+    knn2_wide_kernel on the integer pipes, UZ_MATCH_MMA_WIDE=2 knn2_mmaw_kernel on two int8 planes: same neighbours on random,
+    tie-heavy and extreme rows, on the 240-row tile boundaries of the 4-bit kernel, and byte-identical edge records"""
+    e = _estimator(UZ_MATCH_MMA_WIDE=other)
     try:
-        for nq, nt in [(500, 500), (1000, 1000), (257, 511), (129, 64), (3, 1000), (1, 1), (4096, 4096), (1000, 127), (130, 129)]:
+        for nq, nt in [(500, 500), (1000, 1000), (257, 511), (129, 64), (3, 1000), (1, 1), (4096, 4096), (1000, 127), (130, 129),
+                       (256, 240), (300, 241), (300, 239), (128, 480), (200, 368), (260, 369), (31, 304), (40, 113), (7, 2), (65, 193)]:
             for mode in range(3):
                 rng = np.random.default_rng(nq * 31 + nt + mode)
                 q = rng.integers(0, 256, (nq, 64), dtype=np.uint8)

@@ -79,7 +79,8 @@ cudaError_t set_carveouts() {
     if (e == cudaSuccess) e = max_shared_carveout(pack_descriptors_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmak_kernel);
-    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaf_kernel);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaf_kernel<false>);
+    if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaf_kernel<true>);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mmaw_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(knn2_mma2_kernel);
     if (e == cudaSuccess) e = max_shared_carveout(derive_layouts_kernel);
@@ -101,7 +102,7 @@ struct BatchPlan {
     int max_nq = 0, cap = 0;
     int64_t compares = 0;
     bool mma = false;                    // 256-bit matchings on the tensor cores (knn2_mmaf_kernel; int8 alternatives)
-    bool mma_wide = false;               // 512-bit matchings on the tensor cores (knn2_mmaw_kernel)
+    bool mma_wide = false;               // 512-bit matchings on the tensor cores (knn2_mmaf_kernel<true>; knn2_mmaw_kernel)
     bool mma2 = false;                   // ... on CTA pairs (knn2_mma2_kernel): launches that keep every pair of SMs busy
     int best_cfg = 3, wide_cfg = 0;      // integer-pipe tile shapes
     int tile_rows = 512, wide_threads = 256, wide_tile_rows = 512;
@@ -493,8 +494,12 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
         unsigned int* d_prog = d_ctl ? &d_ctl->progress : nullptr;
         if (bp.n_tiles_wide > 0 && bp.mma_wide) {
             const int ntw = (int)bp.n_tiles_wide;
-            knn2_mmaw_kernel<<<std::min(ntw, ctx->sm_count), kMmaThreads, kMmawSmemBytes, ctx->stream>>>(
-                reinterpret_cast<const MmaTask*>(d_tk), d_tw, ntw, d_k, uz_knn2_mma_desc());
+            if (ctx->wide_e4)            // default: 4-bit operands, K = 512 in eight instructions
+                knn2_mmaf_kernel<true><<<std::min(ntw, ctx->sm_count), kF4Threads, F4<true>::kSmemBytes, ctx->stream>>>(
+                    reinterpret_cast<const MmaTask*>(d_tk), d_tw, ntw, d_k, uz_knn2_mma_desc(), nullptr, nullptr, ctx->f4_zeros);
+            else                         // two int8 planes (UZ_MATCH_MMA_WIDE=2)
+                knn2_mmaw_kernel<<<std::min(ntw, ctx->sm_count), kMmaThreads, kMmawSmemBytes, ctx->stream>>>(
+                    reinterpret_cast<const MmaTask*>(d_tk), d_tw, ntw, d_k, uz_knn2_mma_desc());
             ctx->launches++; ctx->mma_launches++;
             UZ_CUDA(ctx, cudaGetLastError());
             if (ctx->timers) ctx->match_launches++;
@@ -527,7 +532,7 @@ uz_status run_pairs(uz_context* ctx, const std::vector<PairRef>& pairs, uz_edge_
             else if (!ctx->narrow_e4)        // int8 operands, keys out of the tensor core
                 knn2_mmak_kernel<<<grid, kMmaThreads, kMmakSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr);
             else                             // default: 4-bit operands, keys out of the tensor core
-                knn2_mmaf_kernel<<<grid, kF4Threads, kF4SmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr, ctx->f4_zeros);
+                knn2_mmaf_kernel<false><<<grid, kF4Threads, F4<false>::kSmemBytes, ctx->stream>>>(mt, d_t, nt, d_k, uz_knn2_mma_desc(), nullptr, nullptr, ctx->f4_zeros);
             ctx->mma_launches++;
         } else if (nt > 0) switch (bp.best_cfg) {
             case 0: launch_knn2<256, 4>(ctx, d_tk, d_t, nt, d_k, d_pending, d_prog, fused, bp.seg_narrow); break;

@@ -139,6 +139,7 @@ uz_status uz_create(int32_t device, uz_context** out) {
         ctx->narrow_e4 = ctx->match_mma == 1;
         const char* mw = getenv("UZ_MATCH_MMA_WIDE");
         if (mw) ctx->match_mma_wide = atoi(mw);
+        ctx->wide_e4 = ctx->match_mma_wide == 1;
 
         const char* stt = getenv("UZ_STAGE_THREADS");
         if (stt && atoi(stt) >= 1 && atoi(stt) <= 64) ctx->stage_threads = atoi(stt);
@@ -156,7 +157,8 @@ uz_status uz_create(int32_t device, uz_context** out) {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmakSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF4SmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4<false>::kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4<true>::kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mmaw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmawSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMma2SmemBytes);
     if (e == cudaSuccess) e = set_carveouts();
@@ -342,7 +344,7 @@ uz_status uz_match_knn2(uz_context* ctx, int32_t desc_bytes, const uint8_t* quer
         const int halves = n * (db / 32);
         c.raw = (uint32_t*)ctx->transient.alloc((size_t)n * db);
         c.csa = (uint32_t*)ctx->transient.alloc((size_t)n * db);
-        c.e8 = (uint8_t*)ctx->transient.alloc(operand_bytes(n, db, ctx->narrow_e4));
+        c.e8 = (uint8_t*)ctx->transient.alloc(operand_bytes(n, db, ctx->operand_fmt()));
         uint8_t* stage = (uint8_t*)ctx->transient.alloc((size_t)n * stride);
         if (!c.raw || !c.csa || !stage || !c.e8) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
         UZ_CUDA(ctx, cudaMemcpyAsync(stage, h, (size_t)(n - 1) * stride + db, cudaMemcpyHostToDevice, ctx->stream));

@@ -29,7 +29,7 @@ int32_t register_keyframe(uz_context* ctx, const Cam& c, const BlockRef& block) 
 uz_status alloc_cam(uz_context* ctx, Arena& arena, int n, int dbytes, int feature_type, int sensor_frame, Cam& c, BlockRef& block) {
     c = Cam();
     c.n = n; c.feature_type = feature_type; c.sensor_frame = sensor_frame; c.dbytes = dbytes;
-    const CamLayout L = cam_layout(0, n, dbytes, ctx->narrow_e4);
+    const CamLayout L = cam_layout(0, n, dbytes, ctx->operand_fmt());
     uint8_t* base = (uint8_t*)arena.alloc(std::max<size_t>(L.end, 1));
     if (!base) return fail(ctx, UZ_ERR_NOMEM, "device arena allocation failed");
     block = BlockRef{base, std::max<size_t>(L.end, 1)};

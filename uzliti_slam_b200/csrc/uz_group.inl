@@ -111,7 +111,7 @@ uz_status group_replicate(uz_context* ctx, const uz_context* src, const int32_t*
         counts[i] = (int32_t)sk.cams.size();
         size_t at = 0;
         std::vector<CamLayout> lay(sk.cams.size());
-        for (size_t c = 0; c < sk.cams.size(); ++c) { lay[c] = cam_layout(at, sk.cams[c].n, sk.cams[c].dbytes, ctx->narrow_e4); at = lay[c].end; }
+        for (size_t c = 0; c < sk.cams.size(); ++c) { lay[c] = cam_layout(at, sk.cams[c].n, sk.cams[c].dbytes, ctx->operand_fmt()); at = lay[c].end; }
         uint8_t* base = (uint8_t*)ctx->store_arena.alloc(std::max<size_t>(at, 1));
         if (!base) {
             for (auto& b : blocks) ctx->store_arena.free(b.p, b.bytes);

@@ -194,8 +194,8 @@ struct HostPool {
 struct Cam {
     uint32_t* raw = nullptr;   // n x dbytes/4 words, bytes as given
     uint32_t* csa = nullptr;   // same rows, every 256-bit half in CSA layout (uz_knn2.cuh)
-    uint8_t* e8 = nullptr;     // the tensor-core operand layout: 32-byte rows one 4-bit value per bit (uz_knn2_mmaf.cuh; one int8 per bit,
-                               // uz_knn2_mma.cuh, when the context runs an int8 kernel); 64-byte rows two int8 planes (uz_knn2_mmaw.cuh)
+    uint8_t* e8 = nullptr;     // the tensor-core operand layout: one 4-bit value per bit (uz_knn2_mmaf.cuh); when the context runs an int8
+                               // kernel, one int8 per bit (32-byte rows: uz_knn2_mma.cuh; 64-byte rows: two planes, uz_knn2_mmaw.cuh)
     double* pos = nullptr;     // 3 x n column-major
     uint8_t* valid = nullptr;  // n
     int32_t n = 0, feature_type = 0, sensor_frame = 0;
@@ -204,8 +204,11 @@ struct Cam {
 
 // where the layouts of one camera live inside a block (offsets are multiples of 256)
 struct CamLayout { size_t raw, csa, e8, pos, valid, end; };
-inline size_t operand_bytes(int n, int dbytes, bool e4) { return dbytes == UZ_DESC_BYTES ? (e4 ? e4_bytes(n) : e8_bytes(n)) : e8w_bytes(n); }
-inline CamLayout cam_layout(size_t at, int n, int dbytes, bool e4) {
+// fmt: bit 0 = 32-byte rows keep the 4-bit layout, bit 1 = 64-byte rows do (else the int8 layouts)
+inline size_t operand_bytes(int n, int dbytes, int fmt) {
+    return dbytes == UZ_DESC_BYTES ? ((fmt & 1) ? e4_bytes(n) : e8_bytes(n)) : ((fmt & 2) ? e4w_bytes(n) : e8w_bytes(n));
+}
+inline CamLayout cam_layout(size_t at, int n, int dbytes, int fmt) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     CamLayout L;
     L.raw = at;
@@ -213,7 +216,7 @@ inline CamLayout cam_layout(size_t at, int n, int dbytes, bool e4) {
     L.valid = up(L.pos + (size_t)n * 24);
     L.csa = up(L.valid + (size_t)n);
     L.e8 = up(L.csa + (size_t)n * dbytes);
-    L.end = up(L.e8 + operand_bytes(n, dbytes, e4));
+    L.end = up(L.e8 + operand_bytes(n, dbytes, fmt));
     return L;
 }
 
@@ -265,13 +268,16 @@ struct uz_context {
     int force_cfg = -1;              // UZ_KNN_CFG: force a knn2 tile shape (tuning knob)
     int xcheck_fused = 1;            // UZ_XCHECK_FUSED=0: cross-check by a second, reversed matching (the measured alternative)
     int force_wide_cfg = -1;         // UZ_KNN_WIDE_CFG: force a knn2_wide tile shape (0 = 256 x 2, 1 = 64 x 2)
-    int match_mma_wide = 1;          // UZ_MATCH_MMA_WIDE=0: 512-bit rows stay on the integer pipes (knn2_wide_kernel)
+    int match_mma_wide = 1;          // UZ_MATCH_MMA_WIDE: 1 = 512-bit rows on 4-bit operands (knn2_mmaf_kernel<true>, default); 2 = on two int8
+                                     // planes (knn2_mmaw_kernel, the measured alternative); 0 = on the integer pipes (knn2_wide_kernel)
     int match_mma = 1;               // UZ_MATCH_MMA: 0 = 256-bit rows on the integer pipes (knn2_kernel); 1 = tensor cores, 4-bit operands
                                      // (kind::mxf4, knn2_mmaf_kernel, default); measured alternatives on int8 operands: 4 = keys formed
                                      // by the MMA (knn2_mmak_kernel), 2 / 3 = CTA pairs (knn2_mma2_kernel) for launches that fill the
                                      // chip / always, 7 = IMAD epilogue (knn2_mma_kernel)
     uint8_t* f4_zeros = nullptr;     // kF4ZeroPageBytes of zeros: what knn2_mmaf_kernel completes a ragged train tile from
     bool narrow_e4 = true;           // 32-byte rows keep the 4-bit operand layout (match_mma == 1), else the int8 one
+    bool wide_e4 = true;             // 64-byte rows: the same (match_mma_wide == 1)
+    int operand_fmt() const { return (narrow_e4 ? 1 : 0) | (wide_e4 ? 2 : 0); }
     std::vector<uint8_t> task_wide;  // per task of the batch being prepared: 64-byte rows
     std::vector<int4> merge_table;   // per batch: tasks whose train rows were cut into segments
     int solve_wide = 1;              // UZ_SOLVE_WIDE=0: never use the 512-thread solve CTA for small launches

@@ -1,42 +1,58 @@
 // uz_knn2_mmaf.cuh — the tensor-core match kernel on the 4-BIT path: tcgen05.mma kind::mxf4 (e2m1 operands, UE8M0 block scales,
-// fp32 accumulate), 128 x 240 x 64 per instruction.
+// fp32 accumulate), 128 x 240 x 64 per instruction.  knn2_mmaf_kernel<false>: 32-byte descriptor rows (K = 256, four
+// instructions per accumulator); knn2_mmaf_kernel<true>: 64-byte rows (K = 512, eight instructions).
 //
-// scripts/mxf4_probe.cu: +-4 operands with constant block scales 2^1 (a product is +-64, as in the int8 kernels) accumulate
-// EXACTLY onto an fp32 accumulator pre-loaded with 2^23 + 16384 - every bit - and the instruction takes 141 clocks for twice
-// the K of an int8 one: 566 clocks per 128 x 256 accumulator of 256-bit compares against 1152 in knn2_mmak_kernel.
+// scripts/mxf4_probe.cu: +-4 operands with constant block scales accumulate EXACTLY onto an fp32 accumulator pre-loaded with
+// 2^23 + 16384 - every bit - and the instruction takes 141-155 clocks for twice the K of an int8 one.
 //
 // Operand layout ("E4"): one NIBBLE per descriptor bit (0x6 = +4 set, 0xE = -4 clear), K-major canonical layout with 16-byte
-// core-matrix rows: byte(row i, bit k) = (i >> 3) * 1024 + (k >> 5) * 128 + (i & 7) * 16 + ((k >> 1) & 15), low nibble = even k.
-// Half the bytes of E8: 16 KB query tiles, 30 KB train tiles - four stages fit.
+// core-matrix rows: byte(row i, bit k) = (i >> 3) * G + (k >> 5) * 128 + (i & 7) * 16 + ((k >> 1) & 15), low nibble = even k,
+// G = 1024 for 32-byte rows and 2048 for 64-byte rows.  Half the bytes of the int8 layouts.
 // Keys.  Every accumulator is STARTED by one kind::f8f6f4 instruction (e5m2 x e5m2, K = 32, not accumulating) over two constant
 // shared-memory blocks - query side [2048, 2048, 128, 64, 8, 1, 0 ...], train side [2048, 2048, 128, d2, d1, d0, 0 ...] with
-// 127 - (row & 127) = 64 d2 + 8 d1 + d0 - which sets it to 2^23 + 16384 + 127 - (column & 127); the four mxf4 instructions add
-// 64 dot on top, exactly (scripts/mxf4_probe.cu).  The low 16 bits of that fp32 value ARE the integer
-// 32895 - ((hamming << 7) | (column & 127)), so the packed 16-bit TMEM load and the packed-max epilogue of knn2_mmak_kernel work
-// unchanged.  640 clocks of tensor pipe per 128 x 256 accumulator against 1152.
+// B - 1 - (row & (B - 1)) = 64 d2 + 8 d1 + d0, B = columns per key block - which sets it to 2^23 + 16384 + B - 1 - (column &
+// (B - 1)); the mxf4 instructions add U dot on top, exactly.  The low 16 bits of that fp32 value ARE the integer
+// TOP - key16, key16 = hamming * B + (column & (B - 1)), so a packed 16-bit TMEM load delivers two keys per register:
+//   32-byte rows: B = 128, block scales 2 x 2, U = 64, TOP = 32895 (257 distances x 128 columns fit 16 bits)
+//   64-byte rows: B = 64,  block scales 2 x 1, U = 32, TOP = 32831 (513 distances x 64 columns)
 // TMEM.  The block scales live in TMEM next to the accumulators, so a train tile is 240 rows, not 256: accumulators at
-// columns 0 and 240, scales at 480.  1000 train rows are four tiles of 240 and one of 40.
+// columns 0 and 240, scales from 480.
 #pragma once
 #include "uz_knn2_mmak.cuh"
 
 namespace uz {
 
 constexpr int kF4N = 240;                              // train rows per tile / accumulator columns
-constexpr int kF4RowBytes = 128;                       // one nibble per descriptor bit
-constexpr int kF4GroupBytes = 8 * kF4RowBytes;
-constexpr int kF4ABytes = kMmaM * kF4RowBytes;         // 16 KB
-constexpr int kF4BBytes = kF4N * kF4RowBytes;          // 30 KB
-constexpr int kF4Stages = 4;
 constexpr int kF4SfCol = 480;                          // TMEM column of the block scales
 constexpr int kF4TailABytes = kMmaM * 32, kF4TailBBytes = kF4N * 32;
-constexpr int kF4SmemBytes = 4 * kF4ABytes + kF4Stages * kF4BBytes + kF4TailABytes + 3 * kF4TailBBytes + 2 * kMmaItemRows * 8 + 256;
-static_assert(kF4SmemBytes <= 232448, "CTA exceeds the 227 KB of shared memory");
+
+template <bool WIDE>
+struct F4 {
+    static constexpr int kRowBytes = WIDE ? 256 : 128;     // one nibble per descriptor bit
+    static constexpr int kGroupBytes = 8 * kRowBytes;
+    static constexpr int kABytes = kMmaM * kRowBytes;      // 16 / 32 KB
+    static constexpr int kBBytes = kF4N * kRowBytes;       // 30 / 60 KB
+    static constexpr int kStages = WIDE ? 2 : 4;           // train tiles in flight
+    static constexpr int kABufs = WIDE ? 1 : 2;            // items whose query tiles are in shared memory
+    static constexpr int kKSteps = kRowBytes / 32;         // instructions per accumulator (K = 64 nibbles = 32 bytes each)
+    static constexpr int kKeyCols = WIDE ? 64 : 128;       // columns per key block
+    static constexpr uint32_t kTop = WIDE ? 32831u : 32895u;
+    static constexpr uint32_t kScaleA = 0x80808080u;       // UE8M0 2^1
+    static constexpr uint32_t kScaleB = WIDE ? 0x7F7F7F7Fu : 0x80808080u;      // 2^0 / 2^1: a product is +-32 / +-64
+    static constexpr int kSfbCol = WIDE ? kF4SfCol + 16 : kF4SfCol + 4;
+    static constexpr int kSmemBytes = 2 * kABufs * kABytes + kStages * kBBytes + kF4TailABytes + 3 * kF4TailBBytes + 2 * kMmaItemRows * 8 + 256;
+    static_assert(kSmemBytes <= 232448, "CTA exceeds the 227 KB of shared memory");
+    __host__ __device__ static constexpr size_t bytes(int n) { return (size_t)((n + 7) / 8) * kGroupBytes; }
+};
+constexpr int kF4RowBytes = F4<false>::kRowBytes, kF4GroupBytes = F4<false>::kGroupBytes, kF4BBytes = F4<false>::kBBytes;
+constexpr int kF4SmemBytes = F4<false>::kSmemBytes;
 
 constexpr uint32_t kE4Set = 0x6u, kE4Clear = 0xEu;      // e2m1: +4 for a set bit, -4 for a clear one
-__host__ __device__ constexpr size_t e4_bytes(int n) { return (size_t)((n + 7) / 8) * kF4GroupBytes; }
+__host__ __device__ constexpr size_t e4_bytes(int n) { return F4<false>::bytes(n); }
+__host__ __device__ constexpr size_t e4w_bytes(int n) { return F4<true>::bytes(n); }
 // The rows [n, round_up(n, 8)) of the last 8-row group hold zero nibbles (value +0), and a ragged train tile is completed to
 // 128 or 240 rows from a page of zeros: a missing row contributes nothing to any sum.
-constexpr size_t kF4ZeroPageBytes = kF4BBytes;
+constexpr size_t kF4ZeroPageBytes = F4<true>::kBBytes;
 // train rows the instructions of a tile with `rows` real rows cover
 __host__ __device__ constexpr int f4_tile_cols(int rows) { return rows <= 128 ? 128 : kF4N; }
 
@@ -70,6 +86,10 @@ __device__ __forceinline__ void tc_mma_mxf4(uint32_t d_tmem, uint64_t adesc, uin
 __device__ __forceinline__ void f4_fill32(uint32_t taddr, uint32_t v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
                  "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void f4_fill16(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
                  ::"r"(taddr), "r"(v) : "memory");
 }
 // the instruction that starts an accumulator: kind::f8f6f4, K = 32, D = A B (no accumulate)
@@ -123,6 +143,36 @@ __device__ __forceinline__ void f4_block(const uint32_t (&dA)[32], const uint32_
     uint32_t S = (max_u16x2(y0, y1) - c) & 0xFFFEFFFFu;
     mmak_merge(m1, m2, P, S, tbase);
 }
+// 64-byte rows: a 64-column block per array.  key16 = hamming * 64 + (column & 63) <= 32831 = TOP; odd columns again give even
+// high-lane values (TOP is odd), so the second sweep works unchanged.
+template <int REGS>
+__device__ __forceinline__ void f4_block64(const uint32_t (&d)[32], uint32_t one, uint32_t& m1, uint32_t& m2, uint32_t tbase) {
+    uint32_t g0 = 0u, g1 = 0u;
+#pragma unroll
+    for (int m = 0; m < REGS; m += 4) {
+        g0 = max_u16x2(max_u16x2(g0, d[m]), d[m + 1]);
+        g1 = max_u16x2(max_u16x2(g1, d[m + 2]), d[m + 3]);
+    }
+    const uint32_t P = max_u16x2(g0, g1);
+    const uint32_t c = 65536u - P;
+    uint32_t y0 = 0u, y1 = 0u;
+#pragma unroll
+    for (int m = 0; m < REGS; m += 4) {
+        y0 = max_u16x2(max_u16x2(y0, f4_mad(d[m], one, c)), f4_mad(d[m + 1], one, c));
+        y1 = max_u16x2(max_u16x2(y1, f4_mad(d[m + 2], one, c)), f4_mad(d[m + 3], one, c));
+    }
+    const uint32_t S = (max_u16x2(y0, y1) - c) & 0xFFFEFFFFu;
+    // the four winners (even and odd columns, best and second) -> (distance << 16) | train row
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t v1 = F4<true>::kTop - (h ? P >> 16 : P & 0xFFFFu), v2 = F4<true>::kTop - (h ? S >> 16 : S & 0xFFFFu);
+        const uint32_t k1 = ((v1 & 0xFFC0u) << 10) | (tbase + (v1 & 63u));
+        const uint32_t k2 = ((v2 & 0xFFC0u) << 10) | (tbase + (v2 & 63u));
+        const uint32_t t = max(m1, k1);
+        m1 = min(m1, k1);
+        m2 = min(min(m2, t), k2);
+    }
+}
 // 20 warps: the producer, two MMA issuers, the writer of the ragged tiles' start operands, and two groups of eight epilogue
 // warps, one group per accumulator, so that the load latency of one accumulator hides behind the sweeps of the other.  Five
 // warps share a sub-partition's 16384 registers: 96 each.
@@ -173,24 +223,26 @@ __device__ __forceinline__ F4Item f4_item(const MmaTask* __restrict__ tasks, int
     }
 
 // items[k] = (task, first query row); CTA b takes items b, b + gridDim.x, ...
+template <bool WIDE>
 __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restrict__ tasks, const int2* __restrict__ items,
                                                                   int n_items, uint2* __restrict__ keys, MmaDesc dsc,
                                                                   int* __restrict__ pair_pending, unsigned int* __restrict__ progress,
                                                                   const uint8_t* __restrict__ zero_page) {
+    using C = F4<WIDE>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                    // [2 items][2][16 KB]  query tiles, 128 rows x 128 B of nibbles: the next
                                                            // item's are fetched while this one's are in use
-    uint8_t* sB = smem + 4 * kF4ABytes;                    // [kF4Stages][30 KB]  train tiles, 240 rows
-    uint8_t* sTailA = sB + kF4Stages * kF4BBytes;           // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
+    uint8_t* sB = smem + 2 * C::kABufs * C::kABytes;                    // [C::kStages][30 KB]  train tiles, 240 rows
+    uint8_t* sTailA = sB + C::kStages * C::kBBytes;           // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
     uint8_t* sTailB = sTailA + kF4TailABytes;               // [240 rows x 32 B]
     uint8_t* sTailR = sTailB + kF4TailBBytes;               // [2][240 rows x 32 B]  start operands of ragged tiles
     uint2* xchg = reinterpret_cast<uint2*>(sTailR + 2 * kF4TailBBytes);     // [2 parities][256 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kMmaItemRows);
     uint64_t* a_full = bars;          // [2 items][2]
     uint64_t* a_empty = bars + 4;     // [2 items][2]
-    uint64_t* b_full = bars + 8;      // [kF4Stages]
-    uint64_t* b_empty = b_full + kF4Stages;
-    uint64_t* acc_full = b_empty + kF4Stages;    // [2]
+    uint64_t* b_full = bars + 8;      // [C::kStages]
+    uint64_t* b_empty = b_full + C::kStages;
+    uint64_t* acc_full = b_empty + C::kStages;    // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint64_t* rag_full = acc_empty + 2;          // [2]
     uint64_t* rag_empty = rag_full + 2;          // [2]
@@ -201,14 +253,14 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); mbar_init(&rag_full[i], 1); mbar_init(&rag_empty[i], kF4Issuers); }
-        for (int s = 0; s < kF4Stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kF4Issuers); }       // every issuer returns a train tile
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kF4Issuers); }       // every issuer returns a train tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the constant operands of the starting instruction (e5m2 bytes; compact canonical layout, 8-row groups of 256 B)
     for (int r = tid; r < kMmaM + kF4N; r += kF4Threads) {
         const bool isB = r >= kMmaM;
         const int row = isB ? r - kMmaM : r;
-        const int v = 127 - (row & 127);
+        const int v = (C::kKeyCols - 1) - (row & (C::kKeyCols - 1));
         const uint32_t dig[8] = {0x00u, 0x3Cu, 0x40u, 0x42u, 0x44u, 0x45u, 0x46u, 0x47u};      // e5m2 of 0..7
         const uint32_t w0 = 0x68u | (0x68u << 8) | (0x58u << 16) | ((isB ? dig[v >> 6] : 0x54u) << 24);     // 2048, 2048, 128, d2 | 64
         const uint32_t w1 = isB ? (dig[(v >> 3) & 7] | (dig[v & 7] << 8)) : (0x48u | (0x3Cu << 8));        // d1, d0 | 8, 1
@@ -231,7 +283,12 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= 4 && warp < 8) {
         // every block scale is 2^1 (UE8M0 128): operands +-4 count as +-8, a product is +-64
-        f4_fill32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kF4SfCol, 0x80808080u);
+        if (WIDE) {          // query-side scales 2^1, train-side scales 2^0, sixteen columns each
+            f4_fill16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kF4SfCol, C::kScaleA);
+            f4_fill16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kSfbCol, C::kScaleB);
+        } else {
+            f4_fill32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kF4SfCol, C::kScaleA);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -245,30 +302,30 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
             F4_ITEM_LOOP_BEGIN
                 const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
                 const int T = (nt + kF4N - 1) / kF4N;
-                const uint32_t ab = (k & 1u) * 2u;
+                const uint32_t ab = C::kABufs == 2 ? (k & 1u) * 2u : 0u;
                 for (int t = 0; t < T; ++t) {
                     if (t == 0) {
                         mbar_wait_wd(&a_empty[ab], ((phA >> ab) & 1u) ^ 1u);
-                        const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0));
+                        const uint32_t bytes = (uint32_t)C::bytes(min(kMmaM, nq - q0));
                         mbar_expect_tx(&a_full[ab], bytes);
-                        bulk_g2s(sA + ab * kF4ABytes, cur.q + (size_t)(q0 >> 3) * kF4GroupBytes, bytes, &a_full[ab]);
+                        bulk_g2s(sA + ab * C::kABytes, cur.q + (size_t)(q0 >> 3) * C::kGroupBytes, bytes, &a_full[ab]);
                         phA ^= 1u << ab;
                     }
                     {
-                        const uint32_t slot = uB % kF4Stages;
-                        mbar_wait_wd(&b_empty[slot], ((uB / kF4Stages) & 1u) ^ 1u);
+                        const uint32_t slot = uB % C::kStages;
+                        mbar_wait_wd(&b_empty[slot], ((uB / C::kStages) & 1u) ^ 1u);
                         const int rows = min(kF4N, nt - t * kF4N);
-                        const uint32_t bytes = (uint32_t)e4_bytes(rows), fill = (uint32_t)e4_bytes(f4_tile_cols(rows)) - bytes;
+                        const uint32_t bytes = (uint32_t)C::bytes(rows), fill = (uint32_t)C::bytes(f4_tile_cols(rows)) - bytes;
                         mbar_expect_tx(&b_full[slot], bytes + fill);
-                        bulk_g2s(sB + slot * kF4BBytes, cur.t + (size_t)t * kF4BBytes, bytes, &b_full[slot]);
-                        if (fill) bulk_g2s(sB + slot * kF4BBytes + bytes, zero_page, fill, &b_full[slot]);
+                        bulk_g2s(sB + slot * C::kBBytes, cur.t + (size_t)t * C::kBBytes, bytes, &b_full[slot]);
+                        if (fill) bulk_g2s(sB + slot * C::kBBytes + bytes, zero_page, fill, &b_full[slot]);
                         uB++;
                     }
                     if (t == 0 && nqt == 2) {
                         mbar_wait_wd(&a_empty[ab + 1], ((phA >> (ab + 1)) & 1u) ^ 1u);
-                        const uint32_t bytes = (uint32_t)e4_bytes(min(kMmaM, nq - q0 - kMmaM));
+                        const uint32_t bytes = (uint32_t)C::bytes(min(kMmaM, nq - q0 - kMmaM));
                         mbar_expect_tx(&a_full[ab + 1], bytes);
-                        bulk_g2s(sA + (ab + 1) * kF4ABytes, cur.q + (size_t)((q0 + kMmaM) >> 3) * kF4GroupBytes, bytes, &a_full[ab + 1]);
+                        bulk_g2s(sA + (ab + 1) * C::kABytes, cur.q + (size_t)((q0 + kMmaM) >> 3) * C::kGroupBytes, bytes, &a_full[ab + 1]);
                         phA ^= 1u << (ab + 1);
                     }
                 }
@@ -287,21 +344,21 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
         int tr = 0;
 #endif
         MmaDesc fdsc = dsc;
-        fdsc.lbo16 = 128 >> 4; fdsc.sbo16 = kF4GroupBytes >> 4;
-        const uint32_t sfa = tmem_base + kF4SfCol, sfb = tmem_base + kF4SfCol + 4;
+        fdsc.lbo16 = 128 >> 4; fdsc.sbo16 = C::kGroupBytes >> 4;
+        const uint32_t sfa = tmem_base + kF4SfCol, sfb = tmem_base + C::kSfbCol;
         MmaDesc tdsc = dsc;
         tdsc.lbo16 = 128 >> 4; tdsc.sbo16 = 256 >> 4;
         const uint64_t tail_a = make_smem_desc(smem_u32(sTailA), tdsc), tail_b = make_smem_desc(smem_u32(sTailB), tdsc);
         F4_ITEM_LOOP_BEGIN
             const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
             const int T = (nt + kF4N - 1) / kF4N;
-            const uint32_t ab = (k & 1u) * 2u;
+            const uint32_t ab = C::kABufs == 2 ? (k & 1u) * 2u : 0u;
             for (int t = 0; t < T; ++t) {
-                const uint32_t slot = uB % kF4Stages;
+                const uint32_t slot = uB % C::kStages;
 #ifdef UZ_F4_TRACE
                 const long long trA = clock64();
 #endif
-                mbar_wait_wd(&b_full[slot], (uB / kF4Stages) & 1u);
+                mbar_wait_wd(&b_full[slot], (uB / C::kStages) & 1u);
 #ifdef UZ_F4_TRACE
                 const long long trB = clock64();
 #endif
@@ -327,11 +384,11 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                         const long long tr0 = clock64();
 #endif
                         if (tc_elect_one()) {
-                            const uint32_t a_addr = smem_u32(sA + (ab + i) * kF4ABytes), b_addr = smem_u32(sB + slot * kF4BBytes);
+                            const uint32_t a_addr = smem_u32(sA + (ab + i) * C::kABytes), b_addr = smem_u32(sB + slot * C::kBBytes);
                             const uint32_t d_acc = tmem_base + (uint32_t)i * kF4N;
                             tc_mma_f8_start(d_acc, tail_a, tail_bt, idesc_start);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)       // K = 64 nibbles = 32 bytes of a row per instruction, on top of the start value
+                            for (int k = 0; k < C::kKSteps; ++k)       // K = 64 nibbles = 32 bytes of a row per instruction, on top of the start value
                                 tc_mma_mxf4(d_acc, make_smem_desc(a_addr + k * 256, fdsc), make_smem_desc(b_addr + k * 256, fdsc), idesc, sfa, sfb);
                             tc_commit(&acc_full[i]);
                             if (t == T - 1) tc_commit(&a_empty[ab + i]);
@@ -374,7 +431,7 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
             mbar_wait_wd(&rag_empty[rb], ((nrag >> 1) & 1u) ^ 1u);
             const uint32_t dig[8] = {0x00u, 0x3Cu, 0x40u, 0x42u, 0x44u, 0x45u, 0x46u, 0x47u};      // e5m2 of 0..7
             for (int row = lane; row < kF4N; row += 32) {
-                const int v = 127 - (row & 127);
+                const int v = (C::kKeyCols - 1) - (row & (C::kKeyCols - 1));
                 const bool real = row < rows;
                 const uint32_t w0 = 0x68u | (0x68u << 8) | (real ? (0x58u << 16) | (dig[v >> 6] << 24) : 0u);       // 2048, 2048, 128 | 0, d2 | 0
                 const uint32_t w1 = real ? (dig[(v >> 3) & 7] | (dig[v & 7] << 8)) : 0u;
@@ -431,7 +488,12 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
 #ifdef UZ_F4_TRACE
                             tr1 = clock64();
 #endif
-                            if (half == 0) f4_block<32>(dA, dB, one, m1[i], m2[i], tbase); else f4_block<24>(dA, dB, one, m1[i], m2[i], tbase);
+                            if (WIDE) {
+                                f4_block64<32>(dA, one, m1[i], m2[i], tbase);
+                                if (half == 0) f4_block64<32>(dB, one, m1[i], m2[i], tbase + 64); else f4_block64<24>(dB, one, m1[i], m2[i], tbase + 64);
+                            } else {
+                                if (half == 0) f4_block<32>(dA, dB, one, m1[i], m2[i], tbase); else f4_block<24>(dA, dB, one, m1[i], m2[i], tbase);
+                            }
                         } else {
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[i]);

@@ -34,15 +34,18 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
     }
     if (j.e8 == nullptr) return;
     if (j.e4) {
-        // 32-byte rows, 4-bit operands (uz_knn2_mmaf.cuh): one thread per (row, 32-bit word): 32 nibbles = one uint4 store
+        // 4-bit operands (uz_knn2_mmaf.cuh): one thread per (row, 32-bit word): 32 nibbles = one uint4 store; a 64-byte row
+        // is sixteen words and an 8-row group 2 KB
         // (the rows that complete the last 8-row group hold zero nibbles: they add nothing to a sum)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((j.n + 7) & ~7) * 8; i += gridDim.x * blockDim.x) {
-            const int row = i >> 3, w = i & 7;
+        const int words = 8 * j.halves_per_row;
+        const size_t group = (size_t)kF4GroupBytes * j.halves_per_row;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((j.n + 7) & ~7) * words; i += gridDim.x * blockDim.x) {
+            const int row = i / words, w = i % words;
             if (row >= j.n) {
-                *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * group + w * 128 + (row & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
                 continue;
             }
-            const uint32_t bits = j.raw[(size_t)row * 8 + w];
+            const uint32_t bits = j.raw[(size_t)row * words + w];
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(256) derive_layouts_kernel(const DeriveJob* __
                 for (int b = 0; b < 8; ++b) v |= (((bits >> (8 * k + b)) & 1u) ? kE4Set : kE4Clear) << (4 * b);
                 o[k] = v;
             }
-            *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * kF4GroupBytes + w * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(j.e8 + (size_t)(row >> 3) * group + w * 128 + (row & 7) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         return;
     }
@@ -266,7 +269,7 @@ uz_status derive_layouts(uz_context* ctx, const Cam* cams, size_t n_cams) {
     for (size_t i = 0; i < n_cams; ++i) {
         const Cam& c = cams[i];
         if (c.n == 0) continue;
-        jobs.push_back(DeriveJob{c.raw, c.csa, c.e8, c.n, (int16_t)(c.dbytes / 32), (int16_t)(ctx->narrow_e4 && c.dbytes == UZ_DESC_BYTES)});
+        jobs.push_back(DeriveJob{c.raw, c.csa, c.e8, c.n, (int16_t)(c.dbytes / 32), (int16_t)(c.dbytes == UZ_DESC_BYTES ? ctx->narrow_e4 : ctx->wide_e4)});
         max_units = std::max(max_units, c.n * 16 * (c.dbytes / 32));
     }
     for (size_t j0 = 0; j0 < jobs.size(); j0 += 32768) {
@@ -301,7 +304,7 @@ uz_status place_cams(uz_context* ctx, Arena& arena, const std::vector<const uz_f
         std::vector<CamLayout> lay(cnt);
         for (size_t c = 0; c < cnt; ++c) {
             const uz_features* f = feats[k + c];
-            lay[c] = cam_layout(at, f->n, desc_width(f->desc_bytes), ctx->narrow_e4);
+            lay[c] = cam_layout(at, f->n, desc_width(f->desc_bytes), ctx->operand_fmt());
             at = lay[c].end;
         }
         uint8_t* base = (uint8_t*)arena.alloc(std::max<size_t>(at, 1));

@@ -16,6 +16,8 @@ F4_TILE_ROWS = 240                   # train rows per accumulator (two accumulat
 F4_EPILOGUE_MINMAX3 = 0.5            # per compare: two sweeps of three-input packed max, each over two compares per register
 F4_EPILOGUE_IMAD = 0.5               # per compare: the 32-bit multiply-add of the second sweep (two compares per register)
 
+F4_WIDE_INSTRUCTIONS_PER_TILE = 8    # knn2_mmaf_kernel<true>: 64-byte rows, K = 512
+
 # knn2_mmak_kernel (UZ_MATCH_MMA=4): tensor cores on int8 operands, per 128 x 256 tile of compares
 MMA_INSTRUCTIONS_PER_TILE = 8        # tcgen05.mma kind::i8, K = 32 each, K = 256 in all
 MMA_KEY_SLICE_INSTRUCTIONS = 1       # + the constant K-slice that turns the accumulator into the packed key (overhead, not counted as work)
