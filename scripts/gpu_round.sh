@@ -25,8 +25,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:solv
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:derive_layouts_kernel -c 1 -f -o gpurun_out/derive_layouts_full_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-places --no-extras > /dev/null 2>&1
-# 512-bit rows: the tensor-core kernel (default) and the integer-pipe one; then the 256-bit integer-pipe fallback
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mmaw_kernel -s 2 -c 1 -f -o gpurun_out/knn2_mmaw_full_$TAG \
+# 512-bit rows: the 4-bit tensor-core kernel (default), the int8 one and the integer-pipe one; then the 256-bit integer-pipe fallback
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mmaf_kernel -s 2 -c 1 -f -o gpurun_out/knn2_mmaf_wide_full_$TAG \
+    python scripts/gpu_wide_probe.py 200 > /dev/null 2>&1
+UZ_MATCH_MMA_WIDE=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_mmaw_kernel -s 2 -c 1 -f -o gpurun_out/knn2_mmaw_full_$TAG \
     python scripts/gpu_wide_probe.py 200 > /dev/null 2>&1
 UZ_MATCH_MMA_WIDE=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn2_wide_kernel -s 2 -c 1 -f -o gpurun_out/knn2_wide_full_$TAG \
     python scripts/gpu_wide_probe.py 200 > /dev/null 2>&1
