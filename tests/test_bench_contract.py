@@ -29,8 +29,8 @@ def test_reference_arm_prints_one_contract_line(built):
 
 
 def test_latest_gpu_profile_line_carries_the_contract_keys():
-    """the newest committed GPU bench line (profiles/bench_r02l.json) has what the contract asks of the GPU arm"""
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r02l.json")))
+    """the newest committed GPU bench line (profiles/bench_r02m.json) has what the contract asks of the GPU arm"""
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r02m.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k

@@ -106,6 +106,25 @@ def test_whole_path_records_identical_on_both_match_kernels(oracle):
         em.close(); ep.close()
 
 
+@pytest.mark.parametrize("n_features", [230, 480, 700, 950])
+def test_many_items_per_cta_with_one_to_four_train_tiles(n_features):
+    """the shared-memory rings of knn2_mmaf_kernel turn over many times per CTA: 1, 2, 3 and 4 train tiles per item against
+    4 train stages and 2 query-tile buffers (a query tile is released by the stage barrier of its item's last train tile - with
+    three tiles per item that stage is refilled by the very next tile).  Records byte-identical to the integer-pipe kernel's."""
+    em, ep = _est(1), _est(0)
+    try:
+        kfs, pairs, _ = S.make_map(240, n_features=n_features, cluster=12, pool=n_features, n_shared=n_features // 2,
+                                   k_candidates=12, cross_cluster=2, seed=100 + n_features)
+        recs = []
+        for e in (em, ep):
+            h = e.add_keyframes(kfs)
+            recs.append([e.estimateEdges(h[pairs[:, 0]], h[pairs[:, 1]]) for _ in range(2)])
+        assert recs[0][0].tobytes() == recs[1][0].tobytes() and recs[0][1].tobytes() == recs[1][1].tobytes()
+        assert (recs[0][0]["ok"] == 1).any() and len(pairs) > 2000
+    finally:
+        em.close(); ep.close()
+
+
 @pytest.mark.parametrize("variant", [4, 7])
 def test_alternative_tensor_core_kernels_equal_oracle(oracle, variant):
     """the measured alternatives that stay selectable (UZ_MATCH_MMA=4: int8 operands, keys formed by the MMA, knn2_mmak_kernel;

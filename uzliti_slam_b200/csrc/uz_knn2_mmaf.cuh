@@ -239,7 +239,6 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     uint2* xchg = reinterpret_cast<uint2*>(sTailR + 2 * kF4TailBBytes);     // [2 parities][256 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kMmaItemRows);
     uint64_t* a_full = bars;          // [2 items][2]
-    uint64_t* a_empty = bars + 4;     // [2 items][2]
     uint64_t* b_full = bars + 8;      // [C::kStages]
     uint64_t* b_empty = b_full + C::kStages;
     uint64_t* acc_full = b_empty + C::kStages;    // [2]
@@ -251,7 +250,7 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&a_full[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); mbar_init(&rag_full[i], 1); mbar_init(&rag_empty[i], kF4Issuers); }
         for (int s = 0; s < C::kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kF4Issuers); }       // every issuer returns a train tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -298,18 +297,25 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     if (warp == 0) {
         // ===================== producer =====================
         if (lane == 0) {
-            uint32_t uB = 0, phA = 0, k = 0;          // phA: one phase bit per query-tile buffer
+            // Query tiles have no "empty" barrier of their own: an item's query tiles are free when the instructions on its LAST
+            // train tile are done, which is what that tile's stage barrier says (both issuers arrive on it) - one
+            // tcgen05.commit per item and issuer less.  a_last[b] = that tile's running number for query-tile buffer b.
+            uint32_t uB = 0, k = 0, a_last0 = 0, a_last1 = 0, a_used = 0;
             F4_ITEM_LOOP_BEGIN
                 const int nqt = (nq - q0 > kMmaM) ? 2 : 1;
                 const int T = (nt + kF4N - 1) / kF4N;
                 const uint32_t ab = C::kABufs == 2 ? (k & 1u) * 2u : 0u;
                 for (int t = 0; t < T; ++t) {
                     if (t == 0) {
-                        mbar_wait_wd(&a_empty[ab], ((phA >> ab) & 1u) ^ 1u);
+                        if (a_used & (1u << (ab >> 1))) {
+                            const uint32_t u = ab ? a_last1 : a_last0;
+                            // (once the stage has been refilled - tile u + kStages is behind us -, the wait before that refill
+                            // has covered this already, and asking again could alias with a later phase of the barrier)
+                            if (uB <= u + C::kStages) mbar_wait_wd(&b_empty[u % C::kStages], (u / C::kStages) & 1u);
+                        }
                         const uint32_t bytes = (uint32_t)C::bytes(min(kMmaM, nq - q0));
                         mbar_expect_tx(&a_full[ab], bytes);
                         bulk_g2s(sA + ab * C::kABytes, cur.q + (size_t)(q0 >> 3) * C::kGroupBytes, bytes, &a_full[ab]);
-                        phA ^= 1u << ab;
                     }
                     {
                         const uint32_t slot = uB % C::kStages;
@@ -322,12 +328,14 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                         uB++;
                     }
                     if (t == 0 && nqt == 2) {
-                        mbar_wait_wd(&a_empty[ab + 1], ((phA >> (ab + 1)) & 1u) ^ 1u);
                         const uint32_t bytes = (uint32_t)C::bytes(min(kMmaM, nq - q0 - kMmaM));
                         mbar_expect_tx(&a_full[ab + 1], bytes);
                         bulk_g2s(sA + (ab + 1) * C::kABytes, cur.q + (size_t)((q0 + kMmaM) >> 3) * C::kGroupBytes, bytes, &a_full[ab + 1]);
-                        phA ^= 1u << (ab + 1);
                     }
+                }
+                if (T > 0) {
+                    if (ab) a_last1 = uB - 1; else a_last0 = uB - 1;
+                    a_used |= 1u << (ab >> 1);
                 }
                 ++k;
             F4_ITEM_LOOP_END
@@ -391,7 +399,6 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                             for (int k = 0; k < C::kKSteps; ++k)       // K = 64 nibbles = 32 bytes of a row per instruction, on top of the start value
                                 tc_mma_mxf4(d_acc, make_smem_desc(a_addr + k * 256, fdsc), make_smem_desc(b_addr + k * 256, fdsc), idesc, sfa, sfb);
                             tc_commit(&acc_full[i]);
-                            if (t == T - 1) tc_commit(&a_empty[ab + i]);
                         }
 #ifdef UZ_F4_TRACE
                         if (lane == 0 && blockIdx.x == 0 && 2 * tr + i < 128) {
