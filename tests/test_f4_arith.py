@@ -145,3 +145,47 @@ def test_e4_layout_is_a_bijection_with_contiguous_row_groups():
     assert max(seen) < groups * 1024                      # e4_bytes(n)
     for g in range(n // 8):                               # a full 8-row group fills its 1 KB exactly: one bulk copy per run of groups
         assert {o for o in seen if g * 1024 <= o < (g + 1) * 1024} == set(range(g * 1024, (g + 1) * 1024))
+
+
+def _ring_violations(T, stages, bufs, wait_rule, items=40):
+    """A model of the producer of knn2_mmaf_kernel: train tile v may be filled once tile v - stages is done (the stage barrier);
+    the query tiles of item k go into buffer k % bufs and may be filled once the LAST tile of item k - bufs is done.  The
+    producer only knows what its own waits told it.  `wait_rule(uB, u)` says whether it waits on the stage barrier of tile u
+    before loading query tiles when uB tiles have been filled.  Returns the loads that happened without that knowledge."""
+    known_done = -1                       # the producer knows tiles <= known_done are done
+    uB, bad = 0, 0
+    last_of = {}
+    for k in range(items):
+        b = k % bufs
+        if b in last_of:
+            u = last_of[b]
+            if wait_rule(uB, u):
+                known_done = max(known_done, u)
+            if known_done < u:
+                bad += 1
+        for _ in range(T):
+            if uB - stages >= 0:
+                known_done = max(known_done, uB - stages)      # the wait before refilling the stage
+            uB += 1
+        last_of[b] = uB - 1
+    return bad
+
+
+def test_query_tiles_are_released_by_the_stage_barrier_of_the_last_train_tile():
+    rule = lambda uB, u, S: uB <= u + S                  # noqa: E731  (uz_knn2_mmaf.cuh, producer)
+    for stages, bufs in ((4, 2), (2, 1)):
+        for T in range(1, 12):
+            assert _ring_violations(T, stages, bufs, lambda uB, u: rule(uB, u, stages)) == 0, (T, stages, bufs)
+    # the rule never waits on a stage that has been refilled since (its barrier is phases ahead: the parity test would alias)
+    for stages, bufs in ((4, 2), (2, 1)):
+        for T in range(1, 12):
+            uB = 0
+            last_of = {}
+            for k in range(30):
+                b = k % bufs
+                if b in last_of and rule(uB, last_of[b], stages):
+                    assert uB <= last_of[b] + stages          # tile last + stages, the refill, is not behind us
+                uB += T
+                last_of[b] = uB - 1
+    # the first version skipped the wait when the refill was the very next tile: items of three tiles, four stages, two buffers
+    assert _ring_violations(3, 4, 2, lambda uB, u: uB < u + 4) > 0
