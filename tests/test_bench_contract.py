@@ -44,7 +44,7 @@ def test_latest_gpu_profile_line_carries_the_contract_keys():
     assert d["cpu_baseline"]["reference_faithful_1thread"]["value"] > 0 and d["adapter_queue"]["same_map_as_this_bench"] is True
     assert d["roofline"]["int_pipe_kernel"]["records_equal_tensor_core_path"] is True
     # the multi-GPU line of the same tree: gathered records equal one GPU's, also through the one-process group
-    d8 = json.load(open(os.path.join(ROOT, "profiles", "bench_r02k_n8.json")))
+    d8 = json.load(open(os.path.join(ROOT, "profiles", "bench_r02m_n8.json")))
     assert d8["n_gpus"] == 8 and d8["sanity"]["gathered_equals_single_gpu"] is True
     assert d8["group"]["records_equal_single_gpu"] is True and d8["group"]["peer_write"]["records_equal"] is True
     assert d8["value"] > 7.5 * d["value"]
