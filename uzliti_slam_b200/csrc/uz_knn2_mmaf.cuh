@@ -230,15 +230,15 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
                                                                   const uint8_t* __restrict__ zero_page) {
     using C = F4<WIDE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;                                    // [2 items][2][16 KB]  query tiles, 128 rows x 128 B of nibbles: the next
-                                                           // item's are fetched while this one's are in use
-    uint8_t* sB = smem + 2 * C::kABufs * C::kABytes;                    // [C::kStages][30 KB]  train tiles, 240 rows
-    uint8_t* sTailA = sB + C::kStages * C::kBBytes;           // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
+    uint8_t* sA = smem;                                    // [kABufs items][2][16 / 32 KB]  query tiles, 128 rows of nibbles; with two
+                                                           // buffers the next item's are fetched while this one's are in use
+    uint8_t* sB = smem + 2 * C::kABufs * C::kABytes;       // [kStages][30 / 60 KB]  train tiles, 240 rows
+    uint8_t* sTailA = sB + C::kStages * C::kBBytes;        // [128 rows x 32 B] e5m2, the instruction that starts an accumulator
     uint8_t* sTailB = sTailA + kF4TailABytes;               // [240 rows x 32 B]
     uint8_t* sTailR = sTailB + kF4TailBBytes;               // [2][240 rows x 32 B]  start operands of ragged tiles
     uint2* xchg = reinterpret_cast<uint2*>(sTailR + 2 * kF4TailBBytes);     // [2 parities][256 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kMmaItemRows);
-    uint64_t* a_full = bars;          // [2 items][2]
+    uint64_t* a_full = bars;          // [2 items][2]  (eight slots reserved)
     uint64_t* b_full = bars + 8;      // [C::kStages]
     uint64_t* b_empty = b_full + C::kStages;
     uint64_t* acc_full = b_empty + C::kStages;    // [2]
@@ -281,8 +281,8 @@ __global__ void __maxnreg__(kF4MaxRegs) knn2_mmaf_kernel(const MmaTask* __restri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= 4 && warp < 8) {
-        // every block scale is 2^1 (UE8M0 128): operands +-4 count as +-8, a product is +-64
-        if (WIDE) {          // query-side scales 2^1, train-side scales 2^0, sixteen columns each
+        // 32-byte rows: every block scale is 2^1 (UE8M0 128): operands +-4 count as +-8, a product is +-64
+        if (WIDE) {          // 64-byte rows: query-side scales 2^1, train-side scales 2^0 (a product is +-32), sixteen columns each
             f4_fill16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kF4SfCol, C::kScaleA);
             f4_fill16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kSfbCol, C::kScaleB);
         } else {
